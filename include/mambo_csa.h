@@ -1,0 +1,138 @@
+/*
+ * mambo_csa.h -- C-ABI of libmambo_b200.so: the B200-native engine for QuantumMAMBO's CSA / CSA_SD
+ * fragment cost + analytic gradient (the per-iteration hot path of the greedy decomposition).
+ *
+ * The reference (pure Julia, /root/reference) has no FFI seam for this path; the boundary is placed at
+ * the narrowest point it offers -- the two closures handed to Optim.jl and the residual update:
+ *
+ *   mambo_csa_cost / mambo_csa_grad / mambo_csa_cost_grad
+ *        replace   cost(x), grad!(storage,x)      src/UTILS/decompose.jl:96-105   (CSA)
+ *                  cost(x), SD_grad!(storage,x)   src/UTILS/decompose.jl:221-231  (CSA_SD)
+ *        i.e. to_OP(CSA_x_to_F_FRAG(x)) + L2_partial_cost + gradient / gradient_csa_sd
+ *        (fermionic.jl:74-92,413-427, unitaries.jl:31-46,254-276, cost.jl:16-25, gradient.jl:1-290)
+ *   mambo_csa_subtract_fragment
+ *        replaces  F_rem = F_rem - to_OP(frag)    decompose.jl:56, 182  and the resume replay :28-32, :154-158
+ *   mambo_csa_residual_cost
+ *        replaces  L2_partial_cost(F_rem)         decompose.jl:40, 166  (cost.jl:44-55)
+ *   mambo_csa_reconstruct
+ *        replaces  to_OP(frag)                    fermionic.jl:1-8
+ *   mambo_csa_get_residual
+ *        hands F_rem back to Julia (F_OP.mbts[2], F_OP.mbts[3])
+ *
+ * Conventions
+ *   - All arrays are FP64.  `tbt` is the Julia Array{Float64,4} as it lies in memory: column-major,
+ *     element (p,q,r,s) (0-based) at p + N*q + N^2*r + N^3*s.  `obt` is N x N column-major.
+ *   - CSA     x = [lambda (N(N+1)/2, lower-tri row-major) ; theta (N(N-1)/2, upper-tri row-major)]
+ *     CSA_SD  x = [lambda1 (N) ; lambda2 (N(N+1)/2) ; theta (N(N-1)/2)]          (fermionic.jl:413-427)
+ *   - "cost" is the squared Frobenius norm (cost.jl:16-25); the gradient is the reference's expression,
+ *     including its one-sided lambda gradient for tensors that are not (pq)<->(rs) symmetric.
+ *   - Every function returns 0 on success, a negative MAMBO_E* code otherwise; mambo_last_error() gives the
+ *     thread-local message.  Nothing throws or aborts across this boundary.
+ *   - A handle is bound to one GPU and is not re-entrant; different handles may be driven concurrently
+ *     from different host threads.  The caller owns every host buffer; buffers are borrowed per call.
+ *   - There is no CPU fallback: if no CUDA device is usable, create fails with MAMBO_ECUDA.
+ */
+#ifndef MAMBO_CSA_H
+#define MAMBO_CSA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mambo_csa mambo_csa;
+
+/* flavour */
+#define MAMBO_CSA     0
+#define MAMBO_CSA_SD  1
+
+/* flags (mambo_csa_create): bits 0-1 choose how the symmetry of tbt is exploited */
+#define MAMBO_SYM_AUTO     0u  /* detect on device (relative tolerance 1e-13) and pick the cheapest valid mode */
+#define MAMBO_SYM_GENERAL  1u  /* no symmetry assumed: D and D^T passes (matches the reference for any tensor) */
+#define MAMBO_SYM_PAIR     2u  /* assume tbt[p,q,r,s] == tbt[r,s,p,q]: one pass over the N^2 x N^2 matrix     */
+#define MAMBO_SYM_FULL     3u  /* assume the 8-fold symmetry of real orbital integrals: packed M x M, M=N(N+1)/2 */
+#define MAMBO_SYM_MASK     3u
+#define MAMBO_TBT_ON_DEVICE 4u /* tbt/obt pointers given to create are device pointers on `device`            */
+
+/* error codes */
+#define MAMBO_OK        0
+#define MAMBO_EINVAL   -1
+#define MAMBO_ECUDA    -2
+#define MAMBO_ENOMEM   -3
+#define MAMBO_ESTATE   -4
+#define MAMBO_ERANGE   -5   /* ||K||_1 needs more squarings than the engine provides */
+
+typedef struct mambo_csa_info_t {
+    int    N, flavour, mode;          /* mode: MAMBO_SYM_GENERAL / _PAIR / _FULL actually in use            */
+    int    num_params;                /* length of x                                                        */
+    int    rows;                      /* logical rows of the residual matrix (N^2 or N(N+1)/2)              */
+    int    rows_padded;               /* rows padded to the 64-row panel                                    */
+    int    shard, nshards;            /* row-panel shard owned by this handle                               */
+    int    local_row_begin, local_row_end;
+    int    partial_len;               /* doubles exchanged per evaluation when sharded: 1 + 2 N^2           */
+    int    num_sms;
+    int    launches_per_eval;         /* kernels launched by one fused cost+grad evaluation                 */
+    double flops_per_eval;            /* DMMA flops executed by the fused kernel(s) per evaluation          */
+    double tensor_bytes;              /* bytes of residual tensor resident on this GPU                      */
+    double asym_pair, asym_pq;        /* measured relative asymmetries of the input tensor                  */
+} mambo_csa_info_t;
+
+/* --- lifetime ------------------------------------------------------------------------------------------ */
+int  mambo_csa_create(mambo_csa** h, int N, int flavour, const double* tbt, const double* obt,
+                      int device, unsigned flags);
+/* Row-panel shard `shard` of `nshards`: this handle keeps only its rows of the residual. */
+int  mambo_csa_create_sharded(mambo_csa** h, int N, int flavour, const double* tbt, const double* obt,
+                              int device, unsigned flags, int shard, int nshards);
+void mambo_csa_destroy(mambo_csa* h);
+int  mambo_csa_get_info(const mambo_csa* h, mambo_csa_info_t* info);
+int  mambo_csa_num_params(const mambo_csa* h);
+const char* mambo_last_error(void);
+
+/* --- the closures (host buffers; H2D of x and D2H of cost/grad happen inside the call) ------------------ */
+int  mambo_csa_cost(mambo_csa* h, const double* x, double* cost);
+int  mambo_csa_grad(mambo_csa* h, const double* x, double* grad);
+int  mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* grad);
+
+/* --- greedy driver state (device-resident residual) ------------------------------------------------------ */
+int  mambo_csa_subtract_fragment(mambo_csa* h, const double* x, double* new_cost);
+int  mambo_csa_residual_cost(mambo_csa* h, double* cost);
+int  mambo_csa_get_residual(mambo_csa* h, double* tbt_out, double* obt_out);
+int  mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double* obt_out);
+
+/* --- device-resident entry points (no host synchronisation; used by the multi-GPU host and bench) -------- */
+/* Run all engine work on `stream` (a cudaStream_t); NULL restores the handle's own stream. */
+int  mambo_csa_set_stream(mambo_csa* h, void* stream);
+/* d_x: num_params doubles on the device; d_out: 1 + num_params doubles [cost, grad...] on the device. */
+int  mambo_csa_eval_device(mambo_csa* h, const double* d_x, double* d_out);
+/* Sharded evaluation in two halves around the caller's allreduce(sum) of d_partial (partial_len doubles):
+ *   partial = [cost_2body, S (N x N), G (N x N)] summed over this shard's rows.                        */
+int  mambo_csa_eval_partial_device(mambo_csa* h, const double* d_x, double* d_partial);
+int  mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double* d_out);
+/* Cost-only evaluation (half the flops: reconstruction + residual norm, no gradient). */
+int  mambo_csa_cost_device(mambo_csa* h, const double* d_x, double* d_cost);
+int  mambo_csa_synchronize(mambo_csa* h);
+
+/* --- multistart scheduler: K independent BFGS runs, one handle per GPU, host thread each ----- */
+typedef struct mambo_opt_options_t {
+    int    max_iter;      /* default 1000 (Optim.jl default)                                   */
+    double g_tol;         /* default 1e-8  (Optim.jl default, inf-norm of the gradient)        */
+    int    lbfgs_memory;  /* 0 = dense BFGS (reference behaviour), >0 = L-BFGS with that memory */
+    int    verbose;
+} mambo_opt_options_t;
+
+typedef struct mambo_opt_result_t {
+    double minimum;
+    int    iterations, evaluations, converged, device;
+} mambo_opt_result_t;
+
+/* Minimise cost(x) from x0 on one handle with the built-in BFGS (Hager-Zhang-style line search). */
+int  mambo_csa_optimize(mambo_csa* h, const double* x0, double* x_min, const mambo_opt_options_t* opt,
+                        mambo_opt_result_t* res);
+/* K starts x0[k*L .. (k+1)*L) distributed over the given handles (one worker thread per handle);
+ * x_min receives the K minimisers, res the K results; *best receives argmin_k res[k].minimum. */
+int  mambo_multistart_run(mambo_csa** handles, int nhandles, int K, const double* x0, double* x_min,
+                          const mambo_opt_options_t* opt, mambo_opt_result_t* res, int* best);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAMBO_CSA_H */

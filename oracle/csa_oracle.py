@@ -1,0 +1,510 @@
+"""CPU ORACLE (test infrastructure, not product code).
+
+A numpy restatement of QuantumMAMBO.jl's CSA / CSA_SD fragment cost + analytic gradient, the greedy
+drivers around them and the 1-norm post-processing.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this file; the product path
+(``quantummambo.jl_b200``) never does.
+
+PARITY UNPINNED: the reference ships no golden vectors, known-answer tests or fixtures for this path
+(``/root/reference/test/runtests.jl:1-5`` runs only Lanczos tests) and it cannot be executed here (no
+``julia`` binary).  Substitute pins, all exercised by ``tests/test_oracle.py``:
+  (1) the *literal* transcription below (loop nests and formulas 1:1 with the Julia source) agrees with
+      the *factored* O(N^5) form to ~1e-13 for N in 3..8;
+  (2) the analytic gradient agrees with central finite differences of the literal cost for
+      pair-swap-symmetric targets;
+  (3) analytic known answers: planted tensor => cost 0 / gradient 0; theta = 0 => U = I and
+      W[i,i,j,j] = Lambda_ij.
+
+Conventions (all arrays are numpy, indices 0-based; the Julia code is 1-based, column-major):
+  * CSA     x = [lambda (cL = N(N+1)/2) ; theta (uL = N(N-1)/2)]
+  * CSA_SD  x = [lambda1 (N) ; lambda2 (cL) ; theta (uL)]
+  * lambda order: lower-triangular row-major (1,1),(2,1),(2,2),(3,1)...   fermionic.jl:23-30, gradient.jl:47-53
+  * theta order : upper-triangular row-major (1,2),(1,3)..(1,N),(2,3)...  unitaries.jl:36-43
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+# ----------------------------------------------------------------------------------------------
+# parameter counting / packing                                       (fermionic.jl:50-56, unitaries.jl:48-51)
+# ----------------------------------------------------------------------------------------------
+
+def cartan_2b_num_params(N: int) -> int:
+    """fermionic.jl:50-52"""
+    return N * (N + 1) // 2
+
+
+def cartan_SD_num_params(N: int) -> int:
+    """fermionic.jl:54-56"""
+    return N + cartan_2b_num_params(N)
+
+
+def real_orbital_rotation_num_params(N: int) -> int:
+    """unitaries.jl:48-51"""
+    return N * (N - 1) // 2
+
+
+def get_rot_indices(n: int, idx: int):
+    """unitaries.jl:418-424 -- 1-based idx -> 1-based (i, j), i < j.  Returned 0-based here."""
+    i = int(np.ceil(((2 * n - 1) - np.sqrt((1 - 2 * n) ** 2 - 8 * idx)) / 2))
+    i_prev = i - 1
+    j = i + int(idx - i_prev * n + i_prev * (i_prev + 1) / 2)
+    return i - 1, j - 1
+
+
+def construct_anti_symmetric(n: int, params) -> np.ndarray:
+    """unitaries.jl:391-415 (get_anti_symmetric + construct_anti_symmetric); same matrix as the Ulog
+    built in unitaries.jl:31-45."""
+    K = np.zeros((n, n))
+    idx = 0
+    for p in range(n):
+        for q in range(p + 1, n):
+            K[p, q] = params[idx]
+            K[q, p] = -params[idx]
+            idx += 1
+    return K
+
+
+def one_body_unitary(theta, n: int) -> np.ndarray:
+    """unitaries.jl:31-46: U = exp(Ulog).  Julia's ``exp`` is Higham-2005 Pade scaling & squaring;
+    scipy's expm (Al-Mohy/Higham 2009) agrees with it to a few ulp for these well-conditioned inputs."""
+    return sla.expm(construct_anti_symmetric(n, theta))
+
+
+def get_cartan_matrix(n: int, lam) -> np.ndarray:
+    """gradient.jl:43-55 / fermionic.jl:20-32: full symmetric lambda matrix from lower-tri row-major."""
+    L = np.zeros((n, n))
+    idx = 0
+    for i in range(n):
+        for j in range(i + 1):
+            L[i, j] = lam[idx]
+            L[j, i] = lam[idx]
+            idx += 1
+    return L
+
+
+def cartan_2b_to_tbt(lam, n: int) -> np.ndarray:
+    """fermionic.jl:20-32"""
+    tbt = np.zeros((n, n, n, n))
+    idx = 0
+    for i in range(n):
+        for j in range(i + 1):
+            tbt[i, i, j, j] = lam[idx]
+            tbt[j, j, i, i] = lam[idx]
+            idx += 1
+    return tbt
+
+
+def split_x(x, n: int, flavour: str):
+    """fermionic.jl:413-427 (CSA_x_to_F_FRAG / CSA_SD_x_to_F_FRAG slicing)."""
+    cL = cartan_2b_num_params(n)
+    if flavour == "CSA":
+        return None, np.asarray(x[:cL]), np.asarray(x[cL:])
+    return np.asarray(x[:n]), np.asarray(x[n:n + cL]), np.asarray(x[n + cL:])
+
+
+# ----------------------------------------------------------------------------------------------
+# LITERAL restatement (N^6 / N^8 loops through einsum, N^6 scratch) -- small N only
+# ----------------------------------------------------------------------------------------------
+
+def cartan_tbt_rotation(U, tbt):
+    """unitaries.jl:254-260: rotated[a,b,c,d] = U[a,l] U[b,l] U[c,m] U[d,m] tbt[l,l,m,m]."""
+    n = U.shape[0]
+    lam = np.einsum("llmm->lm", tbt)
+    return np.einsum("al,bl,cm,dm,lm->abcd", U, U, U, U, lam, optimize=False) if n <= 5 else \
+        np.einsum("al,bl,cm,dm,lm->abcd", U, U, U, U, lam, optimize=True)
+
+
+def tbt_rotation(U, tbt):
+    """unitaries.jl:266-272 (the general 4-index rotation used by the CSA_SD representer)."""
+    return np.einsum("al,bk,cm,dp,lkmp->abcd", U, U, U, U, tbt, optimize=True)
+
+
+def obt_rotation(U, obt):
+    """unitaries.jl:314-320"""
+    return np.einsum("ai,bj,ij->ab", U, U, obt)
+
+
+def to_OP(x, n: int, flavour: str = "CSA"):
+    """to_OP(CSA_x_to_F_FRAG(x)) -- fermionic.jl:1-8, 74-92, 58-72.  Returns (obt or None, tbt)."""
+    lam1, lam2, theta = split_x(x, n, flavour)
+    U = one_body_unitary(theta, n)
+    tbt = cartan_2b_to_tbt(lam2, n)
+    if flavour == "CSA":
+        return None, cartan_tbt_rotation(U, tbt)
+    obt = np.diag(lam1)
+    return obt_rotation(U, obt), tbt_rotation(U, tbt)
+
+
+def L2_partial_cost(tbt_a, tbt_b=None, obt_a=None, obt_b=None) -> float:
+    """cost.jl:16-55 -- squared Frobenius norm over the filled (one- and) two-body tensors."""
+    c = float(np.sum((tbt_a - (0.0 if tbt_b is None else tbt_b)) ** 2))
+    if obt_a is not None:
+        c += float(np.sum((obt_a - (0.0 if obt_b is None else obt_b)) ** 2))
+    return c
+
+
+def cost_literal(x, tbt, obt=None, flavour: str = "CSA") -> float:
+    """decompose.jl:96-99 (CSA) / :221-224 (CSA_SD)."""
+    n = tbt.shape[0]
+    h, W = to_OP(x, n, flavour)
+    if flavour == "CSA":
+        return L2_partial_cost(tbt, W)
+    return L2_partial_cost(tbt, W, obt, h)
+
+
+def del_wr_lr(n, l, m, U):
+    """gradient.jl:5-11"""
+    return np.einsum("p,q,r,s->pqrs", U[:, l], U[:, l], U[:, m], U[:, m])
+
+
+def grad_lr(n, U, diff):
+    """gradient.jl:13-41 (grad_lr_ij folded in; the per-(i,j) expm recomputation is the same U)."""
+    g = np.zeros(cartan_2b_num_params(n))
+    idx = 0
+    cw = 2 * diff
+    for i in range(n):
+        for j in range(i + 1):
+            cl = np.sum(cw * del_wr_lr(n, i, j, U))
+            if i != j:
+                cl *= 2
+            g[idx] = cl
+            idx += 1
+    return g
+
+
+def del_w_u(n, U, L):
+    """gradient.jl:57-74 -- dW[p,q,r,s]/dU[a,b] as a dense N^6 array (4 product-rule terms)."""
+    wu = np.zeros((n,) * 6)
+    UL = np.einsum("rm,sm,bm->rsb", U, U, L)          # sum_m U[r,m] U[s,m] L[b,m]
+    ULl = np.einsum("pl,ql,lb->pqb", U, U, L)         # sum_l U[p,l] U[q,l] L[l,b]
+    for p in range(n):
+        wu[p, :, :, :, p, :] += np.einsum("qb,rsb->qrsb", U, UL)
+    for q in range(n):
+        wu[:, q, :, :, q, :] += np.einsum("pb,rsb->prsb", U, UL)
+    for r in range(n):
+        wu[:, :, r, :, r, :] += np.einsum("pqb,sb->pqsb", ULl, U)
+    for s in range(n):
+        wu[:, :, :, s, s, :] += np.einsum("pqb,rb->pqrb", ULl, U)
+    return wu
+
+
+def del_u_theta(n, u_params, idx0):
+    """gradient.jl:113-126 (exp branch): dU/dtheta_idx through the eigendecomposition of K, with the
+    hard 1e-8 switch of gradient.jl:119-121.  idx0 is 0-based."""
+    i, j = get_rot_indices(n, idx0 + 1)
+    kappa = np.zeros((n, n))
+    kappa[i, j] = 1
+    kappa[j, i] = -1
+    K = construct_anti_symmetric(n, u_params)
+    D, O = np.linalg.eig(K)
+    I = O.conj().T @ kappa @ O
+    for a in range(n):
+        for b in range(n):
+            if abs(D[a] - D[b]) > 1e-8:
+                I[a, b] *= (np.exp(D[a] - D[b]) - 1) / (D[a] - D[b])
+    expD = np.diag(np.exp(D))
+    return np.real(O @ I @ expD @ O.conj().T)
+
+
+def grad_theta(n, U, L, u_params, diff, diff_ob=None, lam1=None):
+    """gradient.jl:131-146 (CSA) and :266-284 (CSA_SD adds the one-body term through del_h_u :218-231)."""
+    wu = del_w_u(n, U, L)
+    opnum = real_orbital_rotation_num_params(n)
+    g = np.zeros(opnum)
+    if diff_ob is not None:
+        hu = np.zeros((n, n, n, n))
+        for r in range(n):
+            hu[r, :, r, :] += U * lam1[None, :]
+        for s in range(n):
+            hu[:, s, s, :] += U * lam1[None, :]
+    for k in range(opnum):
+        ut = del_u_theta(n, u_params, k)
+        w_theta = np.einsum("pqrsab,ab->pqrs", wu, ut)
+        val = np.sum(diff * w_theta)
+        if diff_ob is not None:
+            h_theta = np.einsum("pqab,ab->pq", hu, ut)
+            val += np.sum(diff_ob * h_theta)
+        g[k] = 2 * val
+    return g
+
+
+def gradient_literal(x, tbt, obt=None, flavour: str = "CSA"):
+    """grad! closures: decompose.jl:101-105 -> gradient.jl:148-151 ; decompose.jl:226-231 -> gradient.jl:287-290."""
+    n = tbt.shape[0]
+    lam1, lam2, theta = split_x(x, n, flavour)
+    U = one_body_unitary(theta, n)
+    L = get_cartan_matrix(n, lam2)
+    h, W = to_OP(x, n, flavour)
+    diff = W - tbt
+    if flavour == "CSA":
+        return np.concatenate([grad_lr(n, U, diff), grad_theta(n, U, L, theta, diff)])
+    diff_ob = h - obt
+    g1 = np.array([np.sum(2 * diff_ob * np.outer(U[:, k], U[:, k])) for k in range(n)])   # gradient.jl:157-186
+    return np.concatenate([g1, grad_lr(n, U, diff), grad_theta(n, U, L, theta, diff, diff_ob, lam1)])
+
+
+# ----------------------------------------------------------------------------------------------
+# FACTORED restatement (O(N^5), BLAS) -- the oracle for N = 50 / 100 / 152 and the CPU baseline
+# ----------------------------------------------------------------------------------------------
+
+def _frechet_adjoint(K, G):
+    """Lf = top-right block of exp([[K^T, G],[0, K^T]]) = Dexp(K^T)[G]; <G, dexp_K(kappa)> = <Lf, kappa>."""
+    n = K.shape[0]
+    M = np.zeros((2 * n, 2 * n))
+    M[:n, :n] = K.T
+    M[n:, n:] = K.T
+    M[:n, n:] = G
+    return sla.expm(M)[:n, n:]
+
+
+def cost_grad_factored(x, tbt, obt=None, flavour: str = "CSA", need_grad: bool = True, U=None):
+    """Same numbers as cost_literal / gradient_literal via
+         A = U (.) U (N^2 x N),  W = A L A^T,  D = W - T,  E = D A,  E' = D^T A,
+         S = A^T E,  F = E L,  G = sum of the 4 product-rule terms,  grad_theta from the adjoint Frechet
+         derivative of expm.
+    The lambda gradient is the reference's one-sided expression (gradient.jl:22-26): S uses E only."""
+    n = tbt.shape[0]
+    lam1, lam2, theta = split_x(x, n, flavour)
+    K = construct_anti_symmetric(n, theta)
+    if U is None:
+        U = sla.expm(K)
+    L = get_cartan_matrix(n, lam2)
+    # row (p,q) of A:  A[p,q,l] = U[p,l] U[q,l];  C-order (p slow) -- only the association with T matters.
+    A = (U[:, None, :] * U[None, :, :]).reshape(n * n, n)
+    T = np.ascontiguousarray(tbt).reshape(n * n, n * n)          # T[(p,q),(r,s)] in C order
+    D = (A @ L) @ A.T - T
+    cost = float(np.sum(D * D))
+    if flavour != "CSA":
+        h = (U * lam1[None, :]) @ U.T
+        Dh = h - obt
+        cost += float(np.sum(Dh * Dh))
+    if not need_grad:
+        return cost, None
+    E = D @ A                                                    # E[(p,q), j]
+    Et = D.T @ A                                                 # E'[(r,s), j]
+    S = A.T @ E
+    cL = cartan_2b_num_params(n)
+    gl = np.zeros(cL)
+    idx = 0
+    for i in range(n):
+        for j in range(i + 1):
+            gl[idx] = 2.0 * S[i, j] * (2.0 if i != j else 1.0)
+            idx += 1
+    F1 = (E @ L).reshape(n, n, n)                                # [p,q,b]
+    F2 = (Et @ L).reshape(n, n, n)
+    G = np.einsum("qb,aqb->ab", U, F1) + np.einsum("qb,qab->ab", U, F1) \
+        + np.einsum("sb,asb->ab", U, F2) + np.einsum("sb,sab->ab", U, F2)
+    g1 = None
+    if flavour != "CSA":
+        G = G + ((Dh + Dh.T) @ U) * lam1[None, :]
+        g1 = 2.0 * np.einsum("rk,rs,sk->k", U, Dh, U)
+    Lf = _frechet_adjoint(K, G)
+    gt = np.zeros(real_orbital_rotation_num_params(n))
+    idx = 0
+    for p in range(n):
+        for q in range(p + 1, n):
+            gt[idx] = 2.0 * (Lf[p, q] - Lf[q, p])
+            idx += 1
+    if flavour == "CSA":
+        return cost, np.concatenate([gl, gt])
+    return cost, np.concatenate([g1, gl, gt])
+
+
+def reconstruct_factored(x, n: int, flavour: str = "CSA"):
+    """to_OP(frag) through the factored form (any N)."""
+    lam1, lam2, theta = split_x(x, n, flavour)
+    U = one_body_unitary(theta, n)
+    L = get_cartan_matrix(n, lam2)
+    A = (U[:, None, :] * U[None, :, :]).reshape(n * n, n)
+    W = ((A @ L) @ A.T).reshape(n, n, n, n)
+    if flavour == "CSA":
+        return None, W
+    return (U * lam1[None, :]) @ U.T, W
+
+
+# ----------------------------------------------------------------------------------------------
+# 1-norms (lcu.jl:139-208, 239-267, fermionic.jl:457-479, 527-538)
+# ----------------------------------------------------------------------------------------------
+
+def CSA_L1(lam, n: int, spin_orb: bool = False) -> float:
+    """lcu.jl:139-182"""
+    l1 = 0.0
+    idx = 0
+    for i in range(n):
+        for j in range(i + 1):
+            if spin_orb:
+                if i != j:
+                    l1 += 0.5 * abs(lam[idx])
+            else:
+                l1 += (2.0 if i != j else 0.5) * abs(lam[idx])
+            idx += 1
+    return l1
+
+
+def ob_correction(tbt, spin_orb: bool = False):
+    """fermionic.jl:457-479"""
+    n = tbt.shape[0]
+    s = sum(tbt[:, :, r, r] for r in range(n))
+    return s if spin_orb else 2 * s
+
+
+def one_body_L1(obt, tbt, spin_orb: bool = False) -> float:
+    """lcu.jl:262-267 with to_OBF (fermionic.jl:527-538) and OBF_L1 (lcu.jl:239-260)."""
+    M = obt + ob_correction(tbt, spin_orb)
+    D = np.linalg.eigvalsh((M + M.T) / 2) if np.allclose(M, M.T) else np.real(np.linalg.eigvals(M))
+    return float(np.sum(np.abs(D))) * (0.5 if spin_orb else 1.0)
+
+
+# ----------------------------------------------------------------------------------------------
+# initial guess (guesses.jl:3-84, unitaries.jl:130-147)
+# ----------------------------------------------------------------------------------------------
+
+def SOn_unitary_to_params(U):
+    """unitaries.jl:130-147: upper-triangular entries of real(log U)."""
+    n = U.shape[0]
+    Ulog = np.real(sla.logm(U))
+    return np.array([Ulog[i, j] for i in range(n) for j in range(i + 1, n)])
+
+
+def tbt_svd_1st(tbt, tiny: float = 1e-12):
+    """guesses.jl:51-84 + SVD_to_CSA (:3-49).  Returns (lambda (cL), theta (uL)).  Note K1 of SURVEY.md:
+    SVD_to_CSA fills lambda in *upper*-triangular order (guesses.jl:12-18) although every consumer reads it
+    lower-triangular -- reproduced on purpose."""
+    n = tbt.shape[0]
+    N2 = n * n
+    # Julia: Symmetric(reshape(tbt,(N,N))) uses the upper triangle of the column-major matrix view.
+    M = np.reshape(tbt, (N2, N2), order="F")
+    Msym = np.triu(M) + np.triu(M, 1).T
+    lamv, Uv = np.linalg.eigh(Msym)
+    ind = np.argsort(np.abs(lamv), kind="stable")[::-1]
+    lamv = lamv[ind]
+    Uv = Uv[:, ind]
+    full_l = np.reshape(Uv[:, 0], (n, n), order="F")
+    cur_l = np.triu(full_l) + np.triu(full_l, 1).T
+    lead = lamv[0]
+    if np.sum(np.abs(cur_l - full_l)) > tiny:
+        if np.sum(np.abs(full_l + full_l.T)) > tiny:
+            raise ValueError("SVD operator is neither Hermitian or anti-Hermitian")
+        cur = 1j * full_l
+        cur = np.triu(cur) + np.triu(cur, 1).conj().T
+        lead = -lead
+        w, Ul = np.linalg.eigh(cur)
+    else:
+        w, Ul = np.linalg.eigh(cur_l)
+    coeffs = np.array([w[i] * w[j] for i in range(n) for j in range(i, n)]) * lead
+    return coeffs, SOn_unitary_to_params(Ul)
+
+
+# ----------------------------------------------------------------------------------------------
+# greedy drivers (decompose.jl:1-246) with scipy BFGS standing in for Optim.jl BFGS
+# ----------------------------------------------------------------------------------------------
+
+def greedy_step(tbt, obt=None, flavour: str = "CSA", x0=None, rng=None, do_svd=None, gtol: float = 1e-8,
+                maxiter: int = 1000, use_literal: bool = False):
+    """decompose.jl:82-120 / 207-246.  x0: explicit start (the reference draws it from the
+    unseeded global RNG); otherwise theta ~ 2*pi*rand, lambda = 0 (CSA) or tbt_svd_1st (CSA_SD default)."""
+    from scipy.optimize import minimize
+    n = tbt.shape[0]
+    cL, uL = cartan_2b_num_params(n), real_orbital_rotation_num_params(n)
+    off = 0 if flavour == "CSA" else n
+    if x0 is None:
+        x0 = np.zeros(off + cL + uL)
+        if do_svd is None:
+            do_svd = flavour != "CSA"            # config.jl:9-10
+        if do_svd:
+            lam, th = tbt_svd_1st(tbt)
+            x0[off:off + cL] = lam
+            x0[off + cL:] = th
+        else:
+            rng = np.random.default_rng() if rng is None else rng
+            x0[off + cL:] = 2 * np.pi * rng.random(uL)
+
+    if use_literal:
+        fun = lambda x: (cost_literal(x, tbt, obt, flavour), gradient_literal(x, tbt, obt, flavour))
+    else:
+        fun = lambda x: cost_grad_factored(x, tbt, obt, flavour)
+    res = minimize(fun, x0, jac=True, method="BFGS", options={"gtol": gtol, "maxiter": maxiter})
+    return res.x, float(res.fun), res
+
+
+def greedy_decomposition(tbt, alpha_max: int, obt=None, flavour: str = "CSA", decomp_tol: float = 1e-5,
+                         x0s=None, rng=None, **kw):
+    """decompose.jl:1-80 / 122-205 (without the HDF5 checkpoint, which stays in Julia).
+    Returns (list of x, list of costs, remaining tbt, remaining obt)."""
+    n = tbt.shape[0]
+    t_rem = np.array(tbt, dtype=float, copy=True)
+    o_rem = None if obt is None else np.array(obt, dtype=float, copy=True)
+    xs, costs = [], []
+    curr = L2_partial_cost(t_rem, None, o_rem, None)
+    a = 0
+    while curr > decomp_tol and a < alpha_max:
+        x0 = None if x0s is None else x0s[a]
+        x, c, _ = greedy_step(t_rem, o_rem, flavour, x0=x0, rng=rng, **kw)
+        h, W = reconstruct_factored(x, n, flavour)
+        t_rem = t_rem - W
+        if o_rem is not None:
+            o_rem = o_rem - h
+        xs.append(x)
+        costs.append(c)
+        curr = c
+        a += 1
+    return xs, costs, t_rem, o_rem
+
+
+# ----------------------------------------------------------------------------------------------
+# synthetic inputs -- deterministic
+# ----------------------------------------------------------------------------------------------
+
+def dense_sym_tbt(n: int, seed: int) -> np.ndarray:
+    """N(0,1) tensor symmetrised over p<->q, r<->s, (pq)<->(rs), scaled 1/N^2."""
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((n, n, n, n))
+    g = g + g.transpose(1, 0, 2, 3)
+    g = g + g.transpose(0, 1, 3, 2)
+    g = g + g.transpose(2, 3, 0, 1)
+    return g / (8.0 * n * n) * 8.0 / 8.0
+
+
+def pairsym_tbt(n: int, seed: int) -> np.ndarray:
+    """Only (pq)<->(rs) symmetric (exercises the un-packed N^2 x N^2 path)."""
+    rng = np.random.default_rng(seed)
+    g = rng.standard_normal((n, n, n, n))
+    return (g + g.transpose(2, 3, 0, 1)) / (2.0 * n * n)
+
+
+def general_tbt(n: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return rng.standard_normal((n, n, n, n)) / (n * n)
+
+
+def random_x(n: int, seed: int, flavour: str = "CSA") -> np.ndarray:
+    """x = [lambda ~ N(0,1)/N ; theta ~ U[0, 2 pi)] (theta matches decompose.jl:93)."""
+    rng = np.random.default_rng(1000 + seed)
+    cL, uL = cartan_2b_num_params(n), real_orbital_rotation_num_params(n)
+    parts = []
+    if flavour != "CSA":
+        parts.append(rng.standard_normal(n) / n)
+    parts.append(rng.standard_normal(cL) / n)
+    parts.append(2 * np.pi * rng.random(uL))
+    return np.concatenate(parts)
+
+
+def planted_tbt(n: int, R: int, seed: int, sigma: float = 0.0):
+    """T = sum_{k<R} W(x_k), lambda ~ N(0,1), theta ~ U[0,2pi).  Returns (tbt, [x_k])."""
+    rng = np.random.default_rng(2000 + seed)
+    cL, uL = cartan_2b_num_params(n), real_orbital_rotation_num_params(n)
+    t = np.zeros((n, n, n, n))
+    xs = []
+    for _ in range(R):
+        x = np.concatenate([rng.standard_normal(cL), 2 * np.pi * rng.random(uL)])
+        t += reconstruct_factored(x, n, "CSA")[1]
+        xs.append(x)
+    if sigma > 0:
+        g = rng.standard_normal((n, n, n, n))
+        g = g + g.transpose(1, 0, 2, 3)
+        g = g + g.transpose(0, 1, 3, 2)
+        g = g + g.transpose(2, 3, 0, 1)
+        t += sigma * g / 8.0
+    return t, xs

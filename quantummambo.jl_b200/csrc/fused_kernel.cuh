@@ -1,0 +1,318 @@
+// fused_kernel.cuh -- the hot kernel of the CSA engine (sm_100a).
+//
+// For a residual matrix T~ (rows i, cols j; j contiguous) and operand matrices A~ (rows x Np) and
+// B~ = A~ Lambda it computes, per 64x64 tile,
+//      D   = B~_I A~_J^T - T~_IJ            (GEMM #1, K = Np, FP64 DMMA.8x8x4)
+//      cost += sum D^2
+//      E_I += D A~_J                        (GEMM #2, K = 64, D never leaves registers)
+// which is the reference's reconstruction (unitaries.jl:254-260), residual (cost.jl:16-25) and the
+// contraction shared by every gradient term (gradient.jl:13-28, 57-74) in one pass over T~.
+//
+// Layout / schedule
+//   * persistent CTAs (one per SM), 8 warps (4 row groups x 2 column groups, warp tile 16 x 32); lane 0 of
+//     warp 0 doubles as the TMA producer (a ninth warp would cap every thread at 168 registers);
+//     the flattened (row panel, column tile) steps are split evenly over CTAs.
+//   * B~ panel (64 x ld) resident in shared memory per row panel; A~ column sub-tiles (32 x ld) stream
+//     through an S-slot ring filled by the TMA engine (cp.async.bulk, SASS UBLKCP) and handed over with
+//     mbarrier full/empty pairs.
+//   * ld = Np + 4 (Np = 8*NB) and the row/column slot permutation perm8 make every LDS.128 of both GEMMs
+//     bank-conflict free; the accumulator fragment of GEMM #1 is, with that permutation, directly the
+//     A fragment of GEMM #2 (no shuffle, no shared-memory round trip).
+//   * T~ is read exactly once, straight into the (negated) accumulators, one step ahead.
+//   * E partials are written per (CTA visit, column group) and reduced in a fixed order later:
+//     results are bit-reproducible run to run.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fused {
+
+constexpr int ROWS = 64;        // rows per panel (CTA)
+constexpr int COLS = 64;        // columns per step (CTA)
+constexpr int SUB = 32;         // columns per warp column group = rows of one A~ ring slot
+constexpr int NCONS = 8;        // consumer warps
+constexpr int NTHREADS = NCONS * 32;
+
+struct Params {
+    const double* T;        // [P*64][ldT] local rows of T~
+    double* Tst;            // STORE: destination for T~ - W~ (may alias T)
+    const double* Brow;     // B~ rows of the local panels  [P*64][ld]
+    const double* Acol;     // A~ rows of all columns       [Q*64][ld]
+    double* Epiece;         // [visits][2][64][Np]
+    double* cost_part;      // [gridDim.x]
+    const int* visit_start; // [gridDim.x]
+    long long ldT;
+    int P, Q, ld, Np, S;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// TMA engine, non-tensor form: contiguous global -> shared, completion counted on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// slot -> position inside an 8-group.  Even slots 2j -> j, odd slots 2j+1 -> 4 + (j+2)%4.
+__host__ __device__ __forceinline__ int perm8(int m) { return (m & 1) ? (4 + (((m >> 1) + 2) & 3)) : (m >> 1); }
+
+inline size_t smem_bytes(int ld, int S) { return (size_t)(ROWS + S * SUB) * ld * 8 + (2 * S + 2) * 8 + NCONS * 8 + 64; }
+
+template <int NB, bool DO_E, bool STORE, bool TPREF>
+__global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int ld = p.ld, S = p.S, Q = p.Q;
+    double* sB = reinterpret_cast<double*>(smem_raw);
+    double* sA = sB + ROWS * ld;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * SUB * ld);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + S;
+    uint64_t* bfull = bars + 2 * S;
+    uint64_t* bempty = bfull + 1;
+    double* sred = reinterpret_cast<double*>(bempty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)p.P * Q;
+    const long long tbeg = total * blockIdx.x / gridDim.x;
+    const long long tend = total * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCONS / 2);
+        }
+        mbar_init(bfull, 1);
+        mbar_init(bempty, NCONS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // ---------------------------------- consumers -------------------------------------------------------
+    const int t0 = lane & 3, t1 = lane >> 2;
+    const int wc = warp & 1, wr = warp >> 1;
+    const int prow = perm8(t1);
+    const int pc0 = t0, pc1 = 4 + ((t0 + 2) & 3);  // perm8(2*t0), perm8(2*t0+1)
+
+    double e[2][NB][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) e[mb][b][0] = e[mb][b][1] = 0.0;
+    double cost = 0.0;
+    double acc[2][4][2];
+    double tn[2][4][2];
+
+    // element (mb, nb, v) of this lane: row 16*wr + 8*mb + prow, col 32*wc + 8*nb + (v ? pc1 : pc0)
+    const long long lane_off = (long long)(16 * wr + prow) * p.ldT + 32 * wc;
+    auto loadT = [&](double(&dst)[2][4][2], int panel_, int ct_) {
+        const double* base = p.T + (long long)panel_ * ROWS * p.ldT + (long long)ct_ * COLS + lane_off;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                dst[mb][nb][0] = __ldcs(base + (long long)mb * 8 * p.ldT + nb * 8 + pc0);
+                dst[mb][nb][1] = __ldcs(base + (long long)mb * 8 * p.ldT + nb * 8 + pc1);
+            }
+    };
+
+    int panel = (int)(tbeg / Q), ct = (int)(tbeg % Q);
+    int gi = 0, pv = 0;
+    if (TPREF && tbeg < tend) loadT(tn, panel, ct);
+
+    // ---- producer state (used by lane 0 of warp 0 only): sub-tile g = 2*step + column group ----------------
+    const int g_total = 2 * (int)(tend - tbeg);
+    const int lookahead = (S >= 6) ? 2 : (S - 2);       // sub-tiles issued beyond the current step
+    int g_issued = 0, ct_p = ct;
+    const uint32_t panel_bytes = (uint32_t)(ROWS * ld * 8), sub_bytes = (uint32_t)(SUB * ld * 8);
+    auto produce_upto = [&](int g_hi) {
+        while (g_issued < g_total && g_issued <= g_hi) {
+            const int slot = g_issued % S, use = g_issued / S, c = g_issued & 1;
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+            mbar_expect_tx(&full[slot], sub_bytes);
+            bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ct_p * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
+            ++g_issued;
+            if (c == 1 && ++ct_p == Q) ct_p = 0;
+        }
+    };
+
+    const double* sBrow = sB + (16 * wr + prow) * ld + 2 * t0;
+
+    for (long long t = tbeg; t < tend; ++t, ++gi) {
+        const bool newpanel = (t == tbeg || ct == 0);
+        if (warp == 0) {
+            if (lane == 0) {
+                if (newpanel) {
+                    if (pv > 0) mbar_wait(bempty, (pv - 1) & 1);   // every warp is done with the old B~ panel
+                    mbar_expect_tx(bfull, panel_bytes);
+                    bulk_g2s(sB, p.Brow + (size_t)panel * ROWS * ld, panel_bytes, bfull);
+                }
+                produce_upto(2 * gi + 1 + lookahead);
+            }
+            __syncwarp();
+        }
+        if (newpanel) {
+            mbar_wait(bfull, pv & 1);
+            ++pv;
+        }
+        if (TPREF) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    acc[mb][nb][0] = -tn[mb][nb][0];
+                    acc[mb][nb][1] = -tn[mb][nb][1];
+                }
+        } else {
+            loadT(acc, panel, ct);
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    acc[mb][nb][0] = -acc[mb][nb][0];
+                    acc[mb][nb][1] = -acc[mb][nb][1];
+                }
+        }
+        const int g = 2 * gi + wc;
+        const int slot = g % S;
+        mbar_wait(&full[slot], (g / S) & 1);
+        const double* sAs = sA + (size_t)slot * SUB * ld;
+
+        // ---------------- GEMM #1: acc += B~_I (16 x Np) . A~_J^T (Np x 32) ----------------------------
+        {
+            const double* sArow = sAs + prow * ld + 2 * t0;
+#pragma unroll
+            for (int kc = 0; kc < NB * 8; kc += 8) {
+                double2 a[2], b[4];
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) a[mb] = *reinterpret_cast<const double2*>(sBrow + mb * 8 * ld + kc);
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) b[nb] = *reinterpret_cast<const double2*>(sArow + nb * 8 * ld + kc);
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < 4; ++nb) {
+                        dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].x, b[nb].x);
+                        dmma(acc[mb][nb][0], acc[mb][nb][1], a[mb].y, b[nb].y);
+                    }
+            }
+        }
+        const bool lastp = (ct == Q - 1) || (t == tend - 1);
+        if (lastp) {  // the B~ panel is no longer needed by this warp: let the producer refill it
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bempty);
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) cost += acc[mb][nb][0] * acc[mb][nb][0] + acc[mb][nb][1] * acc[mb][nb][1];
+
+        if (STORE) {
+            double* base = p.Tst + (long long)panel * ROWS * p.ldT + (long long)ct * COLS + lane_off;
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    base[(long long)mb * 8 * p.ldT + nb * 8 + pc0] = -acc[mb][nb][0];
+                    base[(long long)mb * 8 * p.ldT + nb * 8 + pc1] = -acc[mb][nb][1];
+                }
+        }
+        // next step's coordinates
+        int npanel = panel, nct = ct + 1;
+        if (nct == Q) { nct = 0; ++npanel; }
+        if (TPREF && t + 1 < tend) loadT(tn, npanel, nct);
+
+        // ---------------- GEMM #2: e += D (16 x 32, registers) . A~_J (32 x Np) ------------------------
+        if (DO_E) {
+#pragma unroll
+            for (int kb = 0; kb < 4; ++kb) {
+                const double* r0 = sAs + (8 * kb + pc0) * ld;
+                const double* r1 = sAs + (8 * kb + pc1) * ld;
+#pragma unroll
+                for (int pr = 0; pr < NB / 2; ++pr) {
+                    const double2 b0 = *reinterpret_cast<const double2*>(r0 + 16 * pr + 2 * t1);
+                    const double2 b1 = *reinterpret_cast<const double2*>(r1 + 16 * pr + 2 * t1);
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) {
+                        dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][0], b0.x);
+                        dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][0], b0.y);
+                        dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b1.x);
+                        dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b1.y);
+                    }
+                }
+                if (NB & 1) {
+                    const double b0 = r0[8 * (NB - 1) + t1];
+                    const double b1 = r1[8 * (NB - 1) + t1];
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) {
+                        dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], b0);
+                        dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], b1);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+
+        if (DO_E && lastp) {
+            // flush this visit's partial E rows: Epiece[visit][wc][row][n]
+            const int visit = p.visit_start[blockIdx.x] + (pv - 1);
+            double* dst = p.Epiece + ((size_t)(visit * 2 + wc) * ROWS + 16 * wr + prow) * p.Np;
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    int n0, n1;
+                    if (b < 2 * (NB / 2)) {
+                        n0 = 16 * (b >> 1) + 2 * (2 * t0) + (b & 1);
+                        n1 = n0 + 2;
+                    } else {
+                        n0 = 8 * (NB - 1) + 2 * t0;
+                        n1 = n0 + 1;
+                    }
+                    dst[(size_t)mb * 8 * p.Np + n0] = e[mb][b][0];
+                    dst[(size_t)mb * 8 * p.Np + n1] = e[mb][b][1];
+                    e[mb][b][0] = e[mb][b][1] = 0.0;
+                }
+            }
+        }
+        panel = npanel;
+        ct = nct;
+    }
+
+    // deterministic cost reduction: lanes -> warp -> CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    if (lane == 0) sred[warp] = cost;
+    asm volatile("bar.sync 1, %0;" ::"n"(NCONS * 32) : "memory");
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NCONS; ++w) s += sred[w];
+        p.cost_part[blockIdx.x] = s;
+    }
+}
+
+}  // namespace fused

@@ -1,0 +1,760 @@
+// mambo_csa.cu -- host side of libmambo_b200.so: handle, buffers, launch sequence, C-ABI (include/mambo_csa.h).
+// Replaces the closures of /root/reference/src/UTILS/decompose.jl:96-105, 221-231 and the residual update
+// decompose.jl:56,182.  There is deliberately no CPU code path for any of the numerics in this file.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mambo_csa.h"
+#include "fused_kernel.cuh"
+#include "small_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? MAMBO_ENOMEM : MAMBO_ECUDA,                        \
+                        std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    } while (0)
+
+const int kNBBuckets[] = {1, 2, 4, 7, 10, 13, 16, 19, 21};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace
+
+struct mambo_csa {
+    int N = 0, flavour = 0, mode = 0, device = 0;
+    int L = 0, cL = 0, uL = 0, lam_off = 0;
+    int nR = 0, nRpad = 0;          // logical / padded rows of the residual matrix
+    int NB = 0, Np = 0, ld = 0;     // n-blocks, padded N, operand pitch
+    long long ldT = 0;
+    int shard = 0, nshards = 1;
+    int prow_begin = 0, prow_end = 0;   // local panels [begin, end)
+    int row_begin = 0, row_end = 0;     // local padded rows
+    int P = 0, Q = 0, G = 0, S = 0, visits = 0;
+    int num_sms = 0;
+    size_t smem = 0;
+    bool packed = false;
+    double asym_pair = 0, asym_pq = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    // device buffers
+    double *T1 = nullptr, *T2 = nullptr;       // residual (and its transpose in GENERAL mode)
+    double *hT = nullptr;                      // one-body residual (column-major), CSA_SD
+    double *At = nullptr, *Bt = nullptr;
+    int *pa = nullptr, *pq = nullptr;
+    double* sw = nullptr;
+    double *Epiece = nullptr, *F1 = nullptr, *F2 = nullptr, *Spart = nullptr, *cost_part = nullptr;
+    int *visit_start = nullptr, *piece_first = nullptr;
+    double* mats = nullptr;                    // all N x N matrices of the expm chains
+    double *X, *X2, *X3, *X4, *P0, *P1, *P2, *Q3, *Q2, *Q1, *R;      // R: (SMAX+1) matrices
+    double *dX, *dX2, *dX4, *dP0, *dP1, *dP2, *dQ3, *dQ2, *dQ1, *dR; // dR: (SMAX+1) matrices
+    double *Lam = nullptr, *Dh = nullptr, *DU = nullptr, *hfrag = nullptr, *g1 = nullptr;
+    int* d_s = nullptr;
+    double* d_scale = nullptr;
+    int* d_status = nullptr;
+    double *d_x = nullptr, *d_out = nullptr, *d_part = nullptr;
+    double *h_x = nullptr, *h_out = nullptr;   // pinned staging
+    int* h_status = nullptr;
+    // memo of the last evaluation through the host API
+    std::vector<double> memo_x;
+    bool memo_valid = false;
+    long long launches = 0;
+    int launches_last_eval = 0;
+};
+
+namespace {
+
+using namespace fused;
+
+template <int NB, bool DO_E, bool STORE>
+int launch_fused_nb(mambo_csa* h, const Params& p) {
+    constexpr bool TPREF = (NB <= 13);
+    auto kern = k_fused<NB, DO_E, STORE, TPREF>;
+    static thread_local int configured_dev = -1;
+    (void)configured_dev;
+    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    kern<<<h->G, NTHREADS, h->smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    h->launches++;
+    return MAMBO_OK;
+}
+
+template <bool DO_E, bool STORE>
+int launch_fused(mambo_csa* h, const Params& p) {
+    switch (h->NB) {
+        case 1: return launch_fused_nb<1, DO_E, STORE>(h, p);
+        case 2: return launch_fused_nb<2, DO_E, STORE>(h, p);
+        case 4: return launch_fused_nb<4, DO_E, STORE>(h, p);
+        case 7: return launch_fused_nb<7, DO_E, STORE>(h, p);
+        case 10: return launch_fused_nb<10, DO_E, STORE>(h, p);
+        case 13: return launch_fused_nb<13, DO_E, STORE>(h, p);
+        case 16: return launch_fused_nb<16, DO_E, STORE>(h, p);
+        case 19: return launch_fused_nb<19, DO_E, STORE>(h, p);
+        case 21: return launch_fused_nb<21, DO_E, STORE>(h, p);
+    }
+    return fail(MAMBO_EINVAL, "unsupported NB bucket");
+}
+
+Params make_params(mambo_csa* h, double* T) {
+    Params p;
+    p.T = T;
+    p.Tst = T;
+    p.Brow = h->Bt;
+    p.Acol = h->At;
+    p.Epiece = h->Epiece;
+    p.cost_part = h->cost_part;
+    p.visit_start = h->visit_start;
+    p.ldT = h->ldT;
+    p.P = h->P;
+    p.Q = h->Q;
+    p.ld = h->ld;
+    p.Np = h->Np;
+    p.S = h->S;
+    return p;
+}
+
+int host_s_for(const mambo_csa* h, const double* x) {
+    // ||K||_1 on the host, same definition as small::k_build; returned s is passed down so host and device agree.
+    const int n = h->N;
+    const double* th = x + h->lam_off + h->cL;
+    double mx = 0.0;
+    for (int j = 0; j < n; ++j) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (i == j) continue;
+            const int a = std::min(i, j), b = std::max(i, j);
+            s += std::fabs(th[(long long)a * n - (long long)a * (a + 1) / 2 + (b - a - 1)]);
+        }
+        mx = std::max(mx, s);
+    }
+    if (!(mx == mx)) return -2;
+    int s = 0;
+    if (mx > 1.0) s = (int)std::ceil(std::log2(mx));
+    return s;
+}
+
+void mm(mambo_csa* h, double* C, const double* Cin, const double* A1, const double* B1, const double* A2, const double* B2,
+        const int* s_ptr, int step) {
+    const int n = h->N;
+    dim3 grid((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS), block(small::TS, small::TS);
+    small::k_mm<<<grid, block, 0, h->stream>>>(C, Cin, A1, B1, A2, B2, n, s_ptr, step);
+    h->launches++;
+}
+
+// U = exp(K): Taylor-16 (Paterson-Stockmeyer, 6 GEMMs) + s squarings; every intermediate is kept for the
+// derivative chain.  s_host >= 0: number of squaring launches needed (known when x came from the host).
+int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
+    const int n = h->N, nn = n * n;
+    small::k_build<<<1, 1024, 0, h->stream>>>(d_x, n, h->lam_off, h->X, h->Lam, h->d_s, h->d_scale, h->d_status);
+    h->launches++;
+    mm(h, h->X2, nullptr, h->X, h->X, nullptr, nullptr, nullptr, 0);
+    dim3 grid((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS), block(small::TS, small::TS);
+    small::k_pow34<<<grid, block, 0, h->stream>>>(h->X, h->X2, h->X3, h->X4, h->P0, h->P1, h->P2, h->Q3, n);
+    h->launches++;
+    mm(h, h->Q2, h->P2, h->X4, h->Q3, nullptr, nullptr, nullptr, 0);
+    mm(h, h->Q1, h->P1, h->X4, h->Q2, nullptr, nullptr, nullptr, 0);
+    mm(h, h->R, h->P0, h->X4, h->Q1, nullptr, nullptr, nullptr, 0);
+    const int nsq = s_host >= 0 ? std::min(s_host, small::SMAX) : small::SMAX;
+    for (int i = 0; i < nsq; ++i)
+        mm(h, h->R + (size_t)(i + 1) * nn, nullptr, h->R + (size_t)i * nn, h->R + (size_t)i * nn, nullptr, nullptr, h->d_s, i);
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
+int enqueue_prep(mambo_csa* h) {
+    const int blocks = h->nRpad / 32;
+    small::k_prep<<<blocks, 256, (size_t)32 * h->Np * 8, h->stream>>>(h->R, h->d_s, h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld,
+                                                                     h->nRpad, h->row_begin, h->row_end, h->At, h->Bt);
+    h->launches++;
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
+// stage A: everything up to the per-shard partial vector [cost, S, G]
+int enqueue_partial(mambo_csa* h, const double* d_x, int s_host, bool need_grad) {
+    int rc = enqueue_unitary(h, d_x, s_host);
+    if (rc) return rc;
+    rc = enqueue_prep(h);
+    if (rc) return rc;
+    const int n = h->N;
+    Params p = make_params(h, h->T1);
+    if (!need_grad) {
+        rc = launch_fused<false, false>(h, p);
+        if (rc) return rc;
+        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(nullptr, 0, h->cost_part, h->G, h->d_part);
+        h->launches++;
+        CU(cudaGetLastError());
+        return MAMBO_OK;
+    }
+    rc = launch_fused<true, false>(h, p);
+    if (rc) return rc;
+    const size_t post_smem = (size_t)2 * 64 * h->Np * 8;
+    CU(cudaFuncSetAttribute(small::k_post_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem));
+    const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
+    small::k_post_rows<<<h->P, 256, post_smem, h->stream>>>(h->Epiece, h->piece_first, h->At, h->Lam, n, h->Np, h->ld, h->row_begin,
+                                                            h->F1, h->Spart, general ? 0 : 1);
+    h->launches++;
+    if (general) {
+        // second pass over the transposed residual: E = D A (pass 1 gave E' = D^T A); S uses E only (gradient.jl:22-26)
+        Params p2 = make_params(h, h->T2);
+        p2.cost_part = h->cost_part + h->G;  // discarded
+        rc = launch_fused<true, false>(h, p2);
+        if (rc) return rc;
+        small::k_post_rows<<<h->P, 256, post_smem, h->stream>>>(h->Epiece, h->piece_first, h->At, h->Lam, n, h->Np, h->ld,
+                                                                h->row_begin, h->F2, h->Spart, 1);
+        h->launches++;
+    }
+    const int nn = n * n;
+    small::k_post_reduce<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->cost_part, h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
+                                                                 h->sw, h->R, h->d_s, n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
+                                                                 h->row_begin, std::min(h->row_end, h->nR), h->d_part);
+    h->launches++;
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
+// stage B: one-body terms, adjoint Frechet derivative, gradient assembly.  part lives in h->d_part.
+int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
+    const int n = h->N, nn = n * n;
+    if (h->flavour == MAMBO_CSA_SD) {
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->R, h->d_s, n, h->d_part, h->g1, h->Dh, h->DU, nullptr);
+        h->launches++;
+    }
+    small::k_build_d<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->d_part, h->d_scale, n, h->dX);
+    h->launches++;
+    mm(h, h->dX2, nullptr, h->dX, h->X, h->X, h->dX, nullptr, 0);
+    dim3 grid((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS), block(small::TS, small::TS);
+    small::k_dpow34<<<grid, block, 0, h->stream>>>(h->X, h->X2, h->dX, h->dX2, h->dX4, h->dP0, h->dP1, h->dP2, h->dQ3, n);
+    h->launches++;
+    mm(h, h->dQ2, h->dP2, h->dX4, h->Q3, h->X4, h->dQ3, nullptr, 0);
+    mm(h, h->dQ1, h->dP1, h->dX4, h->Q2, h->X4, h->dQ2, nullptr, 0);
+    mm(h, h->dR, h->dP0, h->dX4, h->Q1, h->X4, h->dQ1, nullptr, 0);
+    const int nsq = s_host >= 0 ? std::min(s_host, small::SMAX) : small::SMAX;
+    for (int i = 0; i < nsq; ++i)
+        mm(h, h->dR + (size_t)(i + 1) * nn, nullptr, h->dR + (size_t)i * nn, h->R + (size_t)i * nn, h->R + (size_t)i * nn,
+           h->dR + (size_t)i * nn, h->d_s, i);
+    small::k_assemble<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->d_part, h->g1, h->dR, h->d_s, n, h->flavour == MAMBO_CSA_SD ? 1 : 0, d_out);
+    h->launches++;
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
+int check_status(mambo_csa* h) {
+    if (*h->h_status != 0) {
+        *h->h_status = 0;
+        cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream);
+        return fail(MAMBO_ERANGE, "||K||_1 exceeds 2^14 (or x contains NaN): orbital-rotation builder out of range");
+    }
+    return MAMBO_OK;
+}
+
+// full evaluation from a host x; results land in h->h_out (pinned) after synchronisation
+int eval_host(mambo_csa* h, const double* x, bool need_grad) {
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "host closures need an unsharded handle (use the *_device entry points)");
+    CU(cudaSetDevice(h->device));
+    const int s_host = host_s_for(h, x);
+    if (s_host < -1 || s_host > small::SMAX) return fail(MAMBO_ERANGE, "||K||_1 exceeds 2^14 (or x contains NaN)");
+    std::memcpy(h->h_x, x, sizeof(double) * h->L);
+    const long long l0 = h->launches;
+    CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
+    int rc = enqueue_partial(h, h->d_x, s_host, need_grad);
+    if (rc) return rc;
+    if (need_grad) {
+        rc = enqueue_finish(h, h->d_x, s_host, h->d_out);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToHost, h->stream));
+    } else {
+        if (h->flavour == MAMBO_CSA_SD) {
+            small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
+            // cost-only: add |Dh|^2 by a second tiny reduction
+            small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->d_part, 1, h->d_part);
+            h->launches += 2;
+        }
+        CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->launches_last_eval = (int)(h->launches - l0);
+    return check_status(h);
+}
+
+template <typename T>
+int dalloc(T** p, size_t count) {
+    CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
+    CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
+    return MAMBO_OK;
+}
+
+#define TRY(expr)               \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__) return rc__;  \
+    } while (0)
+
+int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned flags) {
+    const int n = h->N;
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) return fail(MAMBO_ECUDA, "libmambo_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+    h->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+
+    h->cL = n * (n + 1) / 2;
+    h->uL = n * (n - 1) / 2;
+    h->lam_off = (h->flavour == MAMBO_CSA_SD) ? n : 0;
+    h->L = h->lam_off + h->cL + h->uL;
+    int nb = (n + 7) / 8;
+    h->NB = 0;
+    for (int b : kNBBuckets)
+        if (b >= nb) {
+            h->NB = b;
+            break;
+        }
+    if (!h->NB) return fail(MAMBO_EINVAL, "N too large for the compiled kernel set (N <= 168)");
+    h->Np = 8 * h->NB;
+    h->ld = h->Np + 4;
+
+    // ---- upload the tensor (or use it in place when it is already on the device) and analyse its symmetry ----
+    const size_t n4 = (size_t)n * n * n * n;
+    const bool on_dev = flags & MAMBO_TBT_ON_DEVICE;
+    double* mem = nullptr;
+    if (on_dev) {
+        mem = const_cast<double*>(tbt);
+    } else {
+        CU(cudaMalloc((void**)&mem, n4 * sizeof(double)));
+        CU(cudaMemcpyAsync(mem, tbt, n4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+    double* d_stats = nullptr;
+    TRY(dalloc(&d_stats, 4));
+    small::k_sym_stats<<<h->num_sms * 8, 256, 0, h->stream>>>(mem, n, d_stats);
+    double stats[4];
+    CU(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaFree(d_stats));
+    const double tmax = stats[0] > 0 ? stats[0] : 1.0;
+    h->asym_pair = stats[1] / tmax;
+    h->asym_pq = std::max(stats[2], stats[3]) / tmax;
+    const double tol = 1e-13;
+    unsigned mode = flags & MAMBO_SYM_MASK;
+    if (mode == MAMBO_SYM_AUTO) {
+        if (h->asym_pair <= tol && h->asym_pq <= tol) mode = MAMBO_SYM_FULL;
+        else if (h->asym_pair <= tol) mode = MAMBO_SYM_PAIR;
+        else mode = MAMBO_SYM_GENERAL;
+    }
+    h->mode = (int)mode;
+    h->packed = (mode == MAMBO_SYM_FULL);
+    if (h->nshards > 1 && mode == MAMBO_SYM_GENERAL)
+        return fail(MAMBO_EINVAL, "row-panel sharding needs a (pq)<->(rs) symmetric tensor (SURVEY 8e.2)");
+
+    // ---- row tables ----
+    h->nR = h->packed ? n * (n + 1) / 2 : n * n;
+    h->nRpad = ((h->nR + ROWS - 1) / ROWS) * ROWS;
+    h->ldT = h->nRpad;
+    const int panels = h->nRpad / ROWS;
+    h->Q = panels;
+    h->prow_begin = (int)((long long)panels * h->shard / h->nshards);
+    h->prow_end = (int)((long long)panels * (h->shard + 1) / h->nshards);
+    h->P = h->prow_end - h->prow_begin;
+    if (h->P <= 0) return fail(MAMBO_EINVAL, "more shards than 64-row panels");
+    h->row_begin = h->prow_begin * ROWS;
+    h->row_end = h->prow_end * ROWS;
+    std::vector<int> pa(h->nRpad, 0), pq(h->nRpad, 0);
+    std::vector<double> sw(h->nRpad, 0.0);
+    if (h->packed) {
+        int r = 0;
+        for (int q = 0; q < n; ++q)
+            for (int a = 0; a <= q; ++a, ++r) {
+                pa[r] = a;
+                pq[r] = q;
+                sw[r] = (a == q) ? 1.0 : std::sqrt(2.0);
+            }
+    } else {
+        for (int r = 0; r < h->nR; ++r) {
+            pa[r] = r % n;
+            pq[r] = r / n;
+            sw[r] = 1.0;
+        }
+    }
+    TRY(dalloc(&h->pa, h->nRpad));
+    TRY(dalloc(&h->pq, h->nRpad));
+    TRY(dalloc(&h->sw, h->nRpad));
+    CU(cudaMemcpy(h->pa, pa.data(), sizeof(int) * h->nRpad, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->pq, pq.data(), sizeof(int) * h->nRpad, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->sw, sw.data(), sizeof(double) * h->nRpad, cudaMemcpyHostToDevice));
+
+    // ---- residual matrix T~ (local rows) ----
+    const size_t tcount = (size_t)h->P * ROWS * h->ldT;
+    CU(cudaMalloc((void**)&h->T1, tcount * sizeof(double)));
+    small::k_pack<<<h->num_sms * 16, 256, 0, h->stream>>>(mem, n, h->pa, h->pq, h->sw, h->row_begin, h->P * ROWS, h->nR, h->ldT, 0, h->T1);
+    if (mode == MAMBO_SYM_GENERAL) {
+        CU(cudaMalloc((void**)&h->T2, tcount * sizeof(double)));
+        small::k_pack<<<h->num_sms * 16, 256, 0, h->stream>>>(mem, n, h->pa, h->pq, h->sw, h->row_begin, h->P * ROWS, h->nR, h->ldT, 1, h->T2);
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(h->stream));
+    if (!on_dev) CU(cudaFree(mem));
+
+    if (h->flavour == MAMBO_CSA_SD) {
+        if (!obt) return fail(MAMBO_EINVAL, "CSA_SD needs the one-body tensor");
+        TRY(dalloc(&h->hT, (size_t)n * n));
+        CU(cudaMemcpy(h->hT, obt, sizeof(double) * n * n, on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    }
+
+    // ---- operands and work buffers ----
+    TRY(dalloc(&h->At, (size_t)h->nRpad * h->ld));
+    TRY(dalloc(&h->Bt, (size_t)h->P * ROWS * h->ld));
+    // schedule of the persistent fused kernel
+    const long long total = (long long)h->P * h->Q;
+    h->G = (int)std::min<long long>(h->num_sms, total);
+    std::vector<int> vstart(h->G + 1, 0), pfirst(h->P + 1, 0);
+    {
+        std::vector<int> seq;
+        for (int b = 0; b < h->G; ++b) {
+            const long long tb = total * b / h->G, te = total * (b + 1) / h->G;
+            vstart[b] = (int)seq.size();
+            if (te > tb)
+                for (int p = (int)(tb / h->Q); p <= (int)((te - 1) / h->Q); ++p) seq.push_back(p);
+        }
+        vstart[h->G] = (int)seq.size();
+        h->visits = (int)seq.size();
+        int v = 0;
+        for (int p = 0; p <= h->P; ++p) {
+            while (v < h->visits && seq[v] < p) ++v;
+            pfirst[p] = v;
+        }
+    }
+    TRY(dalloc(&h->visit_start, h->G + 1));
+    TRY(dalloc(&h->piece_first, h->P + 1));
+    CU(cudaMemcpy(h->visit_start, vstart.data(), sizeof(int) * (h->G + 1), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(h->piece_first, pfirst.data(), sizeof(int) * (h->P + 1), cudaMemcpyHostToDevice));
+    TRY(dalloc(&h->Epiece, (size_t)h->visits * 2 * ROWS * h->Np));
+    TRY(dalloc(&h->F1, (size_t)h->P * ROWS * h->Np));
+    if (mode == MAMBO_SYM_GENERAL) TRY(dalloc(&h->F2, (size_t)h->P * ROWS * h->Np));
+    TRY(dalloc(&h->Spart, (size_t)h->P * n * n));
+    TRY(dalloc(&h->cost_part, (size_t)2 * h->G));
+    // shared-memory ring depth
+    const size_t limit = prop.sharedMemPerBlockOptin;
+    int S = 8;
+    while (S > 2 && smem_bytes(h->ld, S) > limit) --S;
+    if (smem_bytes(h->ld, S) > limit) return fail(MAMBO_EINVAL, "operand panel does not fit in shared memory");
+    h->S = S;
+    h->smem = smem_bytes(h->ld, S);
+
+    // expm chain storage
+    const size_t nn = (size_t)n * n;
+    const size_t nm = 10 + (small::SMAX + 1) + 9 + (small::SMAX + 1) + 4;
+    TRY(dalloc(&h->mats, nm * nn));
+    double* m = h->mats;
+    auto take = [&](size_t k) { double* r = m; m += k * nn; return r; };
+    h->X = take(1); h->X2 = take(1); h->X3 = take(1); h->X4 = take(1);
+    h->P0 = take(1); h->P1 = take(1); h->P2 = take(1); h->Q3 = take(1); h->Q2 = take(1); h->Q1 = take(1);
+    h->R = take(small::SMAX + 1);
+    h->dX = take(1); h->dX2 = take(1); h->dX4 = take(1);
+    h->dP0 = take(1); h->dP1 = take(1); h->dP2 = take(1); h->dQ3 = take(1); h->dQ2 = take(1); h->dQ1 = take(1);
+    h->dR = take(small::SMAX + 1);
+    h->Lam = take(1); h->Dh = take(1); h->DU = take(1); h->hfrag = take(1);
+    TRY(dalloc(&h->g1, (size_t)n));
+    TRY(dalloc(&h->d_s, 1));
+    TRY(dalloc(&h->d_scale, 1));
+    TRY(dalloc(&h->d_status, 1));
+    TRY(dalloc(&h->d_x, (size_t)h->L));
+    TRY(dalloc(&h->d_out, (size_t)h->L + 1));
+    TRY(dalloc(&h->d_part, (size_t)1 + 2 * nn));
+    CU(cudaMallocHost((void**)&h->h_x, sizeof(double) * h->L));
+    CU(cudaMallocHost((void**)&h->h_out, sizeof(double) * (h->L + 1)));
+    CU(cudaMallocHost((void**)&h->h_status, sizeof(int)));
+    *h->h_status = 0;
+    h->memo_x.assign(h->L, 0.0);
+    return MAMBO_OK;
+}
+
+int subtract_impl(mambo_csa* h, const double* d_x, int s_host) {
+    TRY(enqueue_unitary(h, d_x, s_host));
+    TRY(enqueue_prep(h));
+    Params p = make_params(h, h->T1);
+    TRY((launch_fused<false, true>(h, p)));
+    if (h->mode == (int)MAMBO_SYM_GENERAL) {
+        Params p2 = make_params(h, h->T2);
+        p2.cost_part = h->cost_part + h->G;
+        TRY((launch_fused<false, true>(h, p2)));
+    }
+    const int n = h->N, nn = n * n;
+    if (h->flavour == MAMBO_CSA_SD) {
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->R, h->d_s, n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
+        small::k_obt_sub<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->hT, h->hfrag, n);
+        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, nn, h->cost_part, h->G, h->d_part);
+        h->launches += 3;
+    } else {
+        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(nullptr, 0, h->cost_part, h->G, h->d_part);
+        h->launches++;
+    }
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
+}  // namespace
+
+// =========================================================================================================
+//                                                C ABI
+// =========================================================================================================
+extern "C" {
+
+const char* mambo_last_error(void) { return g_err.c_str(); }
+
+int mambo_csa_create_sharded(mambo_csa** out, int N, int flavour, const double* tbt, const double* obt, int device, unsigned flags,
+                             int shard, int nshards) {
+    if (!out || !tbt || N < 1) return fail(MAMBO_EINVAL, "bad arguments to mambo_csa_create");
+    if (flavour != MAMBO_CSA && flavour != MAMBO_CSA_SD) return fail(MAMBO_EINVAL, "flavour must be MAMBO_CSA or MAMBO_CSA_SD");
+    if (nshards < 1 || shard < 0 || shard >= nshards) return fail(MAMBO_EINVAL, "bad shard index");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(MAMBO_ECUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(MAMBO_EINVAL, "device index out of range");
+    mambo_csa* h = new (std::nothrow) mambo_csa();
+    if (!h) return fail(MAMBO_ENOMEM, "host allocation failed");
+    h->N = N;
+    h->flavour = flavour;
+    h->device = device;
+    h->shard = shard;
+    h->nshards = nshards;
+    int rc = build_handle(h, tbt, obt, flags);
+    if (rc) {
+        std::string keep = g_err;
+        mambo_csa_destroy(h);
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
+    return MAMBO_OK;
+}
+
+int mambo_csa_create(mambo_csa** out, int N, int flavour, const double* tbt, const double* obt, int device, unsigned flags) {
+    return mambo_csa_create_sharded(out, N, flavour, tbt, obt, device, flags, 0, 1);
+}
+
+void mambo_csa_destroy(mambo_csa* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->own_stream) cudaStreamSynchronize(h->own_stream);
+    void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->F1, h->F2, h->Spart, h->cost_part,
+                    h->visit_start, h->piece_first, h->mats, h->g1, h->d_s, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
+    for (void* b : bufs)
+        if (b) cudaFree(b);
+    if (h->h_x) cudaFreeHost(h->h_x);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_status) cudaFreeHost(h->h_status);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int mambo_csa_num_params(const mambo_csa* h) { return h ? h->L : MAMBO_EINVAL; }
+
+int mambo_csa_get_info(const mambo_csa* h, mambo_csa_info_t* info) {
+    if (!h || !info) return fail(MAMBO_EINVAL, "null argument");
+    info->N = h->N;
+    info->flavour = h->flavour;
+    info->mode = h->mode;
+    info->num_params = h->L;
+    info->rows = h->nR;
+    info->rows_padded = h->nRpad;
+    info->shard = h->shard;
+    info->nshards = h->nshards;
+    info->local_row_begin = h->row_begin;
+    info->local_row_end = std::min(h->row_end, h->nR);
+    info->partial_len = 1 + 2 * h->N * h->N;
+    info->num_sms = h->num_sms;
+    info->launches_per_eval = h->launches_last_eval;
+    const double passes = (h->mode == (int)MAMBO_SYM_GENERAL) ? 2.0 : 1.0;
+    info->flops_per_eval = passes * 4.0 * (double)h->P * ROWS * (double)h->nRpad * h->Np;
+    info->tensor_bytes = passes * (double)h->P * ROWS * (double)h->ldT * 8.0;
+    info->asym_pair = h->asym_pair;
+    info->asym_pq = h->asym_pq;
+    return MAMBO_OK;
+}
+
+int mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* grad) {
+    if (!h || !x) return fail(MAMBO_EINVAL, "null argument");
+    if (!(h->memo_valid && std::memcmp(h->memo_x.data(), x, sizeof(double) * h->L) == 0)) {
+        h->memo_valid = false;
+        TRY(eval_host(h, x, true));
+        std::memcpy(h->memo_x.data(), x, sizeof(double) * h->L);
+        h->memo_valid = true;
+    }
+    if (cost) *cost = h->h_out[0];
+    if (grad) std::memcpy(grad, h->h_out + 1, sizeof(double) * h->L);
+    return MAMBO_OK;
+}
+
+// Optim.jl calls cost(x) and grad!(g, x) at the same x back to back (also inside the HagerZhang line
+// search): one fused evaluation serves both.
+int mambo_csa_cost(mambo_csa* h, const double* x, double* cost) { return mambo_csa_cost_grad(h, x, cost, nullptr); }
+int mambo_csa_grad(mambo_csa* h, const double* x, double* grad) { return mambo_csa_cost_grad(h, x, nullptr, grad); }
+
+int mambo_csa_set_stream(mambo_csa* h, void* stream) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return MAMBO_OK;
+}
+
+int mambo_csa_synchronize(mambo_csa* h) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaMemcpy(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    return check_status(h);
+}
+
+int mambo_csa_eval_partial_device(mambo_csa* h, const double* d_x, double* d_partial) {
+    if (!h || !d_x || !d_partial) return fail(MAMBO_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const long long l0 = h->launches;
+    CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(enqueue_partial(h, h->d_x, -1, true));
+    CU(cudaMemcpyAsync(d_partial, h->d_part, sizeof(double) * (1 + 2 * (size_t)h->N * h->N), cudaMemcpyDeviceToDevice, h->stream));
+    h->launches_last_eval = (int)(h->launches - l0);
+    return MAMBO_OK;
+}
+
+int mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double* d_out) {
+    if (!h || !d_partial || !d_out) return fail(MAMBO_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const long long l0 = h->launches;
+    CU(cudaMemcpyAsync(h->d_part, d_partial, sizeof(double) * (1 + 2 * (size_t)h->N * h->N), cudaMemcpyDeviceToDevice, h->stream));
+    TRY(enqueue_finish(h, h->d_x, -1, d_out));
+    h->launches_last_eval += (int)(h->launches - l0);
+    return MAMBO_OK;
+}
+
+int mambo_csa_eval_device(mambo_csa* h, const double* d_x, double* d_out) {
+    if (!h || !d_x || !d_out) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "sharded handle: use eval_partial_device / eval_finish_device around an allreduce");
+    CU(cudaSetDevice(h->device));
+    const long long l0 = h->launches;
+    TRY(enqueue_partial(h, d_x, -1, true));
+    TRY(enqueue_finish(h, d_x, -1, d_out));
+    h->launches_last_eval = (int)(h->launches - l0);
+    return MAMBO_OK;
+}
+
+int mambo_csa_cost_device(mambo_csa* h, const double* d_x, double* d_cost) {
+    if (!h || !d_x || !d_cost) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "cost_device needs an unsharded handle");
+    CU(cudaSetDevice(h->device));
+    TRY(enqueue_partial(h, d_x, -1, false));
+    if (h->flavour == MAMBO_CSA_SD) {
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
+        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->d_part, 1, h->d_part);
+        h->launches += 2;
+    }
+    CU(cudaMemcpyAsync(d_cost, h->d_part, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    return MAMBO_OK;
+}
+
+int mambo_csa_subtract_fragment(mambo_csa* h, const double* x, double* new_cost) {
+    if (!h || !x) return fail(MAMBO_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    const int s_host = host_s_for(h, x);
+    if (s_host < -1 || s_host > small::SMAX) return fail(MAMBO_ERANGE, "||K||_1 exceeds 2^14 (or x contains NaN)");
+    std::memcpy(h->h_x, x, sizeof(double) * h->L);
+    CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
+    TRY(subtract_impl(h, h->d_x, s_host));
+    CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->memo_valid = false;
+    if (new_cost) *new_cost = h->h_out[0];
+    return MAMBO_OK;
+}
+
+int mambo_csa_residual_cost(mambo_csa* h, double* cost) {
+    if (!h || !cost) return fail(MAMBO_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    // L2_partial_cost(F_rem): evaluate the residual against the zero fragment (lambda = 0 => W = 0), theta = 0
+    CU(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->L, h->stream));
+    TRY(enqueue_partial(h, h->d_x, 0, false));
+    if (h->flavour == MAMBO_CSA_SD) {
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
+        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->d_part, 1, h->d_part);
+        h->launches += 2;
+    }
+    CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *cost = h->h_out[0];
+    return MAMBO_OK;
+}
+
+int mambo_csa_get_residual(mambo_csa* h, double* tbt_out, double* obt_out) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    const int n = h->N;
+    if (tbt_out) {
+        const size_t n4 = (size_t)n * n * n * n;
+        double* tmp = nullptr;
+        CU(cudaMalloc((void**)&tmp, n4 * sizeof(double)));
+        small::k_unpack<<<h->num_sms * 16, 256, 0, h->stream>>>(h->T1, n, h->packed ? 1 : 0, h->sw, h->row_begin, std::min(h->row_end, h->nR),
+                                                              h->ldT, tmp);
+        cudaError_t e = cudaMemcpyAsync(tbt_out, tmp, n4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+        CU(e);
+    }
+    if (obt_out && h->flavour == MAMBO_CSA_SD) {
+        CU(cudaMemcpyAsync(obt_out, h->hT, sizeof(double) * n * n, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return MAMBO_OK;
+}
+
+int mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double* obt_out) {
+    if (!h || !x) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "reconstruct needs an unsharded handle");
+    CU(cudaSetDevice(h->device));
+    const int n = h->N, nn = n * n;
+    const int s_host = host_s_for(h, x);
+    if (s_host < -1 || s_host > small::SMAX) return fail(MAMBO_ERANGE, "||K||_1 exceeds 2^14 (or x contains NaN)");
+    std::memcpy(h->h_x, x, sizeof(double) * h->L);
+    CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
+    TRY(enqueue_unitary(h, h->d_x, s_host));
+    TRY(enqueue_prep(h));
+    h->memo_valid = false;
+    if (tbt_out) {
+        const size_t n4 = (size_t)nn * nn;
+        double* tmp = nullptr;
+        CU(cudaMalloc((void**)&tmp, n4 * sizeof(double)));
+        small::k_reconstruct<<<h->num_sms * 16, 256, 0, h->stream>>>(h->At, h->Bt, n, h->ld, h->packed ? 1 : 0, h->sw, tmp);
+        cudaError_t e = cudaMemcpyAsync(tbt_out, tmp, n4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(tmp);
+        CU(e);
+    }
+    if (obt_out && h->flavour == MAMBO_CSA_SD) {
+        // h = U diag(l1) U^T: reuse the one-body kernel against the stored target, keep h in hfrag
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
+        small::k_obt_colmajor<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->hfrag, n, h->Dh);
+        CU(cudaMemcpyAsync(obt_out, h->Dh, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return MAMBO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,561 @@
+// small_kernels.cuh -- everything around the fused kernel: orbital-rotation builder (expm and its adjoint
+// Frechet derivative by scaling & squaring), operand construction, packing, the O(N^4) gradient epilogues.
+// All FP64, all deterministic (fixed-order reductions, no floating-point atomics).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace small {
+
+constexpr int SMAX = 14;            // maximum number of squarings (||K||_1 <= 2^14)
+constexpr int TS = 16;              // tile of the small N x N GEMMs
+
+// Taylor coefficients 1/k!, k = 0..16
+__constant__ double c_tay[17] = {1.0,
+                                 1.0,
+                                 0.5,
+                                 1.0 / 6,
+                                 1.0 / 24,
+                                 1.0 / 120,
+                                 1.0 / 720,
+                                 1.0 / 5040,
+                                 1.0 / 40320,
+                                 1.0 / 362880,
+                                 1.0 / 3628800,
+                                 1.0 / 39916800,
+                                 1.0 / 479001600,
+                                 1.0 / 6227020800.0,
+                                 1.0 / 87178291200.0,
+                                 1.0 / 1307674368000.0,
+                                 1.0 / 20922789888000.0};
+
+// ------------------------------------------------------------------------------------------------------
+// k_build: x -> Lambda (full symmetric), X = K / 2^s, s  (unitaries.jl:31-44, gradient.jl:43-55)
+//   one CTA; the 1-norm of K picks s so that ||X||_1 <= 1 (Taylor degree 16 is then exact to ~3e-15).
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_build(const double* __restrict__ x, int n, int lam_off, double* __restrict__ X, double* __restrict__ Lam,
+                        int* __restrict__ s_out, double* __restrict__ scale_out, int* __restrict__ status) {
+    __shared__ double red[32];
+    __shared__ double s_scale;
+    const int cL = n * (n + 1) / 2;
+    const double* lam = x + lam_off;
+    const double* th = x + lam_off + cL;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    // column abs sums (K antisymmetric: column j holds -K[j][i] ...)
+    double mx = 0.0;
+    for (int j = tid; j < n; j += nt) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) {
+            if (i == j) continue;
+            const int a = i < j ? i : j, b = i < j ? j : i;
+            s += fabs(th[a * n - a * (a + 1) / 2 + (b - a - 1)]);
+        }
+        mx = fmax(mx, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        double m = 0.0;
+        for (int w = 0; w < (nt + 31) / 32; ++w) m = fmax(m, red[w]);
+        int s = 0;
+        if (m > 1.0) s = (int)ceil(log2(m));
+        if (!(m == m) || s > SMAX) {  // NaN or too large
+            *status = 1;
+            s = SMAX;
+        }
+        *s_out = s;
+        s_scale = ldexp(1.0, -s);
+        *scale_out = s_scale;
+    }
+    __syncthreads();
+    const double sc = s_scale;
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, j = idx % n;
+        double k = 0.0;
+        if (i < j) k = th[i * n - i * (i + 1) / 2 + (j - i - 1)];
+        else if (i > j) k = -th[j * n - j * (j + 1) / 2 + (i - j - 1)];
+        X[idx] = k * sc;
+        const int a = i > j ? i : j, b = i > j ? j : i;
+        Lam[idx] = lam[a * (a + 1) / 2 + b];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// small N x N GEMM building block: acc += A[i,:] . B[:,j] for the (i,j) of this thread (16x16 tile / CTA)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_mm(double& acc, const double* __restrict__ A, const double* __restrict__ B, int n,
+                                        double (*As)[TS + 1], double (*Bs)[TS + 1]) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.y * TS + ty, j0 = blockIdx.x * TS;
+    for (int k0 = 0; k0 < n; k0 += TS) {
+        As[ty][tx] = (i < n && k0 + tx < n) ? A[i * n + k0 + tx] : 0.0;
+        Bs[ty][tx] = (k0 + ty < n && j0 + tx < n) ? B[(k0 + ty) * n + j0 + tx] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TS; ++k) acc = fma(As[ty][k], Bs[k][tx], acc);
+        __syncthreads();
+    }
+}
+// two products sharing the A operand rows: acc1 += A.B1, acc2 += A.B2
+__device__ __forceinline__ void tile_mm2(double& acc1, double& acc2, const double* __restrict__ A, const double* __restrict__ B1,
+                                         const double* __restrict__ B2, int n, double (*As)[TS + 1], double (*Bs)[TS + 1],
+                                         double (*Cs)[TS + 1]) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int i = blockIdx.y * TS + ty, j0 = blockIdx.x * TS;
+    for (int k0 = 0; k0 < n; k0 += TS) {
+        As[ty][tx] = (i < n && k0 + tx < n) ? A[i * n + k0 + tx] : 0.0;
+        const bool ok = (k0 + ty < n && j0 + tx < n);
+        Bs[ty][tx] = ok ? B1[(k0 + ty) * n + j0 + tx] : 0.0;
+        Cs[ty][tx] = ok ? B2[(k0 + ty) * n + j0 + tx] : 0.0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+            acc1 = fma(As[ty][k], Bs[k][tx], acc1);
+            acc2 = fma(As[ty][k], Cs[k][tx], acc2);
+        }
+        __syncthreads();
+    }
+}
+
+// C = Cin + A1.B1 + A2.B2   (null pointers skip a term).  step >= *s_ptr => no-op (squaring chain past s).
+__global__ void k_mm(double* __restrict__ C, const double* __restrict__ Cin, const double* __restrict__ A1,
+                     const double* __restrict__ B1, const double* __restrict__ A2, const double* __restrict__ B2, int n,
+                     const int* __restrict__ s_ptr, int step) {
+    if (s_ptr && step >= *s_ptr) return;
+    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];
+    double acc = 0.0;
+    tile_mm(acc, A1, B1, n, As, Bs);
+    if (A2) tile_mm(acc, A2, B2, n, As, Bs);
+    const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
+    if (i < n && j < n) C[i * n + j] = acc + (Cin ? Cin[i * n + j] : 0.0);
+}
+
+// X3 = X2.X, X4 = X2.X2, then P0,P1,P2 (degree-3 pieces) and Q3 = P3 + c16 X4.
+__global__ void k_pow34(const double* __restrict__ X, const double* __restrict__ X2, double* __restrict__ X3,
+                        double* __restrict__ X4, double* __restrict__ P0, double* __restrict__ P1, double* __restrict__ P2,
+                        double* __restrict__ Q3, int n) {
+    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1], Cs[TS][TS + 1];
+    double x3 = 0.0, x4 = 0.0;
+    tile_mm2(x3, x4, X2, X, X2, n, As, Bs, Cs);
+    const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
+    if (i < n && j < n) {
+        const int o = i * n + j;
+        const double id = (i == j) ? 1.0 : 0.0, x1 = X[o], x2 = X2[o];
+        X3[o] = x3;
+        X4[o] = x4;
+        P0[o] = c_tay[0] * id + c_tay[1] * x1 + c_tay[2] * x2 + c_tay[3] * x3;
+        P1[o] = c_tay[4] * id + c_tay[5] * x1 + c_tay[6] * x2 + c_tay[7] * x3;
+        P2[o] = c_tay[8] * id + c_tay[9] * x1 + c_tay[10] * x2 + c_tay[11] * x3;
+        Q3[o] = c_tay[12] * id + c_tay[13] * x1 + c_tay[14] * x2 + c_tay[15] * x3 + c_tay[16] * x4;
+    }
+}
+
+// dX3 = dX2.X + X2.dX, dX4 = dX2.X2 + X2.dX2, then dP0..dP2, dQ3.
+__global__ void k_dpow34(const double* __restrict__ X, const double* __restrict__ X2, const double* __restrict__ dX,
+                         const double* __restrict__ dX2, double* __restrict__ dX4, double* __restrict__ dP0,
+                         double* __restrict__ dP1, double* __restrict__ dP2, double* __restrict__ dQ3, int n) {
+    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1], Cs[TS][TS + 1];
+    double d3 = 0.0, d4 = 0.0;
+    tile_mm2(d3, d4, dX2, X, X2, n, As, Bs, Cs);   // dX2.X , dX2.X2
+    tile_mm2(d3, d4, X2, dX, dX2, n, As, Bs, Cs);  // X2.dX , X2.dX2
+    const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
+    if (i < n && j < n) {
+        const int o = i * n + j;
+        const double d1 = dX[o], d2 = dX2[o];
+        dX4[o] = d4;
+        dP0[o] = c_tay[1] * d1 + c_tay[2] * d2 + c_tay[3] * d3;
+        dP1[o] = c_tay[5] * d1 + c_tay[6] * d2 + c_tay[7] * d3;
+        dP2[o] = c_tay[9] * d1 + c_tay[10] * d2 + c_tay[11] * d3;
+        dQ3[o] = c_tay[13] * d1 + c_tay[14] * d2 + c_tay[15] * d3 + c_tay[16] * d4;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_prep: A~[r][l] = sw_r U[pa_r][l] U[pq_r][l],  B~[r][m] = sum_l A~[r][l] Lambda[l][m]
+//   U = Rchain[s].  32 rows per CTA, 256 threads.  Rows >= nR (padding) have sw = 0.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_prep(const double* __restrict__ Rchain, const int* __restrict__ s_ptr, const double* __restrict__ Lam,
+                       const int* __restrict__ pa, const int* __restrict__ pq, const double* __restrict__ sw, int n, int Np,
+                       int ld, int rows_total, int brow_begin, int brow_end, double* __restrict__ At, double* __restrict__ Bt) {
+    extern __shared__ double sAt[];  // [32][Np]
+    const double* U = Rchain + (size_t)(*s_ptr) * n * n;
+    const int r0 = blockIdx.x * 32;
+    for (int idx = threadIdx.x; idx < 32 * Np; idx += blockDim.x) {
+        const int rr = idx / Np, l = idx % Np, r = r0 + rr;
+        double v = 0.0;
+        if (r < rows_total && l < n) {
+            const double w = sw[r];
+            if (w != 0.0) v = w * U[pa[r] * n + l] * U[pq[r] * n + l];
+        }
+        sAt[idx] = v;
+        if (r < rows_total) At[(size_t)r * ld + l] = v;
+    }
+    __syncthreads();
+    if (r0 + 32 <= brow_begin || r0 >= brow_end) return;  // B~ only for this shard's rows
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 groups x 4 rows
+    for (int m0 = 0; m0 < Np; m0 += 32) {
+        const int m = m0 + lane;
+        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        if (m < n) {
+            const double* s0 = sAt + (grp * 4) * Np;
+            for (int l = 0; l < n; ++l) {
+                const double lm = Lam[l * n + m];
+                a0 = fma(s0[l], lm, a0);
+                a1 = fma(s0[Np + l], lm, a1);
+                a2 = fma(s0[2 * Np + l], lm, a2);
+                a3 = fma(s0[3 * Np + l], lm, a3);
+            }
+        }
+        if (m < Np) {
+            const int r = r0 + grp * 4;
+            if (r + 0 >= brow_begin && r + 0 < brow_end) Bt[(size_t)(r + 0 - brow_begin) * ld + m] = a0;
+            if (r + 1 >= brow_begin && r + 1 < brow_end) Bt[(size_t)(r + 1 - brow_begin) * ld + m] = a1;
+            if (r + 2 >= brow_begin && r + 2 < brow_end) Bt[(size_t)(r + 2 - brow_begin) * ld + m] = a2;
+            if (r + 3 >= brow_begin && r + 3 < brow_end) Bt[(size_t)(r + 3 - brow_begin) * ld + m] = a3;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_post_rows: per local 64-row panel: E~ = fixed-order sum of the fused kernel's pieces,
+//   F = E~ Lambda (rows of the gradient's F tensor), Spart = A~_panel^T E~ (lambda gradient, gradient.jl:13-41).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_post_rows(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
+                                                   const double* __restrict__ At, const double* __restrict__ Lam, int n, int Np,
+                                                   int ld, int row_begin, double* __restrict__ F, double* __restrict__ Spart,
+                                                   int do_S) {
+    extern __shared__ double sm[];
+    double* sE = sm;                 // [64][Np]
+    double* sAp = sm + 64 * Np;      // [64][Np]
+    const int panel = blockIdx.x;
+    const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
+    for (int idx = threadIdx.x; idx < 64 * Np; idx += blockDim.x) {
+        double s = 0.0;
+        for (int v = v0; v < v1; ++v) {
+            s += Epiece[(size_t)(v * 2 + 0) * 64 * Np + idx];
+            s += Epiece[(size_t)(v * 2 + 1) * 64 * Np + idx];
+        }
+        sE[idx] = s;
+        if (do_S) {
+            const int rr = idx / Np, l = idx % Np;
+            sAp[idx] = At[(size_t)(row_begin + panel * 64 + rr) * ld + l];
+        }
+    }
+    __syncthreads();
+    // F rows: 8 warps x 8 rows
+    {
+        const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+        const double* s0 = sE + grp * 8 * Np;
+        for (int b0 = 0; b0 < Np; b0 += 32) {
+            const int b = b0 + lane;
+            double a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = 0.0;
+            if (b < n) {
+                for (int m = 0; m < n; ++m) {
+                    const double lm = Lam[m * n + b];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = fma(s0[i * Np + m], lm, a[i]);
+                }
+            }
+            if (b < Np) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) F[(size_t)(panel * 64 + grp * 8 + i) * Np + b] = a[i];
+            }
+        }
+    }
+    if (!do_S) return;
+    // Spart[i][j] = sum_r sAp[r][i] sE[r][j]; 64x64 output chunks, 4x4 per thread
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    for (int i0 = 0; i0 < n; i0 += 64)
+        for (int j0 = 0; j0 < n; j0 += 64) {
+            double acc[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+            for (int r = 0; r < 64; ++r) {
+                double av[4], ev[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const int i = i0 + ty + 16 * a;
+                    av[a] = (i < Np) ? sAp[r * Np + i] : 0.0;
+                }
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int j = j0 + tx + 16 * b;
+                    ev[b] = (j < Np) ? sE[r * Np + j] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], ev[b], acc[a][b]);
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+                    if (i < n && j < n) Spart[(size_t)panel * n * n + i * n + j] = acc[a][b];
+                }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_post_reduce: part = [cost, S (n x n), G (n x n)]
+//   S = sum over panels of Spart;   G[a,b] = sum_q coef(a,q) U[q,b] (F1 + F2)[row(a,q)][b] + mirrored rows
+//   (the four product-rule terms of gradient.jl:57-74 contracted with D).  Only locally owned rows contribute.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_post_reduce(const double* __restrict__ cost_part, int ncost, const double* __restrict__ Spart, int npanels,
+                              const double* __restrict__ F1, const double* __restrict__ F2, const double* __restrict__ sw,
+                              const double* __restrict__ Rchain, const int* __restrict__ s_ptr, int n, int Np, int packed,
+                              double gcoef, int row_begin, int row_end, double* __restrict__ part) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx == 0) {
+        double c = 0.0;
+        for (int i = 0; i < ncost; ++i) c += cost_part[i];
+        part[0] = c;
+    }
+    if (idx >= n * n) return;
+    const double* U = Rchain + (size_t)(*s_ptr) * n * n;
+    double s = 0.0;
+    for (int p = 0; p < npanels; ++p) s += Spart[(size_t)p * n * n + idx];
+    part[1 + idx] = s;
+    const int a = idx / n, b = idx % n;
+    double g = 0.0;
+    for (int q = 0; q < n; ++q) {
+        const double u = U[q * n + b];
+        if (packed) {
+            const int lo = a < q ? a : q, hi = a < q ? q : a;
+            const int r = hi * (hi + 1) / 2 + lo;
+            if (r >= row_begin && r < row_end) {
+                double f = F1[(size_t)(r - row_begin) * Np + b];
+                if (F2) f += F2[(size_t)(r - row_begin) * Np + b];
+                g = fma(2.0 * u / sw[r], f, g);
+            }
+        } else {
+            const int r1 = a + n * q, r2 = q + n * a;
+            double f = 0.0;
+            if (r1 >= row_begin && r1 < row_end) {
+                f += F1[(size_t)(r1 - row_begin) * Np + b];
+                if (F2) f += F2[(size_t)(r1 - row_begin) * Np + b];
+            }
+            if (r2 >= row_begin && r2 < row_end) {
+                f += F1[(size_t)(r2 - row_begin) * Np + b];
+                if (F2) f += F2[(size_t)(r2 - row_begin) * Np + b];
+            }
+            g = fma(u, f, g);
+        }
+    }
+    part[1 + n * n + idx] = gcoef * g;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// CSA_SD one-body terms (single CTA; N is small where CSA_SD is used, N^3 work):
+//   h = U diag(l1) U^T, Dh = h - hT; cost += |Dh|^2; G += ((Dh + Dh^T) U) .* l1; g1[k] = 2 (U^T Dh U)[k,k]
+//   (fermionic.jl:58-72, unitaries.jl:314-320, cost.jl:21-25, gradient.jl:157-186, 218-231)
+//   hT is the Julia column-major obt: hT(r,s) at r + n*s.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_sd_onebody(const double* __restrict__ x, const double* __restrict__ hT, const double* __restrict__ Rchain,
+                             const int* __restrict__ s_ptr, int n, double* __restrict__ part, double* __restrict__ g1,
+                             double* __restrict__ Dh /* n*n scratch */, double* __restrict__ DU /* n*n scratch */,
+                             double* __restrict__ hstore /* optional: h - for residual update */) {
+    __shared__ double red[32];
+    const double* U = Rchain + (size_t)(*s_ptr) * n * n;
+    const double* l1 = x;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    double c = 0.0;
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int r = idx / n, s = idx % n;
+        double h = 0.0;
+        for (int i = 0; i < n; ++i) h = fma(U[r * n + i] * l1[i], U[s * n + i], h);
+        const double d = h - hT[r + n * s];
+        Dh[idx] = d;
+        if (hstore) hstore[idx] = h;
+        c += d * d;
+    }
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((tid & 31) == 0) red[tid >> 5] = c;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (nt + 31) / 32; ++w) t += red[w];
+        if (part) part[0] += t;
+    }
+    if (!part) return;
+    // DU = (Dh + Dh^T) U ; G += DU .* l1
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int a = idx / n, b = idx % n;
+        double s = 0.0;
+        for (int r = 0; r < n; ++r) s = fma(Dh[a * n + r] + Dh[r * n + a], U[r * n + b], s);
+        part[1 + n * n + idx] += s * l1[b];
+        // DU2[a][b] = sum_s Dh[a][s] U[s][b]   (for g1)
+        double s2 = 0.0;
+        for (int r = 0; r < n; ++r) s2 = fma(Dh[a * n + r], U[r * n + b], s2);
+        DU[idx] = s2;
+    }
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) {
+        double s = 0.0;
+        for (int r = 0; r < n; ++r) s = fma(U[r * n + k], DU[r * n + k], s);
+        g1[k] = 2.0 * s;
+    }
+}
+
+// dX = G^T * 2^-s  (start of the derivative chain; Lt = Dexp(K)[G^T])
+__global__ void k_build_d(const double* __restrict__ part, const double* __restrict__ scale, int n, double* __restrict__ dX) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int i = idx / n, j = idx % n;
+    dX[idx] = part[1 + n * n + j * n + i] * (*scale);
+}
+
+// out = [cost, (g1), g_lambda, g_theta]   (gradient.jl:148-151, 287-290)
+__global__ void k_assemble(const double* __restrict__ part, const double* __restrict__ g1, const double* __restrict__ dRchain,
+                           const int* __restrict__ s_ptr, int n, int sd, double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int cL = n * (n + 1) / 2, uL = n * (n - 1) / 2, off = sd ? n : 0;
+    if (idx == 0) out[0] = part[0];
+    if (sd && idx < n) out[1 + idx] = g1[idx];
+    if (idx < n * n) {
+        const int i = idx / n, j = idx % n;
+        if (j <= i) out[1 + off + i * (i + 1) / 2 + j] = 2.0 * part[1 + idx] * (i != j ? 2.0 : 1.0);
+        if (i < j) {
+            const double* Lt = dRchain + (size_t)(*s_ptr) * n * n;
+            out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (Lt[j * n + i] - Lt[i * n + j]);
+        }
+    }
+    (void)uL;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// packing / symmetry analysis / unpacking of the residual tensor
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {  // v >= 0
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+// stats[0] = max|T|, [1] = max|T[pq,rs]-T[rs,pq]|, [2] = max|T[pq,rs]-T[qp,rs]|, [3] = max|T[pq,rs]-T[pq,sr]|
+__global__ void k_sym_stats(const double* __restrict__ mem, int n, double* __restrict__ stats) {
+    const long long n2 = (long long)n * n, total = n2 * n2;
+    double m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long pq = idx % n2, rs = idx / n2;
+        const int p = (int)(pq % n), q = (int)(pq / n), r = (int)(rs % n), s = (int)(rs / n);
+        const double v = mem[idx];
+        m0 = fmax(m0, fabs(v));
+        m1 = fmax(m1, fabs(v - mem[rs + n2 * pq]));
+        m2 = fmax(m2, fabs(v - mem[(q + (long long)n * p) + n2 * rs]));
+        m3 = fmax(m3, fabs(v - mem[pq + n2 * (s + (long long)n * r)]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+        m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+        m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        m3 = fmax(m3, __shfl_xor_sync(0xffffffffu, m3, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomic_max_pos(&stats[0], m0);
+        atomic_max_pos(&stats[1], m1);
+        atomic_max_pos(&stats[2], m2);
+        atomic_max_pos(&stats[3], m3);
+    }
+}
+
+// T~[i - row_begin][j] = sw_i sw_j mem[mrow(j) + n^2 mrow(i)]   (transpose=1: mem[mrow(i) + n^2 mrow(j)])
+__global__ void k_pack(const double* __restrict__ mem, int n, const int* __restrict__ pa, const int* __restrict__ pq,
+                       const double* __restrict__ sw, int row_begin, int rows_local_pad, int rows_total, long long ldT,
+                       int transpose, double* __restrict__ Tt) {
+    const long long n2 = (long long)n * n;
+    const long long total = (long long)rows_local_pad * ldT;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int il = (int)(idx / ldT), j = (int)(idx % ldT), i = row_begin + il;
+        double v = 0.0;
+        if (i < rows_total && j < rows_total) {
+            const double w = sw[i] * sw[j];
+            if (w != 0.0) {
+                const long long mi = pa[i] + (long long)n * pq[i], mj = pa[j] + (long long)n * pq[j];
+                v = w * (transpose ? mem[mi + n2 * mj] : mem[mj + n2 * mi]);
+            }
+        }
+        Tt[idx] = v;
+    }
+}
+
+// out[p + nq + n^2 r + n^3 s] = T~[pair(r,s)][pair(p,q)] / (sw sw); rows not owned by this shard give 0.
+__global__ void k_unpack(const double* __restrict__ Tt, int n, int packed, const double* __restrict__ sw, int row_begin,
+                         int row_end, long long ldT, double* __restrict__ out) {
+    const long long n2 = (long long)n * n, total = n2 * n2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long pqi = idx % n2, rsi = idx / n2;
+        int i, j;
+        if (packed) {
+            const int p = (int)(pqi % n), q = (int)(pqi / n), r = (int)(rsi % n), s = (int)(rsi / n);
+            const int lo1 = r < s ? r : s, hi1 = r < s ? s : r, lo2 = p < q ? p : q, hi2 = p < q ? q : p;
+            i = hi1 * (hi1 + 1) / 2 + lo1;
+            j = hi2 * (hi2 + 1) / 2 + lo2;
+        } else {
+            i = (int)rsi;
+            j = (int)pqi;
+        }
+        double v = 0.0;
+        if (i >= row_begin && i < row_end) v = Tt[(long long)(i - row_begin) * ldT + j] / (sw[i] * sw[j]);
+        out[idx] = v;
+    }
+}
+
+// W[p + nq + n^2 r + n^3 s] = sum_m B~[pair(r,s)][m] A~[pair(p,q)][m] / (sw sw)   (to_OP(frag), not hot)
+__global__ void k_reconstruct(const double* __restrict__ At, const double* __restrict__ Bt, int n, int ld, int packed,
+                              const double* __restrict__ sw, double* __restrict__ out) {
+    const long long n2 = (long long)n * n, total = n2 * n2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long pqi = idx % n2, rsi = idx / n2;
+        int i, j;
+        if (packed) {
+            const int p = (int)(pqi % n), q = (int)(pqi / n), r = (int)(rsi % n), s = (int)(rsi / n);
+            const int lo1 = r < s ? r : s, hi1 = r < s ? s : r, lo2 = p < q ? p : q, hi2 = p < q ? q : p;
+            i = hi1 * (hi1 + 1) / 2 + lo1;
+            j = hi2 * (hi2 + 1) / 2 + lo2;
+        } else {
+            i = (int)rsi;
+            j = (int)pqi;
+        }
+        const double* b = Bt + (size_t)i * ld;
+        const double* a = At + (size_t)j * ld;
+        double s = 0.0;
+        for (int m = 0; m < n; ++m) s = fma(b[m], a[m], s);
+        out[idx] = s / (sw[i] * sw[j]);
+    }
+}
+
+// obt residual update / copy helpers for CSA_SD:  hT(r,s) (column-major) -= h[r][s]
+__global__ void k_obt_sub(double* __restrict__ hT, const double* __restrict__ h, int n) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int r = idx / n, s = idx % n;
+    hT[r + n * s] -= h[idx];
+}
+__global__ void k_obt_colmajor(const double* __restrict__ h, int n, double* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    const int r = idx / n, s = idx % n;
+    out[r + n * s] = h[idx];
+}
+// sum of squares of a vector (one-body residual norm) added into dst[0]; single CTA
+__global__ void k_sumsq_add(const double* __restrict__ v, int len, const double* __restrict__ cost_part, int ncost,
+                            double* __restrict__ dst) {
+    __shared__ double red[32];
+    double c = 0.0;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) c += v[i] * v[i];
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += red[w];
+        for (int i = 0; i < ncost; ++i) t += cost_part[i];
+        dst[0] = t;
+    }
+}
+
+}  // namespace small

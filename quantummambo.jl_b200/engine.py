@@ -1,0 +1,158 @@
+"""CSAEngine: object wrapper over one libmambo_b200 handle (one GPU, one residual tensor).
+
+Host-side mirror of the closures the reference builds in CSA_greedy_step / CSA_SD_greedy_step
+(/root/reference/src/UTILS/decompose.jl:96-105, 221-231): `cost(x)`, `grad(x)`, plus the residual update of
+decompose.jl:56,182.  All numerics run in the CUDA library; numpy only carries buffers across the C-ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+CSA, CSA_SD = 0, 1
+SYM_AUTO, SYM_GENERAL, SYM_PAIR, SYM_FULL = 0, 1, 2, 3
+TBT_ON_DEVICE = 4
+MODE_NAMES = {SYM_GENERAL: "general", SYM_PAIR: "pairsym", SYM_FULL: "fullsym-packed"}
+
+
+def _flavour_id(flavour) -> int:
+    if flavour in (CSA, "CSA"):
+        return CSA
+    if flavour in (CSA_SD, "CSA_SD"):
+        return CSA_SD
+    raise ValueError(f"unknown flavour {flavour!r}")
+
+
+def _f64(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} values, got {a.size}")
+    return a
+
+
+class CSAEngine:
+    """Device-resident CSA / CSA_SD cost+gradient evaluator for one two-body tensor.
+
+    tbt : (N,N,N,N) array with Julia semantics tbt[p,q,r,s]; it is handed to the library in column-major
+          order exactly as a Julia Array{Float64,4} lies in memory.
+    obt : (N,N) one-body tensor (CSA_SD only).
+    """
+
+    def __init__(self, tbt, obt=None, flavour="CSA", device: int = 0, sym: int = SYM_AUTO,
+                 shard: int = 0, nshards: int = 1):
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        tbt = np.asarray(tbt, dtype=np.float64)
+        if tbt.ndim != 4 or len(set(tbt.shape)) != 1:
+            raise ValueError("tbt must have shape (N,N,N,N)")
+        self.N = int(tbt.shape[0])
+        self.flavour = _flavour_id(flavour)
+        tf = np.asfortranarray(tbt)                     # memory order of the Julia array
+        of = None
+        if self.flavour == CSA_SD:
+            if obt is None:
+                raise ValueError("CSA_SD needs obt")
+            of = np.asfortranarray(np.asarray(obt, dtype=np.float64))
+        _lib.check(self._lib.mambo_csa_create_sharded(
+            C.byref(self._h), self.N, self.flavour, tf.ctypes.data, None if of is None else of.ctypes.data,
+            device, sym, shard, nshards))
+        self.device = device
+        self.L = self._lib.mambo_csa_num_params(self._h)
+
+    # -- lifetime -----------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.mambo_csa_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def handle(self):
+        return self._h
+
+    def info(self) -> dict:
+        s = _lib.MamboInfo()
+        _lib.check(self._lib.mambo_csa_get_info(self._h, C.byref(s)))
+        d = {k: getattr(s, k) for k, _ in s._fields_}
+        d["mode_name"] = MODE_NAMES.get(d["mode"], "?")
+        return d
+
+    # -- closures (host buffers) ---------------------------------------------------------------------------
+    def cost(self, x) -> float:
+        x = _f64(x, self.L)
+        c = C.c_double()
+        _lib.check(self._lib.mambo_csa_cost(self._h, x.ctypes.data, C.byref(c)))
+        return c.value
+
+    def grad(self, x) -> np.ndarray:
+        x = _f64(x, self.L)
+        g = np.empty(self.L)
+        _lib.check(self._lib.mambo_csa_grad(self._h, x.ctypes.data, g.ctypes.data))
+        return g
+
+    def cost_grad(self, x):
+        x = _f64(x, self.L)
+        g = np.empty(self.L)
+        c = C.c_double()
+        _lib.check(self._lib.mambo_csa_cost_grad(self._h, x.ctypes.data, C.byref(c), g.ctypes.data))
+        return c.value, g
+
+    # -- greedy state ---------------------------------------------------------------------------------------
+    def subtract_fragment(self, x) -> float:
+        x = _f64(x, self.L)
+        c = C.c_double()
+        _lib.check(self._lib.mambo_csa_subtract_fragment(self._h, x.ctypes.data, C.byref(c)))
+        return c.value
+
+    def residual_cost(self) -> float:
+        c = C.c_double()
+        _lib.check(self._lib.mambo_csa_residual_cost(self._h, C.byref(c)))
+        return c.value
+
+    def get_residual(self):
+        n = self.N
+        t = np.empty((n, n, n, n), order="F")
+        o = np.empty((n, n), order="F") if self.flavour == CSA_SD else None
+        _lib.check(self._lib.mambo_csa_get_residual(self._h, t.ctypes.data, None if o is None else o.ctypes.data))
+        return t, o
+
+    def reconstruct(self, x):
+        x = _f64(x, self.L)
+        n = self.N
+        t = np.empty((n, n, n, n), order="F")
+        o = np.empty((n, n), order="F") if self.flavour == CSA_SD else None
+        _lib.check(self._lib.mambo_csa_reconstruct(self._h, x.ctypes.data, t.ctypes.data, None if o is None else o.ctypes.data))
+        return t, o
+
+    # -- device-resident entry points (torch tensors carry the device memory; no host sync) -------------------
+    def set_stream(self, cuda_stream_ptr: int | None):
+        _lib.check(self._lib.mambo_csa_set_stream(self._h, cuda_stream_ptr))
+
+    def eval_device(self, d_x_ptr: int, d_out_ptr: int):
+        _lib.check(self._lib.mambo_csa_eval_device(self._h, d_x_ptr, d_out_ptr))
+
+    def cost_device(self, d_x_ptr: int, d_cost_ptr: int):
+        _lib.check(self._lib.mambo_csa_cost_device(self._h, d_x_ptr, d_cost_ptr))
+
+    def eval_partial_device(self, d_x_ptr: int, d_partial_ptr: int):
+        _lib.check(self._lib.mambo_csa_eval_partial_device(self._h, d_x_ptr, d_partial_ptr))
+
+    def eval_finish_device(self, d_partial_ptr: int, d_out_ptr: int):
+        _lib.check(self._lib.mambo_csa_eval_finish_device(self._h, d_partial_ptr, d_out_ptr))
+
+    def synchronize(self):
+        _lib.check(self._lib.mambo_csa_synchronize(self._h))
