@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- CSA fragment cost+gradient throughput (BASELINE.json metric) on N GPUs of one node.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...     # the reference algorithm's CPU path (oracle port) on the host cores
+
+Workload (config.workload): synthetic dense-sym two-body tensor, N=100 (SURVEY.md 8d / BASELINE.json configs[3]),
+seed 0; one *step* = one fused cost+gradient evaluation at each of 8 distinct points x (theta ~ U[0,2pi),
+lambda ~ N(0,1)/N).  metric = cost+grad evaluations per second, FP64.
+
+  value   : device-resident leg -- x and (cost, grad) live in HBM, CUDA-event timed on the launching stream.
+  e2e     : the same evaluations through the public host API (CSAEngine.cost_grad == the C-ABI call the Julia
+            shim makes): host x in, H2D, kernels, D2H of cost+grad, inside the timed region.
+  N > 1   : multistart replicas: every rank holds the tensor and evaluates its own batch, no
+            data-path collective -> "scaling": "weak".  The row-panel-sharded variant (8e.2, NCCL allreduce of
+            1+2N^2 doubles per evaluation) is measured as well and reported under "rowpanel".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 8  # evaluation points per step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=100, help="orbitals of the synthetic tensor")
+    ap.add_argument("--sym", default="auto", choices=["auto", "general", "pair", "full"],
+                    help="symmetry mode of the engine (auto detects the 8-fold symmetry of the synthetic tensor)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-rowpanel", action="store_true")
+    ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations timed for the CPU baseline (0 = auto)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(self.samples), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_rate(n: int, T, xs, budget_s: float, max_evals: int):
+    """The reference algorithm on the host cores: the oracle's factored restatement (numpy/OpenBLAS, all
+    threads).  Returns (evals_per_s, evals_timed, cores)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import csa_oracle as oracle  # noqa: E402  (checker / baseline only -- never on the product path)
+    cores = os.cpu_count() or 1
+    oracle.cost_grad_factored(xs[0], T)  # warm-up (BLAS thread pool, page faults)
+    t0 = time.perf_counter()
+    done = 0
+    while done < max_evals:
+        oracle.cost_grad_factored(xs[done % len(xs)], T)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, done, cores
+
+
+def run_reference(args, rank: int):
+    """--impl reference: the reference's CPU path (oracle port) timed on this box's host cores, rank 0 only."""
+    if rank != 0:
+        return
+    from mambo_b200 import pkg  # only for the synthetic generator (no GPU work on this arm)
+    import importlib
+    syn = importlib.import_module("quantummambo_jl_b200.synthetic")
+    n = args.n
+    T = syn.dense_sym_tbt(n, 0)
+    xs = [syn.random_x(n, i) for i in range(BATCH)]
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import csa_oracle as oracle
+    for _ in range(max(args.warmup, 1)):
+        oracle.cost_grad_factored(xs[0], T)
+    # each step: a bounded sample of the BATCH-point workload (2 of the 8 points), so K steps stay within minutes
+    sample = 2 if n >= 100 else BATCH
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for i in range(sample):
+            oracle.cost_grad_factored(xs[(s * sample + i) % BATCH], T)
+    dt = time.perf_counter() - t0
+    evals = args.steps * sample
+    v = evals / dt
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "csa_cost_grad_evals_per_s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense-sym N={n} seed 0, CSA cost+grad at {BATCH} points/step", "N": n,
+                   "points_per_step": BATCH},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of the {BATCH} points per step x {args.steps} steps, oracle factored numpy/OpenBLAS, "
+                                   f"{cores} threads (the literal reference needs 8*N^6 B = 8 TB scratch at N=100: not runnable)"},
+        "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import mambo_b200 as mb
+    import importlib
+    syn = importlib.import_module("quantummambo_jl_b200.synthetic")
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CSA engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n = args.n
+    sym = {"auto": mb.SYM_AUTO, "general": mb.SYM_GENERAL, "pair": mb.SYM_PAIR, "full": mb.SYM_FULL}[args.sym]
+    T = syn.dense_sym_tbt(n, 0)                       # same tensor on every rank (multistart replicas)
+    xs = [syn.random_x(n, rank * BATCH + i) for i in range(BATCH)]   # distinct start points per rank
+    eng = mb.CSAEngine(T, flavour="CSA", device=local_rank, sym=sym)
+    info = eng.info()
+    L = eng.L
+
+    # ---- measured FP64 peak (cuBLAS DGEMM through torch) : the tensor roofline denominator -------------------
+    a = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    b = torch.randn(4096, 4096, dtype=torch.float64, device=dev)
+    for _ in range(2):
+        a @ b
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    dgemm_tflops = 2.0 * 4096 ** 3 / (best * 1e-3) / 1e12
+    del a, b
+
+    # ---- device-resident leg ------------------------------------------------------------------------------
+    stream = torch.cuda.current_stream(dev)
+    eng.set_stream(stream.cuda_stream)
+    d_x = torch.from_numpy(np.stack(xs)).to(dev)                     # [BATCH, L] in HBM
+    d_out = torch.empty(BATCH, L + 1, dtype=torch.float64, device=dev)
+
+    def step_device():
+        for i in range(BATCH):
+            eng.eval_device(d_x[i].data_ptr(), d_out[i].data_ptr())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    torch.cuda.synchronize()
+    eng.synchronize()
+    launches0 = eng.get_profile()["total_launches"]
+    eng.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    prof = eng.get_profile()
+    eng.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    launches = prof["total_launches"] - launches0
+    evals_total = world * BATCH * args.steps
+    value = evals_total / (ms * 1e-3)
+    cost_check = float(d_out[0, 0].item())
+
+    # ---- end-to-end leg: public host API, host buffers, H2D + D2H inside the timed region --------------------
+    eng.set_stream(None)
+    for i in range(BATCH):
+        eng.cost_grad(xs[i] + 0.0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    acc = 0.0
+    for s in range(args.steps):
+        for i in range(BATCH):
+            xi = xs[i].copy()
+            xi[0] += 1e-9 * (s + 1)          # a fresh point every call: the memo of the last x never hits
+            c, g = eng.cost_grad(xi)
+            acc += c
+    t_e2e = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_e2e = float(t.item())
+    sampler.stop()
+    e2e_value = evals_total / t_e2e
+
+    # ---- row-panel sharded variant (strong scaling, NCCL allreduce of the partial vector) -----------------------
+    rowpanel = None
+    if world > 1 and not args.no_rowpanel:
+        eng.close()
+        torch.cuda.empty_cache()
+        engs = mb.CSAEngine(T, flavour="CSA", device=local_rank, sym=sym, shard=rank, nshards=world)
+        engs.set_stream(stream.cuda_stream)
+        plen = engs.info()["partial_len"]
+        xs0 = [syn.random_x(n, i) for i in range(BATCH)]              # the same points on every rank
+        d_x0 = torch.from_numpy(np.stack(xs0)).to(dev)
+        d_part = torch.empty(plen, dtype=torch.float64, device=dev)
+
+        def step_sharded():
+            for i in range(BATCH):
+                engs.eval_partial_device(d_x0[i].data_ptr(), d_part.data_ptr())
+                dist.all_reduce(d_part)
+                engs.eval_finish_device(d_part.data_ptr(), d_out[i].data_ptr())
+
+        for _ in range(3):
+            step_sharded()
+        torch.cuda.synchronize(); dist.barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_sharded()
+        e1.record(stream)
+        torch.cuda.synchronize(); dist.barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rp_ms = float(t.item())
+        rowpanel = {"value": BATCH * args.steps / (rp_ms * 1e-3), "unit": "evals/s", "scaling": "strong",
+                    "allreduce_doubles_per_eval": plen, "ms_per_eval": rp_ms / (BATCH * args.steps)}
+        engs.close()
+
+    # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ----------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        max_evals = args.cpu_evals or (24 if n >= 100 else 200)
+        rate, done, cores = cpu_reference_rate(n, T, xs, budget_s=15.0, max_evals=max_evals)
+        cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
+               "sample": f"{done} cost+grad evaluations of the same N={n} workload, oracle factored numpy/OpenBLAS on {cores} threads"}
+
+    if rank == 0:
+        clocks = sampler.summary()
+        fused_ms = prof["fused_ms"] / max(prof["fused_launches"], 1)
+        rows = info["rows"]
+        passes = 2.0 if info["mode"] == mb.SYM_GENERAL else 1.0
+        alg_flops = 4.0 * rows * rows * n                       # per fused launch (both GEMMs), algorithm actually run
+        exec_flops = info["flops_per_eval"] / passes             # incl. tile padding
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "fused_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(f"N{n}_{info['mode_name']}")
+            except Exception:
+                traffic = None
+        roof = {
+            "bound": "tensor", "kernel": "fused::k_fused (FP64 DMMA.8x8x4)",
+            "achieved": alg_flops / (fused_ms * 1e-3) / 1e12, "peak": dgemm_tflops, "unit": "TFLOP/s",
+            "frac": alg_flops / (fused_ms * 1e-3) / 1e12 / dgemm_tflops,
+            "peak_source": "cuBLAS DGEMM 4096^3 (torch.matmul f64) measured in this run; MEASURED_PEAKS.json has no FP64 entry"
+                           + ("" if os.path.exists(peaks_path) else " (file absent)"),
+            "traffic": traffic, "ms_per_launch": fused_ms, "launches_timed": prof["fused_launches"],
+            "algorithmic_flops_per_launch": alg_flops, "executed_flops_per_launch": exec_flops,
+            "executed_frac": exec_flops / (fused_ms * 1e-3) / 1e12 / dgemm_tflops,
+            "unsymmetrised_4N5_equivalent_tflops": 4.0 * n ** 5 / (fused_ms * 1e-3) / 1e12,
+            "share_of_step": prof["fused_ms"] / ms,
+        }
+        line = {
+            "metric": "csa_cost_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"dense-sym N={n} seed 0, CSA cost+grad at {BATCH} points/step per GPU", "N": n,
+                       "points_per_step": BATCH, "mode": info["mode_name"], "rows": rows,
+                       "tensor_bytes_per_gpu": info["tensor_bytes"], "l2_policy": "inputs larger than L2 (residual "
+                       f"{info['tensor_bytes'] / 1e6:.0f} MB streamed once per evaluation; L2 is 126 MB)",
+                       "parallelism": "multistart replicas, one per GPU" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": BATCH * L * 8,
+                    "d2h_bytes_per_step": BATCH * (L + 1) * 8, "timer": "host perf_counter around synchronous C-ABI calls"},
+            "gpu_launches": int(launches), "launches_per_eval": launches / (BATCH * args.steps),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "cost_check": cost_check,
+        }
+        if rowpanel is not None:
+            line["rowpanel"] = rowpanel
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

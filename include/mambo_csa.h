@@ -110,6 +110,11 @@ int  mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double*
 /* Cost-only evaluation (half the flops: reconstruction + residual norm, no gradient). */
 int  mambo_csa_cost_device(mambo_csa* h, const double* d_x, double* d_cost);
 int  mambo_csa_synchronize(mambo_csa* h);
+/* Live profiling: CUDA events bracket every fused-kernel launch on the launching stream.  get_profile
+ * synchronises, returns the summed device time (ms) and count of those launches since the last call, and
+ * the handle's running total of kernel launches.                                                         */
+int  mambo_csa_set_profiling(mambo_csa* h, int enable);
+int  mambo_csa_get_profile(mambo_csa* h, double* fused_ms, int* fused_launches, long long* total_launches);
 
 /* --- multistart scheduler: K independent BFGS runs, one handle per GPU, host thread each ----- */
 typedef struct mambo_opt_options_t {

@@ -464,7 +464,8 @@ def dense_sym_tbt(n: int, seed: int) -> np.ndarray:
     g = g + g.transpose(1, 0, 2, 3)
     g = g + g.transpose(0, 1, 3, 2)
     g = g + g.transpose(2, 3, 0, 1)
-    return g / (8.0 * n * n) * 8.0 / 8.0
+    g *= 1.0 / (n * n)
+    return g
 
 
 def pairsym_tbt(n: int, seed: int) -> np.ndarray:

@@ -79,6 +79,10 @@ struct mambo_csa {
     bool memo_valid = false;
     long long launches = 0;
     int launches_last_eval = 0;
+    // optional live profiling of the fused kernel (CUDA events on the launching stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev_pool;   // pairs: [2k] before, [2k+1] after
+    size_t ev_used = 0;
 };
 
 namespace {
@@ -89,10 +93,22 @@ template <int NB, bool DO_E, bool STORE>
 int launch_fused_nb(mambo_csa* h, const Params& p) {
     constexpr bool TPREF = (NB <= 13);
     auto kern = k_fused<NB, DO_E, STORE, TPREF>;
-    static thread_local int configured_dev = -1;
-    (void)configured_dev;
     CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (h->profiling) {
+        if (h->ev_used + 2 > h->ev_pool.size()) {
+            cudaEvent_t a, b;
+            CU(cudaEventCreate(&a));
+            CU(cudaEventCreate(&b));
+            h->ev_pool.push_back(a);
+            h->ev_pool.push_back(b);
+        }
+        e0 = h->ev_pool[h->ev_used++];
+        e1 = h->ev_pool[h->ev_used++];
+        CU(cudaEventRecord(e0, h->stream));
+    }
     kern<<<h->G, NTHREADS, h->smem, h->stream>>>(p);
+    if (e1) CU(cudaEventRecord(e1, h->stream));
     CU(cudaGetLastError());
     h->launches++;
     return MAMBO_OK;
@@ -564,6 +580,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (h->h_x) cudaFreeHost(h->h_x);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_status) cudaFreeHost(h->h_status);
+    for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -614,6 +631,31 @@ int mambo_csa_grad(mambo_csa* h, const double* x, double* grad) { return mambo_c
 int mambo_csa_set_stream(mambo_csa* h, void* stream) {
     if (!h) return fail(MAMBO_EINVAL, "null handle");
     h->stream = stream ? (cudaStream_t)stream : h->own_stream;
+    return MAMBO_OK;
+}
+
+int mambo_csa_set_profiling(mambo_csa* h, int enable) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    h->profiling = enable != 0;
+    h->ev_used = 0;
+    return MAMBO_OK;
+}
+
+// Sum of the device durations of the fused-kernel launches recorded since profiling was (re)enabled.
+int mambo_csa_get_profile(mambo_csa* h, double* fused_ms, int* fused_launches, long long* total_launches) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    double ms = 0.0;
+    for (size_t i = 0; i + 1 < h->ev_used; i += 2) {
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, h->ev_pool[i], h->ev_pool[i + 1]));
+        ms += t;
+    }
+    if (fused_ms) *fused_ms = ms;
+    if (fused_launches) *fused_launches = (int)(h->ev_used / 2);
+    if (total_launches) *total_launches = h->launches;
+    h->ev_used = 0;
     return MAMBO_OK;
 }
 

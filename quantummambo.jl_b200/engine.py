@@ -154,5 +154,13 @@ class CSAEngine:
     def eval_finish_device(self, d_partial_ptr: int, d_out_ptr: int):
         _lib.check(self._lib.mambo_csa_eval_finish_device(self._h, d_partial_ptr, d_out_ptr))
 
+    def set_profiling(self, enable: bool):
+        _lib.check(self._lib.mambo_csa_set_profiling(self._h, 1 if enable else 0))
+
+    def get_profile(self) -> dict:
+        ms, nl, tot = C.c_double(), C.c_int(), C.c_longlong()
+        _lib.check(self._lib.mambo_csa_get_profile(self._h, C.byref(ms), C.byref(nl), C.byref(tot)))
+        return {"fused_ms": ms.value, "fused_launches": nl.value, "total_launches": tot.value}
+
     def synchronize(self):
         _lib.check(self._lib.mambo_csa_synchronize(self._h))
