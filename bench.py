@@ -197,7 +197,8 @@ def main():
     del a, b
 
     # ---- device-resident leg ------------------------------------------------------------------------------
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # a real side stream: handle 0 (legacy default) would mean "own stream"
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     d_x = torch.from_numpy(np.stack(xs)).to(dev)                     # [BATCH, L] in HBM
     d_out = torch.empty(BATCH, L + 1, dtype=torch.float64, device=dev)
@@ -226,6 +227,8 @@ def main():
     if world > 1:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    info = eng.info()
+    segs = eng.get_segments()
     prof = eng.get_profile()
     eng.set_profiling(False)
     if world > 1:
@@ -327,6 +330,7 @@ def main():
             "executed_frac": exec_flops / (fused_ms * 1e-3) / 1e12 / dgemm_tflops,
             "unsymmetrised_4N5_equivalent_tflops": 4.0 * n ** 5 / (fused_ms * 1e-3) / 1e12,
             "share_of_step": prof["fused_ms"] / ms,
+            "segments_ms_per_eval": segs,
         }
         line = {
             "metric": "csa_cost_grad_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": world,

@@ -115,6 +115,10 @@ int  mambo_csa_synchronize(mambo_csa* h);
  * the handle's running total of kernel launches.                                                         */
 int  mambo_csa_set_profiling(mambo_csa* h, int enable);
 int  mambo_csa_get_profile(mambo_csa* h, double* fused_ms, int* fused_launches, long long* total_launches);
+/* Per-segment device time (ms) summed over the evaluations profiled since the last call:
+ * seg_ms[0] orbital-rotation chain + operand build, [1] fused kernel(s) + row epilogues, [2] adjoint Frechet
+ * chain + gradient assembly.  Call before mambo_csa_get_profile (which resets the event pools).            */
+int  mambo_csa_get_segments(mambo_csa* h, double* seg_ms, int* evals);
 
 /* --- multistart scheduler: K independent BFGS runs, one handle per GPU, host thread each ----- */
 typedef struct mambo_opt_options_t {

@@ -32,11 +32,17 @@ int fail(int code, const std::string& msg) {
                         std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
     } while (0)
 
+#define TRY(expr)               \
+    do {                        \
+        int rc__ = (expr);      \
+        if (rc__) return rc__;  \
+    } while (0)
+
 const int kNBBuckets[] = {1, 2, 4, 7, 10, 13, 16, 19, 21};
 
-struct DevBuf {
-    void* p = nullptr;
-    size_t bytes = 0;
+struct GraphSeg {
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
 };
 
 }  // namespace
@@ -62,7 +68,7 @@ struct mambo_csa {
     double *At = nullptr, *Bt = nullptr;
     int *pa = nullptr, *pq = nullptr;
     double* sw = nullptr;
-    double *Epiece = nullptr, *F1 = nullptr, *F2 = nullptr, *Spart = nullptr, *cost_part = nullptr;
+    double *Epiece = nullptr, *Et = nullptr, *F1 = nullptr, *F2 = nullptr, *Spart = nullptr, *cost_part = nullptr;
     int *visit_start = nullptr, *piece_first = nullptr;
     double* mats = nullptr;                    // all N x N matrices of the expm chains
     double *X, *X2, *X3, *X4, *P0, *P1, *P2, *Q3, *Q2, *Q1, *R;      // R: (SMAX+1) matrices
@@ -79,21 +85,41 @@ struct mambo_csa {
     bool memo_valid = false;
     long long launches = 0;
     int launches_last_eval = 0;
+    // CUDA-graph segments of the small-kernel sequences
+    bool use_graphs = true;
+    std::vector<GraphSeg> g_pre, g_fin;   // index 0: device-decided s; 1+s: s squarings
+    GraphSeg g_mid, g_post, g_costonly;
     // optional live profiling of the fused kernel (CUDA events on the launching stream)
     bool profiling = false;
     std::vector<cudaEvent_t> ev_pool;   // pairs: [2k] before, [2k+1] after
     size_t ev_used = 0;
+    std::vector<cudaEvent_t> seg_pool;  // 4 marks per evaluation: start, after pre, after fused+post, after finish
+    size_t seg_used = 0;
 };
 
 namespace {
 
 using namespace fused;
 
+int seg_mark(mambo_csa* h) {
+    if (!h->profiling) return MAMBO_OK;
+    if (h->seg_used >= h->seg_pool.size()) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        h->seg_pool.push_back(e);
+    }
+    CU(cudaEventRecord(h->seg_pool[h->seg_used++], h->stream));
+    return MAMBO_OK;
+}
+
 template <int NB, bool DO_E, bool STORE>
 int launch_fused_nb(mambo_csa* h, const Params& p) {
     constexpr bool TPREF = (NB <= 13);
     auto kern = k_fused<NB, DO_E, STORE, TPREF>;
-    CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    if (p.P < 0) {   // configuration call from create
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        return MAMBO_OK;
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (h->profiling) {
         if (h->ev_used + 2 > h->ev_pool.size()) {
@@ -168,23 +194,25 @@ int host_s_for(const mambo_csa* h, const double* x) {
     return s;
 }
 
+dim3 mm_grid(int n) { return dim3((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS); }
+dim3 mm_block() { return dim3(small::TS, small::TS); }
+
 void mm(mambo_csa* h, double* C, const double* Cin, const double* A1, const double* B1, const double* A2, const double* B2,
         const int* s_ptr, int step) {
     const int n = h->N;
-    dim3 grid((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS), block(small::TS, small::TS);
-    small::k_mm<<<grid, block, 0, h->stream>>>(C, Cin, A1, B1, A2, B2, n, s_ptr, step);
+    small::k_mm<<<mm_grid(n), mm_block(), small::strip_bytes(n, A2 ? 2 : 1, A2 ? 2 : 1), h->stream>>>(C, Cin, A1, B1, A2, B2, n, s_ptr, step);
     h->launches++;
 }
 
 // U = exp(K): Taylor-16 (Paterson-Stockmeyer, 6 GEMMs) + s squarings; every intermediate is kept for the
-// derivative chain.  s_host >= 0: number of squaring launches needed (known when x came from the host).
+// derivative chain.  s_host >= 0: number of squarings (known when x came from the host; passed down so that
+// host and device agree); s_host < 0: the device decides and SMAX guarded launches are enqueued.
 int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
     const int n = h->N, nn = n * n;
-    small::k_build<<<1, 1024, 0, h->stream>>>(d_x, n, h->lam_off, h->X, h->Lam, h->d_s, h->d_scale, h->d_status);
+    small::k_build<<<1, 1024, (size_t)nn * 8, h->stream>>>(d_x, n, h->lam_off, h->X, h->Lam, h->d_s, h->d_scale, h->d_status, s_host);
     h->launches++;
     mm(h, h->X2, nullptr, h->X, h->X, nullptr, nullptr, nullptr, 0);
-    dim3 grid((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS), block(small::TS, small::TS);
-    small::k_pow34<<<grid, block, 0, h->stream>>>(h->X, h->X2, h->X3, h->X4, h->P0, h->P1, h->P2, h->Q3, n);
+    small::k_pow34<<<mm_grid(n), mm_block(), small::strip_bytes(n, 1, 2), h->stream>>>(h->X, h->X2, h->X3, h->X4, h->P0, h->P1, h->P2, h->Q3, n);
     h->launches++;
     mm(h, h->Q2, h->P2, h->X4, h->Q3, nullptr, nullptr, nullptr, 0);
     mm(h, h->Q1, h->P1, h->X4, h->Q2, nullptr, nullptr, nullptr, 0);
@@ -197,53 +225,29 @@ int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
 }
 
 int enqueue_prep(mambo_csa* h) {
-    const int blocks = h->nRpad / 32;
-    small::k_prep<<<blocks, 256, (size_t)32 * h->Np * 8, h->stream>>>(h->R, h->d_s, h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld,
-                                                                     h->nRpad, h->row_begin, h->row_end, h->At, h->Bt);
+    const int blocks = h->nRpad / small::PREP_ROWS;
+    small::k_prep<<<blocks, 256, small::prep_smem(h->N, h->Np), h->stream>>>(h->R, h->d_s, h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld,
+                                                                            h->nRpad, h->row_begin, h->row_end, h->At, h->Bt);
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
 }
 
-// stage A: everything up to the per-shard partial vector [cost, S, G]
-int enqueue_partial(mambo_csa* h, const double* d_x, int s_host, bool need_grad) {
-    int rc = enqueue_unitary(h, d_x, s_host);
-    if (rc) return rc;
-    rc = enqueue_prep(h);
-    if (rc) return rc;
-    const int n = h->N;
-    Params p = make_params(h, h->T1);
-    if (!need_grad) {
-        rc = launch_fused<false, false>(h, p);
-        if (rc) return rc;
-        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(nullptr, 0, h->cost_part, h->G, h->d_part);
-        h->launches++;
-        CU(cudaGetLastError());
-        return MAMBO_OK;
-    }
-    rc = launch_fused<true, false>(h, p);
-    if (rc) return rc;
-    const size_t post_smem = (size_t)2 * 64 * h->Np * 8;
-    CU(cudaFuncSetAttribute(small::k_post_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)post_smem));
-    const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
-    small::k_post_rows<<<h->P, 256, post_smem, h->stream>>>(h->Epiece, h->piece_first, h->At, h->Lam, n, h->Np, h->ld, h->row_begin,
-                                                            h->F1, h->Spart, general ? 0 : 1);
+int enqueue_post_f(mambo_csa* h, double* F) {
+    small::k_post_f<<<h->P, 256, small::postf_smem(h->Np), h->stream>>>(h->Epiece, h->piece_first, h->Lam, h->N, h->Np, h->Et, F);
     h->launches++;
-    if (general) {
-        // second pass over the transposed residual: E = D A (pass 1 gave E' = D^T A); S uses E only (gradient.jl:22-26)
-        Params p2 = make_params(h, h->T2);
-        p2.cost_part = h->cost_part + h->G;  // discarded
-        rc = launch_fused<true, false>(h, p2);
-        if (rc) return rc;
-        small::k_post_rows<<<h->P, 256, post_smem, h->stream>>>(h->Epiece, h->piece_first, h->At, h->Lam, n, h->Np, h->ld,
-                                                                h->row_begin, h->F2, h->Spart, 1);
-        h->launches++;
-    }
-    const int nn = n * n;
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
+int enqueue_post_sr(mambo_csa* h) {
+    const int n = h->N, nn = n * n;
+    const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
+    small::k_post_s<<<h->P, 256, small::posts_smem(h->Np), h->stream>>>(h->Et, h->At, n, h->Np, h->ld, h->row_begin, h->Spart);
     small::k_post_reduce<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->cost_part, h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
                                                                  h->sw, h->R, h->d_s, n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
                                                                  h->row_begin, std::min(h->row_end, h->nR), h->d_part);
-    h->launches++;
+    h->launches += 2;
     CU(cudaGetLastError());
     return MAMBO_OK;
 }
@@ -258,8 +262,8 @@ int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
     small::k_build_d<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->d_part, h->d_scale, n, h->dX);
     h->launches++;
     mm(h, h->dX2, nullptr, h->dX, h->X, h->X, h->dX, nullptr, 0);
-    dim3 grid((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS), block(small::TS, small::TS);
-    small::k_dpow34<<<grid, block, 0, h->stream>>>(h->X, h->X2, h->dX, h->dX2, h->dX4, h->dP0, h->dP1, h->dP2, h->dQ3, n);
+    small::k_dpow34<<<mm_grid(n), mm_block(), small::strip_bytes(n, 2, 4), h->stream>>>(h->X, h->X2, h->dX, h->dX2, h->dX4, h->dP0, h->dP1,
+                                                                                      h->dP2, h->dQ3, n);
     h->launches++;
     mm(h, h->dQ2, h->dP2, h->dX4, h->Q3, h->X4, h->dQ3, nullptr, 0);
     mm(h, h->dQ1, h->dP1, h->dX4, h->Q2, h->X4, h->dQ2, nullptr, 0);
@@ -272,6 +276,96 @@ int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
+}
+
+// ---- CUDA-graph segments ------------------------------------------------------------------------------------
+// The ~45 small launches of one evaluation are captured once into graph segments (keyed by the squaring count
+// where it matters) and replayed; the fused kernel itself is launched directly between them so that it can
+// be bracketed by profiling events.  All pointers inside a segment are handle-internal and therefore fixed.
+template <class F>
+int run_segment(mambo_csa* h, GraphSeg& seg, F&& body) {
+    if (!h->use_graphs) return body();
+    if (!seg.exec) {
+        cudaStream_t saved = h->stream;
+        h->stream = h->own_stream;
+        const long long l0 = h->launches;
+        cudaError_t e = cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {
+            h->stream = saved;
+            CU(e);
+        }
+        int rc = body();
+        cudaGraph_t graph = nullptr;
+        e = cudaStreamEndCapture(h->own_stream, &graph);
+        h->stream = saved;
+        seg.kernels = (int)(h->launches - l0);
+        h->launches = l0;
+        if (rc) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        CU(e);
+        e = cudaGraphInstantiate(&seg.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        CU(e);
+    }
+    CU(cudaGraphLaunch(seg.exec, h->stream));
+    h->launches += seg.kernels;
+    return MAMBO_OK;
+}
+
+GraphSeg& seg_for(std::vector<GraphSeg>& v, int s_host) {  // index 0: device-decided s, 1 + s otherwise
+    const size_t idx = s_host < 0 ? 0 : (size_t)(1 + std::min(s_host, small::SMAX));
+    if (v.size() <= idx) v.resize(idx + 1);
+    return v[idx];
+}
+
+// stage A: everything up to the per-shard partial vector [cost, S, G] (x must already be in h->d_x)
+int enqueue_partial(mambo_csa* h, int s_host, bool need_grad) {
+    if (need_grad) TRY(seg_mark(h));
+    TRY(run_segment(h, seg_for(h->g_pre, s_host), [&]() -> int {
+        TRY(enqueue_unitary(h, h->d_x, s_host));
+        return enqueue_prep(h);
+    }));
+    if (need_grad) TRY(seg_mark(h));
+    Params p = make_params(h, h->T1);
+    if (!need_grad) {
+        TRY((launch_fused<false, false>(h, p)));
+        return run_segment(h, h->g_costonly, [&]() -> int {
+            if (h->flavour == MAMBO_CSA_SD) {
+                small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
+                small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->cost_part, h->G, h->d_part);
+                h->launches += 2;
+            } else {
+                small::k_sumsq_add<<<1, 256, 0, h->stream>>>(nullptr, 0, h->cost_part, h->G, h->d_part);
+                h->launches++;
+            }
+            CU(cudaGetLastError());
+            return MAMBO_OK;
+        });
+    }
+    TRY((launch_fused<true, false>(h, p)));
+    if (h->mode == (int)MAMBO_SYM_GENERAL) {
+        // second pass over the transposed residual: E = D A (pass 1 gave E' = D^T A); S uses E only (gradient.jl:22-26)
+        TRY(run_segment(h, h->g_mid, [&]() -> int { return enqueue_post_f(h, h->F1); }));
+        Params p2 = make_params(h, h->T2);
+        p2.cost_part = h->cost_part + h->G;  // discarded
+        TRY((launch_fused<true, false>(h, p2)));
+        return run_segment(h, h->g_post, [&]() -> int {
+            TRY(enqueue_post_f(h, h->F2));
+            return enqueue_post_sr(h);
+        });
+    }
+    return run_segment(h, h->g_post, [&]() -> int {
+        TRY(enqueue_post_f(h, h->F1));
+        return enqueue_post_sr(h);
+    });
+}
+
+int enqueue_finish_seg(mambo_csa* h, int s_host) {
+    TRY(seg_mark(h));
+    TRY(run_segment(h, seg_for(h->g_fin, s_host), [&]() -> int { return enqueue_finish(h, h->d_x, s_host, h->d_out); }));
+    return seg_mark(h);
 }
 
 int check_status(mambo_csa* h) {
@@ -292,19 +386,13 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad) {
     std::memcpy(h->h_x, x, sizeof(double) * h->L);
     const long long l0 = h->launches;
     CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
-    int rc = enqueue_partial(h, h->d_x, s_host, need_grad);
+    int rc = enqueue_partial(h, s_host, need_grad);
     if (rc) return rc;
     if (need_grad) {
-        rc = enqueue_finish(h, h->d_x, s_host, h->d_out);
+        rc = enqueue_finish_seg(h, s_host);
         if (rc) return rc;
         CU(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToHost, h->stream));
     } else {
-        if (h->flavour == MAMBO_CSA_SD) {
-            small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
-            // cost-only: add |Dh|^2 by a second tiny reduction
-            small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->d_part, 1, h->d_part);
-            h->launches += 2;
-        }
         CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -319,12 +407,6 @@ int dalloc(T** p, size_t count) {
     CU(cudaMemset(*p, 0, std::max<size_t>(count, 1) * sizeof(T)));
     return MAMBO_OK;
 }
-
-#define TRY(expr)               \
-    do {                        \
-        int rc__ = (expr);      \
-        if (rc__) return rc__;  \
-    } while (0)
 
 int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned flags) {
     const int n = h->N;
@@ -465,6 +547,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     CU(cudaMemcpy(h->visit_start, vstart.data(), sizeof(int) * (h->G + 1), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(h->piece_first, pfirst.data(), sizeof(int) * (h->P + 1), cudaMemcpyHostToDevice));
     TRY(dalloc(&h->Epiece, (size_t)h->visits * 2 * ROWS * h->Np));
+    TRY(dalloc(&h->Et, (size_t)h->P * ROWS * h->Np));
     TRY(dalloc(&h->F1, (size_t)h->P * ROWS * h->Np));
     if (mode == MAMBO_SYM_GENERAL) TRY(dalloc(&h->F2, (size_t)h->P * ROWS * h->Np));
     TRY(dalloc(&h->Spart, (size_t)h->P * n * n));
@@ -502,6 +585,28 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     CU(cudaMallocHost((void**)&h->h_status, sizeof(int)));
     *h->h_status = 0;
     h->memo_x.assign(h->L, 0.0);
+    h->use_graphs = (std::getenv("MAMBO_NO_GRAPH") == nullptr);
+
+    // opt-in shared-memory sizes, set once per handle
+    {
+        Params cfg = make_params(h, h->T1);
+        cfg.P = -1;
+        TRY((launch_fused<true, false>(h, cfg)));
+        TRY((launch_fused<false, false>(h, cfg)));
+        TRY((launch_fused<false, true>(h, cfg)));
+        const size_t lim = prop.sharedMemPerBlockOptin;
+        const size_t need[] = {nn * 8, small::strip_bytes(n, 2, 4), small::prep_smem(n, h->Np), small::postf_smem(h->Np),
+                               small::posts_smem(h->Np)};
+        for (size_t b : need)
+            if (b > lim) return fail(MAMBO_EINVAL, "N too large for the shared-memory resident small kernels");
+        CU(cudaFuncSetAttribute(small::k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nn * 8)));
+        CU(cudaFuncSetAttribute(small::k_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 2, 2)));
+        CU(cudaFuncSetAttribute(small::k_pow34, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 1, 2)));
+        CU(cudaFuncSetAttribute(small::k_dpow34, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 2, 4)));
+        CU(cudaFuncSetAttribute(small::k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::prep_smem(n, h->Np)));
+        CU(cudaFuncSetAttribute(small::k_post_f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::postf_smem(h->Np)));
+        CU(cudaFuncSetAttribute(small::k_post_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::posts_smem(h->Np)));
+    }
     return MAMBO_OK;
 }
 
@@ -573,7 +678,12 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->F1, h->F2, h->Spart, h->cost_part,
+    for (auto* v : {&h->g_pre, &h->g_fin})
+        for (GraphSeg& g : *v)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+    void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
                     h->visit_start, h->piece_first, h->mats, h->g1, h->d_s, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -581,6 +691,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_status) cudaFreeHost(h->h_status);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->seg_pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -638,6 +749,7 @@ int mambo_csa_set_profiling(mambo_csa* h, int enable) {
     if (!h) return fail(MAMBO_EINVAL, "null handle");
     h->profiling = enable != 0;
     h->ev_used = 0;
+    h->seg_used = 0;
     return MAMBO_OK;
 }
 
@@ -659,6 +771,25 @@ int mambo_csa_get_profile(mambo_csa* h, double* fused_ms, int* fused_launches, l
     return MAMBO_OK;
 }
 
+// Segment breakdown of the evaluations recorded since profiling was (re)enabled:
+// seg_ms[0] = unitary chain + operand build, [1] = fused kernel(s) + row epilogues, [2] = Frechet chain + assembly.
+int mambo_csa_get_segments(mambo_csa* h, double* seg_ms, int* evals) {
+    if (!h || !seg_ms) return fail(MAMBO_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    seg_ms[0] = seg_ms[1] = seg_ms[2] = 0.0;
+    int n = 0;
+    for (size_t i = 0; i + 3 < h->seg_used; i += 4, ++n)
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, h->seg_pool[i + k], h->seg_pool[i + k + 1]));
+            seg_ms[k] += t;
+        }
+    if (evals) *evals = n;
+    h->seg_used = 0;
+    return MAMBO_OK;
+}
+
 int mambo_csa_synchronize(mambo_csa* h) {
     if (!h) return fail(MAMBO_EINVAL, "null handle");
     CU(cudaSetDevice(h->device));
@@ -671,10 +802,11 @@ int mambo_csa_eval_partial_device(mambo_csa* h, const double* d_x, double* d_par
     if (!h || !d_x || !d_partial) return fail(MAMBO_EINVAL, "null argument");
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
-    CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
-    TRY(enqueue_partial(h, h->d_x, -1, true));
+    if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(enqueue_partial(h, -1, true));
     CU(cudaMemcpyAsync(d_partial, h->d_part, sizeof(double) * (1 + 2 * (size_t)h->N * h->N), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval = (int)(h->launches - l0);
+    h->memo_valid = false;
     return MAMBO_OK;
 }
 
@@ -683,7 +815,8 @@ int mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double* 
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
     CU(cudaMemcpyAsync(h->d_part, d_partial, sizeof(double) * (1 + 2 * (size_t)h->N * h->N), cudaMemcpyDeviceToDevice, h->stream));
-    TRY(enqueue_finish(h, h->d_x, -1, d_out));
+    TRY(enqueue_finish_seg(h, -1));
+    if (d_out != h->d_out) CU(cudaMemcpyAsync(d_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval += (int)(h->launches - l0);
     return MAMBO_OK;
 }
@@ -693,9 +826,12 @@ int mambo_csa_eval_device(mambo_csa* h, const double* d_x, double* d_out) {
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "sharded handle: use eval_partial_device / eval_finish_device around an allreduce");
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
-    TRY(enqueue_partial(h, d_x, -1, true));
-    TRY(enqueue_finish(h, d_x, -1, d_out));
+    if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(enqueue_partial(h, -1, true));
+    TRY(enqueue_finish_seg(h, -1));
+    if (d_out != h->d_out) CU(cudaMemcpyAsync(d_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval = (int)(h->launches - l0);
+    h->memo_valid = false;
     return MAMBO_OK;
 }
 
@@ -703,13 +839,10 @@ int mambo_csa_cost_device(mambo_csa* h, const double* d_x, double* d_cost) {
     if (!h || !d_x || !d_cost) return fail(MAMBO_EINVAL, "null argument");
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "cost_device needs an unsharded handle");
     CU(cudaSetDevice(h->device));
-    TRY(enqueue_partial(h, d_x, -1, false));
-    if (h->flavour == MAMBO_CSA_SD) {
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
-        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->d_part, 1, h->d_part);
-        h->launches += 2;
-    }
+    if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(enqueue_partial(h, -1, false));
     CU(cudaMemcpyAsync(d_cost, h->d_part, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    h->memo_valid = false;
     return MAMBO_OK;
 }
 
@@ -733,12 +866,8 @@ int mambo_csa_residual_cost(mambo_csa* h, double* cost) {
     CU(cudaSetDevice(h->device));
     // L2_partial_cost(F_rem): evaluate the residual against the zero fragment (lambda = 0 => W = 0), theta = 0
     CU(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->L, h->stream));
-    TRY(enqueue_partial(h, h->d_x, 0, false));
-    if (h->flavour == MAMBO_CSA_SD) {
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
-        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->d_part, 1, h->d_part);
-        h->launches += 2;
-    }
+    h->memo_valid = false;
+    TRY(enqueue_partial(h, 0, false));
     CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     *cost = h->h_out[0];

@@ -30,26 +30,45 @@ __constant__ double c_tay[17] = {1.0,
                                  1.0 / 20922789888000.0};
 
 // ------------------------------------------------------------------------------------------------------
-// k_build: x -> Lambda (full symmetric), X = K / 2^s, s  (unitaries.jl:31-44, gradient.jl:43-55)
-//   one CTA; the 1-norm of K picks s so that ||X||_1 <= 1 (Taylor degree 16 is then exact to ~3e-15).
+// async global -> shared copies (LDGSTS): every load of a strip is in flight at once, no register staging
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_build(const double* __restrict__ x, int n, int lam_off, double* __restrict__ X, double* __restrict__ Lam,
-                        int* __restrict__ s_out, double* __restrict__ scale_out, int* __restrict__ status) {
+__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------------
+// k_build: x -> Lambda (full symmetric), X = K / 2^s, s  (unitaries.jl:31-44, gradient.jl:43-55)
+//   one CTA, K staged in shared memory; the 1-norm of K picks s so that ||X||_1 <= 1 (Taylor degree 16 is
+//   then exact to ~3e-15).  s_override >= 0: the host already knows s (x came through the host API).
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_build(const double* __restrict__ x, int n, int lam_off, double* __restrict__ X,
+                                                double* __restrict__ Lam, int* __restrict__ s_out, double* __restrict__ scale_out,
+                                                int* __restrict__ status, int s_override) {
+    extern __shared__ double Ks[];  // n*n
     __shared__ double red[32];
     __shared__ double s_scale;
     const int cL = n * (n + 1) / 2;
     const double* lam = x + lam_off;
     const double* th = x + lam_off + cL;
     const int tid = threadIdx.x, nt = blockDim.x;
-    // column abs sums (K antisymmetric: column j holds -K[j][i] ...)
+    for (int idx = tid; idx < n * n; idx += nt) {
+        const int i = idx / n, j = idx % n;
+        double k = 0.0;
+        if (i < j) k = th[i * n - i * (i + 1) / 2 + (j - i - 1)];
+        else if (i > j) k = -th[j * n - j * (j + 1) / 2 + (i - j - 1)];
+        Ks[idx] = k;
+        const int a = i > j ? i : j, b = i > j ? j : i;
+        Lam[idx] = lam[a * (a + 1) / 2 + b];
+    }
+    __syncthreads();
     double mx = 0.0;
-    for (int j = tid; j < n; j += nt) {
+    for (int j = tid; j < n; j += nt) {   // K antisymmetric: column sums == row sums; rows are contiguous
         double s = 0.0;
-        for (int i = 0; i < n; ++i) {
-            if (i == j) continue;
-            const int a = i < j ? i : j, b = i < j ? j : i;
-            s += fabs(th[a * n - a * (a + 1) / 2 + (b - a - 1)]);
-        }
+        for (int i = 0; i < n; ++i) s += fabs(Ks[j * n + i]);
         mx = fmax(mx, s);
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -60,6 +79,7 @@ __global__ void k_build(const double* __restrict__ x, int n, int lam_off, double
         for (int w = 0; w < (nt + 31) / 32; ++w) m = fmax(m, red[w]);
         int s = 0;
         if (m > 1.0) s = (int)ceil(log2(m));
+        if (s_override >= 0) s = s_override;
         if (!(m == m) || s > SMAX) {  // NaN or too large
             *status = 1;
             s = SMAX;
@@ -70,74 +90,86 @@ __global__ void k_build(const double* __restrict__ x, int n, int lam_off, double
     }
     __syncthreads();
     const double sc = s_scale;
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx % n;
-        double k = 0.0;
-        if (i < j) k = th[i * n - i * (i + 1) / 2 + (j - i - 1)];
-        else if (i > j) k = -th[j * n - j * (j + 1) / 2 + (i - j - 1)];
-        X[idx] = k * sc;
-        const int a = i > j ? i : j, b = i > j ? j : i;
-        Lam[idx] = lam[a * (a + 1) / 2 + b];
-    }
+    for (int idx = tid; idx < n * n; idx += nt) X[idx] = Ks[idx] * sc;
 }
 
 // ------------------------------------------------------------------------------------------------------
-// small N x N GEMM building block: acc += A[i,:] . B[:,j] for the (i,j) of this thread (16x16 tile / CTA)
+// small N x N GEMM building blocks.  One CTA = one 16x16 output tile; the full 16 x n strip of every A
+// operand and the n x 16 strip of every B operand are brought into shared memory with one wave of async
+// copies (one L2 latency per launch instead of one per k-chunk), then reduced from shared memory.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_mm(double& acc, const double* __restrict__ A, const double* __restrict__ B, int n,
-                                        double (*As)[TS + 1], double (*Bs)[TS + 1]) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int i = blockIdx.y * TS + ty, j0 = blockIdx.x * TS;
-    for (int k0 = 0; k0 < n; k0 += TS) {
-        As[ty][tx] = (i < n && k0 + tx < n) ? A[i * n + k0 + tx] : 0.0;
-        Bs[ty][tx] = (k0 + ty < n && j0 + tx < n) ? B[(k0 + ty) * n + j0 + tx] : 0.0;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < TS; ++k) acc = fma(As[ty][k], Bs[k][tx], acc);
-        __syncthreads();
+__device__ __forceinline__ int strip_lda(int n) { return n | 1; }
+__device__ __forceinline__ void load_a_strip(double* As, const double* __restrict__ A, int n) {
+    const int lda = strip_lda(n), i0 = blockIdx.y * TS, tid = threadIdx.y * TS + threadIdx.x;
+    for (int idx = tid; idx < TS * n; idx += TS * TS) {
+        const int r = idx / n, c = idx % n;
+        if (i0 + r < n) cp_async8(As + r * lda + c, A + (size_t)(i0 + r) * n + c);
+        else As[r * lda + c] = 0.0;
     }
 }
-// two products sharing the A operand rows: acc1 += A.B1, acc2 += A.B2
-__device__ __forceinline__ void tile_mm2(double& acc1, double& acc2, const double* __restrict__ A, const double* __restrict__ B1,
-                                         const double* __restrict__ B2, int n, double (*As)[TS + 1], double (*Bs)[TS + 1],
-                                         double (*Cs)[TS + 1]) {
-    const int tx = threadIdx.x, ty = threadIdx.y;
-    const int i = blockIdx.y * TS + ty, j0 = blockIdx.x * TS;
-    for (int k0 = 0; k0 < n; k0 += TS) {
-        As[ty][tx] = (i < n && k0 + tx < n) ? A[i * n + k0 + tx] : 0.0;
-        const bool ok = (k0 + ty < n && j0 + tx < n);
-        Bs[ty][tx] = ok ? B1[(k0 + ty) * n + j0 + tx] : 0.0;
-        Cs[ty][tx] = ok ? B2[(k0 + ty) * n + j0 + tx] : 0.0;
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < TS; ++k) {
-            acc1 = fma(As[ty][k], Bs[k][tx], acc1);
-            acc2 = fma(As[ty][k], Cs[k][tx], acc2);
-        }
-        __syncthreads();
+__device__ __forceinline__ void load_b_strip(double* Bs, const double* __restrict__ B, int n) {
+    const int j0 = blockIdx.x * TS, tid = threadIdx.y * TS + threadIdx.x;
+    for (int idx = tid; idx < TS * n; idx += TS * TS) {
+        const int k = idx / TS, c = idx % TS;
+        if (j0 + c < n) cp_async8(Bs + idx, B + (size_t)k * n + j0 + c);
+        else Bs[idx] = 0.0;
     }
 }
+__device__ __forceinline__ double strip_dot(const double* As, const double* Bs, int n) {
+    const double* a = As + threadIdx.y * strip_lda(n);
+    const double* b = Bs + threadIdx.x;
+    double acc0 = 0.0, acc1 = 0.0;
+    int k = 0;
+    for (; k + 1 < n; k += 2) {
+        acc0 = fma(a[k], b[k * TS], acc0);
+        acc1 = fma(a[k + 1], b[(k + 1) * TS], acc1);
+    }
+    if (k < n) acc0 = fma(a[k], b[k * TS], acc0);
+    return acc0 + acc1;
+}
+inline size_t strip_bytes(int n, int na, int nb) { return ((size_t)na * TS * (n | 1) + (size_t)nb * TS * n) * sizeof(double); }
 
-// C = Cin + A1.B1 + A2.B2   (null pointers skip a term).  step >= *s_ptr => no-op (squaring chain past s).
-__global__ void k_mm(double* __restrict__ C, const double* __restrict__ Cin, const double* __restrict__ A1,
-                     const double* __restrict__ B1, const double* __restrict__ A2, const double* __restrict__ B2, int n,
-                     const int* __restrict__ s_ptr, int step) {
+// C = Cin + A1.B1 + A2.B2   (A2 == nullptr skips the second product).  step >= *s_ptr => no-op (squaring
+// chain past s).
+__global__ void __launch_bounds__(TS * TS) k_mm(double* __restrict__ C, const double* __restrict__ Cin, const double* __restrict__ A1,
+                                              const double* __restrict__ B1, const double* __restrict__ A2,
+                                              const double* __restrict__ B2, int n, const int* __restrict__ s_ptr, int step) {
     if (s_ptr && step >= *s_ptr) return;
-    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1];
-    double acc = 0.0;
-    tile_mm(acc, A1, B1, n, As, Bs);
-    if (A2) tile_mm(acc, A2, B2, n, As, Bs);
+    extern __shared__ double sm[];
+    const int sa = TS * strip_lda(n), sb = TS * n;
+    double* As1 = sm;
+    double* Bs1 = As1 + sa;
+    double* As2 = Bs1 + sb;
+    double* Bs2 = As2 + sa;
+    load_a_strip(As1, A1, n);
+    load_b_strip(Bs1, B1, n);
+    if (A2) {
+        load_a_strip(As2, A2, n);
+        load_b_strip(Bs2, B2, n);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    double acc = strip_dot(As1, Bs1, n);
+    if (A2) acc += strip_dot(As2, Bs2, n);
     const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
     if (i < n && j < n) C[i * n + j] = acc + (Cin ? Cin[i * n + j] : 0.0);
 }
 
 // X3 = X2.X, X4 = X2.X2, then P0,P1,P2 (degree-3 pieces) and Q3 = P3 + c16 X4.
-__global__ void k_pow34(const double* __restrict__ X, const double* __restrict__ X2, double* __restrict__ X3,
-                        double* __restrict__ X4, double* __restrict__ P0, double* __restrict__ P1, double* __restrict__ P2,
-                        double* __restrict__ Q3, int n) {
-    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1], Cs[TS][TS + 1];
-    double x3 = 0.0, x4 = 0.0;
-    tile_mm2(x3, x4, X2, X, X2, n, As, Bs, Cs);
+__global__ void __launch_bounds__(TS * TS) k_pow34(const double* __restrict__ X, const double* __restrict__ X2, double* __restrict__ X3,
+                                                 double* __restrict__ X4, double* __restrict__ P0, double* __restrict__ P1,
+                                                 double* __restrict__ P2, double* __restrict__ Q3, int n) {
+    extern __shared__ double sm[];
+    const int sa = TS * strip_lda(n), sb = TS * n;
+    double* A2s = sm;            // rows of X2
+    double* B1s = A2s + sa;      // cols of X
+    double* B2s = B1s + sb;      // cols of X2
+    load_a_strip(A2s, X2, n);
+    load_b_strip(B1s, X, n);
+    load_b_strip(B2s, X2, n);
+    cp_async_wait_all();
+    __syncthreads();
+    const double x3 = strip_dot(A2s, B1s, n), x4 = strip_dot(A2s, B2s, n);
     const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
     if (i < n && j < n) {
         const int o = i * n + j;
@@ -152,13 +184,28 @@ __global__ void k_pow34(const double* __restrict__ X, const double* __restrict__
 }
 
 // dX3 = dX2.X + X2.dX, dX4 = dX2.X2 + X2.dX2, then dP0..dP2, dQ3.
-__global__ void k_dpow34(const double* __restrict__ X, const double* __restrict__ X2, const double* __restrict__ dX,
-                         const double* __restrict__ dX2, double* __restrict__ dX4, double* __restrict__ dP0,
-                         double* __restrict__ dP1, double* __restrict__ dP2, double* __restrict__ dQ3, int n) {
-    __shared__ double As[TS][TS + 1], Bs[TS][TS + 1], Cs[TS][TS + 1];
-    double d3 = 0.0, d4 = 0.0;
-    tile_mm2(d3, d4, dX2, X, X2, n, As, Bs, Cs);   // dX2.X , dX2.X2
-    tile_mm2(d3, d4, X2, dX, dX2, n, As, Bs, Cs);  // X2.dX , X2.dX2
+__global__ void __launch_bounds__(TS * TS) k_dpow34(const double* __restrict__ X, const double* __restrict__ X2,
+                                                  const double* __restrict__ dX, const double* __restrict__ dX2,
+                                                  double* __restrict__ dX4, double* __restrict__ dP0, double* __restrict__ dP1,
+                                                  double* __restrict__ dP2, double* __restrict__ dQ3, int n) {
+    extern __shared__ double sm[];
+    const int sa = TS * strip_lda(n), sb = TS * n;
+    double* AdX2 = sm;
+    double* AX2 = AdX2 + sa;
+    double* BX = AX2 + sa;
+    double* BX2 = BX + sb;
+    double* BdX = BX2 + sb;
+    double* BdX2 = BdX + sb;
+    load_a_strip(AdX2, dX2, n);
+    load_a_strip(AX2, X2, n);
+    load_b_strip(BX, X, n);
+    load_b_strip(BX2, X2, n);
+    load_b_strip(BdX, dX, n);
+    load_b_strip(BdX2, dX2, n);
+    cp_async_wait_all();
+    __syncthreads();
+    const double d3 = strip_dot(AdX2, BX, n) + strip_dot(AX2, BdX, n);
+    const double d4 = strip_dot(AdX2, BX2, n) + strip_dot(AX2, BdX2, n);
     const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
     if (i < n && j < n) {
         const int o = i * n + j;
@@ -173,15 +220,31 @@ __global__ void k_dpow34(const double* __restrict__ X, const double* __restrict_
 
 // ------------------------------------------------------------------------------------------------------
 // k_prep: A~[r][l] = sw_r U[pa_r][l] U[pq_r][l],  B~[r][m] = sum_l A~[r][l] Lambda[l][m]
-//   U = Rchain[s].  32 rows per CTA, 256 threads.  Rows >= nR (padding) have sw = 0.
+//   U = Rchain[s].  32 rows per CTA, 256 threads, Lambda resident in shared memory.
+//   Rows >= nR (padding) have sw = 0.
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_prep(const double* __restrict__ Rchain, const int* __restrict__ s_ptr, const double* __restrict__ Lam,
-                       const int* __restrict__ pa, const int* __restrict__ pq, const double* __restrict__ sw, int n, int Np,
-                       int ld, int rows_total, int brow_begin, int brow_end, double* __restrict__ At, double* __restrict__ Bt) {
-    extern __shared__ double sAt[];  // [32][Np]
+constexpr int PREP_ROWS = 32;
+constexpr int CMAX = 6;   // column chunks of 32 covering Np <= 192
+inline size_t prep_smem(int n, int Np) { return ((size_t)n * Np + (size_t)PREP_ROWS * Np) * sizeof(double); }
+
+__global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Rchain, const int* __restrict__ s_ptr,
+                                              const double* __restrict__ Lam, const int* __restrict__ pa, const int* __restrict__ pq,
+                                              const double* __restrict__ sw, int n, int Np, int ld, int rows_total, int brow_begin,
+                                              int brow_end, double* __restrict__ At, double* __restrict__ Bt) {
+    extern __shared__ double sm[];
+    double* sL = sm;                     // [n][Np]  (columns >= n are zero)
+    double* sAt = sm + (size_t)n * Np;   // [32][Np]
     const double* U = Rchain + (size_t)(*s_ptr) * n * n;
-    const int r0 = blockIdx.x * 32;
-    for (int idx = threadIdx.x; idx < 32 * Np; idx += blockDim.x) {
+    const int r0 = blockIdx.x * PREP_ROWS;
+    const bool need_b = !(r0 + PREP_ROWS <= brow_begin || r0 >= brow_end);
+    if (need_b) {
+        for (int idx = threadIdx.x; idx < n * Np; idx += blockDim.x) {
+            const int l = idx / Np, m = idx % Np;
+            if (m < n) cp_async8(sL + idx, Lam + (size_t)l * n + m);
+            else sL[idx] = 0.0;
+        }
+    }
+    for (int idx = threadIdx.x; idx < PREP_ROWS * Np; idx += blockDim.x) {
         const int rr = idx / Np, l = idx % Np, r = r0 + rr;
         double v = 0.0;
         if (r < rows_total && l < n) {
@@ -191,45 +254,70 @@ __global__ void k_prep(const double* __restrict__ Rchain, const int* __restrict_
         sAt[idx] = v;
         if (r < rows_total) At[(size_t)r * ld + l] = v;
     }
+    if (!need_b) return;  // B~ only for this shard's rows
+    cp_async_wait_all();
     __syncthreads();
-    if (r0 + 32 <= brow_begin || r0 >= brow_end) return;  // B~ only for this shard's rows
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 groups x 4 rows
-    for (int m0 = 0; m0 < Np; m0 += 32) {
-        const int m = m0 + lane;
-        double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        if (m < n) {
-            const double* s0 = sAt + (grp * 4) * Np;
-            for (int l = 0; l < n; ++l) {
-                const double lm = Lam[l * n + m];
-                a0 = fma(s0[l], lm, a0);
-                a1 = fma(s0[Np + l], lm, a1);
-                a2 = fma(s0[2 * Np + l], lm, a2);
-                a3 = fma(s0[3 * Np + l], lm, a3);
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 warps x 4 rows
+    const int nchunk = (Np + 31) / 32;
+    double acc[4][CMAX];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) acc[i][c] = 0.0;
+    const double* s0 = sAt + (grp * 4) * Np;
+    for (int l = 0; l < n; ++l) {
+        const double a0 = s0[l], a1 = s0[Np + l], a2 = s0[2 * Np + l], a3 = s0[3 * Np + l];
+        const double* lrow = sL + (size_t)l * Np + lane;
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c) {
+            if (c < nchunk) {
+                const double lm = (32 * c + lane < Np) ? lrow[32 * c] : 0.0;
+                acc[0][c] = fma(a0, lm, acc[0][c]);
+                acc[1][c] = fma(a1, lm, acc[1][c]);
+                acc[2][c] = fma(a2, lm, acc[2][c]);
+                acc[3][c] = fma(a3, lm, acc[3][c]);
             }
         }
-        if (m < Np) {
-            const int r = r0 + grp * 4;
-            if (r + 0 >= brow_begin && r + 0 < brow_end) Bt[(size_t)(r + 0 - brow_begin) * ld + m] = a0;
-            if (r + 1 >= brow_begin && r + 1 < brow_end) Bt[(size_t)(r + 1 - brow_begin) * ld + m] = a1;
-            if (r + 2 >= brow_begin && r + 2 < brow_end) Bt[(size_t)(r + 2 - brow_begin) * ld + m] = a2;
-            if (r + 3 >= brow_begin && r + 3 < brow_end) Bt[(size_t)(r + 3 - brow_begin) * ld + m] = a3;
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+        const int m = 32 * c + lane;
+        if (c < nchunk && m < Np) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = r0 + grp * 4 + i;
+                if (r >= brow_begin && r < brow_end) Bt[(size_t)(r - brow_begin) * ld + m] = acc[i][c];
+            }
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_post_rows: per local 64-row panel: E~ = fixed-order sum of the fused kernel's pieces,
-//   F = E~ Lambda (rows of the gradient's F tensor), Spart = A~_panel^T E~ (lambda gradient, gradient.jl:13-41).
+// k_post_f: per local 64-row panel: E~ = fixed-order sum of the fused kernel's pieces (also stored),
+//   F = E~ Lambda (rows of the F tensor of the theta gradient).  Lambda streams through shared memory
+//   in 32-row chunks (double-buffered async copies).
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_post_rows(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
-                                                   const double* __restrict__ At, const double* __restrict__ Lam, int n, int Np,
-                                                   int ld, int row_begin, double* __restrict__ F, double* __restrict__ Spart,
-                                                   int do_S) {
+inline size_t postf_smem(int Np) { return ((size_t)64 * Np + 2 * (size_t)32 * Np) * sizeof(double); }
+
+__global__ void __launch_bounds__(256) k_post_f(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
+                                                const double* __restrict__ Lam, int n, int Np, double* __restrict__ Et,
+                                                double* __restrict__ F) {
     extern __shared__ double sm[];
-    double* sE = sm;                 // [64][Np]
-    double* sAp = sm + 64 * Np;      // [64][Np]
+    double* sE = sm;                         // [64][Np]
+    double* sL = sm + (size_t)64 * Np;       // [2][32][Np]
     const int panel = blockIdx.x;
     const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
+    const int nch = (n + 31) / 32;
+    auto load_chunk = [&](int ch, int buf) {
+        double* dst = sL + (size_t)buf * 32 * Np;
+        for (int idx = threadIdx.x; idx < 32 * Np; idx += blockDim.x) {
+            const int l = ch * 32 + idx / Np, m = idx % Np;
+            if (l < n && m < n) cp_async8(dst + idx, Lam + (size_t)l * n + m);
+            else dst[idx] = 0.0;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    load_chunk(0, 0);
     for (int idx = threadIdx.x; idx < 64 * Np; idx += blockDim.x) {
         double s = 0.0;
         for (int v = v0; v < v1; ++v) {
@@ -237,36 +325,71 @@ __global__ void __launch_bounds__(256) k_post_rows(const double* __restrict__ Ep
             s += Epiece[(size_t)(v * 2 + 1) * 64 * Np + idx];
         }
         sE[idx] = s;
-        if (do_S) {
-            const int rr = idx / Np, l = idx % Np;
-            sAp[idx] = At[(size_t)(row_begin + panel * 64 + rr) * ld + l];
-        }
+        Et[(size_t)panel * 64 * Np + idx] = s;
     }
-    __syncthreads();
-    // F rows: 8 warps x 8 rows
-    {
-        const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-        const double* s0 = sE + grp * 8 * Np;
-        for (int b0 = 0; b0 < Np; b0 += 32) {
-            const int b = b0 + lane;
-            double a[8];
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;   // 8 warps x 8 rows
+    const int nchunk = (Np + 31) / 32;
+    double acc[8][CMAX];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = 0.0;
-            if (b < n) {
-                for (int m = 0; m < n; ++m) {
-                    const double lm = Lam[m * n + b];
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = fma(s0[i * Np + m], lm, a[i]);
+        for (int c = 0; c < CMAX; ++c) acc[i][c] = 0.0;
+    const double* s0 = sE + (size_t)grp * 8 * Np;
+    for (int ch = 0; ch < nch; ++ch) {
+        if (ch + 1 < nch) {
+            load_chunk(ch + 1, (ch + 1) & 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const double* L = sL + (size_t)(ch & 1) * 32 * Np + lane;
+        const int mmax = min(32, n - ch * 32);
+        for (int mm = 0; mm < mmax; ++mm) {
+            const int m = ch * 32 + mm;
+            double ev[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ev[i] = s0[i * Np + m];
+#pragma unroll
+            for (int c = 0; c < CMAX; ++c) {
+                if (c < nchunk) {
+                    const double lm = (32 * c + lane < Np) ? L[(size_t)mm * Np + 32 * c] : 0.0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i][c] = fma(ev[i], lm, acc[i][c]);
                 }
             }
-            if (b < Np) {
+        }
+        __syncthreads();
+    }
 #pragma unroll
-                for (int i = 0; i < 8; ++i) F[(size_t)(panel * 64 + grp * 8 + i) * Np + b] = a[i];
-            }
+    for (int c = 0; c < CMAX; ++c) {
+        const int b = 32 * c + lane;
+        if (c < nchunk && b < Np) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) F[(size_t)(panel * 64 + grp * 8 + i) * Np + b] = acc[i][c];
         }
     }
-    if (!do_S) return;
-    // Spart[i][j] = sum_r sAp[r][i] sE[r][j]; 64x64 output chunks, 4x4 per thread
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_post_s: Spart[panel] = A~_panel^T E~_panel  (lambda gradient, gradient.jl:13-41), 64 x 64 output chunks,
+//   4 x 4 register tiles, both operands resident in shared memory.
+// ------------------------------------------------------------------------------------------------------
+inline size_t posts_smem(int Np) { return (size_t)2 * 64 * Np * sizeof(double); }
+
+__global__ void __launch_bounds__(256) k_post_s(const double* __restrict__ Et, const double* __restrict__ At, int n, int Np, int ld,
+                                                int row_begin, double* __restrict__ Spart) {
+    extern __shared__ double sm[];
+    double* sE = sm;                 // [64][Np]
+    double* sAp = sm + 64 * Np;      // [64][Np]
+    const int panel = blockIdx.x;
+    for (int idx = threadIdx.x; idx < 64 * Np; idx += blockDim.x) {
+        const int rr = idx / Np, l = idx % Np;
+        cp_async8(sE + idx, Et + (size_t)panel * 64 * Np + idx);
+        cp_async8(sAp + idx, At + (size_t)(row_begin + panel * 64 + rr) * ld + l);
+    }
+    cp_async_wait_all();
+    __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     for (int i0 = 0; i0 < n; i0 += 64)
         for (int j0 = 0; j0 < n; j0 += 64) {
@@ -275,17 +398,19 @@ __global__ void __launch_bounds__(256) k_post_rows(const double* __restrict__ Ep
             for (int a = 0; a < 4; ++a)
 #pragma unroll
                 for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+            int ia[4], jb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                ia[a] = min(i0 + ty + 16 * a, Np - 1);
+                jb[a] = min(j0 + tx + 16 * a, Np - 1);
+            }
+#pragma unroll 4
             for (int r = 0; r < 64; ++r) {
                 double av[4], ev[4];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
-                    const int i = i0 + ty + 16 * a;
-                    av[a] = (i < Np) ? sAp[r * Np + i] : 0.0;
-                }
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int j = j0 + tx + 16 * b;
-                    ev[b] = (j < Np) ? sE[r * Np + j] : 0.0;
+                    av[a] = sAp[r * Np + ia[a]];
+                    ev[a] = sE[r * Np + jb[a]];
                 }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
@@ -307,10 +432,11 @@ __global__ void __launch_bounds__(256) k_post_rows(const double* __restrict__ Ep
 //   S = sum over panels of Spart;   G[a,b] = sum_q coef(a,q) U[q,b] (F1 + F2)[row(a,q)][b] + mirrored rows
 //   (the four product-rule terms of gradient.jl:57-74 contracted with D).  Only locally owned rows contribute.
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_post_reduce(const double* __restrict__ cost_part, int ncost, const double* __restrict__ Spart, int npanels,
-                              const double* __restrict__ F1, const double* __restrict__ F2, const double* __restrict__ sw,
-                              const double* __restrict__ Rchain, const int* __restrict__ s_ptr, int n, int Np, int packed,
-                              double gcoef, int row_begin, int row_end, double* __restrict__ part) {
+__global__ void __launch_bounds__(128) k_post_reduce(const double* __restrict__ cost_part, int ncost, const double* __restrict__ Spart,
+                                                     int npanels, const double* __restrict__ F1, const double* __restrict__ F2,
+                                                     const double* __restrict__ sw, const double* __restrict__ Rchain,
+                                                     const int* __restrict__ s_ptr, int n, int Np, int packed, double gcoef,
+                                                     int row_begin, int row_end, double* __restrict__ part) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx == 0) {
         double c = 0.0;
@@ -319,33 +445,43 @@ __global__ void k_post_reduce(const double* __restrict__ cost_part, int ncost, c
     }
     if (idx >= n * n) return;
     const double* U = Rchain + (size_t)(*s_ptr) * n * n;
-    double s = 0.0;
-    for (int p = 0; p < npanels; ++p) s += Spart[(size_t)p * n * n + idx];
-    part[1 + idx] = s;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int p = 0;
+    for (; p + 3 < npanels; p += 4) {
+        s0 += Spart[(size_t)p * n * n + idx];
+        s1 += Spart[(size_t)(p + 1) * n * n + idx];
+        s2 += Spart[(size_t)(p + 2) * n * n + idx];
+        s3 += Spart[(size_t)(p + 3) * n * n + idx];
+    }
+    for (; p < npanels; ++p) s0 += Spart[(size_t)p * n * n + idx];
+    part[1 + idx] = (s0 + s1) + (s2 + s3);
     const int a = idx / n, b = idx % n;
     double g = 0.0;
-    for (int q = 0; q < n; ++q) {
-        const double u = U[q * n + b];
-        if (packed) {
+    if (packed) {
+#pragma unroll 8
+        for (int q = 0; q < n; ++q) {
             const int lo = a < q ? a : q, hi = a < q ? q : a;
             const int r = hi * (hi + 1) / 2 + lo;
-            if (r >= row_begin && r < row_end) {
-                double f = F1[(size_t)(r - row_begin) * Np + b];
-                if (F2) f += F2[(size_t)(r - row_begin) * Np + b];
-                g = fma(2.0 * u / sw[r], f, g);
-            }
-        } else {
+            const bool own = (r >= row_begin && r < row_end);
+            const int rl = own ? r - row_begin : 0;
+            double f = F1[(size_t)rl * Np + b];
+            if (F2) f += F2[(size_t)rl * Np + b];
+            const double w = own ? 2.0 * U[q * n + b] / sw[r] : 0.0;
+            g = fma(w, f, g);
+        }
+    } else {
+#pragma unroll 8
+        for (int q = 0; q < n; ++q) {
             const int r1 = a + n * q, r2 = q + n * a;
-            double f = 0.0;
-            if (r1 >= row_begin && r1 < row_end) {
-                f += F1[(size_t)(r1 - row_begin) * Np + b];
-                if (F2) f += F2[(size_t)(r1 - row_begin) * Np + b];
+            const bool o1 = (r1 >= row_begin && r1 < row_end), o2 = (r2 >= row_begin && r2 < row_end);
+            const int l1 = o1 ? r1 - row_begin : 0, l2 = o2 ? r2 - row_begin : 0;
+            double f1 = F1[(size_t)l1 * Np + b], f2 = F1[(size_t)l2 * Np + b];
+            if (F2) {
+                f1 += F2[(size_t)l1 * Np + b];
+                f2 += F2[(size_t)l2 * Np + b];
             }
-            if (r2 >= row_begin && r2 < row_end) {
-                f += F1[(size_t)(r2 - row_begin) * Np + b];
-                if (F2) f += F2[(size_t)(r2 - row_begin) * Np + b];
-            }
-            g = fma(u, f, g);
+            const double f = (o1 ? f1 : 0.0) + (o2 ? f2 : 0.0);
+            g = fma(U[q * n + b], f, g);
         }
     }
     part[1 + n * n + idx] = gcoef * g;

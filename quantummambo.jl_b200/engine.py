@@ -157,6 +157,13 @@ class CSAEngine:
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.mambo_csa_set_profiling(self._h, 1 if enable else 0))
 
+    def get_segments(self) -> dict:
+        seg = (C.c_double * 3)()
+        ne = C.c_int()
+        _lib.check(self._lib.mambo_csa_get_segments(self._h, seg, C.byref(ne)))
+        k = max(ne.value, 1)
+        return {"evals": ne.value, "pre_ms": seg[0] / k, "fused_post_ms": seg[1] / k, "finish_ms": seg[2] / k}
+
     def get_profile(self) -> dict:
         ms, nl, tot = C.c_double(), C.c_int(), C.c_longlong()
         _lib.check(self._lib.mambo_csa_get_profile(self._h, C.byref(ms), C.byref(nl), C.byref(tot)))

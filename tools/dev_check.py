@@ -16,8 +16,8 @@ def run(n, kind, sym, flavour, seed=0):
     x = o.random_x(n, seed + 1, flavour)
     c0, g0 = o.cost_grad_factored(x, T, obt, flavour)
     with m.CSAEngine(T, obt, flavour, sym=sym) as e:
-        info = e.info()
         c1, g1 = e.cost_grad(x)
+        info = e.info()
         rc = e.residual_cost()
         rc0 = o.L2_partial_cost(T, None, obt, None)
         ok = abs(c1 - c0) / abs(c0) < 1e-10 and rel(g1, g0) < 1e-10
