@@ -99,8 +99,10 @@ int  mambo_csa_get_residual(mambo_csa* h, double* tbt_out, double* obt_out);
 int  mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double* obt_out);
 
 /* --- device-resident entry points (no host synchronisation; used by the multi-GPU host and bench) -------- */
-/* Run all engine work on `stream` (a cudaStream_t); NULL restores the handle's own stream. */
+/* Run all engine work on `stream` (a cudaStream_t); NULL restores the handle's own stream (so the legacy
+ * default stream, whose handle is 0, cannot be selected: pass a created stream). */
 int  mambo_csa_set_stream(mambo_csa* h, void* stream);
+int  mambo_csa_get_stream(mambo_csa* h, void** stream, int* device);
 /* d_x: num_params doubles on the device; d_out: 1 + num_params doubles [cost, grad...] on the device. */
 int  mambo_csa_eval_device(mambo_csa* h, const double* d_x, double* d_out);
 /* Sharded evaluation in two halves around the caller's allreduce(sum) of d_partial (partial_len doubles):

@@ -1,0 +1,54 @@
+"""ctypes wrapper of oracle/csa_literal.c (CPU ORACLE, test infrastructure): the reference's loop nests in C,
+single-threaded like the Einsum.jl loops they restate.  expm / eigen stay with numpy (oracle/csa_oracle.py)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import csa_oracle as o
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(HERE, "libcsa_literal.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            subprocess.run(["make", "-C", HERE], check=True)
+        L = C.CDLL(_SO)
+        L.csa_lit_cost.restype = C.c_double
+        L.csa_lit_del_w_u.restype = C.c_void_p
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def cost_grad_literal_c(x, tbt):
+    """(cost, grad) of the CSA closures (decompose.jl:96-105) through the C loop nests."""
+    L = lib()
+    n = tbt.shape[0]
+    cL, uL = o.cartan_2b_num_params(n), o.real_orbital_rotation_num_params(n)
+    lam, th = np.asarray(x[:cL]), np.asarray(x[cL:])
+    U = np.ascontiguousarray(o.one_body_unitary(th, n))
+    Lam = np.ascontiguousarray(o.get_cartan_matrix(n, lam))
+    T = np.ascontiguousarray(tbt, dtype=np.float64)
+    W = np.empty_like(T)
+    L.csa_lit_reconstruct(n, _p(U), _p(Lam), _p(W))
+    cost = L.csa_lit_cost(n, _p(T), _p(W))
+    diff = np.ascontiguousarray(W - T)
+    gl = np.empty(cL)
+    L.csa_lit_grad_lambda(n, _p(U), _p(diff), _p(gl))
+    wu = L.csa_lit_del_w_u(n, _p(U), _p(Lam))
+    if not wu:
+        raise MemoryError("n^6 scratch")
+    dU = np.ascontiguousarray(np.stack([o.del_u_theta(n, th, k) for k in range(uL)])) if uL else np.zeros((0, n, n))
+    gt = np.empty(uL)
+    L.csa_lit_grad_theta(n, C.c_void_p(wu), _p(dU), uL, _p(diff), _p(gt))
+    L.csa_lit_free(C.c_void_p(wu))
+    return cost, np.concatenate([gl, gt])

@@ -312,6 +312,53 @@ def cost_grad_factored(x, tbt, obt=None, flavour: str = "CSA", need_grad: bool =
     return cost, np.concatenate([g1, gl, gt])
 
 
+def partial_factored(x, tbt, row_begin: int, row_end: int):
+    """Row-sharded first half of cost_grad_factored for a (pq)<->(rs)-symmetric tensor:
+    [cost, S (n x n), G (n x n)] restricted to rows [row_begin, row_end) of the n^2 x n^2 residual, rows indexed
+    as in the Julia memory layout (row (p,q) -> p + n q).  Summing the partials of a disjoint cover of the rows
+    gives the unsharded vector."""
+    n = tbt.shape[0]
+    cL = cartan_2b_num_params(n)
+    off = len(x) - cL - real_orbital_rotation_num_params(n)
+    lam2, theta = np.asarray(x[off:off + cL]), np.asarray(x[off + cL:])
+    U = one_body_unitary(theta, n)
+    L = get_cartan_matrix(n, lam2)
+    Af = (U[None, :, :] * U[:, None, :]).reshape(n * n, n)       # row index p + n q  (q slow)
+    T = np.asarray(tbt).reshape(n * n, n * n, order="F")          # T[(pq),(rs)] with p fastest
+    rows = np.arange(row_begin, min(row_end, n * n))
+    D = (Af[rows] @ L) @ Af.T - T[rows]
+    cost = float(np.sum(D * D))
+    E = D @ Af
+    S = Af[rows].T @ E
+    F = E @ L
+    G = np.zeros((n, n))
+    for k, r in enumerate(rows):
+        a, q = r % n, r // n
+        G[a] += 2.0 * U[q] * F[k]
+        G[q] += 2.0 * U[a] * F[k]
+    return np.concatenate([[cost], S.ravel(), G.ravel()])
+
+
+def finish_factored(part, x, n: int, flavour: str = "CSA", obt=None):
+    """Second half: one-body terms, adjoint Frechet derivative, gradient assembly (replicated on every rank)."""
+    lam1, lam2, theta = split_x(x, n, flavour)
+    K = construct_anti_symmetric(n, theta)
+    U = sla.expm(K)
+    cost = float(part[0])
+    S = np.asarray(part[1:1 + n * n]).reshape(n, n)
+    G = np.asarray(part[1 + n * n:]).reshape(n, n).copy()
+    g1 = None
+    if flavour != "CSA":
+        Dh = (U * lam1[None, :]) @ U.T - obt
+        cost += float(np.sum(Dh * Dh))
+        G += ((Dh + Dh.T) @ U) * lam1[None, :]
+        g1 = 2.0 * np.einsum("rk,rs,sk->k", U, Dh, U)
+    gl = np.array([2.0 * S[i, j] * (2.0 if i != j else 1.0) for i in range(n) for j in range(i + 1)])
+    Lf = _frechet_adjoint(K, G)
+    gt = np.array([2.0 * (Lf[p, q] - Lf[q, p]) for p in range(n) for q in range(p + 1, n)])
+    return cost, (np.concatenate([gl, gt]) if g1 is None else np.concatenate([g1, gl, gt]))
+
+
 def reconstruct_factored(x, n: int, flavour: str = "CSA"):
     """to_OP(frag) through the factored form (any N)."""
     lam1, lam2, theta = split_x(x, n, flavour)

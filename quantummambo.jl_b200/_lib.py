@@ -76,6 +76,7 @@ SIGNATURES = {
     "mambo_csa_get_residual": (C.c_int, [_P, _P, _P]),
     "mambo_csa_reconstruct": (C.c_int, [_P, _P, _P, _P]),
     "mambo_csa_set_stream": (C.c_int, [_P, _P]),
+    "mambo_csa_get_stream": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),
     "mambo_csa_eval_device": (C.c_int, [_P, _P, _P]),
     "mambo_csa_eval_partial_device": (C.c_int, [_P, _P, _P]),
     "mambo_csa_eval_finish_device": (C.c_int, [_P, _P, _P]),

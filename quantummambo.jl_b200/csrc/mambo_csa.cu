@@ -186,9 +186,9 @@ int host_s_for(const mambo_csa* h, const double* x) {
             const int a = std::min(i, j), b = std::max(i, j);
             s += std::fabs(th[(long long)a * n - (long long)a * (a + 1) / 2 + (b - a - 1)]);
         }
+        if (!(s == s) || std::isinf(s)) return -2;   // NaN / Inf in theta
         mx = std::max(mx, s);
     }
-    if (!(mx == mx)) return -2;
     int s = 0;
     if (mx > 1.0) s = (int)std::ceil(std::log2(mx));
     return s;
@@ -642,6 +642,14 @@ int subtract_impl(mambo_csa* h, const double* d_x, int s_host) {
 extern "C" {
 
 const char* mambo_last_error(void) { return g_err.c_str(); }
+void mambo_set_error(const char* msg) { g_err = msg ? msg : ""; }
+
+int mambo_csa_get_stream(mambo_csa* h, void** stream, int* device) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    if (stream) *stream = (void*)h->stream;
+    if (device) *device = h->device;
+    return MAMBO_OK;
+}
 
 int mambo_csa_create_sharded(mambo_csa** out, int N, int flavour, const double* tbt, const double* obt, int device, unsigned flags,
                              int shard, int nshards) {

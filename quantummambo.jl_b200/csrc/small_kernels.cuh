@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(1024) k_build(const double* __restrict__ x, in
     for (int j = tid; j < n; j += nt) {   // K antisymmetric: column sums == row sums; rows are contiguous
         double s = 0.0;
         for (int i = 0; i < n; ++i) s += fabs(Ks[j * n + i]);
+        if (!(s == s)) s = INFINITY;      // fmax would drop a NaN: force the out-of-range path
         mx = fmax(mx, s);
     }
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -80,7 +81,7 @@ __global__ void __launch_bounds__(1024) k_build(const double* __restrict__ x, in
         int s = 0;
         if (m > 1.0) s = (int)ceil(log2(m));
         if (s_override >= 0) s = s_override;
-        if (!(m == m) || s > SMAX) {  // NaN or too large
+        if (!(m == m) || isinf(m) || s > SMAX || s < 0) {  // NaN / Inf or too large
             *status = 1;
             s = SMAX;
         }

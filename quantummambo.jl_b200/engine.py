@@ -138,6 +138,16 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_reconstruct(self._h, x.ctypes.data, t.ctypes.data, None if o is None else o.ctypes.data))
         return t, o
 
+    # -- native optimiser / multistart ---------------------------------------------------------------------------
+    def optimize(self, x0, g_tol: float = 1e-8, max_iter: int = 1000, lbfgs_memory: int = 0, verbose: int = 0):
+        """Minimise cost(x) from x0 with the library's BFGS (mambo_csa_optimize)."""
+        x0 = _f64(x0, self.L)
+        xm = np.empty(self.L)
+        opt = _lib.OptOptions(max_iter, g_tol, lbfgs_memory, verbose)
+        res = _lib.OptResult()
+        _lib.check(self._lib.mambo_csa_optimize(self._h, x0.ctypes.data, xm.ctypes.data, C.byref(opt), C.byref(res)))
+        return xm, {k: getattr(res, k) for k, _ in res._fields_}
+
     # -- device-resident entry points (torch tensors carry the device memory; no host sync) -------------------
     def set_stream(self, cuda_stream_ptr: int | None):
         _lib.check(self._lib.mambo_csa_set_stream(self._h, cuda_stream_ptr))

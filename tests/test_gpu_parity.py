@@ -1,0 +1,298 @@
+"""GPU parity tests (run by the driver with `-m gpu` on a B200): the CUDA path, called through the C-ABI, against
+the oracle on the same seeded inputs; against the committed golden vectors; and, at BASELINE.json's full sizes,
+through size-independent properties.  Tolerance (north_star): 1e-10 relative for cost and (norm-wise) gradient in
+FP64; final 1-norms 1e-8."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import csa_oracle as o
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+KINDS = {"dense_sym": o.dense_sym_tbt, "pairsym": o.pairsym_tbt, "general": o.general_tbt}
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b))) / max(float(np.max(np.abs(b))), 1e-300))
+
+
+def _obt(n, seed):
+    return np.random.default_rng(100 + seed).standard_normal((n, n)) / n
+
+
+@pytest.fixture(scope="module")
+def lib(mb):
+    if not os.path.exists(os.path.join(os.path.dirname(mb.__file__), "quantummambo.jl_b200", "csrc", "libmambo_b200.so")):
+        mb.build()
+    return mb.load()
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 6, 7, 10, 17, 24, 33])
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+@pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
+def test_cost_and_gradient_match_oracle(mb, lib, n, flavour, kind):
+    T = KINDS[kind](n, n)
+    obt = _obt(n, n) if flavour == "CSA_SD" else None
+    x = o.random_x(n, 3, flavour)
+    c0, g0 = o.cost_grad_factored(x, T, obt, flavour)
+    with mb.CSAEngine(T, obt, flavour) as e:
+        c, g = e.cost_grad(x)
+        assert e.cost(x) == c and np.array_equal(e.grad(x), g)          # memoised closures (decompose.jl:96-105)
+        mode = e.info()["mode_name"]
+    assert mode == {"dense_sym": "fullsym-packed", "pairsym": "pairsym", "general": "general"}[kind] or n == 1
+    assert abs(c - c0) <= RTOL * abs(c0)
+    assert rel(g, g0) <= RTOL
+
+
+@pytest.mark.parametrize("sym", ["general", "pair", "full"])
+def test_forced_modes_agree_on_a_symmetric_tensor(mb, lib, sym):
+    n = 12
+    T = o.dense_sym_tbt(n, 0)
+    x = o.random_x(n, 1)
+    c0, g0 = o.cost_grad_factored(x, T)
+    flag = {"general": mb.SYM_GENERAL, "pair": mb.SYM_PAIR, "full": mb.SYM_FULL}[sym]
+    with mb.CSAEngine(T, sym=flag) as e:
+        c, g = e.cost_grad(x)
+    assert abs(c - c0) <= RTOL * abs(c0) and rel(g, g0) <= RTOL
+
+
+def test_golden_vectors(mb, lib, golden):
+    for name, c in golden.items():
+        n, sd = int(c["meta"][0]), int(c["meta"][1])
+        fl = "CSA_SD" if sd else "CSA"
+        with mb.CSAEngine(c["tbt"], c.get("obt"), fl) as e:
+            cost, grad = e.cost_grad(c["x"])
+            W, h = e.reconstruct(c["x"])
+        assert abs(cost - float(c["cost"])) <= RTOL * abs(float(c["cost"])), name
+        assert rel(grad, c["grad"]) <= RTOL, name
+        assert rel(W, c["W"]) <= RTOL, name
+        if sd:
+            assert rel(h, c["h"]) <= RTOL, name
+
+
+def test_theta_zero_and_zero_lambda_edge_cases(mb, lib):
+    n = 6
+    T = o.dense_sym_tbt(n, 2)
+    cL, uL = o.cartan_2b_num_params(n), o.real_orbital_rotation_num_params(n)
+    lam = np.random.default_rng(0).standard_normal(cL)
+    with mb.CSAEngine(T) as e:
+        for x in (np.concatenate([lam, np.zeros(uL)]),                     # U = I
+                  np.zeros(cL + uL),                                       # zero fragment: cost = |T|^2
+                  np.concatenate([np.zeros(cL), 2 * np.pi * np.random.default_rng(1).random(uL)])):   # reference x0
+            c0, g0 = o.cost_grad_factored(x, T)
+            c, g = e.cost_grad(x)
+            assert abs(c - c0) <= RTOL * abs(c0) and np.max(np.abs(g - g0)) <= RTOL * max(np.max(np.abs(g0)), 1.0)
+        assert e.residual_cost() == pytest.approx(float(np.sum(T * T)), rel=1e-13)
+
+
+def test_zero_tensor_and_planted_tensor(mb, lib):
+    n = 8
+    with mb.CSAEngine(np.zeros((n, n, n, n))) as e:
+        x = o.random_x(n, 0)
+        c0, g0 = o.cost_grad_factored(x, np.zeros((n, n, n, n)))
+        c, g = e.cost_grad(x)
+        assert abs(c - c0) <= RTOL * abs(c0) and rel(g, g0) <= RTOL
+    T, xs = o.planted_tbt(n, 1, 0)
+    with mb.CSAEngine(T) as e:
+        c, g = e.cost_grad(xs[0])
+        assert c <= 1e-20 * float(np.sum(T * T))
+        assert np.max(np.abs(g)) <= 1e-9 * np.sqrt(float(np.sum(T * T)))
+
+
+def test_error_paths(mb, lib):
+    n = 4
+    T = o.dense_sym_tbt(n, 0)
+    with mb.CSAEngine(T) as e:
+        x = o.random_x(n, 0)
+        xb = x.copy()
+        xb[-1] = np.nan
+        with pytest.raises(mb.MamboError) as ei:
+            e.cost_grad(xb)
+        assert ei.value.code == -5                                   # MAMBO_ERANGE
+        xb[-1] = 1e9                                                 # ||K||_1 > 2^14
+        with pytest.raises(mb.MamboError):
+            e.cost_grad(xb)
+        c, g = e.cost_grad(x)                                        # the handle stays usable
+        c0, g0 = o.cost_grad_factored(x, T)
+        assert abs(c - c0) <= RTOL * abs(c0)
+        with pytest.raises(ValueError):
+            e.cost_grad(x[:-1])
+    with pytest.raises(ValueError):
+        mb.CSAEngine(T, flavour="CSA_SD")                            # CSA_SD without obt
+    with pytest.raises(mb.MamboError):
+        mb.CSAEngine(o.general_tbt(6, 0), shard=0, nshards=2)        # sharding needs a pair-symmetric tensor
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+@pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
+def test_greedy_state_round_trip(mb, lib, flavour, kind):
+    """subtract_fragment == F_rem - to_OP(frag) (decompose.jl:56,182); reconstruct == to_OP; get_residual hands F_rem back."""
+    n = 9
+    T = KINDS[kind](n, 4)
+    obt = _obt(n, 4) if flavour == "CSA_SD" else None
+    x = o.random_x(n, 5, flavour)
+    h0, W0 = o.reconstruct_factored(x, n, flavour)
+    c0 = o.cost_grad_factored(x, T, obt, flavour, need_grad=False)[0]
+    with mb.CSAEngine(T, obt, flavour) as e:
+        W, h = e.reconstruct(x)
+        assert rel(W, W0) <= RTOL
+        new_cost = e.subtract_fragment(x)
+        assert abs(new_cost - c0) <= RTOL * abs(c0)                    # |T - W|^2 is the cost at x
+        assert e.residual_cost() == pytest.approx(c0, rel=1e-12)
+        Tr, orr = e.get_residual()
+        assert rel(Tr, T - W0) <= RTOL
+        if obt is not None:
+            assert rel(h, h0) <= RTOL and rel(orr, obt - h0) <= RTOL
+        # a second fragment is fitted against the updated residual
+        x2 = o.random_x(n, 6, flavour)
+        c2, g2 = e.cost_grad(x2)
+        c20, g20 = o.cost_grad_factored(x2, T - W0, None if obt is None else obt - h0, flavour)
+        assert abs(c2 - c20) <= RTOL * abs(c20) and rel(g2, g20) <= RTOL
+
+
+def test_bitwise_reproducible(mb, lib):
+    n = 20
+    T = o.dense_sym_tbt(n, 1)
+    x = o.random_x(n, 2)
+    with mb.CSAEngine(T) as e:
+        c1, g1 = e.cost_grad(x)
+        e.cost_grad(o.random_x(n, 3))
+        c2, g2 = e.cost_grad(x)
+    assert c1 == c2 and np.array_equal(g1, g2)
+
+
+def test_sharded_partials_sum_to_unsharded(mb, lib):
+    """Row-panel sharding emulated on one GPU: the shards' partial vectors add up to the unsharded
+    one, and finishing from the sum gives the unsharded cost+gradient."""
+    import torch
+    n = 14                                       # 105 packed rows -> 2 panels; 196 full rows -> 4 panels
+    for kind, sym, world in (("dense_sym", None, 2), ("pairsym", None, 4), ("dense_sym", "pair", 3)):
+        T = KINDS[kind](n, 0)
+        x = o.random_x(n, 1)
+        c0, g0 = o.cost_grad_factored(x, T)
+        flag = 0 if sym is None else 2
+        dev = torch.device("cuda", 0)
+        d_x = torch.from_numpy(x).to(dev)
+        total = None
+        engines = [mb.CSAEngine(T, sym=flag, shard=r, nshards=world) for r in range(world)]
+        try:
+            plen = engines[0].info()["partial_len"]
+            for e in engines:
+                d_p = torch.zeros(plen, dtype=torch.float64, device=dev)
+                e.eval_partial_device(d_x.data_ptr(), d_p.data_ptr())
+                e.synchronize()
+                total = d_p if total is None else total + d_p
+            for e in engines:
+                d_o = torch.zeros(len(x) + 1, dtype=torch.float64, device=dev)
+                e.eval_finish_device(total.data_ptr(), d_o.data_ptr())
+                e.synchronize()
+                out = d_o.cpu().numpy()
+                assert abs(out[0] - c0) <= RTOL * abs(c0) and rel(out[1:], g0) <= RTOL
+        finally:
+            for e in engines:
+                e.close()
+
+
+def test_device_entry_points_match_host_closures(mb, lib):
+    import torch
+    n = 11
+    T = o.dense_sym_tbt(n, 5)
+    obt = _obt(n, 5)
+    x = o.random_x(n, 6, "CSA_SD")
+    dev = torch.device("cuda", 0)
+    with mb.CSAEngine(T, obt, "CSA_SD") as e:
+        c, g = e.cost_grad(x)
+        s = torch.cuda.Stream(dev)
+        e.set_stream(s.cuda_stream)
+        d_x = torch.from_numpy(x).to(dev)
+        d_o = torch.zeros(len(x) + 1, dtype=torch.float64, device=dev)
+        d_c = torch.zeros(1, dtype=torch.float64, device=dev)
+        torch.cuda.synchronize()
+        e.eval_device(d_x.data_ptr(), d_o.data_ptr())
+        e.cost_device(d_x.data_ptr(), d_c.data_ptr())
+        e.synchronize()
+        out = d_o.cpu().numpy()
+        assert abs(out[0] - c) <= 1e-13 * abs(c) and rel(out[1:], g) <= 1e-12
+        assert abs(float(d_c.item()) - c) <= 1e-13 * abs(c)
+
+
+# ------------------------------------------------------------------------------------------------------------
+def test_native_bfgs_finds_planted_fragment(mb, lib):
+    n = 6
+    T, xs = o.planted_tbt(n, 1, 1)
+    rng = np.random.default_rng(0)
+    x0 = xs[0] + 0.02 * rng.standard_normal(xs[0].shape)
+    with mb.CSAEngine(T) as e:
+        c_start = e.cost(x0)
+        xm, res = e.optimize(x0, g_tol=1e-9, max_iter=500)
+        assert res["minimum"] < 1e-12 * float(np.sum(T * T)) and res["minimum"] < c_start
+        assert res["evaluations"] >= res["iterations"] > 0
+        assert e.cost(xm) == pytest.approx(res["minimum"], abs=1e-14)
+
+
+def test_greedy_decomposition_matches_oracle_driver(mb, lib):
+    """decompose.jl:1-80 end to end at LiH size (N=6 stand-in: planted R=2 + small symmetric noise): same x0s, same
+    BFGS (scipy) on both sides -> same fragments' cost trail and final 1-norm."""
+    n = 6
+    T, xs = o.planted_tbt(n, 2, 2, sigma=1e-3)
+    rng = np.random.default_rng(3)
+    x0s = [xs[k] + 0.05 * rng.standard_normal(xs[k].shape) for k in range(2)] + [o.random_x(n, 9)]
+    H = mb.F_OP(([0.0], [0.0], T))
+    frags = mb.CSA_greedy_decomposition(H, 3, x0s=x0s, decomp_tol=1e-7)
+    oxs, ocosts, t_rem, _ = o.greedy_decomposition(T, 3, x0s=x0s, decomp_tol=1e-7)
+    assert len(frags) == len(oxs)
+    l1 = sum(mb.CSA_L1(f) for f in frags)
+    l1_o = sum(o.CSA_L1(x[:o.cartan_2b_num_params(n)], n) for x in oxs)
+    assert l1 == pytest.approx(l1_o, rel=1e-6)
+    # the fragments reproduce the tensor to the same residual as the oracle's
+    W = sum(o.reconstruct_factored(f.x(), n)[1] for f in frags)
+    assert float(np.sum((T - W) ** 2)) == pytest.approx(float(np.sum(t_rem ** 2)), rel=1e-4, abs=1e-10)
+
+
+def test_csa_sd_greedy_step_molecule_sizes(mb, lib):
+    """H2O / N2 sizes (N = 7, 10; configs[1]): integrals cannot be generated here (no pyscf), planted stand-ins."""
+    for n in (7, 10):
+        T, xs = o.planted_tbt(n, 1, n)
+        lam1 = np.random.default_rng(n).standard_normal(n)
+        U = o.one_body_unitary(xs[0][o.cartan_2b_num_params(n):], n)
+        obt = (U * lam1) @ U.T
+        x_true = np.concatenate([lam1, xs[0]])
+        x0 = x_true + 0.01 * np.random.default_rng(1).standard_normal(x_true.shape)
+        H = mb.F_OP(([0.0], obt, T))
+        sol = mb.CSA_SD_greedy_step(H, x0=x0)
+        assert sol.minimum < 1e-10 * (float(np.sum(T * T)) + float(np.sum(obt * obt)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [50, 100])
+def test_full_size_properties(mb, lib, n):
+    """BASELINE.json sizes.  (1) pointwise parity with the factored oracle at one x; (2) the three symmetry modes of
+    the engine agree with each other; (3) planted round trip: subtracting W(x) then evaluating the zero fragment
+    gives the cost at x; (4) cost-only evaluation equals the fused evaluation's cost."""
+    import torch
+    T = o.dense_sym_tbt(n, 0)
+    x = o.random_x(n, 1)
+    c0, g0 = o.cost_grad_factored(x, T)
+    res = {}
+    for name, flag in (("full", mb.SYM_AUTO), ("pair", mb.SYM_PAIR)) + ((("general", mb.SYM_GENERAL),) if n <= 50 else ()):
+        with mb.CSAEngine(T, sym=flag) as e:
+            res[name] = e.cost_grad(x)
+            if name == "full":
+                assert e.info()["mode_name"] == "fullsym-packed"
+                dev = torch.device("cuda", 0)
+                d_x = torch.from_numpy(x).to(dev)
+                d_c = torch.zeros(1, dtype=torch.float64, device=dev)
+                e.cost_device(d_x.data_ptr(), d_c.data_ptr())
+                e.synchronize()
+                assert abs(float(d_c.item()) - res[name][0]) <= 1e-13 * abs(c0)
+                nc = e.subtract_fragment(x)
+                assert abs(nc - c0) <= RTOL * abs(c0)
+                assert e.residual_cost() == pytest.approx(c0, rel=1e-11)
+    for name, (c, g) in res.items():
+        assert abs(c - c0) <= RTOL * abs(c0), name
+        assert rel(g, g0) <= RTOL, name
