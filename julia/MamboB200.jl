@@ -1,0 +1,145 @@
+# MamboB200.jl -- drop-in binding of libmambo_b200.so for QuantumMAMBO.jl (ccall, no extra Julia packages).
+#
+# Include this file after `using QuantumMAMBO` (or from inside src/QuantumMAMBO.jl after UTILS/decompose.jl).
+# It redefines the two greedy steps so that the closures handed to Optim.jl evaluate on the B200:
+#     CSA_greedy_step      src/UTILS/decompose.jl:82-120
+#     CSA_SD_greedy_step   src/UTILS/decompose.jl:207-246
+# and adds device-resident variants of the outer loops (decompose.jl:1-80, 122-205) that keep F_rem on the GPU.
+# Everything else -- F_OP / F_FRAG, CSA_x_to_F_FRAG, Optim.jl BFGS, HDF5 checkpoints, L1 post-processing -- is
+# untouched.  NOTE: this file could not be executed in the build image (no julia binary); tests/ drive the same
+# C-ABI through Python ctypes with identical memory layout (column-major arrays).
+module MamboB200
+
+using QuantumMAMBO
+import QuantumMAMBO: F_OP, F_FRAG, CSA_x_to_F_FRAG, CSA_SD_x_to_F_FRAG, cartan_2b_num_params,
+                     real_orbital_rotation_num_params, tbt_svd_1st, SVD_for_CSA, SVD_for_CSA_SD,
+                     DECOMPOSITION_PRINT, ϵ
+using Optim
+
+const LIB = get(ENV, "MAMBO_B200_LIB", joinpath(@__DIR__, "..", "quantummambo.jl_b200", "csrc", "libmambo_b200.so"))
+
+const MAMBO_CSA = Cint(0)
+const MAMBO_CSA_SD = Cint(1)
+
+lasterr() = unsafe_string(ccall((:mambo_last_error, LIB), Cstring, ()))
+check(rc::Cint) = rc == 0 ? nothing : error("libmambo_b200 error $rc: $(lasterr())")
+
+mutable struct Engine
+    h::Ptr{Cvoid}
+    L::Int
+end
+
+"Upload F.mbts[3] (and F.mbts[2] for CSA_SD) once; the residual then lives on the device."
+function Engine(F::F_OP, flavour::Cint; device::Integer = 0, flags::Integer = 0)
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    tbt = F.mbts[3]::Array{Float64,4}                       # column-major, passed as it lies in memory
+    obt = flavour == MAMBO_CSA_SD ? Matrix{Float64}(F.mbts[2]) : Float64[]
+    GC.@preserve tbt obt begin
+        check(ccall((:mambo_csa_create, LIB), Cint,
+                    (Ref{Ptr{Cvoid}}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Cint, Cuint),
+                    href, F.N, flavour, tbt, flavour == MAMBO_CSA_SD ? pointer(obt) : C_NULL, device, flags))
+    end
+    e = Engine(href[], Int(ccall((:mambo_csa_num_params, LIB), Cint, (Ptr{Cvoid},), href[])))
+    finalizer(x -> (x.h != C_NULL && ccall((:mambo_csa_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), e)
+    return e
+end
+
+function cost(e::Engine, x::Vector{Float64})
+    c = Ref{Float64}(0.0)
+    GC.@preserve x check(ccall((:mambo_csa_cost, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), e.h, x, c))
+    return c[]
+end
+
+function grad!(e::Engine, storage::Vector{Float64}, x::Vector{Float64})
+    GC.@preserve storage x check(ccall((:mambo_csa_grad, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), e.h, x, storage))
+    return storage
+end
+
+"fg! form for Optim.only_fg!: one fused evaluation per point."
+function fg!(e::Engine, F, G, x::Vector{Float64})
+    c = Ref{Float64}(0.0)
+    g = G === nothing ? Ptr{Float64}(C_NULL) : pointer(G)
+    GC.@preserve x G check(ccall((:mambo_csa_cost_grad, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}, Ptr{Float64}), e.h, x, c, g))
+    return F === nothing ? nothing : c[]
+end
+
+function subtract_fragment!(e::Engine, x::Vector{Float64})
+    c = Ref{Float64}(0.0)
+    GC.@preserve x check(ccall((:mambo_csa_subtract_fragment, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), e.h, x, c))
+    return c[]
+end
+
+function residual_cost(e::Engine)
+    c = Ref{Float64}(0.0)
+    check(ccall((:mambo_csa_residual_cost, LIB), Cint, (Ptr{Cvoid}, Ref{Float64}), e.h, c))
+    return c[]
+end
+
+# ---- drop-in greedy steps (same signatures as decompose.jl:82, :207) ---------------------------------------------
+function _optimize(e::Engine, x0, print)
+    c(x) = cost(e, x)                                       # decompose.jl:96-99   / :221-224
+    g!(storage::Vector{Float64}, x::Vector{Float64}) = grad!(e, storage, x)   # decompose.jl:101-105 / :226-231
+    if print == false
+        return optimize(c, g!, x0, BFGS())
+    else
+        return optimize(c, g!, x0, BFGS(), Optim.Options(show_every = print, show_trace = true, extended_trace = true))
+    end
+end
+
+function QuantumMAMBO.CSA_greedy_step(F::F_OP, do_svd = SVD_for_CSA, print = DECOMPOSITION_PRINT, do_grad = true; engine = nothing)
+    cartan_L = cartan_2b_num_params(F.N)
+    unitary_L = real_orbital_rotation_num_params(F.N)
+    x0 = zeros(cartan_L + unitary_L)
+    if do_svd
+        frag = tbt_svd_1st(F.mbts[3])
+        x0[1:cartan_L] = frag.C.λ
+        x0[cartan_L+1:end] = frag.U[1].θs
+    else
+        x0[cartan_L+1:end] = 2π * rand(unitary_L)
+    end
+    e = engine === nothing ? Engine(F, MAMBO_CSA) : engine
+    return _optimize(e, x0, print)
+end
+
+function QuantumMAMBO.CSA_SD_greedy_step(F::F_OP, do_svd = SVD_for_CSA_SD, print = DECOMPOSITION_PRINT, do_grad = true; engine = nothing)
+    cartan_L = cartan_2b_num_params(F.N)
+    unitary_L = real_orbital_rotation_num_params(F.N)
+    x0 = zeros(cartan_L + unitary_L + F.N)
+    if do_svd
+        frag = tbt_svd_1st(F.mbts[3])
+        x0[F.N+1:F.N+cartan_L] = frag.C.λ
+        x0[F.N+cartan_L+1:end] = frag.U[1].θs
+    else
+        x0[F.N+cartan_L+1:end] = 2π * rand(unitary_L)
+    end
+    e = engine === nothing ? Engine(F, MAMBO_CSA_SD) : engine
+    return _optimize(e, x0, print)
+end
+
+"""
+    CSA_greedy_decomposition_b200(H, α_max; decomp_tol = ϵ, verbose = false)
+
+decompose.jl:1-80 with F_rem resident on the GPU: one upload of H.mbts[3], `subtract_fragment!` instead of
+`F_rem = F_rem - to_OP(frag)` (decompose.jl:56).  The HDF5 checkpoint code of the original can be kept verbatim
+around this loop (X[:, α] = sol.minimizer); on resume replay the saved columns with `subtract_fragment!`.
+"""
+function CSA_greedy_decomposition_b200(H::F_OP, α_max; decomp_tol = ϵ, verbose = false, flavour = MAMBO_CSA)
+    e = Engine(H, flavour)
+    cartan_L = cartan_2b_num_params(H.N)
+    Farr = F_FRAG[]
+    curr_cost = residual_cost(e)                                           # decompose.jl:40
+    α = 0
+    while curr_cost > decomp_tol && α < α_max
+        α += 1
+        sol = flavour == MAMBO_CSA ? QuantumMAMBO.CSA_greedy_step(H; engine = e) : QuantumMAMBO.CSA_SD_greedy_step(H, false; engine = e)
+        frag = flavour == MAMBO_CSA ? CSA_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L) :
+                                      CSA_SD_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L)
+        push!(Farr, frag)
+        subtract_fragment!(e, sol.minimizer)                                # decompose.jl:56
+        curr_cost = sol.minimum
+        verbose && println("Current L2 cost after $α fragments is $(sol.minimum)")
+    end
+    return Farr
+end
+
+end # module
