@@ -84,7 +84,8 @@ inline size_t smem_bytes(int ld, int S) { return (size_t)(ROWS + S * SUB) * ld *
 template <int NB, bool DO_E, bool STORE, bool TPREF>
 __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    const int ld = p.ld, S = p.S, Q = p.Q;
+    constexpr int ld = 8 * NB + 4;   // == p.ld: compile-time pitch turns the fragment addressing into immediates
+    const int S = p.S, Q = p.Q;
     double* sB = reinterpret_cast<double*>(smem_raw);
     double* sA = sB + ROWS * ld;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)S * SUB * ld);
@@ -248,28 +249,59 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
         if (DO_E) {
 #pragma unroll
             for (int kb = 0; kb < 4; ++kb) {
-                const double* r0 = sAs + (8 * kb + pc0) * ld;
-                const double* r1 = sAs + (8 * kb + pc1) * ld;
+                const double* r0 = sAs + (8 * kb + pc0) * ld + 2 * t1;
+                const double* r1 = sAs + (8 * kb + pc1) * ld + 2 * t1;
+                // two column pairs (4 n-blocks x 2 m-blocks = 8 independent accumulators) per round: the two DMMAs
+                // that hit the same accumulator (v = 0, 1) are 8 issues apart
 #pragma unroll
-                for (int pr = 0; pr < NB / 2; ++pr) {
-                    const double2 b0 = *reinterpret_cast<const double2*>(r0 + 16 * pr + 2 * t1);
-                    const double2 b1 = *reinterpret_cast<const double2*>(r1 + 16 * pr + 2 * t1);
+                for (int pr = 0; pr + 1 < NB / 2; pr += 2) {
+                    const double2 b00 = *reinterpret_cast<const double2*>(r0 + 16 * pr);
+                    const double2 b01 = *reinterpret_cast<const double2*>(r0 + 16 * (pr + 1));
+                    const double2 b10 = *reinterpret_cast<const double2*>(r1 + 16 * pr);
+                    const double2 b11 = *reinterpret_cast<const double2*>(r1 + 16 * (pr + 1));
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) {
+                        dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][0], b00.x);
+                        dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][0], b00.y);
+                        dmma(e[mb][2 * pr + 2][0], e[mb][2 * pr + 2][1], acc[mb][kb][0], b01.x);
+                        dmma(e[mb][2 * pr + 3][0], e[mb][2 * pr + 3][1], acc[mb][kb][0], b01.y);
+                    }
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) {
+                        dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b10.x);
+                        dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b10.y);
+                        dmma(e[mb][2 * pr + 2][0], e[mb][2 * pr + 2][1], acc[mb][kb][1], b11.x);
+                        dmma(e[mb][2 * pr + 3][0], e[mb][2 * pr + 3][1], acc[mb][kb][1], b11.y);
+                    }
+                }
+                if ((NB / 2) & 1) {   // one column pair left (+ the odd tail block): 4 or 6 independent accumulators
+                    constexpr int pr = (NB / 2) - 1;
+                    const double2 b0 = *reinterpret_cast<const double2*>(r0 + 16 * pr);
+                    const double2 b1 = *reinterpret_cast<const double2*>(r1 + 16 * pr);
+                    double t0v = 0.0, t1v = 0.0;
+                    if (NB & 1) {
+                        t0v = (r0 - 2 * t1)[8 * (NB - 1) + t1];
+                        t1v = (r1 - 2 * t1)[8 * (NB - 1) + t1];
+                    }
 #pragma unroll
                     for (int mb = 0; mb < 2; ++mb) {
                         dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][0], b0.x);
                         dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][0], b0.y);
-                        dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b1.x);
-                        dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b1.y);
+                        if (NB & 1) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], t0v);
                     }
-                }
-                if (NB & 1) {
-                    const double b0 = r0[8 * (NB - 1) + t1];
-                    const double b1 = r1[8 * (NB - 1) + t1];
 #pragma unroll
                     for (int mb = 0; mb < 2; ++mb) {
-                        dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], b0);
-                        dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], b1);
+                        dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b1.x);
+                        dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b1.y);
+                        if (NB & 1) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
                     }
+                } else if (NB & 1) {  // only the odd tail block is left
+                    const double t0v = (r0 - 2 * t1)[8 * (NB - 1) + t1];
+                    const double t1v = (r1 - 2 * t1)[8 * (NB - 1) + t1];
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], t0v);
+#pragma unroll
+                    for (int mb = 0; mb < 2; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
                 }
             }
         }

@@ -14,6 +14,7 @@
 #include "../../include/mambo_csa.h"
 #include "fused_kernel.cuh"
 #include "small_kernels.cuh"
+#include "chain_kernels.cuh"
 
 namespace {
 
@@ -75,6 +76,9 @@ struct mambo_csa {
     double *dX, *dX2, *dX4, *dP0, *dP1, *dP2, *dQ3, *dQ2, *dQ1, *dR; // dR: (SMAX+1) matrices
     double *Lam = nullptr, *Dh = nullptr, *DU = nullptr, *hfrag = nullptr, *g1 = nullptr;
     int* d_s = nullptr;
+    unsigned* d_bar = nullptr;                 // grid-barrier counters of the persistent chain kernels
+    bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
+    bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
     double* d_scale = nullptr;
     int* d_status = nullptr;
     double *d_x = nullptr, *d_out = nullptr, *d_part = nullptr;
@@ -207,7 +211,39 @@ void mm(mambo_csa* h, double* C, const double* Cin, const double* A1, const doub
 // U = exp(K): Taylor-16 (Paterson-Stockmeyer, 6 GEMMs) + s squarings; every intermediate is kept for the
 // derivative chain.  s_host >= 0: number of squarings (known when x came from the host; passed down so that
 // host and device agree); s_host < 0: the device decides and SMAX guarded launches are enqueued.
+int launch_coop(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelExC(&cfg, func, args));
+    return MAMBO_OK;
+}
+
+int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host);
+
+// U = exp(K) in ONE persistent kernel (chain::k_chain_u): grid barriers instead of kernel boundaries.
 int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
+    if (!h->use_chain) return enqueue_unitary_legacy(h, d_x, s_host);
+    const int n = h->N, tiles = (n + chain::CT - 1) / chain::CT;
+    chain::UParams p;
+    p.x = d_x; p.n = n; p.lam_off = h->lam_off; p.s_override = s_host;
+    p.X = h->X; p.X2 = h->X2; p.X4 = h->X4; p.P0 = h->P0; p.P1 = h->P1; p.P2 = h->P2; p.Q3 = h->Q3; p.Q2 = h->Q2; p.Q1 = h->Q1;
+    p.R = h->R; p.Lam = h->Lam; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
+    void* args[] = {&p};
+    TRY(launch_coop((const void*)chain::k_chain_u, dim3(tiles, tiles), dim3(chain::NTHR), chain::smem_bytes(n), h->stream, args));
+    h->launches++;
+    return MAMBO_OK;
+}
+
+int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host) {
     const int n = h->N, nn = n * n;
     small::k_build<<<1, 1024, (size_t)nn * 8, h->stream>>>(d_x, n, h->lam_off, h->X, h->Lam, h->d_s, h->d_scale, h->d_status, s_host);
     h->launches++;
@@ -224,17 +260,32 @@ int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
     return MAMBO_OK;
 }
 
+#define NCH_DISPATCH(nch, CALL)                \
+    switch (nch) {                             \
+        case 1: { constexpr int NCH = 1; CALL; break; } \
+        case 2: { constexpr int NCH = 2; CALL; break; } \
+        case 3: { constexpr int NCH = 3; CALL; break; } \
+        case 4: { constexpr int NCH = 4; CALL; break; } \
+        case 5: { constexpr int NCH = 5; CALL; break; } \
+        default: { constexpr int NCH = 6; CALL; break; } \
+    }
+
 int enqueue_prep(mambo_csa* h) {
     const int blocks = h->nRpad / small::PREP_ROWS;
-    small::k_prep<<<blocks, 256, small::prep_smem(h->N, h->Np), h->stream>>>(h->R, h->d_s, h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld,
-                                                                            h->nRpad, h->row_begin, h->row_end, h->At, h->Bt);
+    NCH_DISPATCH((h->Np + 31) / 32,
+                 (small::k_prep<NCH><<<blocks, 256, small::prep_smem(h->N, h->Np), h->stream>>>(
+                     h->R, h->d_s, h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld, h->nRpad, h->row_begin, h->row_end, h->At, h->Bt)));
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
 }
 
 int enqueue_post_f(mambo_csa* h, double* F) {
-    small::k_post_f<<<h->P, 256, small::postf_smem(h->Np), h->stream>>>(h->Epiece, h->piece_first, h->Lam, h->N, h->Np, h->Et, F);
+    if (h->postf32) {
+        NCH_DISPATCH((h->Np + 31) / 32, (small::k_post_f32<NCH><<<2 * h->P, 256, small::postf32_smem(h->N, h->Np), h->stream>>>(
+                                            h->Epiece, h->piece_first, h->Lam, h->N, h->Np, h->Et, F)));
+    } else
+        small::k_post_f<<<h->P, 256, small::postf_smem(h->Np), h->stream>>>(h->Epiece, h->piece_first, h->Lam, h->N, h->Np, h->Et, F);
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
@@ -243,8 +294,10 @@ int enqueue_post_f(mambo_csa* h, double* F) {
 int enqueue_post_sr(mambo_csa* h) {
     const int n = h->N, nn = n * n;
     const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
-    small::k_post_s<<<h->P, 256, small::posts_smem(h->Np), h->stream>>>(h->Et, h->At, n, h->Np, h->ld, h->row_begin, h->Spart);
-    small::k_post_reduce<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->cost_part, h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
+    const int nch = (n + 63) / 64;
+    small::k_post_s<<<dim3(h->P, nch * nch), 256, small::posts_smem(h->Np), h->stream>>>(h->Et, h->At, n, h->Np, h->ld, h->row_begin, h->Spart);
+    (void)nn;
+    small::k_post_reduce<<<n, 1024, 0, h->stream>>>(h->cost_part, h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
                                                                  h->sw, h->R, h->d_s, n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
                                                                  h->row_begin, std::min(h->row_end, h->nR), h->d_part);
     h->launches += 2;
@@ -258,6 +311,18 @@ int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
     if (h->flavour == MAMBO_CSA_SD) {
         small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->R, h->d_s, n, h->d_part, h->g1, h->Dh, h->DU, nullptr);
         h->launches++;
+    }
+    if (h->use_chain) {
+        const int tiles = (n + chain::CT - 1) / chain::CT;
+        chain::DParams p;
+        p.part = h->d_part; p.g1 = h->g1; p.n = n; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0;
+        p.X = h->X; p.X2 = h->X2; p.X4 = h->X4; p.Q3 = h->Q3; p.Q2 = h->Q2; p.Q1 = h->Q1; p.R = h->R;
+        p.dX2 = h->dX2; p.dX4 = h->dX4; p.dP0 = h->dP0; p.dP1 = h->dP1; p.dP2 = h->dP2; p.dQ3 = h->dQ3; p.dQ2 = h->dQ2; p.dQ1 = h->dQ1;
+        p.dR = h->dR; p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar;
+        void* args[] = {&p};
+        TRY(launch_coop((const void*)chain::k_chain_d, dim3(tiles, tiles), dim3(chain::NTHR), chain::smem_bytes(n), h->stream, args));
+        h->launches++;
+        return MAMBO_OK;
     }
     small::k_build_d<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->d_part, h->d_scale, n, h->dX);
     h->launches++;
@@ -575,6 +640,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->Lam = take(1); h->Dh = take(1); h->DU = take(1); h->hfrag = take(1);
     TRY(dalloc(&h->g1, (size_t)n));
     TRY(dalloc(&h->d_s, 1));
+    TRY(dalloc(&h->d_bar, 2));
     TRY(dalloc(&h->d_scale, 1));
     TRY(dalloc(&h->d_status, 1));
     TRY(dalloc(&h->d_x, (size_t)h->L));
@@ -586,6 +652,12 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     *h->h_status = 0;
     h->memo_x.assign(h->L, 0.0);
     h->use_graphs = (std::getenv("MAMBO_NO_GRAPH") == nullptr);
+    h->use_chain = (std::getenv("MAMBO_LEGACY_CHAIN") == nullptr);
+    if (chain::smem_bytes(n) > prop.sharedMemPerBlockOptin) h->use_chain = false;
+    if (h->use_chain) {
+        CU(cudaFuncSetAttribute(chain::k_chain_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::smem_bytes(n)));
+        CU(cudaFuncSetAttribute(chain::k_chain_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::smem_bytes(n)));
+    }
 
     // opt-in shared-memory sizes, set once per handle
     {
@@ -603,8 +675,13 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         CU(cudaFuncSetAttribute(small::k_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 2, 2)));
         CU(cudaFuncSetAttribute(small::k_pow34, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 1, 2)));
         CU(cudaFuncSetAttribute(small::k_dpow34, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 2, 4)));
-        CU(cudaFuncSetAttribute(small::k_prep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::prep_smem(n, h->Np)));
+        NCH_DISPATCH((h->Np + 31) / 32, CU(cudaFuncSetAttribute(small::k_prep<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                (int)small::prep_smem(n, h->Np))));
         CU(cudaFuncSetAttribute(small::k_post_f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::postf_smem(h->Np)));
+        h->postf32 = small::postf32_smem(n, h->Np) <= 113 * 1024;   // two CTAs per SM
+        if (h->postf32)
+            NCH_DISPATCH((h->Np + 31) / 32, CU(cudaFuncSetAttribute(small::k_post_f32<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                                    (int)small::postf32_smem(n, h->Np))));
         CU(cudaFuncSetAttribute(small::k_post_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::posts_smem(h->Np)));
     }
     return MAMBO_OK;
@@ -692,7 +769,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
-                    h->visit_start, h->piece_first, h->mats, h->g1, h->d_s, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
+                    h->visit_start, h->piece_first, h->mats, h->g1, h->d_s, h->d_bar, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_x) cudaFreeHost(h->h_x);

@@ -220,14 +220,56 @@ __global__ void __launch_bounds__(TS * TS) k_dpow34(const double* __restrict__ X
 }
 
 // ------------------------------------------------------------------------------------------------------
+// rows x Lambda core shared by k_prep (B~ = A~ Lambda) and k_post_f32 (F = E~ Lambda):
+//   this warp's 4 rows (shared memory, pitch Np) times Lambda (shared memory [n][Np]) -> acc[4][NCH], column
+//   32*c + lane.  NCH = ceil(Np/32) is a template parameter so the loop body is branch-free.
+// ------------------------------------------------------------------------------------------------------
+constexpr int CMAX = 6;   // column chunks of 32 covering Np <= 192
+template <int NCH>
+__device__ __forceinline__ void rows4_times_lambda(const double* __restrict__ rows, const double* __restrict__ sL, int n, int Np,
+                                                   double (&acc)[4][NCH]) {
+    const int lane = threadIdx.x & 31;
+    const bool last_ok = (32 * (NCH - 1) + lane) < Np;
+    const double* lrow = sL + lane;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) acc[i][c] = 0.0;
+#pragma unroll 4
+    for (int l = 0; l < n; ++l) {
+        const double a0 = rows[l], a1 = rows[Np + l], a2 = rows[2 * Np + l], a3 = rows[3 * Np + l];
+        double lm[NCH];
+#pragma unroll
+        for (int c = 0; c < NCH - 1; ++c) lm[c] = lrow[(size_t)l * Np + 32 * c];
+        lm[NCH - 1] = last_ok ? lrow[(size_t)l * Np + 32 * (NCH - 1)] : 0.0;
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+            acc[0][c] = fma(a0, lm[c], acc[0][c]);
+            acc[1][c] = fma(a1, lm[c], acc[1][c]);
+            acc[2][c] = fma(a2, lm[c], acc[2][c]);
+            acc[3][c] = fma(a3, lm[c], acc[3][c]);
+        }
+    }
+}
+// Lambda (row-major n x n in global memory) -> shared [n][Np], columns >= n zero; one wave of async copies
+__device__ __forceinline__ void stage_lambda(double* sL, const double* __restrict__ Lam, int n, int Np) {
+    const int c0 = threadIdx.x & 31, r0 = threadIdx.x >> 5, nr = blockDim.x >> 5;
+    for (int l = r0; l < n; l += nr)
+        for (int m = c0; m < Np; m += 32) {
+            if (m < n) cp_async8(sL + (size_t)l * Np + m, Lam + (size_t)l * n + m);
+            else sL[(size_t)l * Np + m] = 0.0;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // k_prep: A~[r][l] = sw_r U[pa_r][l] U[pq_r][l],  B~[r][m] = sum_l A~[r][l] Lambda[l][m]
-//   U = Rchain[s].  32 rows per CTA, 256 threads, Lambda resident in shared memory.
+//   U = Rchain[s].  32 rows per CTA, 256 threads (8 threads gather one row), Lambda resident in shared memory.
 //   Rows >= nR (padding) have sw = 0.
 // ------------------------------------------------------------------------------------------------------
 constexpr int PREP_ROWS = 32;
-constexpr int CMAX = 6;   // column chunks of 32 covering Np <= 192
 inline size_t prep_smem(int n, int Np) { return ((size_t)n * Np + (size_t)PREP_ROWS * Np) * sizeof(double); }
 
+template <int NCH>
 __global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Rchain, const int* __restrict__ s_ptr,
                                               const double* __restrict__ Lam, const int* __restrict__ pa, const int* __restrict__ pq,
                                               const double* __restrict__ sw, int n, int Np, int ld, int rows_total, int brow_begin,
@@ -238,52 +280,30 @@ __global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Rchain,
     const double* U = Rchain + (size_t)(*s_ptr) * n * n;
     const int r0 = blockIdx.x * PREP_ROWS;
     const bool need_b = !(r0 + PREP_ROWS <= brow_begin || r0 >= brow_end);
-    if (need_b) {
-        for (int idx = threadIdx.x; idx < n * Np; idx += blockDim.x) {
-            const int l = idx / Np, m = idx % Np;
-            if (m < n) cp_async8(sL + idx, Lam + (size_t)l * n + m);
-            else sL[idx] = 0.0;
+    if (need_b) stage_lambda(sL, Lam, n, Np);
+    {
+        const int rr = threadIdx.x >> 3, l0 = threadIdx.x & 7, r = r0 + rr;
+        const bool live = r < rows_total;
+        const double w = live ? sw[r] : 0.0;
+        const double* ua = U + (size_t)(live ? pa[r] : 0) * n;
+        const double* uq = U + (size_t)(live ? pq[r] : 0) * n;
+#pragma unroll 4
+        for (int l = l0; l < Np; l += 8) {
+            const double v = (l < n && w != 0.0) ? w * ua[l] * uq[l] : 0.0;
+            sAt[rr * Np + l] = v;
+            if (live) At[(size_t)r * ld + l] = v;
         }
-    }
-    for (int idx = threadIdx.x; idx < PREP_ROWS * Np; idx += blockDim.x) {
-        const int rr = idx / Np, l = idx % Np, r = r0 + rr;
-        double v = 0.0;
-        if (r < rows_total && l < n) {
-            const double w = sw[r];
-            if (w != 0.0) v = w * U[pa[r] * n + l] * U[pq[r] * n + l];
-        }
-        sAt[idx] = v;
-        if (r < rows_total) At[(size_t)r * ld + l] = v;
     }
     if (!need_b) return;  // B~ only for this shard's rows
     cp_async_wait_all();
     __syncthreads();
     const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 warps x 4 rows
-    const int nchunk = (Np + 31) / 32;
-    double acc[4][CMAX];
+    double acc[4][NCH];
+    rows4_times_lambda<NCH>(sAt + (size_t)(grp * 4) * Np, sL, n, Np, acc);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) acc[i][c] = 0.0;
-    const double* s0 = sAt + (grp * 4) * Np;
-    for (int l = 0; l < n; ++l) {
-        const double a0 = s0[l], a1 = s0[Np + l], a2 = s0[2 * Np + l], a3 = s0[3 * Np + l];
-        const double* lrow = sL + (size_t)l * Np + lane;
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) {
-            if (c < nchunk) {
-                const double lm = (32 * c + lane < Np) ? lrow[32 * c] : 0.0;
-                acc[0][c] = fma(a0, lm, acc[0][c]);
-                acc[1][c] = fma(a1, lm, acc[1][c]);
-                acc[2][c] = fma(a2, lm, acc[2][c]);
-                acc[3][c] = fma(a3, lm, acc[3][c]);
-            }
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
+    for (int c = 0; c < NCH; ++c) {
         const int m = 32 * c + lane;
-        if (c < nchunk && m < Np) {
+        if (m < Np) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const int r = r0 + grp * 4 + i;
@@ -373,119 +393,185 @@ __global__ void __launch_bounds__(256) k_post_f(const double* __restrict__ Epiec
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_post_s: Spart[panel] = A~_panel^T E~_panel  (lambda gradient, gradient.jl:13-41), 64 x 64 output chunks,
-//   4 x 4 register tiles, both operands resident in shared memory.
+// k_post_f32: same as k_post_f for N where Lambda fits in shared memory next to a 32-row half panel:
+//   grid = 2 x panels (158 CTAs at N=100 packed, two resident per SM), one wave of async copies, no chunk loop.
 // ------------------------------------------------------------------------------------------------------
-inline size_t posts_smem(int Np) { return (size_t)2 * 64 * Np * sizeof(double); }
+inline size_t postf32_smem(int n, int Np) { return ((size_t)n * Np + (size_t)32 * Np) * sizeof(double); }
+
+template <int NCH>
+__global__ void __launch_bounds__(256) k_post_f32(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
+                                                  const double* __restrict__ Lam, int n, int Np, double* __restrict__ Et,
+                                                  double* __restrict__ F) {
+    extern __shared__ double sm[];
+    double* sL = sm;                        // [n][Np]
+    double* sE = sm + (size_t)n * Np;       // [32][Np]
+    const int panel = blockIdx.x >> 1, half = blockIdx.x & 1;
+    const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
+    stage_lambda(sL, Lam, n, Np);
+    const size_t hoff = (size_t)half * 32 * Np;
+    const int total = 32 * Np;
+    for (int base = threadIdx.x; base < total; base += 4 * 256) {
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int v = v0; v < v1; ++v) {
+            const double* p0 = Epiece + (size_t)(v * 2 + 0) * 64 * Np + hoff;
+            const double* p1 = Epiece + (size_t)(v * 2 + 1) * 64 * Np + hoff;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 256;
+                if (idx < total) acc[u] += p0[idx] + p1[idx];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * 256;
+            if (idx < total) {
+                sE[idx] = acc[u];
+                Et[(size_t)panel * 64 * Np + hoff + idx] = acc[u];
+            }
+        }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;   // 8 warps x 4 rows
+    double acc[4][NCH];
+    rows4_times_lambda<NCH>(sE + (size_t)grp * 4 * Np, sL, n, Np, acc);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+        const int b = 32 * c + lane;
+        if (b < Np) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) F[(size_t)(panel * 64 + half * 32 + grp * 4 + i) * Np + b] = acc[i][c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// k_post_s: Spart[panel] = A~_panel^T E~_panel  (lambda gradient, gradient.jl:13-41).  grid = (panels, chunks^2):
+//   one CTA = one 64 x 64 output chunk of one panel, 4 x 4 register tiles, operands in shared memory.
+// ------------------------------------------------------------------------------------------------------
+inline size_t posts_smem(int Np) { (void)Np; return (size_t)2 * 64 * 64 * sizeof(double); }
 
 __global__ void __launch_bounds__(256) k_post_s(const double* __restrict__ Et, const double* __restrict__ At, int n, int Np, int ld,
                                                 int row_begin, double* __restrict__ Spart) {
     extern __shared__ double sm[];
-    double* sE = sm;                 // [64][Np]
-    double* sAp = sm + 64 * Np;      // [64][Np]
+    double* sE = sm;                 // [64 rows][64 cols j]
+    double* sAp = sm + 64 * 64;      // [64 rows][64 cols i]
     const int panel = blockIdx.x;
-    for (int idx = threadIdx.x; idx < 64 * Np; idx += blockDim.x) {
-        const int rr = idx / Np, l = idx % Np;
-        cp_async8(sE + idx, Et + (size_t)panel * 64 * Np + idx);
-        cp_async8(sAp + idx, At + (size_t)(row_begin + panel * 64 + rr) * ld + l);
+    const int nch = (n + 63) / 64;
+    const int i0 = (blockIdx.y / nch) * 64, j0 = (blockIdx.y % nch) * 64;
+    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
+        const int rr = idx >> 6, c = idx & 63;
+        if (j0 + c < Np) cp_async8(sE + idx, Et + (size_t)(panel * 64 + rr) * Np + j0 + c);
+        else sE[idx] = 0.0;
+        if (i0 + c < Np) cp_async8(sAp + idx, At + (size_t)(row_begin + panel * 64 + rr) * ld + i0 + c);
+        else sAp[idx] = 0.0;
     }
     cp_async_wait_all();
     __syncthreads();
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    for (int i0 = 0; i0 < n; i0 += 64)
-        for (int j0 = 0; j0 < n; j0 += 64) {
-            double acc[4][4];
+    double acc[4][4];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-            int ia[4], jb[4];
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                ia[a] = min(i0 + ty + 16 * a, Np - 1);
-                jb[a] = min(j0 + tx + 16 * a, Np - 1);
-            }
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
 #pragma unroll 4
-            for (int r = 0; r < 64; ++r) {
-                double av[4], ev[4];
+    for (int r = 0; r < 64; ++r) {
+        double av[4], ev[4];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    av[a] = sAp[r * Np + ia[a]];
-                    ev[a] = sE[r * Np + jb[a]];
-                }
+        for (int a = 0; a < 4; ++a) {
+            av[a] = sAp[r * 64 + ty + 16 * a];
+            ev[a] = sE[r * 64 + tx + 16 * a];
+        }
 #pragma unroll
-                for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 4; ++a)
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], ev[b], acc[a][b]);
-            }
+            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], ev[b], acc[a][b]);
+    }
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-                    if (i < n && j < n) Spart[(size_t)panel * n * n + i * n + j] = acc[a][b];
-                }
+        for (int b = 0; b < 4; ++b) {
+            const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
+            if (i < n && j < n) Spart[(size_t)panel * n * n + i * n + j] = acc[a][b];
         }
 }
 
 // ------------------------------------------------------------------------------------------------------
-// k_post_reduce: part = [cost, S (n x n), G (n x n)]
-//   S = sum over panels of Spart;   G[a,b] = sum_q coef(a,q) U[q,b] (F1 + F2)[row(a,q)][b] + mirrored rows
+// k_post_reduce: part = [cost, S (n x n), G (n x n)];  one CTA per output row a, 128 columns x 8 groups.
+//   S = sum over panels of Spart (groups split the panels);
+//   G[a,b] = sum_q coef(a,q) U[q,b] (F1 + F2)[row(a,q)][b] + mirrored rows (groups split q)
 //   (the four product-rule terms of gradient.jl:57-74 contracted with D).  Only locally owned rows contribute.
+//   Group partials are combined in a fixed order: deterministic.
 // ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_post_reduce(const double* __restrict__ cost_part, int ncost, const double* __restrict__ Spart,
-                                                     int npanels, const double* __restrict__ F1, const double* __restrict__ F2,
-                                                     const double* __restrict__ sw, const double* __restrict__ Rchain,
-                                                     const int* __restrict__ s_ptr, int n, int Np, int packed, double gcoef,
-                                                     int row_begin, int row_end, double* __restrict__ part) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx == 0) {
+__global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__ cost_part, int ncost, const double* __restrict__ Spart,
+                                                      int npanels, const double* __restrict__ F1, const double* __restrict__ F2,
+                                                      const double* __restrict__ sw, const double* __restrict__ Rchain,
+                                                      const int* __restrict__ s_ptr, int n, int Np, int packed, double gcoef,
+                                                      int row_begin, int row_end, double* __restrict__ part) {
+    __shared__ double redS[8][128], redG[8][128];
+    const int a = blockIdx.x, tx = threadIdx.x & 127, grp = threadIdx.x >> 7;
+    const double* U = Rchain + (size_t)(*s_ptr) * n * n;
+    if (a == 0 && threadIdx.x == 0) {
         double c = 0.0;
         for (int i = 0; i < ncost; ++i) c += cost_part[i];
         part[0] = c;
     }
-    if (idx >= n * n) return;
-    const double* U = Rchain + (size_t)(*s_ptr) * n * n;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    int p = 0;
-    for (; p + 3 < npanels; p += 4) {
-        s0 += Spart[(size_t)p * n * n + idx];
-        s1 += Spart[(size_t)(p + 1) * n * n + idx];
-        s2 += Spart[(size_t)(p + 2) * n * n + idx];
-        s3 += Spart[(size_t)(p + 3) * n * n + idx];
-    }
-    for (; p < npanels; ++p) s0 += Spart[(size_t)p * n * n + idx];
-    part[1 + idx] = (s0 + s1) + (s2 + s3);
-    const int a = idx / n, b = idx % n;
-    double g = 0.0;
-    if (packed) {
-#pragma unroll 8
-        for (int q = 0; q < n; ++q) {
-            const int lo = a < q ? a : q, hi = a < q ? q : a;
-            const int r = hi * (hi + 1) / 2 + lo;
-            const bool own = (r >= row_begin && r < row_end);
-            const int rl = own ? r - row_begin : 0;
-            double f = F1[(size_t)rl * Np + b];
-            if (F2) f += F2[(size_t)rl * Np + b];
-            const double w = own ? 2.0 * U[q * n + b] / sw[r] : 0.0;
-            g = fma(w, f, g);
-        }
-    } else {
-#pragma unroll 8
-        for (int q = 0; q < n; ++q) {
-            const int r1 = a + n * q, r2 = q + n * a;
-            const bool o1 = (r1 >= row_begin && r1 < row_end), o2 = (r2 >= row_begin && r2 < row_end);
-            const int l1 = o1 ? r1 - row_begin : 0, l2 = o2 ? r2 - row_begin : 0;
-            double f1 = F1[(size_t)l1 * Np + b], f2 = F1[(size_t)l2 * Np + b];
-            if (F2) {
-                f1 += F2[(size_t)l1 * Np + b];
-                f2 += F2[(size_t)l2 * Np + b];
+    for (int b0 = 0; b0 < n; b0 += 128) {
+        const int b = b0 + tx;
+        double s = 0.0, g = 0.0;
+        if (b < n) {
+            const size_t o = (size_t)a * n + b;
+            double s0 = 0.0, s1 = 0.0;
+            int p = grp;
+            for (; p + 8 < npanels; p += 16) {
+                s0 += Spart[(size_t)p * n * n + o];
+                s1 += Spart[(size_t)(p + 8) * n * n + o];
             }
-            const double f = (o1 ? f1 : 0.0) + (o2 ? f2 : 0.0);
-            g = fma(U[q * n + b], f, g);
+            if (p < npanels) s0 += Spart[(size_t)p * n * n + o];
+            s = s0 + s1;
+            if (packed) {
+#pragma unroll 4
+                for (int q = grp; q < n; q += 8) {
+                    const int lo = a < q ? a : q, hi = a < q ? q : a;
+                    const int r = hi * (hi + 1) / 2 + lo;
+                    const bool own = (r >= row_begin && r < row_end);
+                    const int rl = own ? r - row_begin : 0;
+                    double f = F1[(size_t)rl * Np + b];
+                    if (F2) f += F2[(size_t)rl * Np + b];
+                    const double w = own ? 2.0 * U[q * n + b] / sw[r] : 0.0;
+                    g = fma(w, f, g);
+                }
+            } else {
+#pragma unroll 4
+                for (int q = grp; q < n; q += 8) {
+                    const int r1 = a + n * q, r2 = q + n * a;
+                    const bool o1 = (r1 >= row_begin && r1 < row_end), o2 = (r2 >= row_begin && r2 < row_end);
+                    const int l1 = o1 ? r1 - row_begin : 0, l2 = o2 ? r2 - row_begin : 0;
+                    double f1 = F1[(size_t)l1 * Np + b], f2 = F1[(size_t)l2 * Np + b];
+                    if (F2) {
+                        f1 += F2[(size_t)l1 * Np + b];
+                        f2 += F2[(size_t)l2 * Np + b];
+                    }
+                    const double f = (o1 ? f1 : 0.0) + (o2 ? f2 : 0.0);
+                    g = fma(U[q * n + b], f, g);
+                }
+            }
         }
+        redS[grp][tx] = s;
+        redG[grp][tx] = g;
+        __syncthreads();
+        if (grp == 0 && b < n) {
+            double ss = 0.0, gg = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                ss += redS[k][tx];
+                gg += redG[k][tx];
+            }
+            part[1 + (size_t)a * n + b] = ss;
+            part[1 + (size_t)n * n + (size_t)a * n + b] = gcoef * gg;
+        }
+        __syncthreads();
     }
-    part[1 + n * n + idx] = gcoef * g;
 }
 
 // ------------------------------------------------------------------------------------------------------
