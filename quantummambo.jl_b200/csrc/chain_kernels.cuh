@@ -6,9 +6,12 @@
 //               (reference: del_u_theta gradient.jl:76-129 contracted as in grad_theta :131-146; `vcat` :148-151).
 //
 // One CTA owns one 16x16 tile of every N x N matrix of the chain; the ~5+s dependent products are separated by a
-// grid-wide barrier (one atomic counter in global memory) instead of kernel boundaries, which removes ~30 launch
-// gaps per evaluation.  Products run on the FP64 tensor pipe (DMMA.8x8x4): 8 warps = 4 (8x8 blocks) x 2 (k halves).
-// The kernels are launched cooperatively (all CTAs co-resident; grid <= 121 CTAs for N <= 168).
+// grid-wide barrier (one counter in global memory) instead of kernel boundaries.  Every matrix that is later a
+// right-hand operand is stored twice (M and M^T), and every matrix has a padded pitch ldm (== 4 mod 16, zero pad), so
+// that each operand of a tile product is ONE contiguous 16 x ldm block: it is fetched by the TMA engine with a single
+// cp.async.bulk (completion on an mbarrier) and lands in shared memory already in a bank-conflict-free layout.  Products run on the FP64 tensor pipe (DMMA.8x8x4) with 16 warps = 4 (8x8 blocks) x 4 (k
+// quarters) and two accumulators per product, which keeps the dependent DMMA chains at ~3.
+// Launched cooperatively (all CTAs co-resident; grid <= 121 CTAs for N <= 168).
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -16,18 +19,21 @@
 namespace chain {
 
 constexpr int CT = 16;       // tile edge
-constexpr int NTHR = 256;    // 8 warps
-constexpr int LDB = 24;      // pitch of a B strip row (16 columns + pad): 192 B == 64 (mod 128) -> conflict-free fragments
+constexpr int KQ = 4;        // k split across warps
+constexpr int NTHR = 4 * KQ * 32;
 constexpr int SMAXC = 14;
+constexpr int NSTRIP = 6;
 
 __constant__ double c_t[17] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
                                1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0,
                                1.0 / 1307674368000.0, 1.0 / 20922789888000.0};
 
+// matrices of the U chain; `*t` = transposed copy
 struct UParams {
     const double* x;
     int n, lam_off, s_override;
-    double *X, *X2, *X4, *P0, *P1, *P2, *Q3, *Q2, *Q1, *R, *Lam;
+    double *X, *Xt, *X2, *X2t, *X4, *P0, *P1, *P2, *Q3t, *Q2t, *Q1t, *R, *Rt;   // pitch ldm, zero padded
+    double *Lam, *U;                                                           // dense n x n outputs
     int* s_out;
     double* scale_out;
     int* status;
@@ -37,23 +43,29 @@ struct DParams {
     const double* part;   // [cost, S, G]
     const double* g1;     // CSA_SD one-body gradient (or null)
     int n, sd;
-    const double *X, *X2, *X4, *Q3, *Q2, *Q1, *R;
-    double *dX2, *dX4, *dP0, *dP1, *dP2, *dQ3, *dQ2, *dQ1, *dR;
+    const double *X, *Xt, *X2, *X2t, *X4, *Q3t, *Q2t, *Q1t, *R, *Rt;
+    double *dX2, *dX2t, *dX4, *dP0, *dP1, *dP2, *dQ3t, *dQ2t, *dQ1t, *dR, *dRt;
     const int* s_in;
     const double* scale_in;
     double* out;          // [cost, grad...]
     unsigned* bar;
+    long long* dbg;       // optional clock64 stamps of CTA 0 (development aid; MAMBO_CHAIN_DEBUG=1)
 };
 
-__host__ __device__ inline int lda_for(int n) { return ((n + 15) / 16) * 16 + 4; }
+// pitch of every chain matrix: smallest ldm >= n with ldm == 4 (mod 16)  (100 -> 100, 152 -> 164)
+__host__ __device__ inline int ldm_for(int n) { return ((n + 11) / 16) * 16 + 4; }
+__host__ __device__ inline int lda_for(int n) { return ldm_for(n); }
+__host__ __device__ inline int rows_pad(int n) { return ((n + CT - 1) / CT) * CT; }
+__host__ __device__ inline size_t mat_stride(int n) { return (size_t)rows_pad(n) * ldm_for(n); }
 __host__ __device__ inline int kpad(int n) { return ((n + 3) / 4) * 4; }
-inline size_t smem_bytes(int n) { return ((size_t)2 * CT * lda_for(n) + (size_t)4 * kpad(n) * LDB + 4 * 32 * 4) * sizeof(double); }
+inline size_t smem_bytes(int n) { return ((size_t)NSTRIP * CT * lda_for(n) + (size_t)(KQ - 1) * 4 * 32 * 4) * sizeof(double) + 64; }
 
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 __device__ __forceinline__ void cp8(double* dst, const double* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -83,69 +95,112 @@ __device__ __forceinline__ void grid_exit(unsigned* bar) {
     }
 }
 
-// rows [i0, i0+16) of a row-major n x n matrix -> As[r*lda + k], zero padded to kpad(n)
-__device__ __forceinline__ void load_a(double* As, const double* __restrict__ M, int n, int i0) {
-    const int lda = lda_for(n), kp = kpad(n);
-    const int r = threadIdx.x >> 4;                 // 16 rows x 16 threads per row: no runtime division
-    const bool rok = i0 + r < n;
-    const double* src = M + (size_t)(i0 + r) * n;
-    for (int k = threadIdx.x & 15; k < kp; k += 16) {
-        if (rok && k < n) cp8(As + r * lda + k, src + k);
-        else As[r * lda + k] = 0.0;
+// ---- strip loader: rows [r0, r0+16) of a chain matrix (pitch ldm, zero padded) -> S, one TMA bulk copy ---------------
+struct Loader {
+    uint64_t* mbar;
+    uint32_t parity;
+    int lda;
+    uint32_t pending;   // bytes expected in the current phase
+    int nissued;        // strips issued in the current phase (the i-th strip is issued by lane 0 of warp i)
+
+    // proxy_fence: needed only when the strips about to be overwritten were last *written* through the generic
+    // proxy (zero fill, operands built in registers); generic reads are ordered by the preceding bar.sync.
+    __device__ __forceinline__ void begin(bool proxy_fence = false) {
+        pending = 0;
+        nissued = 0;
+        if (proxy_fence) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-}
-// columns [j0, j0+16) -> Bs[k*LDB + c]
-__device__ __forceinline__ void load_b(double* Bs, const double* __restrict__ M, int n, int j0) {
-    const int kp = kpad(n);
-    for (int idx = threadIdx.x; idx < CT * kp; idx += NTHR) {
-        const int k = idx / CT, c = idx % CT;
-        if (k < n && j0 + c < n) cp8(Bs + k * LDB + c, M + (size_t)k * n + j0 + c);
-        else Bs[k * LDB + c] = 0.0;
+    __device__ __forceinline__ void rows(double* S, const double* __restrict__ M, int r0) {
+        const uint32_t bytes = (uint32_t)(CT * lda * 8);
+        pending += bytes;
+        if ((int)threadIdx.x == 32 * nissued)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(S)),
+                         "l"(M + (size_t)r0 * lda), "r"(bytes), "r"(s32(mbar))
+                         : "memory");
+        ++nissued;
     }
-}
-// this warp's share (k half) of the 8x8 block product: c += As[block rows] . Bs[block cols]
-__device__ __forceinline__ void mm_half(const double* As, const double* Bs, int n, double& c0, double& c1) {
+    __device__ __forceinline__ void wait() {
+        if (threadIdx.x == 0)
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(mbar)), "r"(pending) : "memory");
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(s32(mbar)), "r"(parity) : "memory");
+        parity ^= 1u;
+    }
+};
+
+// this warp's k quarter of an 8x8 block product, two accumulators: (c, d) += SA[block rows] . SB[block cols]^T
+// SA: [16 rows i][lda] (k contiguous), SB: [16 cols j][lda] (k contiguous)
+__device__ __forceinline__ void mm_q(const double* SA, const double* SB, int lda, int ks, double (&c)[2], double (&d)[2]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t0 = lane & 3, t1 = lane >> 2, b = warp & 3, half = warp >> 2;
-    const int lda = lda_for(n), ks = kpad(n) / 4;
-    const double* a = As + (8 * (b >> 1) + t1) * lda + t0;
-    const double* bb = Bs + t0 * LDB + 8 * (b & 1) + t1;
-    double d0 = 0.0, d1 = 0.0;                       // second accumulator: halves the dependent DMMA chain
-    int kk = half;
-    for (; kk + 2 < ks; kk += 4) {
-        dmma(c0, c1, a[4 * kk], bb[4 * kk * LDB]);
-        dmma(d0, d1, a[4 * (kk + 2)], bb[4 * (kk + 2) * LDB]);
+    const int t0 = lane & 3, t1 = lane >> 2, b = warp & 3, kq = warp >> 2;
+    const double* a = SA + (8 * (b >> 1) + t1) * lda + t0;
+    const double* bb = SB + (8 * (b & 1) + t1) * lda + t0;
+    int kk = kq;
+    for (; kk + KQ < ks; kk += 2 * KQ) {
+        dmma(c[0], c[1], a[4 * kk], bb[4 * kk]);
+        dmma(d[0], d[1], a[4 * (kk + KQ)], bb[4 * (kk + KQ)]);
     }
-    if (kk < ks) dmma(c0, c1, a[4 * kk], bb[4 * kk * LDB]);
-    c0 += d0;
-    c1 += d1;
+    if (kk < ks) dmma(c[0], c[1], a[4 * kk], bb[4 * kk]);
 }
-// combine the two k halves; afterwards warps 0..3 hold the full sums (warps 4..7 must not use them)
+// combine the k quarters; afterwards warps 0..3 hold the full sums
 __device__ __forceinline__ void combine(double* red, double* v, int nv) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp >= 4)
-        for (int i = 0; i < nv; ++i) red[((warp - 4) * 32 + lane) * 4 + i] = v[i];
+        for (int i = 0; i < nv; ++i) red[(((warp >> 2) - 1) * 128 + (warp & 3) * 32 + lane) * 4 + i] = v[i];
     __syncthreads();
     if (warp < 4)
-        for (int i = 0; i < nv; ++i) v[i] += red[(warp * 32 + lane) * 4 + i];
+        for (int q = 0; q < KQ - 1; ++q)
+            for (int i = 0; i < nv; ++i) v[i] += red[((q * 128) + warp * 32 + lane) * 4 + i];
+}
+
+struct Ctx {
+    double* S[NSTRIP];
+    double* red;
+    int n, lda, ks, i0, j0, ei, ej;
+};
+
+__device__ __forceinline__ Ctx make_ctx(double* sm, int n, uint64_t** mbar) {
+    Ctx c;
+    c.n = n;
+    c.lda = lda_for(n);
+    c.ks = kpad(n) / 4;
+    for (int i = 0; i < NSTRIP; ++i) c.S[i] = sm + (size_t)i * CT * c.lda;
+    c.red = sm + (size_t)NSTRIP * CT * c.lda;
+    *mbar = reinterpret_cast<uint64_t*>(c.red + (KQ - 1) * 4 * 32 * 4);
+    c.i0 = blockIdx.y * CT;
+    c.j0 = blockIdx.x * CT;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = warp & 3;
+    c.ei = c.i0 + 8 * (b >> 1) + (lane >> 2);
+    c.ej = c.j0 + 8 * (b & 1) + 2 * (lane & 3);
+    for (int idx = threadIdx.x; idx < NSTRIP * CT * c.lda; idx += NTHR) sm[idx] = 0.0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(*mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    return c;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
-    extern __shared__ double sm[];
-    const int n = p.n, lda = lda_for(n), kp = kpad(n), nn = n * n;
-    double* As0 = sm;
-    double* As1 = As0 + CT * lda;
-    double* Bs0 = As1 + CT * lda;
-    double* Bs1 = Bs0 + kp * LDB;
-    double* red = Bs0 + 4 * kp * LDB;
-    __shared__ double s_red[8];
+    extern __shared__ __align__(128) double sm[];
+    const int n = p.n;
+    const size_t nn = mat_stride(n);
+    uint64_t* mbar;
+    Ctx c = make_ctx(sm, n, &mbar);
+    Loader ld{mbar, 0u, c.lda, 0u, 0};
+    __shared__ double s_red[NTHR / 32];
     __shared__ double s_scale;
     __shared__ int s_s;
-    const int i0 = blockIdx.y * CT, j0 = blockIdx.x * CT;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t0 = lane & 3, t1 = lane >> 2, b = warp & 3;
-    const int ei = i0 + 8 * (b >> 1) + t1, ej = j0 + 8 * (b & 1) + 2 * t0;   // this lane's output elements (ei, ej), (ei, ej+1)
+    const int i0 = c.i0, j0 = c.j0, lda = c.lda, ks = c.ks, ei = c.ei, ej = c.ej;
     const int cL = n * (n + 1) / 2;
     const double* lam = p.x + p.lam_off;
     const double* th = p.x + p.lam_off + cL;
@@ -167,7 +222,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
         __syncthreads();
         if (threadIdx.x == 0) {
             double m = 0.0;
-            for (int w = 0; w < 8; ++w) m = fmax(m, s_red[w]);
+            for (int w = 0; w < NTHR / 32; ++w) m = fmax(m, s_red[w]);
             int s = 0;
             if (m > 1.0) s = (int)ceil(log2(m));
             if (p.s_override >= 0) s = p.s_override;
@@ -190,78 +245,108 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
         if (i >= n || j >= n || i == j) return 0.0;
         return (i < j ? th[(size_t)i * n - (size_t)i * (i + 1) / 2 + (j - i - 1)] : -th[(size_t)j * n - (size_t)j * (j + 1) / 2 + (i - j - 1)]) * sc;
     };
-    // ---- step 1: X2 = X.X with the strips of X built straight from theta --------------------------------------
+    // ---- step 1: X2 = X.X; rows I of X -> S0, columns J of X (as rows of X^T) -> S1, built straight from theta ----
     {
-        const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+        const int r = threadIdx.x >> 5;
 #pragma unroll 4
-        for (int k = c; k < kp; k += 16) As0[r * lda + k] = kval(i0 + r, k);
-#pragma unroll 4
-        for (int k = r; k < kp; k += 16) Bs0[k * LDB + c] = kval(k, j0 + c);
+        for (int k = lane; k < n; k += 32) {
+            c.S[0][r * lda + k] = kval(i0 + r, k);
+            c.S[1][r * lda + k] = kval(k, j0 + r);
+        }
     }
     __syncthreads();
     double v[4] = {0, 0, 0, 0};
-    mm_half(As0, Bs0, n, v[0], v[1]);
-    combine(red, v, 2);
+    {
+        double a2[2] = {0, 0}, b2[2] = {0, 0};
+        mm_q(c.S[0], c.S[1], lda, ks, a2, b2);
+        v[0] = a2[0] + b2[0];
+        v[1] = a2[1] + b2[1];
+    }
+    combine(c.red, v, 2);
     double x1[2] = {0, 0}, x2[2] = {0, 0};
     if (warp < 4) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = ei, j = ej + e;
             if (i < n && j < n) {
-                const int o = i * n + j;
+                const int o = i * lda + j, ot = j * lda + i;
                 x1[e] = kval(i, j);
                 x2[e] = v[e];
                 p.X[o] = x1[e];
+                p.Xt[ot] = x1[e];
                 p.X2[o] = x2[e];
+                p.X2t[ot] = x2[e];
                 const int a = i > j ? i : j, bq = i > j ? j : i;
-                p.Lam[o] = lam[a * (a + 1) / 2 + bq];
+                p.Lam[i * n + j] = lam[a * (a + 1) / 2 + bq];        // Lambda stays dense n x n (read by prep / post kernels)
             }
         }
     }
     grid_barrier(p.bar, target);
-    // ---- step 2: X3 = X2.X, X4 = X2.X2; P0..P2, Q3 ----------------------------------------------------------------
-    load_a(As0, p.X2, n, i0);
-    load_b(Bs1, p.X2, n, j0);     // Bs0 still holds the columns of X
-    cp_wait();
-    __syncthreads();
-    v[0] = v[1] = v[2] = v[3] = 0.0;
-    mm_half(As0, Bs0, n, v[0], v[1]);
-    mm_half(As0, Bs1, n, v[2], v[3]);
-    combine(red, v, 4);
+    // ---- step 2: X3 = X2.X, X4 = X2.X2; P0..P2, Q3 (S1 still holds the columns of X) -----------------------------
+    ld.begin(true);
+    ld.rows(c.S[0], p.X2, i0);
+    ld.rows(c.S[2], p.X2t, j0);
+    ld.wait();
+    {
+        double a3[2] = {0, 0}, b3[2] = {0, 0}, a4[2] = {0, 0}, b4[2] = {0, 0};
+        mm_q(c.S[0], c.S[1], lda, ks, a3, b3);
+        mm_q(c.S[0], c.S[2], lda, ks, a4, b4);
+        v[0] = a3[0] + b3[0];
+        v[1] = a3[1] + b3[1];
+        v[2] = a4[0] + b4[0];
+        v[3] = a4[1] + b4[1];
+    }
+    combine(c.red, v, 4);
     if (warp < 4) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = ei, j = ej + e;
             if (i < n && j < n) {
-                const int o = i * n + j;
+                const int o = i * lda + j, ot = j * lda + i;
                 const double id = (i == j) ? 1.0 : 0.0, x3 = v[e], x4 = v[2 + e];
                 p.X4[o] = x4;
                 p.P0[o] = c_t[0] * id + c_t[1] * x1[e] + c_t[2] * x2[e] + c_t[3] * x3;
                 p.P1[o] = c_t[4] * id + c_t[5] * x1[e] + c_t[6] * x2[e] + c_t[7] * x3;
                 p.P2[o] = c_t[8] * id + c_t[9] * x1[e] + c_t[10] * x2[e] + c_t[11] * x3;
-                p.Q3[o] = c_t[12] * id + c_t[13] * x1[e] + c_t[14] * x2[e] + c_t[15] * x3 + c_t[16] * x4;
+                p.Q3t[ot] = c_t[12] * id + c_t[13] * x1[e] + c_t[14] * x2[e] + c_t[15] * x3 + c_t[16] * x4;
             }
         }
     }
     grid_barrier(p.bar, target);
     // ---- steps 3-5: Q2 = P2 + X4.Q3, Q1 = P1 + X4.Q2, R0 = P0 + X4.Q1 (rows of X4 loaded once) ---------------------
-    load_a(As0, p.X4, n, i0);
     {
-        const double* Bsrc[3] = {p.Q3, p.Q2, p.Q1};
+        const double* Bsrc[3] = {p.Q3t, p.Q2t, p.Q1t};
         const double* Csrc[3] = {p.P2, p.P1, p.P0};
-        double* Cdst[3] = {p.Q2, p.Q1, p.R};
         for (int st = 0; st < 3; ++st) {
-            load_b(Bs0, Bsrc[st], n, j0);
-            cp_wait();
-            __syncthreads();
-            v[0] = v[1] = 0.0;
-            mm_half(As0, Bs0, n, v[0], v[1]);
-            combine(red, v, 2);
+            ld.begin(st == 0);
+            if (st == 0) ld.rows(c.S[0], p.X4, i0);
+            ld.rows(c.S[1], Bsrc[st], j0);
+            double cin[2] = {0, 0};
+            if (warp < 4) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (ei < n && ej + e < n) cin[e] = Csrc[st][ei * lda + ej + e];
+            }
+            ld.wait();
+            double a2[2] = {0, 0}, b2[2] = {0, 0};
+            mm_q(c.S[0], c.S[1], lda, ks, a2, b2);
+            v[0] = a2[0] + b2[0];
+            v[1] = a2[1] + b2[1];
+            combine(c.red, v, 2);
             if (warp < 4) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int i = ei, j = ej + e;
-                    if (i < n && j < n) Cdst[st][i * n + j] = v[e] + Csrc[st][i * n + j];
+                    if (i < n && j < n) {
+                        const double val = v[e] + cin[e];
+                        if (st == 0) p.Q2t[j * lda + i] = val;
+                        else if (st == 1) p.Q1t[j * lda + i] = val;
+                        else {
+                            p.R[i * lda + j] = val;
+                            p.Rt[j * lda + i] = val;
+                            if (s == 0) p.U[i * n + j] = val;
+                        }
+                    }
                 }
             }
             grid_barrier(p.bar, target);
@@ -269,19 +354,24 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
     }
     // ---- s squarings: R[q+1] = R[q].R[q] -------------------------------------------------------------------------
     for (int q = 0; q < s; ++q) {
-        const double* Rq = p.R + (size_t)q * nn;
-        load_a(As0, Rq, n, i0);
-        load_b(Bs0, Rq, n, j0);
-        cp_wait();
-        __syncthreads();
-        v[0] = v[1] = 0.0;
-        mm_half(As0, Bs0, n, v[0], v[1]);
-        combine(red, v, 2);
+        ld.begin();
+        ld.rows(c.S[0], p.R + (size_t)q * nn, i0);
+        ld.rows(c.S[1], p.Rt + (size_t)q * nn, j0);
+        ld.wait();
+        double a2[2] = {0, 0}, b2[2] = {0, 0};
+        mm_q(c.S[0], c.S[1], lda, ks, a2, b2);
+        v[0] = a2[0] + b2[0];
+        v[1] = a2[1] + b2[1];
+        combine(c.red, v, 2);
         if (warp < 4) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int i = ei, j = ej + e;
-                if (i < n && j < n) p.R[(size_t)(q + 1) * nn + i * n + j] = v[e];
+                if (i < n && j < n) {
+                    p.R[(size_t)(q + 1) * nn + i * lda + j] = v[e];
+                    p.Rt[(size_t)(q + 1) * nn + j * lda + i] = v[e];
+                    if (q == s - 1) p.U[i * n + j] = v[e];            // dense copy of U = exp(K) for the other kernels
+                }
             }
         }
         grid_barrier(p.bar, target);
@@ -291,41 +381,44 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
 
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
-    extern __shared__ double sm[];
-    const int n = p.n, lda = lda_for(n), kp = kpad(n), nn = n * n;
-    double* As0 = sm;
-    double* As1 = As0 + CT * lda;
-    double* Bs0 = As1 + CT * lda;
-    double* Bs1 = Bs0 + kp * LDB;
-    double* Bs2 = Bs1 + kp * LDB;
-    double* Bs3 = Bs2 + kp * LDB;
-    double* red = Bs0 + 4 * kp * LDB;
-    const int i0 = blockIdx.y * CT, j0 = blockIdx.x * CT;
+    extern __shared__ __align__(128) double sm[];
+    const int n = p.n;
+    const size_t nn = mat_stride(n);
+    uint64_t* mbar;
+    Ctx c = make_ctx(sm, n, &mbar);
+    Loader ld{mbar, 0u, c.lda, 0u, 0};
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[91] = clock64();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t0 = lane & 3, t1 = lane >> 2, b = warp & 3;
-    const int ei = i0 + 8 * (b >> 1) + t1, ej = j0 + 8 * (b & 1) + 2 * t0;
+    const int i0 = c.i0, j0 = c.j0, lda = c.lda, ks = c.ks, ei = c.ei, ej = c.ej;
     const int s = *p.s_in;
     const double sc = *p.scale_in;
-    const double* G = p.part + 1 + nn;
+    const double* G = p.part + 1 + (size_t)n * n;
     unsigned target = 0;
     auto dxval = [&](int i, int j) -> double { return (i < n && j < n) ? G[(size_t)j * n + i] * sc : 0.0; };   // dX = G^T 2^-s
+    double v[4];
 
-    // ---- step 1: dX2 = dX.X + X.dX --------------------------------------------------------------------------------
+    // ---- step 1: dX2 = dX.X + X.dX : S0 = rows of dX, S1 = rows of X, S2 = cols of X, S3 = cols of dX --------------
+    ld.begin(true);
+    ld.rows(c.S[1], p.X, i0);
+    ld.rows(c.S[2], p.Xt, j0);
     {
-        const int r = threadIdx.x >> 4, c = threadIdx.x & 15;
+        const int r = threadIdx.x >> 5;
 #pragma unroll 4
-        for (int k = c; k < kp; k += 16) As0[r * lda + k] = dxval(i0 + r, k);
-#pragma unroll 4
-        for (int k = r; k < kp; k += 16) Bs1[k * LDB + c] = dxval(k, j0 + c);
+        for (int k = lane; k < n; k += 32) {
+            c.S[0][r * lda + k] = dxval(i0 + r, k);
+            c.S[3][r * lda + k] = dxval(k, j0 + r);
+        }
     }
-    load_a(As1, p.X, n, i0);
-    load_b(Bs0, p.X, n, j0);
-    cp_wait();
     __syncthreads();
-    double v[4] = {0, 0, 0, 0};
-    mm_half(As0, Bs0, n, v[0], v[1]);   // dX.X
-    mm_half(As1, Bs1, n, v[0], v[1]);   // X.dX
-    combine(red, v, 2);
+    ld.wait();
+    {
+        double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
+        mm_q(c.S[0], c.S[2], lda, ks, a1, b1);   // dX.X
+        mm_q(c.S[1], c.S[3], lda, ks, a2, b2);   // X.dX
+        v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
+        v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
+    }
+    combine(c.red, v, 2);
     double d1[2] = {0, 0}, d2[2] = {0, 0};
     if (warp < 4) {
 #pragma unroll
@@ -334,101 +427,137 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
             if (i < n && j < n) {
                 d1[e] = dxval(i, j);
                 d2[e] = v[e];
-                p.dX2[i * n + j] = v[e];
+                p.dX2[i * lda + j] = v[e];
+                p.dX2t[j * lda + i] = v[e];
             }
         }
     }
     grid_barrier(p.bar, target);
     // ---- step 2: dX3 = dX2.X + X2.dX ; dX4 = dX2.X2 + X2.dX2 ; dP0..dP2, dQ3 -----------------------------------------
-    // Bs0 = cols of X (kept), Bs1 = cols of dX (kept); As0 <- rows of dX2, As1 <- rows of X2, Bs2 <- cols X2, Bs3 <- cols dX2
-    __syncthreads();
-    load_a(As0, p.dX2, n, i0);
-    load_a(As1, p.X2, n, i0);
-    load_b(Bs2, p.X2, n, j0);
-    load_b(Bs3, p.dX2, n, j0);
-    cp_wait();
-    __syncthreads();
-    v[0] = v[1] = v[2] = v[3] = 0.0;
-    mm_half(As0, Bs0, n, v[0], v[1]);   // dX2.X
-    mm_half(As1, Bs1, n, v[0], v[1]);   // X2.dX
-    mm_half(As0, Bs2, n, v[2], v[3]);   // dX2.X2
-    mm_half(As1, Bs3, n, v[2], v[3]);   // X2.dX2
-    combine(red, v, 4);
+    // kept: S2 = cols X, S3 = cols dX.  S0 <- rows dX2, S1 <- rows X2, S4 <- cols X2, S5 <- cols dX2
+    ld.begin(true);
+    ld.rows(c.S[0], p.dX2, i0);
+    ld.rows(c.S[1], p.X2, i0);
+    ld.rows(c.S[4], p.X2t, j0);
+    ld.rows(c.S[5], p.dX2t, j0);
+    ld.wait();
+    {
+        double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
+        mm_q(c.S[0], c.S[2], lda, ks, a1, b1);   // dX2.X
+        mm_q(c.S[1], c.S[3], lda, ks, a2, b2);   // X2.dX
+        v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
+        v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
+        double a3[2] = {0, 0}, b3[2] = {0, 0}, a4[2] = {0, 0}, b4[2] = {0, 0};
+        mm_q(c.S[0], c.S[4], lda, ks, a3, b3);   // dX2.X2
+        mm_q(c.S[1], c.S[5], lda, ks, a4, b4);   // X2.dX2
+        v[2] = (a3[0] + b3[0]) + (a4[0] + b4[0]);
+        v[3] = (a3[1] + b3[1]) + (a4[1] + b4[1]);
+    }
+    combine(c.red, v, 4);
     if (warp < 4) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = ei, j = ej + e;
             if (i < n && j < n) {
-                const int o = i * n + j;
+                const int o = i * lda + j, ot = j * lda + i;
                 const double d3 = v[e], d4 = v[2 + e];
                 p.dX4[o] = d4;
                 p.dP0[o] = c_t[1] * d1[e] + c_t[2] * d2[e] + c_t[3] * d3;
                 p.dP1[o] = c_t[5] * d1[e] + c_t[6] * d2[e] + c_t[7] * d3;
                 p.dP2[o] = c_t[9] * d1[e] + c_t[10] * d2[e] + c_t[11] * d3;
-                p.dQ3[o] = c_t[13] * d1[e] + c_t[14] * d2[e] + c_t[15] * d3 + c_t[16] * d4;
+                p.dQ3t[ot] = c_t[13] * d1[e] + c_t[14] * d2[e] + c_t[15] * d3 + c_t[16] * d4;
             }
         }
     }
     grid_barrier(p.bar, target);
     // ---- steps 3-5: dQ2 = dP2 + dX4.Q3 + X4.dQ3 ; dQ1 = dP1 + dX4.Q2 + X4.dQ2 ; dR0 = dP0 + dX4.Q1 + X4.dQ1 ----------
-    load_a(As0, p.dX4, n, i0);
-    load_a(As1, p.X4, n, i0);
     {
-        const double* B1[3] = {p.Q3, p.Q2, p.Q1};
-        const double* B2[3] = {p.dQ3, p.dQ2, p.dQ1};
+        const double* B1[3] = {p.Q3t, p.Q2t, p.Q1t};
+        const double* B2[3] = {p.dQ3t, p.dQ2t, p.dQ1t};
         const double* Csrc[3] = {p.dP2, p.dP1, p.dP0};
-        double* Cdst[3] = {p.dQ2, p.dQ1, p.dR};
         for (int st = 0; st < 3; ++st) {
-            load_b(Bs0, B1[st], n, j0);
-            load_b(Bs1, B2[st], n, j0);
-            cp_wait();
-            __syncthreads();
-            v[0] = v[1] = 0.0;
-            mm_half(As0, Bs0, n, v[0], v[1]);
-            mm_half(As1, Bs1, n, v[0], v[1]);
-            combine(red, v, 2);
+            ld.begin(st == 0);
+            if (st == 0) {
+                ld.rows(c.S[0], p.dX4, i0);
+                ld.rows(c.S[1], p.X4, i0);
+            }
+            ld.rows(c.S[2], B1[st], j0);
+            ld.rows(c.S[3], B2[st], j0);
+            double cin[2] = {0, 0};
+            if (warp < 4) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e)
+                    if (ei < n && ej + e < n) cin[e] = Csrc[st][ei * lda + ej + e];
+            }
+            ld.wait();
+            double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
+            mm_q(c.S[0], c.S[2], lda, ks, a1, b1);
+            mm_q(c.S[1], c.S[3], lda, ks, a2, b2);
+            v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
+            v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
+            combine(c.red, v, 2);
             if (warp < 4) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int i = ei, j = ej + e;
-                    if (i < n && j < n) Cdst[st][i * n + j] = v[e] + Csrc[st][i * n + j];
+                    if (i < n && j < n) {
+                        const double val = v[e] + cin[e];
+                        if (st == 0) p.dQ2t[j * lda + i] = val;
+                        else if (st == 1) p.dQ1t[j * lda + i] = val;
+                        else {
+                            p.dR[i * lda + j] = val;
+                            p.dRt[j * lda + i] = val;
+                        }
+                    }
                 }
             }
             grid_barrier(p.bar, target);
         }
     }
     // ---- s squarings: dR[q+1] = dR[q].R[q] + R[q].dR[q] ---------------------------------------------------------------
+    const bool dbg = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+    if (dbg) p.dbg[90] = clock64();
     for (int q = 0; q < s; ++q) {
-        const double* Rq = p.R + (size_t)q * nn;
-        const double* dRq = p.dR + (size_t)q * nn;
-        load_a(As0, dRq, n, i0);
-        load_a(As1, Rq, n, i0);
-        load_b(Bs0, Rq, n, j0);
-        load_b(Bs1, dRq, n, j0);
-        cp_wait();
-        __syncthreads();
-        v[0] = v[1] = 0.0;
-        mm_half(As0, Bs0, n, v[0], v[1]);
-        mm_half(As1, Bs1, n, v[0], v[1]);
-        combine(red, v, 2);
+        if (dbg) p.dbg[q * 6 + 0] = clock64();
+        ld.begin();
+        ld.rows(c.S[0], p.dR + (size_t)q * nn, i0);
+        ld.rows(c.S[1], p.R + (size_t)q * nn, i0);
+        ld.rows(c.S[2], p.Rt + (size_t)q * nn, j0);
+        ld.rows(c.S[3], p.dRt + (size_t)q * nn, j0);
+        if (dbg) p.dbg[q * 6 + 1] = clock64();
+        ld.wait();
+        if (dbg) p.dbg[q * 6 + 2] = clock64();
+        double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
+        mm_q(c.S[0], c.S[2], lda, ks, a1, b1);
+        mm_q(c.S[1], c.S[3], lda, ks, a2, b2);
+        v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
+        v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
+        if (dbg) p.dbg[q * 6 + 3] = clock64();
+        combine(c.red, v, 2);
         if (warp < 4) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int i = ei, j = ej + e;
-                if (i < n && j < n) p.dR[(size_t)(q + 1) * nn + i * n + j] = v[e];
+                if (i < n && j < n) {
+                    p.dR[(size_t)(q + 1) * nn + i * lda + j] = v[e];
+                    p.dRt[(size_t)(q + 1) * nn + j * lda + i] = v[e];
+                }
             }
         }
+        if (dbg) p.dbg[q * 6 + 4] = clock64();
         grid_barrier(p.bar, target);
+        if (dbg) p.dbg[q * 6 + 5] = clock64();
     }
     // ---- gradient in x order (gradient.jl:148-151, 287-290): out = [cost, (g1), g_lambda, g_theta] -------------------
     {
         const double* Lt = p.dR + (size_t)s * nn;
+        const double* Ltt = p.dRt + (size_t)s * nn;
         const int cL = n * (n + 1) / 2, off = p.sd ? n : 0;
-        for (int idx = threadIdx.x; idx < CT * CT; idx += NTHR) {
-            const int i = i0 + idx / CT, j = j0 + idx % CT;
+        if (threadIdx.x < CT * CT) {
+            const int i = i0 + threadIdx.x / CT, j = j0 + threadIdx.x % CT;
             if (i < n && j < n) {
                 if (j <= i) p.out[1 + off + i * (i + 1) / 2 + j] = 2.0 * p.part[1 + i * n + j] * (i != j ? 2.0 : 1.0);
-                else p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (Lt[j * n + i] - Lt[i * n + j]);
+                else p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (Ltt[i * lda + j] - Lt[i * lda + j]);
             }
         }
         if (blockIdx.x == 0 && blockIdx.y == 0) {
@@ -437,6 +566,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
                 for (int k = threadIdx.x; k < n; k += NTHR) p.out[1 + k] = p.g1[k];
         }
     }
+    if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[92] = clock64();
     grid_exit(p.bar);
 }
 

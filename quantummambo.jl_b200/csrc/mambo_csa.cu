@@ -74,9 +74,16 @@ struct mambo_csa {
     double* mats = nullptr;                    // all N x N matrices of the expm chains
     double *X, *X2, *X3, *X4, *P0, *P1, *P2, *Q3, *Q2, *Q1, *R;      // R: (SMAX+1) matrices
     double *dX, *dX2, *dX4, *dP0, *dP1, *dP2, *dQ3, *dQ2, *dQ1, *dR; // dR: (SMAX+1) matrices
+    // persistent-chain kernels: padded-pitch matrices (chain::mat_stride each) and their transposed copies
+    double* cmats = nullptr;
+    chain::UParams cu;
+    chain::DParams cd;
+    double* U = nullptr;                       // dense n x n copy of exp(K) written by k_chain_u
+    int* d_zero = nullptr;
     double *Lam = nullptr, *Dh = nullptr, *DU = nullptr, *hfrag = nullptr, *g1 = nullptr;
     int* d_s = nullptr;
     unsigned* d_bar = nullptr;                 // grid-barrier counters of the persistent chain kernels
+    long long* d_dbg = nullptr;                // MAMBO_CHAIN_DEBUG=1: clock64 stamps of the derivative chain
     bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
     bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
     double* d_scale = nullptr;
@@ -233,10 +240,9 @@ int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host);
 int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
     if (!h->use_chain) return enqueue_unitary_legacy(h, d_x, s_host);
     const int n = h->N, tiles = (n + chain::CT - 1) / chain::CT;
-    chain::UParams p;
+    chain::UParams p = h->cu;
     p.x = d_x; p.n = n; p.lam_off = h->lam_off; p.s_override = s_host;
-    p.X = h->X; p.X2 = h->X2; p.X4 = h->X4; p.P0 = h->P0; p.P1 = h->P1; p.P2 = h->P2; p.Q3 = h->Q3; p.Q2 = h->Q2; p.Q1 = h->Q1;
-    p.R = h->R; p.Lam = h->Lam; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
+    p.Lam = h->Lam; p.U = h->U; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
     void* args[] = {&p};
     TRY(launch_coop((const void*)chain::k_chain_u, dim3(tiles, tiles), dim3(chain::NTHR), chain::smem_bytes(n), h->stream, args));
     h->launches++;
@@ -270,11 +276,15 @@ int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host) {
         default: { constexpr int NCH = 6; CALL; break; } \
     }
 
+// exp(K) for the kernels outside the chain: dense copy (chain kernels) or R[s] of the legacy launch-per-product chain
+const double* u_base(const mambo_csa* h) { return h->use_chain ? h->U : h->R; }
+const int* u_sptr(const mambo_csa* h) { return h->use_chain ? h->d_zero : h->d_s; }
+
 int enqueue_prep(mambo_csa* h) {
     const int blocks = h->nRpad / small::PREP_ROWS;
     NCH_DISPATCH((h->Np + 31) / 32,
                  (small::k_prep<NCH><<<blocks, 256, small::prep_smem(h->N, h->Np), h->stream>>>(
-                     h->R, h->d_s, h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld, h->nRpad, h->row_begin, h->row_end, h->At, h->Bt)));
+                     u_base(h), u_sptr(h), h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld, h->nRpad, h->row_begin, h->row_end, h->At, h->Bt)));
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
@@ -298,7 +308,7 @@ int enqueue_post_sr(mambo_csa* h) {
     small::k_post_s<<<dim3(h->P, nch * nch), 256, small::posts_smem(h->Np), h->stream>>>(h->Et, h->At, n, h->Np, h->ld, h->row_begin, h->Spart);
     (void)nn;
     small::k_post_reduce<<<n, 1024, 0, h->stream>>>(h->cost_part, h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
-                                                                 h->sw, h->R, h->d_s, n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
+                                                                 h->sw, u_base(h), u_sptr(h), n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
                                                                  h->row_begin, std::min(h->row_end, h->nR), h->d_part);
     h->launches += 2;
     CU(cudaGetLastError());
@@ -309,16 +319,14 @@ int enqueue_post_sr(mambo_csa* h) {
 int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
     const int n = h->N, nn = n * n;
     if (h->flavour == MAMBO_CSA_SD) {
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->R, h->d_s, n, h->d_part, h->g1, h->Dh, h->DU, nullptr);
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, u_base(h), u_sptr(h), n, h->d_part, h->g1, h->Dh, h->DU, nullptr);
         h->launches++;
     }
     if (h->use_chain) {
         const int tiles = (n + chain::CT - 1) / chain::CT;
-        chain::DParams p;
+        chain::DParams p = h->cd;
         p.part = h->d_part; p.g1 = h->g1; p.n = n; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0;
-        p.X = h->X; p.X2 = h->X2; p.X4 = h->X4; p.Q3 = h->Q3; p.Q2 = h->Q2; p.Q1 = h->Q1; p.R = h->R;
-        p.dX2 = h->dX2; p.dX4 = h->dX4; p.dP0 = h->dP0; p.dP1 = h->dP1; p.dP2 = h->dP2; p.dQ3 = h->dQ3; p.dQ2 = h->dQ2; p.dQ1 = h->dQ1;
-        p.dR = h->dR; p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar;
+        p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar; p.dbg = h->d_dbg;
         void* args[] = {&p};
         TRY(launch_coop((const void*)chain::k_chain_d, dim3(tiles, tiles), dim3(chain::NTHR), chain::smem_bytes(n), h->stream, args));
         h->launches++;
@@ -398,7 +406,7 @@ int enqueue_partial(mambo_csa* h, int s_host, bool need_grad) {
         TRY((launch_fused<false, false>(h, p)));
         return run_segment(h, h->g_costonly, [&]() -> int {
             if (h->flavour == MAMBO_CSA_SD) {
-                small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
+                small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, u_base(h), u_sptr(h), h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
                 small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->cost_part, h->G, h->d_part);
                 h->launches += 2;
             } else {
@@ -638,9 +646,28 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->dP0 = take(1); h->dP1 = take(1); h->dP2 = take(1); h->dQ3 = take(1); h->dQ2 = take(1); h->dQ1 = take(1);
     h->dR = take(small::SMAX + 1);
     h->Lam = take(1); h->Dh = take(1); h->DU = take(1); h->hfrag = take(1);
+    TRY(dalloc(&h->U, nn));
+    TRY(dalloc(&h->d_zero, 1));
+    {
+        const size_t ms = chain::mat_stride(n);
+        const size_t ncm = 11 + 11 + 4 * (size_t)(chain::SMAXC + 1);
+        TRY(dalloc(&h->cmats, ncm * ms));
+        double* cm = h->cmats;
+        auto ctake = [&](size_t k) { double* r = cm; cm += k * ms; return r; };
+        chain::UParams& u = h->cu;
+        u.X = ctake(1); u.Xt = ctake(1); u.X2 = ctake(1); u.X2t = ctake(1); u.X4 = ctake(1);
+        u.P0 = ctake(1); u.P1 = ctake(1); u.P2 = ctake(1); u.Q3t = ctake(1); u.Q2t = ctake(1); u.Q1t = ctake(1);
+        u.R = ctake(chain::SMAXC + 1); u.Rt = ctake(chain::SMAXC + 1);
+        chain::DParams& d = h->cd;
+        d.X = u.X; d.Xt = u.Xt; d.X2 = u.X2; d.X2t = u.X2t; d.X4 = u.X4; d.Q3t = u.Q3t; d.Q2t = u.Q2t; d.Q1t = u.Q1t; d.R = u.R; d.Rt = u.Rt;
+        d.dX2 = ctake(1); d.dX2t = ctake(1); d.dX4 = ctake(1); d.dP0 = ctake(1); d.dP1 = ctake(1); d.dP2 = ctake(1);
+        d.dQ3t = ctake(1); d.dQ2t = ctake(1); d.dQ1t = ctake(1); (void)ctake(2);
+        d.dR = ctake(chain::SMAXC + 1); d.dRt = ctake(chain::SMAXC + 1);
+    }
     TRY(dalloc(&h->g1, (size_t)n));
     TRY(dalloc(&h->d_s, 1));
     TRY(dalloc(&h->d_bar, 2));
+    if (std::getenv("MAMBO_CHAIN_DEBUG")) TRY(dalloc(&h->d_dbg, 6 * 16));
     TRY(dalloc(&h->d_scale, 1));
     TRY(dalloc(&h->d_status, 1));
     TRY(dalloc(&h->d_x, (size_t)h->L));
@@ -699,7 +726,7 @@ int subtract_impl(mambo_csa* h, const double* d_x, int s_host) {
     }
     const int n = h->N, nn = n * n;
     if (h->flavour == MAMBO_CSA_SD) {
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->R, h->d_s, n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, u_base(h), u_sptr(h), n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
         small::k_obt_sub<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->hT, h->hfrag, n);
         small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, nn, h->cost_part, h->G, h->d_part);
         h->launches += 3;
@@ -769,7 +796,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
-                    h->visit_start, h->piece_first, h->mats, h->g1, h->d_s, h->d_bar, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
+                    h->visit_start, h->piece_first, h->mats, h->cmats, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_x) cudaFreeHost(h->h_x);
@@ -872,6 +899,12 @@ int mambo_csa_get_segments(mambo_csa* h, double* seg_ms, int* evals) {
         }
     if (evals) *evals = n;
     h->seg_used = 0;
+    return MAMBO_OK;
+}
+
+int mambo_csa_debug_stamps(mambo_csa* h, long long* out96) {
+    if (!h || !h->d_dbg) return fail(MAMBO_ESTATE, "set MAMBO_CHAIN_DEBUG=1 before create");
+    CU(cudaMemcpy(out96, h->d_dbg, sizeof(long long) * 96, cudaMemcpyDeviceToHost));
     return MAMBO_OK;
 }
 
@@ -1005,7 +1038,7 @@ int mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double
     }
     if (obt_out && h->flavour == MAMBO_CSA_SD) {
         // h = U diag(l1) U^T: reuse the one-body kernel against the stored target, keep h in hfrag
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->R, h->d_s, n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, u_base(h), u_sptr(h), n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
         small::k_obt_colmajor<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->hfrag, n, h->Dh);
         CU(cudaMemcpyAsync(obt_out, h->Dh, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));

@@ -254,6 +254,14 @@ __device__ __forceinline__ void rows4_times_lambda(const double* __restrict__ ro
 // Lambda (row-major n x n in global memory) -> shared [n][Np], columns >= n zero; one wave of async copies
 __device__ __forceinline__ void stage_lambda(double* sL, const double* __restrict__ Lam, int n, int Np) {
     const int c0 = threadIdx.x & 31, r0 = threadIdx.x >> 5, nr = blockDim.x >> 5;
+    if ((n & 1) == 0) {   // 16-byte async copies (rows of Lambda are 16-byte aligned when n is even; Np is a multiple of 8)
+        for (int l = r0; l < n; l += nr)
+            for (int m = 2 * c0; m < Np; m += 64) {
+                if (m < n) cp_async16(sL + (size_t)l * Np + m, Lam + (size_t)l * n + m);
+                else sL[(size_t)l * Np + m] = sL[(size_t)l * Np + m + 1] = 0.0;
+            }
+        return;
+    }
     for (int l = r0; l < n; l += nr)
         for (int m = c0; m < Np; m += 32) {
             if (m < n) cp_async8(sL + (size_t)l * Np + m, Lam + (size_t)l * n + m);
@@ -459,12 +467,12 @@ __global__ void __launch_bounds__(256) k_post_s(const double* __restrict__ Et, c
     const int panel = blockIdx.x;
     const int nch = (n + 63) / 64;
     const int i0 = (blockIdx.y / nch) * 64, j0 = (blockIdx.y % nch) * 64;
-    for (int idx = threadIdx.x; idx < 64 * 64; idx += blockDim.x) {
-        const int rr = idx >> 6, c = idx & 63;
-        if (j0 + c < Np) cp_async8(sE + idx, Et + (size_t)(panel * 64 + rr) * Np + j0 + c);
-        else sE[idx] = 0.0;
-        if (i0 + c < Np) cp_async8(sAp + idx, At + (size_t)(row_begin + panel * 64 + rr) * ld + i0 + c);
-        else sAp[idx] = 0.0;
+    for (int idx = threadIdx.x; idx < 64 * 32; idx += blockDim.x) {   // 16-byte chunks: Np, ld, i0, j0 are all even
+        const int rr = idx >> 5, c = (idx & 31) * 2;
+        if (j0 + c < Np) cp_async16(sE + rr * 64 + c, Et + (size_t)(panel * 64 + rr) * Np + j0 + c);
+        else sE[rr * 64 + c] = sE[rr * 64 + c + 1] = 0.0;
+        if (i0 + c < Np) cp_async16(sAp + rr * 64 + c, At + (size_t)(row_begin + panel * 64 + rr) * ld + i0 + c);
+        else sAp[rr * 64 + c] = sAp[rr * 64 + c + 1] = 0.0;
     }
     cp_async_wait_all();
     __syncthreads();
