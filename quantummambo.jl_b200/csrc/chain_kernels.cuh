@@ -69,7 +69,9 @@ __device__ __forceinline__ void cp8(double* dst, const double* src) {
 }
 __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// Grid-wide barrier: release-reduction on arrival, relaxed (L2) polling, one acquire fence on the way out.
+// Grid-wide barrier: release-reduction on arrival, acquire polling at L2.  Data produced by other CTAs is afterwards
+// read only through L2 (TMA bulk copies and ld.global.cg), never through this SM's L1, so no L1 invalidation
+// (fence.acq_rel.gpu -> CCTL.IVALL) is paid per barrier.
 __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
     __syncthreads();
     target += gridDim.x * gridDim.y;
@@ -79,7 +81,6 @@ __device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
         do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         } while (v < target);
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
     __syncthreads();
 }
@@ -557,7 +558,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
             const int i = i0 + threadIdx.x / CT, j = j0 + threadIdx.x % CT;
             if (i < n && j < n) {
                 if (j <= i) p.out[1 + off + i * (i + 1) / 2 + j] = 2.0 * p.part[1 + i * n + j] * (i != j ? 2.0 : 1.0);
-                else p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (Ltt[i * lda + j] - Lt[i * lda + j]);
+                else p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (__ldcg(Ltt + i * lda + j) - __ldcg(Lt + i * lda + j));
             }
         }
         if (blockIdx.x == 0 && blockIdx.y == 0) {
