@@ -94,12 +94,25 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------------
+def use_all_host_threads() -> int:
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core, so lift the BLAS pool
+    limit at run time and report the thread count actually in force."""
+    cores = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=cores)
+        blas = [p["num_threads"] for p in threadpool_info() if p.get("user_api") == "blas"]
+        return max(blas) if blas else cores
+    except Exception:
+        return int(os.environ.get("OMP_NUM_THREADS", cores))
+
+
 def cpu_reference_rate(n: int, T, xs, budget_s: float, max_evals: int):
     """The reference algorithm on the host cores: the oracle's factored restatement (numpy/OpenBLAS, all
     threads).  Returns (evals_per_s, evals_timed, cores)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import csa_oracle as oracle  # noqa: E402  (checker / baseline only -- never on the product path)
-    cores = os.cpu_count() or 1
+    cores = use_all_host_threads()
     oracle.cost_grad_factored(xs[0], T)  # warm-up (BLAS thread pool, page faults)
     t0 = time.perf_counter()
     done = 0
@@ -124,6 +137,7 @@ def run_reference(args, rank: int):
     xs = [syn.random_x(n, i) for i in range(BATCH)]
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import csa_oracle as oracle
+    cores = use_all_host_threads()
     for _ in range(max(args.warmup, 1)):
         oracle.cost_grad_factored(xs[0], T)
     # each step: a bounded sample of the BATCH-point workload (2 of the 8 points), so K steps stay within minutes
@@ -135,7 +149,6 @@ def run_reference(args, rank: int):
     dt = time.perf_counter() - t0
     evals = args.steps * sample
     v = evals / dt
-    cores = os.cpu_count() or 1
     line = {
         "impl": "reference", "metric": "csa_cost_grad_evals_per_s", "value": v, "unit": "evals/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,

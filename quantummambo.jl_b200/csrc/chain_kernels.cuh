@@ -34,6 +34,8 @@ struct UParams {
     int n, lam_off, s_override;
     double *X, *Xt, *X2, *X2t, *X4, *P0, *P1, *P2, *Q3t, *Q2t, *Q1t, *R, *Rt;   // pitch ldm, zero padded
     double *Lam, *U;                                                           // dense n x n outputs
+    double* LamP;                                                              // optional padded copy [Np][ldl] for the panel GEMMs
+    int ldl;
     int* s_out;
     double* scale_out;
     int* status;
@@ -278,7 +280,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
                 p.X2[o] = x2[e];
                 p.X2t[ot] = x2[e];
                 const int a = i > j ? i : j, bq = i > j ? j : i;
-                p.Lam[i * n + j] = lam[a * (a + 1) / 2 + bq];        // Lambda stays dense n x n (read by prep / post kernels)
+                const double lv = lam[a * (a + 1) / 2 + bq];
+                p.Lam[i * n + j] = lv;                               // dense n x n (FMA epilogues)
+                if (p.LamP) p.LamP[i * p.ldl + j] = lv;              // padded pitch (tensor-core panel GEMMs)
             }
         }
     }

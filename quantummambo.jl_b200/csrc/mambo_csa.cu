@@ -15,6 +15,7 @@
 #include "fused_kernel.cuh"
 #include "small_kernels.cuh"
 #include "chain_kernels.cuh"
+#include "panel_kernels.cuh"
 
 namespace {
 
@@ -86,6 +87,8 @@ struct mambo_csa {
     long long* d_dbg = nullptr;                // MAMBO_CHAIN_DEBUG=1: clock64 stamps of the derivative chain
     bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
     bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
+    bool use_panel = false;                    // tensor-core panel GEMMs for the operand build and the epilogues
+    double* LamP = nullptr;                    // Lambda with the panel pitch [Np][ld] (written by k_chain_u)
     double* d_scale = nullptr;
     int* d_status = nullptr;
     double *d_x = nullptr, *d_out = nullptr, *d_part = nullptr;
@@ -242,7 +245,7 @@ int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
     const int n = h->N, tiles = (n + chain::CT - 1) / chain::CT;
     chain::UParams p = h->cu;
     p.x = d_x; p.n = n; p.lam_off = h->lam_off; p.s_override = s_host;
-    p.Lam = h->Lam; p.U = h->U; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
+    p.Lam = h->Lam; p.U = h->U; p.LamP = h->use_panel ? h->LamP : nullptr; p.ldl = h->ld; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
     void* args[] = {&p};
     TRY(launch_coop((const void*)chain::k_chain_u, dim3(tiles, tiles), dim3(chain::NTHR), chain::smem_bytes(n), h->stream, args));
     h->launches++;
@@ -280,7 +283,24 @@ int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host) {
 const double* u_base(const mambo_csa* h) { return h->use_chain ? h->U : h->R; }
 const int* u_sptr(const mambo_csa* h) { return h->use_chain ? h->d_zero : h->d_s; }
 
+#define NB_PANEL_DISPATCH(nb, CALL)                 \
+    switch (nb) {                                   \
+        case 1: { constexpr int NBT = 1; CALL; break; }   \
+        case 2: { constexpr int NBT = 2; CALL; break; }   \
+        case 4: { constexpr int NBT = 4; CALL; break; }   \
+        case 7: { constexpr int NBT = 7; CALL; break; }   \
+        case 10: { constexpr int NBT = 10; CALL; break; } \
+        default: { constexpr int NBT = 13; CALL; break; } \
+    }
+
 int enqueue_prep(mambo_csa* h) {
+    if (h->use_panel) {
+        NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT><<<h->nRpad / panel::ROWS, panel::NTHR, panel::prep_smem<NBT>(), h->stream>>>(
+                                     u_base(h), h->LamP, h->pa, h->pq, h->sw, h->N, h->prow_begin, h->prow_end, h->At, h->Bt)));
+        h->launches++;
+        CU(cudaGetLastError());
+        return MAMBO_OK;
+    }
     const int blocks = h->nRpad / small::PREP_ROWS;
     NCH_DISPATCH((h->Np + 31) / 32,
                  (small::k_prep<NCH><<<blocks, 256, small::prep_smem(h->N, h->Np), h->stream>>>(
@@ -290,7 +310,14 @@ int enqueue_prep(mambo_csa* h) {
     return MAMBO_OK;
 }
 
-int enqueue_post_f(mambo_csa* h, double* F) {
+int enqueue_post_f(mambo_csa* h, double* F, bool with_S = false) {
+    if (h->use_panel) {
+        NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT><<<h->P, panel::NTHR, panel::post_smem<NBT>(), h->stream>>>(
+                                     h->Epiece, h->piece_first, h->LamP, h->At, h->N, h->row_begin, F, h->Spart, with_S ? 1 : 0)));
+        h->launches++;
+        CU(cudaGetLastError());
+        return MAMBO_OK;
+    }
     if (h->postf32) {
         NCH_DISPATCH((h->Np + 31) / 32, (small::k_post_f32<NCH><<<2 * h->P, 256, small::postf32_smem(h->N, h->Np), h->stream>>>(
                                             h->Epiece, h->piece_first, h->Lam, h->N, h->Np, h->Et, F)));
@@ -305,12 +332,15 @@ int enqueue_post_sr(mambo_csa* h) {
     const int n = h->N, nn = n * n;
     const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
     const int nch = (n + 63) / 64;
-    small::k_post_s<<<dim3(h->P, nch * nch), 256, small::posts_smem(h->Np), h->stream>>>(h->Et, h->At, n, h->Np, h->ld, h->row_begin, h->Spart);
+    if (!h->use_panel) {
+        small::k_post_s<<<dim3(h->P, nch * nch), 256, small::posts_smem(h->Np), h->stream>>>(h->Et, h->At, n, h->Np, h->ld, h->row_begin, h->Spart);
+        h->launches++;
+    }
     (void)nn;
     small::k_post_reduce<<<n, 1024, 0, h->stream>>>(h->cost_part, h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
                                                                  h->sw, u_base(h), u_sptr(h), n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
                                                                  h->row_begin, std::min(h->row_end, h->nR), h->d_part);
-    h->launches += 2;
+    h->launches += 1;
     CU(cudaGetLastError());
     return MAMBO_OK;
 }
@@ -425,12 +455,12 @@ int enqueue_partial(mambo_csa* h, int s_host, bool need_grad) {
         p2.cost_part = h->cost_part + h->G;  // discarded
         TRY((launch_fused<true, false>(h, p2)));
         return run_segment(h, h->g_post, [&]() -> int {
-            TRY(enqueue_post_f(h, h->F2));
+            TRY(enqueue_post_f(h, h->F2, true));
             return enqueue_post_sr(h);
         });
     }
     return run_segment(h, h->g_post, [&]() -> int {
-        TRY(enqueue_post_f(h, h->F1));
+        TRY(enqueue_post_f(h, h->F1, true));
         return enqueue_post_sr(h);
     });
 }
@@ -680,6 +710,19 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->memo_x.assign(h->L, 0.0);
     h->use_graphs = (std::getenv("MAMBO_NO_GRAPH") == nullptr);
     h->use_chain = (std::getenv("MAMBO_LEGACY_CHAIN") == nullptr);
+    h->use_panel = false;
+    if (h->NB <= 13 && std::getenv("MAMBO_NO_PANEL") == nullptr) {
+        size_t need_post = 0;
+        NB_PANEL_DISPATCH(h->NB, need_post = panel::post_smem<NBT>());
+        h->use_panel = need_post <= prop.sharedMemPerBlockOptin;
+    }
+    if (chain::smem_bytes(n) > prop.sharedMemPerBlockOptin) h->use_chain = false;
+    h->use_panel = h->use_panel && h->use_chain;          // Lambda's padded copy is written by k_chain_u
+    if (h->use_panel) {
+        TRY(dalloc(&h->LamP, (size_t)h->Np * h->ld));
+        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_prep_mma<NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel::prep_smem<NBT>())));
+        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_post_mma<NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel::post_smem<NBT>())));
+    }
     if (chain::smem_bytes(n) > prop.sharedMemPerBlockOptin) h->use_chain = false;
     if (h->use_chain) {
         CU(cudaFuncSetAttribute(chain::k_chain_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::smem_bytes(n)));
@@ -796,7 +839,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
-                    h->visit_start, h->piece_first, h->mats, h->cmats, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
+                    h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_x) cudaFreeHost(h->h_x);
