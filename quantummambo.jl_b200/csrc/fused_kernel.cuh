@@ -43,6 +43,7 @@ struct Params {
     const int* visit_start; // [gridDim.x]
     long long ldT;
     int P, Q, ld, Np, S;
+    int dephase;            // cycles by which column group 1 starts late (0 = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,7 +114,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
 
     // ---------------------------------- consumers -------------------------------------------------------
     const int t0 = lane & 3, t1 = lane >> 2;
-    const int wc = warp & 1, wr = warp >> 1;
+    // Warps w and w+4 share a scheduler (SMSP w%4): give each scheduler one warp of either column group, and start
+    // column group 1 half a step late, so that the non-DMMA stretches of one warp (operand/T loads, barrier waits,
+    // phase changes) fall into the DMMA stretches of the other instead of lining up.
+    const int wc = (warp >> 2) & 1, wr = warp & 3;
+    if (p.dephase && wc == 1) {
+        const long long t_start = clock64();
+        while (clock64() - t_start < (long long)p.dephase) { }
+    }
     const int prow = perm8(t1);
     const int pc0 = t0, pc1 = 4 + ((t0 + 2) & 3);  // perm8(2*t0), perm8(2*t0+1)
 

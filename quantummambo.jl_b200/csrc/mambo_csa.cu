@@ -87,6 +87,7 @@ struct mambo_csa {
     long long* d_dbg = nullptr;                // MAMBO_CHAIN_DEBUG=1: clock64 stamps of the derivative chain
     bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
     bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
+    int dephase = 0;                           // fused kernel: start offset (cycles) of column group 1
     bool use_panel = false;                    // tensor-core panel GEMMs for the operand build and the epilogues
     double* LamP = nullptr;                    // Lambda with the panel pitch [Np][ld] (written by k_chain_u)
     double* d_scale = nullptr;
@@ -185,6 +186,7 @@ Params make_params(mambo_csa* h, double* T) {
     p.ld = h->ld;
     p.Np = h->Np;
     p.S = h->S;
+    p.dephase = h->dephase;
     return p;
 }
 
@@ -709,6 +711,8 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     *h->h_status = 0;
     h->memo_x.assign(h->L, 0.0);
     h->use_graphs = (std::getenv("MAMBO_NO_GRAPH") == nullptr);
+    h->dephase = 512 * h->NB;                   // half a step of DMMA issue time (32*NB DMMAs x 32 cycles / 2)
+    if (const char* e = std::getenv("MAMBO_DEPHASE")) h->dephase = std::atoi(e);
     h->use_chain = (std::getenv("MAMBO_LEGACY_CHAIN") == nullptr);
     h->use_panel = false;
     if (h->NB <= 13 && std::getenv("MAMBO_NO_PANEL") == nullptr) {
