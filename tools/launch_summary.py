@@ -9,7 +9,7 @@ def main(path):
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
     seq = [(r[ki], float(r[vi].replace(",", ""))) for r in data if len(r) > vi]
-    idx = [i for i, (k, _) in enumerate(seq) if "k_build(" in k]
+    idx = [i for i, (k, _) in enumerate(seq) if "k_build(" in k or "k_chain_u" in k]
     if len(idx) < 2:
         print("fewer than two evaluations captured"); return
     n_ev = len(idx) - 1
