@@ -73,10 +73,14 @@ __global__ void __launch_bounds__(1024) k_dot_absmax(const double* __restrict__ 
         res[1] = M;
     }
 }
-__global__ void k_set_identity(double* __restrict__ H, long long n) {
+__global__ void k_set_identity(double* __restrict__ H, long long n, double diag) {
     const long long total = n * n;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
-        H[idx] = (idx / n == idx % n) ? 1.0 : 0.0;
+        H[idx] = (idx / n == idx % n) ? diag : 0.0;
+}
+__global__ void k_scale(double* __restrict__ out, const double* __restrict__ a, double f, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = f * a[i];
 }
 // One pass over the dense inverse Hessian: (optionally) apply the pending BFGS update
 //     H <- H - rho (s Hy^T + Hy s^T) + c s s^T
@@ -301,7 +305,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         return false;
     };
     if (CK(cudaMemcpyAsync(o->x, x0, sizeof(double) * L, cudaMemcpyHostToDevice, o->stream), "H2D x0")) return finish(MAMBO_ECUDA);
-    k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L);
+    k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
 
     // f, g at x0
     double f = 0, dfdummy = 0;
@@ -318,6 +322,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     // The rank-2 update of iteration k is applied to H in memory during iteration k+1, in the same pass that
     // forms u = H g_new: (s_prev, Hy_prev, rho, cc) describe that pending update.
     bool pending = false;
+    bool fresh = true;             // H is still the (re)start identity: rescale it by s.y / y.y before the first update
     double rho = 0, cc = 0;
     double *s_cur = o->s, *Hy_cur = o->Hy, *s_prev = o->s2, *Hy_prev = o->Hy2;
     for (; it < opt.max_iter; ++it) {
@@ -329,8 +334,9 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         rc = dot_host(o, o->g, o->p, &df0, nullptr);
         if (rc) return finish(rc);
         if (!(df0 < 0)) {  // not a descent direction: restart from steepest descent
-            k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L);
+            k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
             pending = false;
+            fresh = true;
             k_scale_neg<<<blocks(L), 256, 0, o->stream>>>(o->p, o->g, L);
             rc = dot_host(o, o->g, o->p, &df0, nullptr);
             if (rc) return finish(rc);
@@ -348,14 +354,26 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         // accepted point = last evaluated: xt, out.  s = xt - x, y = g_new - g
         k_sub<<<blocks(L), 256, 0, o->stream>>>(s_cur, o->xt, o->x, L);
         k_sub<<<blocks(L), 256, 0, o->stream>>>(o->y, o->out + 1, o->g, L);
-        // one pass over H: fold in the pending update of the previous iteration and form u = H g_new
-        k_update_gemv<<<(L + 7) / 8, 256, 0, o->stream>>>(o->H, L, s_prev, Hy_prev, rho, cc, pending ? 1 : 0, o->out + 1, o->u);
-        pending = false;
-        // Hy = H y = H g_new - H g = u + p   (p = -H g)
-        k_axpy<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->u, o->p, 1.0, L);
         double sy = 0, yHy = 0, hyg = 0, sg = 0;
         rc = dot_host(o, s_cur, o->y, &sy, nullptr);
         if (rc) return finish(rc);
+        if (fresh && sy > 1e-300) {
+            // Nocedal & Wright (6.20): H0 <- (s.y / y.y) I before the first update, so the first curvature pair sets the scale
+            double yy = 0;
+            rc = dot_host(o, o->y, o->y, &yy, nullptr);
+            if (rc) return finish(rc);
+            const double gamma = sy / yy;
+            k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, gamma);
+            k_scale<<<blocks(L), 256, 0, o->stream>>>(o->u, o->out + 1, gamma, L);     // u  = H g_new
+            k_scale<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->y, gamma, L);          // Hy = H y
+            fresh = false;
+        } else {
+            // one pass over H: fold in the pending update of the previous iteration and form u = H g_new
+            k_update_gemv<<<(L + 7) / 8, 256, 0, o->stream>>>(o->H, L, s_prev, Hy_prev, rho, cc, pending ? 1 : 0, o->out + 1, o->u);
+            // Hy = H y = H g_new - H g = u + p   (p = -H g)
+            k_axpy<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->u, o->p, 1.0, L);
+        }
+        pending = false;
         cudaMemcpyAsync(o->x, o->xt, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
         cudaMemcpyAsync(o->g, o->out + 1, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
         f = fnew;
