@@ -90,6 +90,7 @@ struct mambo_csa {
     int dephase = 0;                           // fused kernel: start offset (cycles) of column group 1
     bool use_panel = false;                    // tensor-core panel GEMMs for the operand build and the epilogues
     double* LamP = nullptr;                    // Lambda with the panel pitch [Np][ld] (written by k_chain_u)
+    double* EtP = nullptr;                     // E~ rows with the panel pitch [P*64][ld] (k_esum)
     double* d_scale = nullptr;
     int* d_status = nullptr;
     double *d_x = nullptr, *d_out = nullptr, *d_part = nullptr;
@@ -285,19 +286,24 @@ int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host) {
 const double* u_base(const mambo_csa* h) { return h->use_chain ? h->U : h->R; }
 const int* u_sptr(const mambo_csa* h) { return h->use_chain ? h->d_zero : h->d_s; }
 
+// NB bucket -> (NBT, CST): panel-kernel instantiation and its column split (CST = 4 above N = 104 so that the
+// panels plus the Lambda slice fit in shared memory)
 #define NB_PANEL_DISPATCH(nb, CALL)                 \
     switch (nb) {                                   \
-        case 1: { constexpr int NBT = 1; CALL; break; }   \
-        case 2: { constexpr int NBT = 2; CALL; break; }   \
-        case 4: { constexpr int NBT = 4; CALL; break; }   \
-        case 7: { constexpr int NBT = 7; CALL; break; }   \
-        case 10: { constexpr int NBT = 10; CALL; break; } \
-        default: { constexpr int NBT = 13; CALL; break; } \
+        case 1: { constexpr int NBT = 1, CST = 1; CALL; break; }   \
+        case 2: { constexpr int NBT = 2, CST = 1; CALL; break; }   \
+        case 4: { constexpr int NBT = 4, CST = 1; CALL; break; }   \
+        case 7: { constexpr int NBT = 7, CST = 1; CALL; break; }   \
+        case 10: { constexpr int NBT = 10, CST = 1; CALL; break; } \
+        case 13: { constexpr int NBT = 13, CST = 1; CALL; break; } \
+        case 16: { constexpr int NBT = 16, CST = 4; CALL; break; } \
+        case 19: { constexpr int NBT = 19, CST = 4; CALL; break; } \
+        default: { constexpr int NBT = 21, CST = 4; CALL; break; } \
     }
 
 int enqueue_prep(mambo_csa* h) {
     if (h->use_panel) {
-        NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT><<<h->nRpad / panel::ROWS, panel::NTHR, panel::prep_smem<NBT>(), h->stream>>>(
+        NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT, CST><<<dim3(h->nRpad / panel::ROWS, CST), panel::NTHR, panel::prep_smem<NBT, CST>(), h->stream>>>(
                                      u_base(h), h->LamP, h->pa, h->pq, h->sw, h->N, h->prow_begin, h->prow_end, h->At, h->Bt)));
         h->launches++;
         CU(cudaGetLastError());
@@ -314,9 +320,11 @@ int enqueue_prep(mambo_csa* h) {
 
 int enqueue_post_f(mambo_csa* h, double* F, bool with_S = false) {
     if (h->use_panel) {
-        NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT><<<h->P, panel::NTHR, panel::post_smem<NBT>(), h->stream>>>(
-                                     h->Epiece, h->piece_first, h->LamP, h->At, h->N, h->row_begin, F, h->Spart, with_S ? 1 : 0)));
-        h->launches++;
+        const int ysplit = std::max(1, std::min(8, (2 * h->num_sms) / std::max(h->P, 1)));
+        panel::k_esum<<<dim3(h->P, ysplit), 256, 0, h->stream>>>(h->Epiece, h->piece_first, h->Np, h->ld, h->EtP);
+        NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT, CST><<<dim3(h->P, CST), panel::NTHR, panel::post_smem<NBT, CST>(), h->stream>>>(
+                                     h->EtP, h->LamP, h->At, h->N, h->row_begin, F, h->Spart, with_S ? 1 : 0)));
+        h->launches += 2;
         CU(cudaGetLastError());
         return MAMBO_OK;
     }
@@ -715,17 +723,20 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     if (const char* e = std::getenv("MAMBO_DEPHASE")) h->dephase = std::atoi(e);
     h->use_chain = (std::getenv("MAMBO_LEGACY_CHAIN") == nullptr);
     h->use_panel = false;
-    if (h->NB <= 13 && std::getenv("MAMBO_NO_PANEL") == nullptr) {
+    if (std::getenv("MAMBO_NO_PANEL") == nullptr) {
         size_t need_post = 0;
-        NB_PANEL_DISPATCH(h->NB, need_post = panel::post_smem<NBT>());
+        NB_PANEL_DISPATCH(h->NB, need_post = (panel::post_smem<NBT, CST>()));
         h->use_panel = need_post <= prop.sharedMemPerBlockOptin;
     }
     if (chain::smem_bytes(n) > prop.sharedMemPerBlockOptin) h->use_chain = false;
     h->use_panel = h->use_panel && h->use_chain;          // Lambda's padded copy is written by k_chain_u
     if (h->use_panel) {
         TRY(dalloc(&h->LamP, (size_t)h->Np * h->ld));
-        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_prep_mma<NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel::prep_smem<NBT>())));
-        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_post_mma<NBT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)panel::post_smem<NBT>())));
+        TRY(dalloc(&h->EtP, (size_t)h->P * ROWS * h->ld));
+        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_prep_mma<NBT, CST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)(panel::prep_smem<NBT, CST>()))));
+        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_post_mma<NBT, CST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)(panel::post_smem<NBT, CST>()))));
     }
     if (chain::smem_bytes(n) > prop.sharedMemPerBlockOptin) h->use_chain = false;
     if (h->use_chain) {
@@ -843,7 +854,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
-                    h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
+                    h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_x) cudaFreeHost(h->h_x);

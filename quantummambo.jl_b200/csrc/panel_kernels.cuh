@@ -7,8 +7,9 @@
 // One CTA per 64-row panel, 8 warps, DMMA.8x8x4.  Lambda is symmetric, so it is staged as [column m][k] with the same
 // pitch LD = Np + 4 as the panels: every fragment load of the k-contiguous products follows the conflict-free
 // (t1 * LD + t0) pattern.  Lambda (padded, written by chain::k_chain_u) and the A~ panel arrive by single TMA bulk copies.
-// Used when the panels and Lambda fit in shared memory together (NB <= 13, i.e. N <= 104); larger N keeps the
-// FMA kernels of small_kernels.cuh.
+// The template parameter CS splits the output columns (and with them the rows of the staged Lambda) over CS CTAs per
+// panel so that the working set fits in shared memory for every supported N (CS = 1 up to N = 104, CS = 4 above).
+// k_esum adds the fused kernel's E pieces in a fixed order once, so the GEMM CTAs fetch their E~ panel with one TMA copy.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -46,20 +47,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
         "}\n" ::"r"(s32(b)), "r"(parity) : "memory");
 }
 
-template <int NB>
+template <int NB, int CS = 1>
 struct Geo {
     static constexpr int Np = 8 * NB, LD = Np + 4;
-    static constexpr int NBW = (NB + 1) / 2;          // n-blocks per warp column (2 warp columns)
+    static constexpr int NBC = (NB + CS - 1) / CS;    // n-blocks per CTA (column split)
+    static constexpr int NBW = (NBC + 1) / 2;         // n-blocks per warp column (2 warp columns)
     static constexpr size_t panel_elems = (size_t)ROWS * LD;
-    static constexpr size_t lam_elems = (size_t)Np * LD;
+    static constexpr size_t lam_elems = (size_t)8 * NBC * LD;   // the Lambda rows (= output columns) of one CTA
 };
-template <int NB> inline size_t prep_smem() { return (Geo<NB>::panel_elems + Geo<NB>::lam_elems) * 8 + 64; }
-template <int NB> inline size_t post_smem() { return (2 * Geo<NB>::panel_elems + Geo<NB>::lam_elems) * 8 + 64; }
+template <int NB, int CS> inline size_t prep_smem() { return (Geo<NB, CS>::panel_elems + Geo<NB, CS>::lam_elems) * 8 + 64; }
+template <int NB, int CS> inline size_t post_smem() { return (2 * Geo<NB, CS>::panel_elems + Geo<NB, CS>::lam_elems) * 8 + 64; }
 
 // C[16 rows of this warp][its n-blocks] += A[rows][k] . B[cols][k]^T ; both operands k-contiguous with pitch LD
-template <int NB>
-__device__ __forceinline__ void gemm_kk(const double* __restrict__ sA, const double* __restrict__ sB, double (&acc)[2][Geo<NB>::NBW][2]) {
-    constexpr int LD = Geo<NB>::LD, NBW = Geo<NB>::NBW, KS = Geo<NB>::Np / 4;
+template <int NB, int CS>
+__device__ __forceinline__ void gemm_kk(const double* __restrict__ sA, const double* __restrict__ sB, int nblk,
+                                        double (&acc)[2][Geo<NB, CS>::NBW][2]) {
+    constexpr int LD = Geo<NB, CS>::LD, NBW = Geo<NB, CS>::NBW, KS = Geo<NB, CS>::Np / 4;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t0 = lane & 3, t1 = lane >> 2, wr = warp >> 1, wc = warp & 1;
     const int nb0 = wc * NBW;                               // first n-block of this warp column
@@ -74,10 +77,10 @@ __device__ __forceinline__ void gemm_kk(const double* __restrict__ sA, const dou
         const double a0 = a[4 * ks], a1 = a[8 * LD + 4 * ks];
         double bv[NBW];
 #pragma unroll
-        for (int nb = 0; nb < NBW; ++nb) bv[nb] = (nb0 + nb < NB) ? b[nb * 8 * LD + 4 * ks] : 0.0;
+        for (int nb = 0; nb < NBW; ++nb) bv[nb] = (nb0 + nb < nblk) ? b[nb * 8 * LD + 4 * ks] : 0.0;
 #pragma unroll
         for (int nb = 0; nb < NBW; ++nb) {
-            if (nb0 + nb < NB) {
+            if (nb0 + nb < nblk) {
                 dmma(acc[0][nb][0], acc[0][nb][1], a0, bv[nb]);
                 dmma(acc[1][nb][0], acc[1][nb][1], a1, bv[nb]);
             }
@@ -87,25 +90,29 @@ __device__ __forceinline__ void gemm_kk(const double* __restrict__ sA, const dou
 
 // ------------------------------------------------------------------------------------------------------------
 // k_prep_mma: A~[r][l] = sw_r U[pa_r][l] U[pq_r][l] (all rows), B~ = A~ Lambda (this shard's panels)
+//   grid (panels, CS): CTA (p, c) produces output n-blocks [c*NBC, min((c+1)*NBC, NB)).
 // ------------------------------------------------------------------------------------------------------------
-template <int NB>
+template <int NB, int CS>
 __global__ void __launch_bounds__(NTHR, 1) k_prep_mma(const double* __restrict__ U, const double* __restrict__ LamP,
                                                       const int* __restrict__ pa, const int* __restrict__ pq, const double* __restrict__ sw,
                                                       int n, int prow_begin, int prow_end, double* __restrict__ At, double* __restrict__ Bt) {
-    using G = Geo<NB>;
-    constexpr int LD = G::LD, NBW = G::NBW;
+    using G = Geo<NB, CS>;
+    constexpr int LD = G::LD, NBW = G::NBW, NBC = G::NBC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sA = reinterpret_cast<double*>(smem_raw);
     double* sL = sA + G::panel_elems;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sL + G::lam_elems);
-    const int panel = blockIdx.x;
-    const bool need_b = panel >= prow_begin && panel < prow_end;
+    const int panel = blockIdx.x, cs = blockIdx.y;
+    const int nb_lo = cs * NBC, nblk = min(NBC, NB - nb_lo);
+    const bool need_b = panel >= prow_begin && panel < prow_end && nblk > 0;
+    if (!need_b && cs != 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         mbar_init(mbar);
         if (need_b) {
-            mbar_expect(mbar, (uint32_t)(G::lam_elems * 8));
-            bulk(sL, LamP, (uint32_t)(G::lam_elems * 8), mbar);
+            const uint32_t bytes = (uint32_t)((size_t)8 * nblk * LD * 8);
+            mbar_expect(mbar, bytes);
+            bulk(sL, LamP + (size_t)8 * nb_lo * LD, bytes, mbar);
         }
     }
     // gather the A~ panel: warp w builds rows 8w .. 8w+7, lanes sweep the columns (coalesced reads of U rows)
@@ -119,122 +126,130 @@ __global__ void __launch_bounds__(NTHR, 1) k_prep_mma(const double* __restrict__
         for (int l = lane; l < LD; l += 32) {
             const double v = (l < n && w != 0.0) ? w * ua[l] * uq[l] : 0.0;
             sA[(8 * warp + rr) * LD + l] = v;
-            At[(size_t)r * LD + l] = v;
+            if (cs == 0) At[(size_t)r * LD + l] = v;
         }
     }
     if (!need_b) return;
     __syncthreads();
     mbar_wait(mbar, 0);
     double acc[2][NBW][2];
-    gemm_kk<NB>(sA, sL, acc);
+    gemm_kk<NB, CS>(sA, sL, nblk, acc);
     const int t0 = lane & 3, t1 = lane >> 2, wr = warp >> 1, wc = warp & 1;
     double* out = Bt + (size_t)((panel - prow_begin) * ROWS + 16 * wr + t1) * LD;
 #pragma unroll
     for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
         for (int nb = 0; nb < NBW; ++nb) {
-            const int col = 8 * (wc * NBW + nb) + 2 * t0;
-            if (wc * NBW + nb < NB) {
-                double2 v2 = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
-                *reinterpret_cast<double2*>(out + (size_t)mb * 8 * LD + col) = v2;
-            }
+            const int blk = wc * NBW + nb;
+            if (blk < nblk)
+                *reinterpret_cast<double2*>(out + (size_t)mb * 8 * LD + 8 * (nb_lo + blk) + 2 * t0) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
         }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// k_post_mma: per local panel: E~ (piece sum) ; F = E~ Lambda ; Spart = A~_panel^T E~
+// k_esum: E~[row][LD] = fixed-order sum of the fused kernel's pieces (two warp-column partials per visit)
 // ------------------------------------------------------------------------------------------------------------
-template <int NB>
-__global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
-                                                      const double* __restrict__ LamP, const double* __restrict__ At, int n, int row_begin,
-                                                      double* __restrict__ F, double* __restrict__ Spart, int do_S) {
-    using G = Geo<NB>;
-    constexpr int Np = G::Np, LD = G::LD, NBW = G::NBW;
+__global__ void __launch_bounds__(256) k_esum(const double* __restrict__ Epiece, const int* __restrict__ piece_first, int Np, int LD,
+                                              double* __restrict__ Et) {
+    const int panel = blockIdx.x;
+    const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
+    const int total = ROWS * Np;
+    for (int base = blockIdx.y * 1024 + threadIdx.x; base < total; base += gridDim.y * 1024) {
+        double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int v = v0; v < v1; ++v) {
+            const double* p0 = Epiece + (size_t)(v * 2 + 0) * ROWS * Np;
+            const double* p1 = Epiece + (size_t)(v * 2 + 1) * ROWS * Np;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int idx = base + u * 256;
+                if (idx < total) acc4[u] += __ldcs(p0 + idx) + __ldcs(p1 + idx);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * 256;
+            if (idx < total) Et[(size_t)(panel * ROWS + idx / Np) * LD + (idx % Np)] = acc4[u];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_post_mma: per local panel and column split: F[:, cols] = E~ Lambda[:, cols] ; Spart[:, cols] = A~_panel^T E~[:, cols]
+// ------------------------------------------------------------------------------------------------------------
+template <int NB, int CS>
+__global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__ Et, const double* __restrict__ LamP,
+                                                      const double* __restrict__ At, int n, int row_begin, double* __restrict__ F,
+                                                      double* __restrict__ Spart, int do_S) {
+    using G = Geo<NB, CS>;
+    constexpr int Np = G::Np, LD = G::LD, NBW = G::NBW, NBC = G::NBC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sE = reinterpret_cast<double*>(smem_raw);
     double* sAp = sE + G::panel_elems;
     double* sL = sAp + G::panel_elems;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sL + G::lam_elems);
-    const int panel = blockIdx.x;
+    const int panel = blockIdx.x, cs = blockIdx.y;
+    const int nb_lo = cs * NBC, nblk = min(NBC, NB - nb_lo);
+    if (nblk <= 0) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t0 = lane & 3, t1 = lane >> 2;
     if (threadIdx.x == 0) {
         mbar_init(mbar);
-        mbar_expect(mbar, (uint32_t)((G::lam_elems + G::panel_elems) * 8));
-        bulk(sL, LamP, (uint32_t)(G::lam_elems * 8), mbar);
-        bulk(sAp, At + (size_t)(row_begin + panel * ROWS) * LD, (uint32_t)(G::panel_elems * 8), mbar);
-    }
-    // E~ panel = sum of pieces in a fixed order (two warp-column partials per visit); pad columns zero
-    {
-        const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
-        for (int base = threadIdx.x; base < ROWS * Np; base += 4 * NTHR) {
-            double acc4[4] = {0.0, 0.0, 0.0, 0.0};
-            for (int v = v0; v < v1; ++v) {
-                const double* p0 = Epiece + (size_t)(v * 2 + 0) * ROWS * Np;
-                const double* p1 = Epiece + (size_t)(v * 2 + 1) * ROWS * Np;
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int idx = base + u * NTHR;
-                    if (idx < ROWS * Np) acc4[u] += p0[idx] + p1[idx];
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base + u * NTHR;
-                if (idx < ROWS * Np) sE[(idx / Np) * LD + (idx % Np)] = acc4[u];
-            }
-        }
-        for (int idx = threadIdx.x; idx < ROWS * 4; idx += NTHR) sE[(idx >> 2) * LD + Np + (idx & 3)] = 0.0;
+        const uint32_t lbytes = (uint32_t)((size_t)8 * nblk * LD * 8), pbytes = (uint32_t)(G::panel_elems * 8);
+        mbar_expect(mbar, lbytes + pbytes + (do_S ? pbytes : 0u));
+        bulk(sE, Et + (size_t)panel * ROWS * LD, pbytes, mbar);
+        bulk(sL, LamP + (size_t)8 * nb_lo * LD, lbytes, mbar);
+        if (do_S) bulk(sAp, At + (size_t)(row_begin + panel * ROWS) * LD, pbytes, mbar);
     }
     __syncthreads();
     mbar_wait(mbar, 0);
     // ---- F = E~ Lambda --------------------------------------------------------------------------------------
     {
         double acc[2][NBW][2];
-        gemm_kk<NB>(sE, sL, acc);
+        gemm_kk<NB, CS>(sE, sL, nblk, acc);
         const int wr = warp >> 1, wc = warp & 1;
         double* out = F + (size_t)(panel * ROWS + 16 * wr + t1) * Np;
 #pragma unroll
         for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
             for (int nb = 0; nb < NBW; ++nb) {
-                const int col = 8 * (wc * NBW + nb) + 2 * t0;
-                if (wc * NBW + nb < NB) *reinterpret_cast<double2*>(out + (size_t)mb * 8 * Np + col) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
+                const int blk = wc * NBW + nb;
+                if (blk < nblk)
+                    *reinterpret_cast<double2*>(out + (size_t)mb * 8 * Np + 8 * (nb_lo + blk) + 2 * t0) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
             }
     }
     if (!do_S) return;
-    // ---- Spart[i][j] = sum_r A~[r][i] E~[r][j] : warps = 4 (i groups) x 2 (j groups) -----------------------------------
+    // ---- Spart[i][j] = sum_r A~[r][i] E~[r][j], j in this CTA's columns: warps = 4 (i groups) x 2 (j groups) -----------
     {
         constexpr int MBW = (NB + 3) / 4;                   // m-blocks per warp row group
         const int wr = warp >> 1, wc = warp & 1;
-        const int mb0 = wr * MBW, nb0 = wc * NBW;
+        const int mb0 = wr * MBW, nbw0 = wc * NBW;
         double acc[MBW][NBW][2];
 #pragma unroll
         for (int mb = 0; mb < MBW; ++mb)
 #pragma unroll
             for (int nb = 0; nb < NBW; ++nb) acc[mb][nb][0] = acc[mb][nb][1] = 0.0;
         const double* a = sAp + t0 * LD + 8 * mb0 + t1;
-        const double* b = sE + t0 * LD + 8 * nb0 + t1;
+        const double* b = sE + t0 * LD + 8 * (nb_lo + nbw0) + t1;
 #pragma unroll 2
         for (int ks = 0; ks < ROWS / 4; ++ks) {
             double av[MBW], bv[NBW];
 #pragma unroll
             for (int mb = 0; mb < MBW; ++mb) av[mb] = (mb0 + mb < NB) ? a[4 * ks * LD + 8 * mb] : 0.0;
 #pragma unroll
-            for (int nb = 0; nb < NBW; ++nb) bv[nb] = (nb0 + nb < NB) ? b[4 * ks * LD + 8 * nb] : 0.0;
+            for (int nb = 0; nb < NBW; ++nb) bv[nb] = (nbw0 + nb < nblk) ? b[4 * ks * LD + 8 * nb] : 0.0;
 #pragma unroll
             for (int mb = 0; mb < MBW; ++mb)
 #pragma unroll
                 for (int nb = 0; nb < NBW; ++nb)
-                    if (mb0 + mb < NB && nb0 + nb < NB) dmma(acc[mb][nb][0], acc[mb][nb][1], av[mb], bv[nb]);
+                    if (mb0 + mb < NB && nbw0 + nb < nblk) dmma(acc[mb][nb][0], acc[mb][nb][1], av[mb], bv[nb]);
         }
         double* out = Spart + (size_t)panel * n * n;
 #pragma unroll
         for (int mb = 0; mb < MBW; ++mb)
 #pragma unroll
             for (int nb = 0; nb < NBW; ++nb) {
-                const int i = 8 * (mb0 + mb) + t1, j = 8 * (nb0 + nb) + 2 * t0;
-                if (mb0 + mb < NB && nb0 + nb < NB && i < n) {
+                const int i = 8 * (mb0 + mb) + t1, j = 8 * (nb_lo + nbw0 + nb) + 2 * t0;
+                if (mb0 + mb < NB && nbw0 + nb < nblk && i < n) {
                     if (j < n) out[(size_t)i * n + j] = acc[mb][nb][0];
                     if (j + 1 < n) out[(size_t)i * n + j + 1] = acc[mb][nb][1];
                 }
