@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-rowpanel", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations timed for the CPU baseline (0 = auto)")
+    ap.add_argument("--no-greedy", action="store_true", help="skip the greedy-CSA time-to-tolerance leg")
     return ap.parse_args()
 
 
@@ -162,6 +163,33 @@ def run_reference(args, rank: int):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def greedy_time_to_tolerance(mb, syn, device: int, n: int = 50, R: int = 2, frags: int = 2, max_iter: int = 300):
+    """Second half of BASELINE.json's metric: greedy CSA on a planted tensor (sum of R random CSA fragments) with the
+    library's device-resident BFGS, bounded to `frags` fragments x `max_iter` iterations so the default bench stays
+    short.  Reports wall time, evaluations and the squared-norm cost trail (tolerance is on the squared norm, like
+    decomp_tol at decompose.jl:45)."""
+    rng = np.random.default_rng(2000)
+    cL, uL = n * (n + 1) // 2, n * (n - 1) // 2
+    T = np.zeros((n, n, n, n), order="F")
+    with mb.CSAEngine(np.zeros((n, n, n, n)), device=device) as e:
+        for _ in range(R):
+            W, _ = e.reconstruct(np.concatenate([rng.standard_normal(cL), 2 * np.pi * rng.random(uL)]))
+            T += W
+    trail, evals = [], 0
+    with mb.CSAEngine(T, device=device) as e:
+        c0 = e.residual_cost()
+        t0 = time.perf_counter()
+        for _ in range(frags):
+            x0 = np.concatenate([np.zeros(cL), 2 * np.pi * rng.random(uL)])      # decompose.jl:86-94
+            xm, res = e.optimize(x0, g_tol=1e-8, max_iter=max_iter)
+            trail.append(e.subtract_fragment(xm))
+            evals += res["evaluations"]
+        dt = time.perf_counter() - t0
+    return {"workload": f"planted N={n} R={R}, {frags} greedy fragments x <= {max_iter} BFGS iterations (native optimiser)",
+            "seconds": dt, "evaluations": evals, "initial_cost": c0, "cost_trail": trail,
+            "ms_per_evaluation_incl_optimizer": dt / max(evals, 1) * 1e3}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -317,6 +345,10 @@ def main():
         cpu = {"value": rate, "unit": "evals/s", "cores": cores, "kind": "port",
                "sample": f"{done} cost+grad evaluations of the same N={n} workload, oracle factored numpy/OpenBLAS on {cores} threads"}
 
+    greedy = None
+    if rank == 0 and world == 1 and not args.no_greedy:
+        greedy = greedy_time_to_tolerance(mb, syn, local_rank)
+
     if rank == 0:
         clocks = sampler.summary()
         fused_ms = prof["fused_ms"] / max(prof["fused_launches"], 1)
@@ -361,6 +393,8 @@ def main():
         }
         if rowpanel is not None:
             line["rowpanel"] = rowpanel
+        if greedy is not None:
+            line["greedy"] = greedy
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

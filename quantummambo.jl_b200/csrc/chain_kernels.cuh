@@ -74,15 +74,23 @@ __device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_all;" ::
 // Grid-wide barrier: release-reduction on arrival, acquire polling at L2.  Data produced by other CTAs is afterwards
 // read only through L2 (TMA bulk copies and ld.global.cg), never through this SM's L1, so no L1 invalidation
 // (fence.acq_rel.gpu -> CCTL.IVALL) is paid per barrier.
-__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target) {
+__device__ __forceinline__ void grid_barrier(unsigned* ctr, unsigned& target, long long* stamps = nullptr) {
     __syncthreads();
     target += gridDim.x * gridDim.y;
     if (threadIdx.x == 0) {
+        if (stamps) stamps[0] = clock64();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        if (stamps) stamps[1] = clock64();
         unsigned v;
+        int polls = 0;
         do {
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+            ++polls;
         } while (v < target);
+        if (stamps) {
+            stamps[2] = clock64();
+            stamps[3] = polls;
+        }
     }
     __syncthreads();
 }
@@ -550,7 +558,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
             }
         }
         if (dbg) p.dbg[q * 6 + 4] = clock64();
-        grid_barrier(p.bar, target);
+        grid_barrier(p.bar, target, dbg ? p.dbg + 56 + 4 * q : nullptr);
         if (dbg) p.dbg[q * 6 + 5] = clock64();
     }
     // ---- gradient in x order (gradient.jl:148-151, 287-290): out = [cost, (g1), g_lambda, g_theta] -------------------

@@ -44,6 +44,7 @@ struct Params {
     long long ldT;
     int P, Q, ld, Np, S;
     int dephase;            // cycles by which column group 1 starts late (0 = off)
+    int lookahead;          // sub-tiles requested ahead of the current step (0 = default)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
 
     // ---- producer state (used by lane 0 of warp 0 only): sub-tile g = 2*step + column group ----------------
     const int g_total = 2 * (int)(tend - tbeg);
-    const int lookahead = (S >= 6) ? 2 : (S - 2);       // sub-tiles issued beyond the current step
+    const int lookahead = p.lookahead > 0 ? min(p.lookahead, S - 2) : ((S >= 6) ? 2 : (S - 2));   // sub-tiles issued beyond the current step
     int g_issued = 0, ct_p = ct;
     const uint32_t panel_bytes = (uint32_t)(ROWS * ld * 8), sub_bytes = (uint32_t)(SUB * ld * 8);
     auto produce_upto = [&](int g_hi) {

@@ -88,6 +88,7 @@ struct mambo_csa {
     bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
     bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
     int dephase = 0;                           // fused kernel: start offset (cycles) of column group 1
+    int lookahead = 0;                         // fused kernel: operand sub-tiles requested ahead (0 = default)
     bool use_panel = false;                    // tensor-core panel GEMMs for the operand build and the epilogues
     double* LamP = nullptr;                    // Lambda with the panel pitch [Np][ld] (written by k_chain_u)
     double* EtP = nullptr;                     // E~ rows with the panel pitch [P*64][ld] (k_esum)
@@ -188,6 +189,7 @@ Params make_params(mambo_csa* h, double* T) {
     p.Np = h->Np;
     p.S = h->S;
     p.dephase = h->dephase;
+    p.lookahead = h->lookahead;
     return p;
 }
 
@@ -719,8 +721,9 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     *h->h_status = 0;
     h->memo_x.assign(h->L, 0.0);
     h->use_graphs = (std::getenv("MAMBO_NO_GRAPH") == nullptr);
-    h->dephase = 512 * h->NB;                   // half a step of DMMA issue time (32*NB DMMAs x 32 cycles / 2)
+    h->dephase = 0;                             // measured: no gain from offsetting the column groups (kept as a knob)
     if (const char* e = std::getenv("MAMBO_DEPHASE")) h->dephase = std::atoi(e);
+    if (const char* e = std::getenv("MAMBO_LOOKAHEAD")) h->lookahead = std::atoi(e);
     h->use_chain = (std::getenv("MAMBO_LEGACY_CHAIN") == nullptr);
     h->use_panel = false;
     if (std::getenv("MAMBO_NO_PANEL") == nullptr) {

@@ -16,4 +16,7 @@ with mb.CSAEngine(T) as e:
     for q in range(9):
         print(q, np.diff(a[q]), "total", a[q, 5] - a[q, 0])
     flat = np.array(buf[:])
+    for q in range(8):
+        b = flat[56 + 4 * q: 60 + 4 * q]
+        print("barrier", q, "red issue", b[1] - b[0], "poll phase", b[2] - b[1], "polls", b[3])
     print("kernel start->squarings", flat[90] - flat[91], "squarings", a[8, 5] - flat[90], "tail", flat[92] - a[8, 5], "total", flat[92] - flat[91])
