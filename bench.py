@@ -316,25 +316,58 @@ def main():
         d_x0 = torch.from_numpy(np.stack(xs0)).to(dev)
         d_part = torch.empty(plen, dtype=torch.float64, device=dev)
 
-        def step_sharded():
+        def step_nccl():
             for i in range(BATCH):
                 engs.eval_partial_device(d_x0[i].data_ptr(), d_part.data_ptr())
                 dist.all_reduce(d_part)
                 engs.eval_finish_device(d_part.data_ptr(), d_out[i].data_ptr())
 
-        for _ in range(3):
-            step_sharded()
-        torch.cuda.synchronize(); dist.barrier()
-        e0.record(stream)
-        for _ in range(args.steps):
-            step_sharded()
-        e1.record(stream)
-        torch.cuda.synchronize(); dist.barrier()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        rp_ms = float(t.item())
-        rowpanel = {"value": BATCH * args.steps / (rp_ms * 1e-3), "unit": "evals/s", "scaling": "strong",
-                    "allreduce_doubles_per_eval": plen, "ms_per_eval": rp_ms / (BATCH * args.steps)}
+        def step_peer():                      # in-library exchange over NVLink peer memory, no host collective
+            for i in range(BATCH):
+                engs.eval_sharded_device(d_x0[i].data_ptr(), d_out[i].data_ptr())
+
+        def timed(step):
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize(); dist.barrier()
+            e0.record(stream)
+            for _ in range(args.steps):
+                step()
+            e1.record(stream)
+            torch.cuda.synchronize(); dist.barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        nccl_ms = timed(step_nccl)
+        chk_nccl = d_out[0].clone()
+        rowpanel = {"value": BATCH * args.steps / (nccl_ms * 1e-3), "unit": "evals/s", "scaling": "strong",
+                    "exchange": "NCCL allreduce of the partial vector", "doubles_exchanged_per_eval": plen,
+                    "ms_per_eval": nccl_ms / (BATCH * args.steps)}
+        # in-library exchange: a failure here (IPC mapping refused, a peer missing) must never cost the main line
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, engs.peer_export())
+            for r, hd in enumerate(handles):
+                if r != rank:
+                    engs.peer_attach(r, hd)
+        except Exception as exc:  # noqa: BLE001
+            ok.zero_()
+            peer_err = repr(exc)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            peer_ms = timed(step_peer)
+            engs.synchronize()
+            agree = float((d_out[0] - chk_nccl).abs().max().item() / chk_nccl.abs().max().item())
+            rowpanel = {"value": BATCH * args.steps / (peer_ms * 1e-3), "unit": "evals/s", "scaling": "strong",
+                        "exchange": "NVLink peer-memory push + rank-ordered sum inside the library (k_peer_push / k_peer_sum)",
+                        "doubles_exchanged_per_eval": plen, "ms_per_eval": peer_ms / (BATCH * args.steps),
+                        "nccl_allreduce_variant": {"value": BATCH * args.steps / (nccl_ms * 1e-3),
+                                                   "ms_per_eval": nccl_ms / (BATCH * args.steps)},
+                        "peer_vs_nccl_max_rel_diff": agree}
+        else:
+            rowpanel["peer_exchange"] = "unavailable on this box (CUDA IPC mapping failed on some rank)"
         engs.close()
 
     # ---- CPU baseline (rank 0, N=1 only): oracle port on a bounded sample ----------------------------------------

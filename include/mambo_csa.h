@@ -109,6 +109,18 @@ int  mambo_csa_eval_device(mambo_csa* h, const double* d_x, double* d_out);
  *   partial = [cost_2body, S (N x N), G (N x N)] summed over this shard's rows.                        */
 int  mambo_csa_eval_partial_device(mambo_csa* h, const double* d_x, double* d_partial);
 int  mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double* d_out);
+/* The same exchange without a host-launched collective (one process per GPU): every shard stores its partial vector
+ * into a slot of every peer's receive buffer over NVLink peer memory and publishes an epoch flag; the finish half waits
+ * for all flags and adds the slots in rank order (deterministic, identical on every rank).
+ *   setup : peer_export on every rank -> exchange the 64-byte handles (e.g. all_gather) -> peer_attach(rank, handle) for
+ *           every other rank (peer_attach_local when the peer handle lives in the same process).
+ *   eval  : eval_sharded_device == eval_sharded_push_device + eval_sharded_finish_device.                            */
+int  mambo_csa_peer_export(mambo_csa* h, unsigned char* handle64);
+int  mambo_csa_peer_attach(mambo_csa* h, int rank, const unsigned char* handle64);
+int  mambo_csa_peer_attach_local(mambo_csa* h, int rank, mambo_csa* peer);
+int  mambo_csa_eval_sharded_push_device(mambo_csa* h, const double* d_x);
+int  mambo_csa_eval_sharded_finish_device(mambo_csa* h, double* d_out);
+int  mambo_csa_eval_sharded_device(mambo_csa* h, const double* d_x, double* d_out);
 /* Cost-only evaluation (half the flops: reconstruction + residual norm, no gradient). */
 int  mambo_csa_cost_device(mambo_csa* h, const double* d_x, double* d_cost);
 int  mambo_csa_synchronize(mambo_csa* h);

@@ -80,6 +80,12 @@ SIGNATURES = {
     "mambo_csa_eval_device": (C.c_int, [_P, _P, _P]),
     "mambo_csa_eval_partial_device": (C.c_int, [_P, _P, _P]),
     "mambo_csa_eval_finish_device": (C.c_int, [_P, _P, _P]),
+    "mambo_csa_peer_export": (C.c_int, [_P, _P]),
+    "mambo_csa_peer_attach": (C.c_int, [_P, C.c_int, _P]),
+    "mambo_csa_peer_attach_local": (C.c_int, [_P, C.c_int, _P]),
+    "mambo_csa_eval_sharded_push_device": (C.c_int, [_P, _P]),
+    "mambo_csa_eval_sharded_finish_device": (C.c_int, [_P, _P]),
+    "mambo_csa_eval_sharded_device": (C.c_int, [_P, _P, _P]),
     "mambo_csa_cost_device": (C.c_int, [_P, _P, _P]),
     "mambo_csa_synchronize": (C.c_int, [_P]),
     "mambo_csa_set_profiling": (C.c_int, [_P, C.c_int]),

@@ -102,6 +102,15 @@ struct mambo_csa {
     bool memo_valid = false;
     long long launches = 0;
     int launches_last_eval = 0;
+    // peer exchange of row-panel shards (one process per GPU, CUDA IPC over NVLink)
+    double* peer_recv = nullptr;               // [2][world][plen_pad] receive slots of THIS rank
+    unsigned long long* peer_flags = nullptr;  // [2][MAXPEERS] epochs published by the peers
+    unsigned* peer_done = nullptr;
+    small::PeerTable peer_tab;
+    void* peer_opened[small::MAXPEERS] = {nullptr};   // IPC mappings to close
+    int peer_attached = 0;
+    int plen_pad = 0;
+    unsigned long long peer_epoch = 0;
     // CUDA-graph segments of the small-kernel sequences
     bool use_graphs = true;
     std::vector<GraphSeg> g_pre, g_fin;   // index 0: device-decided s; 1+s: s squarings
@@ -484,6 +493,11 @@ int enqueue_finish_seg(mambo_csa* h, int s_host) {
 }
 
 int check_status(mambo_csa* h) {
+    if (*h->h_status == 2) {
+        *h->h_status = 0;
+        cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream);
+        return fail(MAMBO_ESTATE, "peer exchange timed out: a shard never published its partial vector");
+    }
     if (*h->h_status != 0) {
         *h->h_status = 0;
         cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream);
@@ -863,6 +877,10 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (h->h_x) cudaFreeHost(h->h_x);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_status) cudaFreeHost(h->h_status);
+    for (void* m : h->peer_opened)
+        if (m) cudaIpcCloseMemHandle(m);
+    if (h->peer_recv) cudaFree(h->peer_recv);
+    if (h->peer_done) cudaFree(h->peer_done);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->seg_pool) cudaEventDestroy(e);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1023,6 +1041,106 @@ int mambo_csa_cost_device(mambo_csa* h, const double* d_x, double* d_cost) {
     CU(cudaMemcpyAsync(d_cost, h->d_part, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     h->memo_valid = false;
     return MAMBO_OK;
+}
+
+// ---- peer exchange of row-panel shards -----------------------------------------------------------------------------
+// Layout of the exported allocation: [2][nshards][plen_pad] doubles, then [2][MAXPEERS] u64 flags.
+int mambo_csa_peer_export(mambo_csa* h, unsigned char* handle64) {
+    if (!h || !handle64) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards > small::MAXPEERS) return fail(MAMBO_EINVAL, "too many shards for the peer exchange");
+    CU(cudaSetDevice(h->device));
+    if (!h->peer_recv) {
+        const int plen = 1 + 2 * h->N * h->N;
+        h->plen_pad = (plen + 15) & ~15;
+        const size_t bytes = (size_t)2 * h->nshards * h->plen_pad * sizeof(double) + (size_t)2 * small::MAXPEERS * sizeof(unsigned long long);
+        CU(cudaMalloc((void**)&h->peer_recv, bytes));
+        CU(cudaMemset(h->peer_recv, 0, bytes));
+        h->peer_flags = reinterpret_cast<unsigned long long*>(h->peer_recv + (size_t)2 * h->nshards * h->plen_pad);
+        TRY(dalloc(&h->peer_done, 1));
+        std::memset(&h->peer_tab, 0, sizeof(h->peer_tab));
+        h->peer_tab.recv[h->shard] = h->peer_recv;
+        h->peer_tab.flags[h->shard] = h->peer_flags;
+        h->peer_attached = 1;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t hd;
+    CU(cudaIpcGetMemHandle(&hd, h->peer_recv));
+    std::memcpy(handle64, &hd, 64);
+    return MAMBO_OK;
+}
+
+static int peer_set(mambo_csa* h, int rank, double* base) {
+    if (rank < 0 || rank >= h->nshards) return fail(MAMBO_EINVAL, "peer rank out of range");
+    if (!h->peer_recv) return fail(MAMBO_ESTATE, "call mambo_csa_peer_export first");
+    if (rank == h->shard) return MAMBO_OK;
+    if (!h->peer_tab.recv[rank]) h->peer_attached++;
+    h->peer_tab.recv[rank] = base;
+    h->peer_tab.flags[rank] = reinterpret_cast<unsigned long long*>(base + (size_t)2 * h->nshards * h->plen_pad);
+    return MAMBO_OK;
+}
+
+// Map the receive buffer another PROCESS exported (cudaIpcOpenMemHandle; NVLink peer access is enabled lazily).
+int mambo_csa_peer_attach(mambo_csa* h, int rank, const unsigned char* handle64) {
+    if (!h || !handle64) return fail(MAMBO_EINVAL, "null argument");
+    if (rank == h->shard) return MAMBO_OK;
+    CU(cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handle64, 64);
+    void* base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, hd, cudaIpcMemLazyEnablePeerAccess));
+    if (rank >= 0 && rank < small::MAXPEERS) h->peer_opened[rank] = base;
+    return peer_set(h, rank, static_cast<double*>(base));
+}
+
+// Same-process variant: the peer handle lives in this process (tests, single-process multi-GPU drivers).
+int mambo_csa_peer_attach_local(mambo_csa* h, int rank, mambo_csa* peer) {
+    if (!h || !peer) return fail(MAMBO_EINVAL, "null argument");
+    if (!peer->peer_recv) return fail(MAMBO_ESTATE, "peer has not exported its receive buffer");
+    if (peer->device != h->device) {
+        CU(cudaSetDevice(h->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+        cudaGetLastError();
+    }
+    return peer_set(h, rank, peer->peer_recv);
+}
+
+int mambo_csa_eval_sharded_push_device(mambo_csa* h, const double* d_x) {
+    if (!h || !d_x) return fail(MAMBO_EINVAL, "null argument");
+    if (h->peer_attached != h->nshards) return fail(MAMBO_ESTATE, "peer exchange not set up: export + attach every shard first");
+    CU(cudaSetDevice(h->device));
+    const long long l0 = h->launches;
+    if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
+    TRY(enqueue_partial(h, -1, true));
+    h->peer_epoch++;
+    const int plen = 1 + 2 * h->N * h->N;
+    small::k_peer_push<<<std::min(64, (plen + 255) / 256), 256, 0, h->stream>>>(h->d_part, plen, h->plen_pad, h->peer_tab, h->nshards, h->shard,
+                                                                              h->peer_epoch, h->peer_done);
+    h->launches++;
+    CU(cudaGetLastError());
+    h->launches_last_eval = (int)(h->launches - l0);
+    h->memo_valid = false;
+    return MAMBO_OK;
+}
+
+int mambo_csa_eval_sharded_finish_device(mambo_csa* h, double* d_out) {
+    if (!h || !d_out) return fail(MAMBO_EINVAL, "null argument");
+    if (h->peer_attached != h->nshards) return fail(MAMBO_ESTATE, "peer exchange not set up");
+    CU(cudaSetDevice(h->device));
+    const long long l0 = h->launches;
+    const int plen = 1 + 2 * h->N * h->N;
+    small::k_peer_sum<<<std::min(64, (plen + 255) / 256), 256, 0, h->stream>>>(h->peer_recv, h->peer_flags, plen, h->plen_pad, h->nshards,
+                                                                             h->peer_epoch, h->d_part, h->d_status);
+    h->launches++;
+    TRY(enqueue_finish_seg(h, -1));
+    if (d_out != h->d_out) CU(cudaMemcpyAsync(d_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToDevice, h->stream));
+    h->launches_last_eval += (int)(h->launches - l0);
+    return MAMBO_OK;
+}
+
+int mambo_csa_eval_sharded_device(mambo_csa* h, const double* d_x, double* d_out) {
+    TRY(mambo_csa_eval_sharded_push_device(h, d_x));
+    return mambo_csa_eval_sharded_finish_device(h, d_out);
 }
 
 int mambo_csa_subtract_fragment(mambo_csa* h, const double* x, double* new_cost) {

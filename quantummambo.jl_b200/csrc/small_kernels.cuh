@@ -789,4 +789,74 @@ __global__ void k_sumsq_add(const double* __restrict__ v, int len, const double*
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Row-panel shards, one process per GPU: exchange of the partial vector [cost, S, G] over NVLink peer memory
+//  instead of a host-launched NCCL allreduce.
+//   k_peer_push : every rank stores its partial vector straight into slot `rank` of EVERY peer's receive buffer
+//                 (P2P stores through NVLink/NVSwitch), then publishes the epoch in the peers' flag words
+//                 (system-scope release).  Last CTA out publishes, so one launch does data + signal.
+//   k_peer_sum  : waits (system-scope acquire polling, with a time-out) until every rank's flag shows the epoch and
+//                 adds the slots in rank order -> deterministic, identical on every rank.
+// Buffers are double-buffered on the epoch parity (see mambo_csa.cu).
+// ------------------------------------------------------------------------------------------------------
+constexpr int MAXPEERS = 16;
+struct PeerTable {
+    double* recv[MAXPEERS];                 // base of each rank's receive buffer (peer-mapped)
+    unsigned long long* flags[MAXPEERS];    // base of each rank's flag words
+};
+
+__global__ void __launch_bounds__(256) k_peer_push(const double* __restrict__ part, int plen, int plen_pad, PeerTable tab, int world,
+                                                   int rank, unsigned long long epoch, unsigned* __restrict__ done_ctr) {
+    const int parity = (int)(epoch & 1ull);
+    const size_t slot = ((size_t)parity * world + rank) * plen_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plen; i += gridDim.x * blockDim.x) {
+        const double v = part[i];
+        for (int r = 0; r < world; ++r) tab.recv[r][slot + i] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(done_ctr, 1u);
+        if (old == gridDim.x - 1) {               // all CTAs of this launch have fenced their stores
+            *done_ctr = 0;
+            __threadfence_system();
+            for (int r = 0; r < world; ++r) {
+                unsigned long long* f = tab.flags[r] + (size_t)parity * MAXPEERS + rank;
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(epoch) : "memory");
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_peer_sum(const double* __restrict__ recv, const unsigned long long* __restrict__ flags, int plen,
+                                                  int plen_pad, int world, unsigned long long epoch, double* __restrict__ part,
+                                                  int* __restrict__ status) {
+    const int parity = (int)(epoch & 1ull);
+    __shared__ int ok;
+    if (threadIdx.x == 0) {
+        ok = 1;
+        const long long t0 = clock64();
+        for (int r = 0; r < world; ++r) {
+            const unsigned long long* f = flags + (size_t)parity * MAXPEERS + r;
+            unsigned long long v;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v < epoch && clock64() - t0 > 8000000000ll) {   // ~4 s: a peer died or never pushed
+                    ok = 0;
+                    break;
+                }
+            } while (v < epoch);
+            if (!ok) break;
+        }
+        if (!ok) *status = 2;
+    }
+    __syncthreads();
+    const size_t base = (size_t)parity * world * plen_pad;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < plen; i += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < world; ++r) s += __ldcg(recv + base + (size_t)r * plen_pad + i);
+        part[i] = s;
+    }
+}
+
 }  // namespace small

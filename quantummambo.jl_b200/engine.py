@@ -164,6 +164,28 @@ class CSAEngine:
     def eval_finish_device(self, d_partial_ptr: int, d_out_ptr: int):
         _lib.check(self._lib.mambo_csa_eval_finish_device(self._h, d_partial_ptr, d_out_ptr))
 
+    # -- peer exchange of row-panel shards (NVLink peer memory, no host collective) ----------------------------------
+    def peer_export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        _lib.check(self._lib.mambo_csa_peer_export(self._h, buf))
+        return bytes(buf)
+
+    def peer_attach(self, rank: int, handle: bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        _lib.check(self._lib.mambo_csa_peer_attach(self._h, rank, buf))
+
+    def peer_attach_local(self, rank: int, peer: "CSAEngine"):
+        _lib.check(self._lib.mambo_csa_peer_attach_local(self._h, rank, peer._h))
+
+    def eval_sharded_push_device(self, d_x_ptr: int):
+        _lib.check(self._lib.mambo_csa_eval_sharded_push_device(self._h, d_x_ptr))
+
+    def eval_sharded_finish_device(self, d_out_ptr: int):
+        _lib.check(self._lib.mambo_csa_eval_sharded_finish_device(self._h, d_out_ptr))
+
+    def eval_sharded_device(self, d_x_ptr: int, d_out_ptr: int):
+        _lib.check(self._lib.mambo_csa_eval_sharded_device(self._h, d_x_ptr, d_out_ptr))
+
     def set_profiling(self, enable: bool):
         _lib.check(self._lib.mambo_csa_set_profiling(self._h, 1 if enable else 0))
 

@@ -91,6 +91,29 @@ class ShardedEngine:
         self.d_part = torch.empty(self.plen, dtype=torch.float64, device=self.dev)
         self.d_out = torch.empty(self.L + 1, dtype=torch.float64, device=self.dev)
 
+    def setup_peers(self, rank: int, world: int):
+        """Exchange CUDA-IPC handles of the receive buffers over the default process group and map every peer's
+        buffer (NVLink peer memory): afterwards `cost_grad_peer` needs no host-launched collective."""
+        import torch.distributed as dist
+        mine = self.eng.peer_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine)
+        for r, hd in enumerate(handles):
+            if r != rank:
+                self.eng.peer_attach(r, hd)
+        dist.barrier()
+        self.peers_ready = True
+
+    def cost_grad_peer(self, x):
+        """Sharded cost+gradient with the in-library peer exchange (push to every peer, wait, rank-ordered sum)."""
+        torch = self.torch
+        with torch.cuda.stream(self.stream):
+            self.d_x.copy_(torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)), non_blocking=False)
+            self.eng.eval_sharded_device(self.d_x.data_ptr(), self.d_out.data_ptr())
+        self.stream.synchronize()
+        out = self.d_out.cpu().numpy()
+        return float(out[0]), out[1:].copy()
+
     def eval_partial(self, x):
         torch = self.torch
         with torch.cuda.stream(self.stream):

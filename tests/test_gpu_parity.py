@@ -198,6 +198,44 @@ def test_sharded_partials_sum_to_unsharded(mb, lib):
                 e.close()
 
 
+def test_peer_exchange_of_shards_on_one_gpu(mb, lib):
+    """The NVLink peer-memory exchange (push -> flag -> rank-ordered sum) with all shards living on one GPU of one
+    process: every shard pushes first, then every shard finishes (no kernel ever waits for a later launch)."""
+    import torch
+    n = 14
+    dev = torch.device("cuda", 0)
+    for kind, world in (("dense_sym", 2), ("pairsym", 3)):
+        T = KINDS[kind](n, 2)
+        engines = [mb.CSAEngine(T, shard=r, nshards=world) for r in range(world)]
+        try:
+            for e in engines:
+                e.peer_export()
+            for r, e in enumerate(engines):
+                for q, peer in enumerate(engines):
+                    if q != r:
+                        e.peer_attach_local(q, peer)
+            for rep in range(3):                                   # three epochs: exercises the parity double buffer
+                x = o.random_x(n, 10 + rep)
+                c0, g0 = o.cost_grad_factored(x, T)
+                d_x = torch.from_numpy(x).to(dev)
+                outs = [torch.zeros(len(x) + 1, dtype=torch.float64, device=dev) for _ in engines]
+                for e in engines:
+                    e.eval_sharded_push_device(d_x.data_ptr())
+                for e in engines:
+                    e.synchronize()
+                for e, d_o in zip(engines, outs):
+                    e.eval_sharded_finish_device(d_o.data_ptr())
+                    e.synchronize()
+                ref = outs[0].cpu().numpy()
+                for d_o in outs:
+                    out = d_o.cpu().numpy()
+                    assert abs(out[0] - c0) <= RTOL * abs(c0) and rel(out[1:], g0) <= RTOL
+                    assert np.array_equal(out, ref)                # identical bits on every shard
+        finally:
+            for e in engines:
+                e.close()
+
+
 def test_device_entry_points_match_host_closures(mb, lib):
     import torch
     n = 11
