@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--no-rowpanel", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations timed for the CPU baseline (0 = auto)")
     ap.add_argument("--no-greedy", action="store_true", help="skip the greedy-CSA time-to-tolerance leg")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="evaluation lanes per GPU (mambo_csa_create_lane); 0 = floor(SMs / orbital-rotation CTAs), 1..8")
     return ap.parse_args()
 
 
@@ -65,7 +67,32 @@ class ClockSampler(threading.Thread):
         self.samples = []
         self._halt = threading.Event()
 
+    def _nvml_loop(self) -> bool:
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+        while not self._halt.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append([str(sm), str(mx), str(pw)] + ["Active" if r & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self._halt.wait(0.01)
+        return True
+
     def run(self):
+        if self._nvml_loop():
+            return
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
@@ -187,9 +214,30 @@ def greedy_time_to_tolerance(mb, syn, device: int, n: int = 50, R: int = 2, frag
             trail.append(e.subtract_fragment(xm))
             evals += res["evaluations"]
         dt = time.perf_counter() - t0
-    return {"workload": f"planted N={n} R={R}, {frags} greedy fragments x <= {max_iter} BFGS iterations (native optimiser)",
-            "seconds": dt, "evaluations": evals, "initial_cost": c0, "cost_trail": trail,
-            "ms_per_evaluation_incl_optimizer": dt / max(evals, 1) * 1e3}
+    out = {"workload": f"planted N={n} R={R}, {frags} greedy fragments x <= {max_iter} BFGS iterations (native optimiser)",
+           "seconds": dt, "evaluations": evals, "initial_cost": c0, "cost_trail": trail,
+           "ms_per_evaluation_incl_optimizer": dt / max(evals, 1) * 1e3}
+    # BASELINE.json configs[2]: 8-way multistart of the first greedy step (random theta guesses), here on ONE GPU:
+    # the 8 runs one after the other on one handle versus spread over evaluation lanes that share the residual
+    K = 8
+    x0s = np.stack([np.concatenate([np.zeros(cL), 2 * np.pi * rng.random(uL)]) for _ in range(K)])
+    with mb.CSAEngine(T, device=device) as e:
+        lanes = [e] + [e.lane() for _ in range(K - 1)]
+        t0 = time.perf_counter()
+        _, r1, b1 = mb.multistart(lanes[:1], x0s, max_iter=max_iter)
+        t_seq = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        _, r8, b8 = mb.multistart(lanes, x0s, max_iter=max_iter)
+        t_lanes = time.perf_counter() - t0
+        for ln in lanes[1:]:
+            ln.close()
+    out["multistart"] = {"workload": f"{K} random-theta starts of the first greedy step, planted N={n} R={R}, <= {max_iter} BFGS iterations each",
+                         "seconds_one_handle": t_seq, "seconds_8_lanes": t_lanes,
+                         "evaluations": sum(r["evaluations"] for r in r8), "best_start": b8,
+                         "minima_agree": bool(max(abs(a["minimum"] - b["minimum"]) for a, b in zip(r1, r8))
+                                              <= 1e-9 * max(abs(r["minimum"]) for r in r1)),
+                         "best_minimum": r8[b8]["minimum"]}
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -237,72 +285,122 @@ def main():
     dgemm_tflops = 2.0 * 4096 ** 3 / (best * 1e-3) / 1e12
     del a, b
 
-    # ---- device-resident leg ------------------------------------------------------------------------------
-    stream = torch.cuda.Stream(dev)          # a real side stream: handle 0 (legacy default) would mean "own stream"
-    torch.cuda.set_stream(stream)
-    eng.set_stream(stream.cuda_stream)
+    # ---- evaluation lanes: independent evaluations of the step overlap on the device (mambo_csa_create_lane) ----------
+    tiles = (n + 15) // 16
+    nl = args.lanes if args.lanes > 0 else max(1, min(8, info["num_sms"] // (tiles * tiles)))
+    nl = min(nl, BATCH)
+    group = [eng] + [eng.lane() for _ in range(nl - 1)]
+    main_stream = torch.cuda.Stream(dev)      # real side streams: handle 0 (legacy default) would mean "own stream"
+    torch.cuda.set_stream(main_stream)
+    streams = [torch.cuda.Stream(dev) for _ in range(nl)]
     d_x = torch.from_numpy(np.stack(xs)).to(dev)                     # [BATCH, L] in HBM
     d_out = torch.empty(BATCH, L + 1, dtype=torch.float64, device=dev)
 
-    def step_device():
-        for i in range(BATCH):
-            eng.eval_device(d_x[i].data_ptr(), d_out[i].data_ptr())
+    def device_leg(lanes: int, profile: bool):
+        """K steps of BATCH evaluations, x and (cost, grad) resident in HBM, round-robin over `lanes` lanes; CUDA events
+        on a main stream that the lane streams fork from and join into.  Returns (ms, launches, prof, segs)."""
+        act, sts = group[:lanes], streams[:lanes]
+        for e, st in zip(act, sts):
+            e.set_stream(st.cuda_stream)
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    torch.cuda.synchronize()
-    eng.synchronize()
-    launches0 = eng.get_profile()["total_launches"]
-    eng.set_profiling(True)
+        def step():
+            for i in range(BATCH):
+                act[i % lanes].eval_device(d_x[i].data_ptr(), d_out[i].data_ptr())
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        torch.cuda.synchronize()
+        l0 = sum(e.get_profile()["total_launches"] for e in act)
+        if profile:
+            act[0].set_profiling(True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main_stream)
+        for st in sts:
+            st.wait_stream(main_stream)
+        for _ in range(args.steps):
+            step()
+        for st in sts:
+            main_stream.wait_stream(st)
+        e1.record(main_stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms_ = e0.elapsed_time(e1)
+        segs_ = act[0].get_segments() if profile else None
+        prof_ = act[0].get_profile() if profile else None
+        if profile:
+            act[0].set_profiling(False)
+        launches_ = sum(e.get_profile()["total_launches"] for e in act) - l0
+        if world > 1:
+            t = torch.tensor([ms_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t.item())
+        for e in act:
+            e.set_stream(None)
+        return ms_, launches_, prof_, segs_
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        step_device()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
+    # single lane: every kernel runs alone, so the fused kernel's CUDA-event time is its own duration (roofline)
+    ms1, launches1, prof, segs = device_leg(1, True)
     info = eng.info()
-    segs = eng.get_segments()
-    prof = eng.get_profile()
-    eng.set_profiling(False)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    launches = prof["total_launches"] - launches0
+    # all lanes: the headline device-resident number
+    if nl > 1:
+        ms, launches, _, _ = device_leg(nl, False)
+    else:
+        ms, launches = ms1, launches1
     evals_total = world * BATCH * args.steps
     value = evals_total / (ms * 1e-3)
+    value1 = evals_total / (ms1 * 1e-3)
     cost_check = float(d_out[0, 0].item())
 
-    # ---- end-to-end leg: public host API, host buffers, H2D + D2H inside the timed region --------------------
-    eng.set_stream(None)
-    for i in range(BATCH):
-        eng.cost_grad(xs[i] + 0.0)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    acc = 0.0
-    for s in range(args.steps):
-        for i in range(BATCH):
-            xi = xs[i].copy()
-            xi[0] += 1e-9 * (s + 1)          # a fresh point every call: the memo of the last x never hits
-            c, g = eng.cost_grad(xi)
-            acc += c
-    t_e2e = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_e2e = float(t.item())
+    # ---- end-to-end leg: public host API, host buffers, H2D + D2H inside the timed region --------------------------
+    def host_leg(lanes: int):
+        """The same K x BATCH evaluations through the synchronous host closure (mambo_csa_cost_grad: host x in, H2D,
+        kernels, D2H of cost+grad), one caller thread per lane, a fresh x every call (the memo never hits)."""
+        act = group[:lanes]
+        for k, e in enumerate(act):
+            e.cost_grad(xs[k] + 0.0)
+        acc = [0.0] * lanes
+
+        def worker(k):
+            for s_ in range(args.steps):
+                for i in range(k, BATCH, lanes):
+                    xi = xs[i].copy()
+                    xi[0] += 1e-9 * (s_ + 1)
+                    c, g = act[k].cost_grad(xi)
+                    acc[k] += c
+
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if lanes == 1:
+            worker(0)
+        else:
+            th = [threading.Thread(target=worker, args=(k,)) for k in range(lanes)]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+        dt_ = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_ = float(t.item())
+        return dt_
+
+    t_e2e1 = host_leg(1)
+    t_e2e = host_leg(nl) if nl > 1 else t_e2e1
     sampler.stop()
     e2e_value = evals_total / t_e2e
+    e2e_value1 = evals_total / t_e2e1
+    for e in group[1:]:
+        e.close()
+    stream = main_stream
 
     # ---- row-panel sharded variant (strong scaling, NCCL allreduce of the partial vector) -----------------------
     rowpanel = None
@@ -325,6 +423,8 @@ def main():
         def step_peer():                      # in-library exchange over NVLink peer memory, no host collective
             for i in range(BATCH):
                 engs.eval_sharded_device(d_x0[i].data_ptr(), d_out[i].data_ptr())
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
         def timed(step):
             for _ in range(3):
@@ -407,7 +507,9 @@ def main():
             "algorithmic_flops_per_launch": alg_flops, "executed_flops_per_launch": exec_flops,
             "executed_frac": exec_flops / (fused_ms * 1e-3) / 1e12 / dgemm_tflops,
             "unsymmetrised_4N5_equivalent_tflops": 4.0 * n ** 5 / (fused_ms * 1e-3) / 1e12,
-            "share_of_step": prof["fused_ms"] / ms,
+            "share_of_step": prof["fused_ms"] / ms1,
+            "timed_in": "the single-lane timed region (each kernel runs alone there; with several lanes a fused launch queues "
+                        "behind other lanes' kernels between its two events)",
             "segments_ms_per_eval": segs,
         }
         line = {
@@ -415,12 +517,16 @@ def main():
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"dense-sym N={n} seed 0, CSA cost+grad at {BATCH} points/step per GPU", "N": n,
-                       "points_per_step": BATCH, "mode": info["mode_name"], "rows": rows,
+                       "points_per_step": BATCH, "lanes_per_gpu": nl, "mode": info["mode_name"], "rows": rows,
                        "tensor_bytes_per_gpu": info["tensor_bytes"], "l2_policy": "inputs larger than L2 (residual "
                        f"{info['tensor_bytes'] / 1e6:.0f} MB streamed once per evaluation; L2 is 126 MB)",
                        "parallelism": "multistart replicas, one per GPU" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": BATCH * L * 8,
-                    "d2h_bytes_per_step": BATCH * (L + 1) * 8, "timer": "host perf_counter around synchronous C-ABI calls"},
+                    "d2h_bytes_per_step": BATCH * (L + 1) * 8,
+                    "timer": "host perf_counter around synchronous C-ABI calls (mambo_csa_cost_grad), one caller thread per lane",
+                    "single_caller": e2e_value1},
+            "single_lane": {"value": value1, "ms_per_step": ms1 / args.steps,
+                            "note": "one evaluation in flight at a time (the sequential BFGS case)"},
             "gpu_launches": int(launches), "launches_per_eval": launches / (BATCH * args.steps),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "cost_check": cost_check,
         }

@@ -82,6 +82,14 @@ int  mambo_csa_create(mambo_csa** h, int N, int flavour, const double* tbt, cons
 /* Row-panel shard `shard` of `nshards`: this handle keeps only its rows of the residual. */
 int  mambo_csa_create_sharded(mambo_csa** h, int N, int flavour, const double* tbt, const double* obt,
                               int device, unsigned flags, int shard, int nshards);
+/* Evaluation lane: another handle on the same GPU that SHARES the device-resident residual of `parent` (tensor, one-body
+ * residual, row tables) but owns its stream, operands, scratch and CUDA graphs.  Independent evaluations issued through
+ * different lanes (multistart runs, one host thread per lane) overlap on the device: the latency-bound orbital-rotation
+ * chains / epilogues of one lane fill the SMs while another lane's are waiting at a grid barrier.  A residual update
+ * (mambo_csa_subtract_fragment) through any handle of the group is seen by all of them; the caller must not run it
+ * concurrently with evaluations on sibling lanes.  The residual is freed when the last handle of the group is
+ * destroyed.  Useful lane counts: floor(148 / ceil(N/16)^2) -- 3 at N=100, 9 at N=50, 1 at N=152.                 */
+int  mambo_csa_create_lane(mambo_csa* parent, mambo_csa** lane);
 void mambo_csa_destroy(mambo_csa* h);
 int  mambo_csa_get_info(const mambo_csa* h, mambo_csa_info_t* info);
 int  mambo_csa_num_params(const mambo_csa* h);

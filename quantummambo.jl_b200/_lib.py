@@ -64,6 +64,7 @@ _D = C.POINTER(C.c_double)
 SIGNATURES = {
     "mambo_csa_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.c_int, C.c_uint]),
     "mambo_csa_create_sharded": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.c_int, C.c_uint, C.c_int, C.c_int]),
+    "mambo_csa_create_lane": (C.c_int, [_P, C.POINTER(_P)]),
     "mambo_csa_destroy": (None, [_P]),
     "mambo_csa_get_info": (C.c_int, [_P, C.POINTER(MamboInfo)]),
     "mambo_csa_num_params": (C.c_int, [_P]),

@@ -2,6 +2,7 @@
 // Replaces the closures of /root/reference/src/UTILS/decompose.jl:96-105, 221-231 and the residual update
 // decompose.jl:56,182.  There is deliberately no CPU code path for any of the numerics in this file.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -47,6 +48,13 @@ struct GraphSeg {
     int kernels = 0;
 };
 
+// Residual state shared by a handle and the evaluation lanes created from it (mambo_csa_create_lane): the tensor,
+// its row tables and the one-body residual exist once per GPU; every lane has its own operands and scratch.
+struct SharedResidual {
+    std::atomic<int> refs{1};             // the last handle out frees T1/T2/hT/pa/pq/sw (every holder has the same pointers)
+    std::atomic<long long> version{0};   // bumped by every residual update: invalidates the memo of every lane
+};
+
 }  // namespace
 
 struct mambo_csa {
@@ -56,6 +64,9 @@ struct mambo_csa {
     int NB = 0, Np = 0, ld = 0;     // n-blocks, padded N, operand pitch
     long long ldT = 0;
     int shard = 0, nshards = 1;
+    SharedResidual* sh = nullptr;       // owner of T1/T2/hT/pa/pq/sw (shared with the lanes of this handle)
+    bool is_lane = false;
+    long long memo_version = -1;
     int prow_begin = 0, prow_end = 0;   // local panels [begin, end)
     int row_begin = 0, row_end = 0;     // local padded rows
     int P = 0, Q = 0, G = 0, S = 0, visits = 0;
@@ -537,31 +548,10 @@ int dalloc(T** p, size_t count) {
     return MAMBO_OK;
 }
 
-int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned flags) {
+int build_residual(mambo_csa* h, const double* tbt, const double* obt, unsigned flags, unsigned* mode_out) {
     const int n = h->N;
-    CU(cudaSetDevice(h->device));
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, h->device));
-    if (prop.major < 10) return fail(MAMBO_ECUDA, "libmambo_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major * 10 + prop.minor));
-    h->num_sms = prop.multiProcessorCount;
-    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-    h->stream = h->own_stream;
-
-    h->cL = n * (n + 1) / 2;
-    h->uL = n * (n - 1) / 2;
-    h->lam_off = (h->flavour == MAMBO_CSA_SD) ? n : 0;
-    h->L = h->lam_off + h->cL + h->uL;
-    int nb = (n + 7) / 8;
-    h->NB = 0;
-    for (int b : kNBBuckets)
-        if (b >= nb) {
-            h->NB = b;
-            break;
-        }
-    if (!h->NB) return fail(MAMBO_EINVAL, "N too large for the compiled kernel set (N <= 168)");
-    h->Np = 8 * h->NB;
-    h->ld = h->Np + 4;
-
+    h->sh = new (std::nothrow) SharedResidual();
+    if (!h->sh) return fail(MAMBO_ENOMEM, "host allocation failed");
     // ---- upload the tensor (or use it in place when it is already on the device) and analyse its symmetry ----
     const size_t n4 = (size_t)n * n * n * n;
     const bool on_dev = flags & MAMBO_TBT_ON_DEVICE;
@@ -646,6 +636,49 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         if (!obt) return fail(MAMBO_EINVAL, "CSA_SD needs the one-body tensor");
         TRY(dalloc(&h->hT, (size_t)n * n));
         CU(cudaMemcpy(h->hT, obt, sizeof(double) * n * n, on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    }
+
+    *mode_out = mode;
+    return MAMBO_OK;
+}
+
+int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned flags, const mambo_csa* parent = nullptr) {
+    const int n = h->N;
+    CU(cudaSetDevice(h->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, h->device));
+    if (prop.major < 10) return fail(MAMBO_ECUDA, "libmambo_b200 needs an sm_100a (B200) device; found sm_" + std::to_string(prop.major * 10 + prop.minor));
+    h->num_sms = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+
+    h->cL = n * (n + 1) / 2;
+    h->uL = n * (n - 1) / 2;
+    h->lam_off = (h->flavour == MAMBO_CSA_SD) ? n : 0;
+    h->L = h->lam_off + h->cL + h->uL;
+    int nb = (n + 7) / 8;
+    h->NB = 0;
+    for (int b : kNBBuckets)
+        if (b >= nb) {
+            h->NB = b;
+            break;
+        }
+    if (!h->NB) return fail(MAMBO_EINVAL, "N too large for the compiled kernel set (N <= 168)");
+    h->Np = 8 * h->NB;
+    h->ld = h->Np + 4;
+
+    unsigned mode = 0;
+    if (parent) {
+        // evaluation lane: same problem, same GPU, same residual; only the per-evaluation state below is new
+        mode = (unsigned)parent->mode;
+        h->mode = parent->mode; h->packed = parent->packed; h->asym_pair = parent->asym_pair; h->asym_pq = parent->asym_pq;
+        h->nR = parent->nR; h->nRpad = parent->nRpad; h->ldT = parent->ldT; h->Q = parent->Q; h->P = parent->P;
+        h->prow_begin = parent->prow_begin; h->prow_end = parent->prow_end; h->row_begin = parent->row_begin; h->row_end = parent->row_end;
+        h->sh = parent->sh;
+        h->sh->refs.fetch_add(1);
+        h->T1 = parent->T1; h->T2 = parent->T2; h->hT = parent->hT; h->pa = parent->pa; h->pq = parent->pq; h->sw = parent->sw;
+    } else {
+        TRY(build_residual(h, tbt, obt, flags, &mode));
     }
 
     // ---- operands and work buffers ----
@@ -857,6 +890,31 @@ int mambo_csa_create_sharded(mambo_csa** out, int N, int flavour, const double* 
     return MAMBO_OK;
 }
 
+// A second evaluation context on the same GPU and the same residual: own stream, operands, scratch and CUDA graphs,
+// shared T~ / one-body residual.  Lanes let independent evaluations (multistart, line-search probes of different runs)
+// overlap: the latency-bound orbital-rotation chains and epilogues of one lane run beside those of another while
+// the tensor-pipe-bound fused kernels queue back to back.
+int mambo_csa_create_lane(mambo_csa* parent, mambo_csa** out) {
+    if (!parent || !out) return fail(MAMBO_EINVAL, "null argument");
+    mambo_csa* h = new (std::nothrow) mambo_csa();
+    if (!h) return fail(MAMBO_ENOMEM, "host allocation failed");
+    h->N = parent->N;
+    h->flavour = parent->flavour;
+    h->device = parent->device;
+    h->shard = parent->shard;
+    h->nshards = parent->nshards;
+    h->is_lane = true;
+    int rc = build_handle(h, nullptr, nullptr, 0, parent);
+    if (rc) {
+        std::string keep = g_err;
+        mambo_csa_destroy(h);
+        g_err = keep;
+        return rc;
+    }
+    *out = h;
+    return MAMBO_OK;
+}
+
 int mambo_csa_create(mambo_csa** out, int N, int flavour, const double* tbt, const double* obt, int device, unsigned flags) {
     return mambo_csa_create_sharded(out, N, flavour, tbt, obt, device, flags, 0, 1);
 }
@@ -870,7 +928,13 @@ void mambo_csa_destroy(mambo_csa* h) {
             if (g.exec) cudaGraphExecDestroy(g.exec);
     for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})
         if (g->exec) cudaGraphExecDestroy(g->exec);
-    void* bufs[] = {h->T1, h->T2, h->hT, h->At, h->Bt, h->pa, h->pq, h->sw, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
+    if (!h->sh || h->sh->refs.fetch_sub(1) == 1) {
+        void* shared[] = {h->T1, h->T2, h->hT, h->pa, h->pq, h->sw};
+        for (void* b : shared)
+            if (b) cudaFree(b);
+        delete h->sh;
+    }
+    void* bufs[] = {h->At, h->Bt, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
                     h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -914,11 +978,13 @@ int mambo_csa_get_info(const mambo_csa* h, mambo_csa_info_t* info) {
 
 int mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* grad) {
     if (!h || !x) return fail(MAMBO_EINVAL, "null argument");
-    if (!(h->memo_valid && std::memcmp(h->memo_x.data(), x, sizeof(double) * h->L) == 0)) {
+    const long long version = h->sh->version.load();   // residual updates through any lane invalidate every memo
+    if (!(h->memo_valid && h->memo_version == version && std::memcmp(h->memo_x.data(), x, sizeof(double) * h->L) == 0)) {
         h->memo_valid = false;
         TRY(eval_host(h, x, true));
         std::memcpy(h->memo_x.data(), x, sizeof(double) * h->L);
         h->memo_valid = true;
+        h->memo_version = version;
     }
     if (cost) *cost = h->h_out[0];
     if (grad) std::memcpy(grad, h->h_out + 1, sizeof(double) * h->L);
@@ -1154,6 +1220,7 @@ int mambo_csa_subtract_fragment(mambo_csa* h, const double* x, double* new_cost)
     CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     h->memo_valid = false;
+    h->sh->version.fetch_add(1);
     if (new_cost) *new_cost = h->h_out[0];
     return MAMBO_OK;
 }

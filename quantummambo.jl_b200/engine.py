@@ -63,6 +63,16 @@ class CSAEngine:
         self.L = self._lib.mambo_csa_num_params(self._h)
 
     # -- lifetime -----------------------------------------------------------------------------------------
+    def lane(self) -> "CSAEngine":
+        """Another evaluation context on the same GPU sharing this engine's device-resident residual
+        (mambo_csa_create_lane): drive it from its own host thread / stream to overlap independent evaluations."""
+        other = object.__new__(CSAEngine)
+        other._h = C.c_void_p()
+        other._lib = self._lib
+        other.N, other.flavour, other.device, other.L = self.N, self.flavour, self.device, self.L
+        _lib.check(self._lib.mambo_csa_create_lane(self._h, C.byref(other._h)))
+        return other
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             self._lib.mambo_csa_destroy(self._h)
@@ -203,3 +213,22 @@ class CSAEngine:
 
     def synchronize(self):
         _lib.check(self._lib.mambo_csa_synchronize(self._h))
+
+
+def multistart(engines, x0s, g_tol: float = 1e-8, max_iter: int = 1000, lbfgs_memory: int = 0, verbose: int = 0):
+    """K independent BFGS runs from the rows of `x0s`, scheduled over `engines` by the library
+    (mambo_multistart_run: one worker thread per handle pulling starts from a shared counter; precedent
+    orbitals.jl:39-67).  `engines` may be handles on different GPUs and/or lanes of one GPU (CSAEngine.lane()).
+    Returns (x_min [K, L], list of K result dicts, index of the best start)."""
+    engines = list(engines)
+    lib = engines[0]._lib
+    L = engines[0].L
+    x0s = np.ascontiguousarray(x0s, dtype=np.float64).reshape(-1, L)
+    K = x0s.shape[0]
+    xm = np.empty((K, L))
+    hs = (C.c_void_p * len(engines))(*[e._h.value for e in engines])
+    opt = _lib.OptOptions(max_iter, g_tol, lbfgs_memory, verbose)
+    res = (_lib.OptResult * K)()
+    best = C.c_int(-1)
+    _lib.check(lib.mambo_multistart_run(hs, len(engines), K, x0s.ctypes.data, xm.ctypes.data, C.byref(opt), res, C.byref(best)))
+    return xm, [{k: getattr(r, k) for k, _ in r._fields_} for r in res], best.value

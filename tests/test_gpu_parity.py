@@ -236,6 +236,75 @@ def test_peer_exchange_of_shards_on_one_gpu(mb, lib):
                 e.close()
 
 
+def test_lanes_share_the_residual_and_run_concurrently(mb, lib):
+    """mambo_csa_create_lane: lanes evaluate independently (one host thread each, overlapping on the device), give the
+    parent's bits, see residual updates made through a sibling, and keep the residual alive after the parent is closed."""
+    import threading
+    for n, flavour in ((13, "CSA"), (9, "CSA_SD"), (40, "CSA")):
+        T = o.dense_sym_tbt(n, 4)
+        obt = _obt(n, 4) if flavour == "CSA_SD" else None
+        parent = mb.CSAEngine(T, obt, flavour)
+        lanes = [parent.lane() for _ in range(3)]
+        group = [parent] + lanes
+        xs = [o.random_x(n, 20 + k, flavour) for k in range(len(group))]
+        want = [o.cost_grad_factored(x, T, obt, flavour) for x in xs]
+        c_par, g_par = parent.cost_grad(xs[1])
+        c_lane, g_lane = lanes[0].cost_grad(xs[1])
+        assert c_par == c_lane and np.array_equal(g_par, g_lane)              # same bits through either context
+        got = [None] * len(group)
+
+        def work(k):
+            for _ in range(6):                                                # repeated so the lanes really overlap
+                got[k] = group[k].cost_grad(xs[k] + 0.0)
+
+        threads = [threading.Thread(target=work, args=(k,)) for k in range(len(group))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        for (c, g), (c0, g0) in zip(got, want):
+            assert abs(c - c0) <= RTOL * abs(c0) and rel(g, g0) <= RTOL
+        # a residual update through one handle is seen by every lane, memoised x included
+        before = lanes[1].cost_grad(xs[0])[0]
+        new_cost = parent.subtract_fragment(xs[0])
+        W, h1 = parent.reconstruct(xs[0])
+        T2 = T - W
+        obt2 = None if obt is None else obt - h1
+        c_after, g_after = lanes[1].cost_grad(xs[0])
+        c0, g0 = o.cost_grad_factored(xs[0], T2, obt2, flavour)
+        assert c_after != before
+        assert abs(c_after - c0) <= 1e-9 * max(abs(c0), abs(before)) and rel(g_after, g0) <= 1e-9
+        assert abs(lanes[2].residual_cost() - new_cost) <= RTOL * new_cost
+        parent.close()                                                         # the lanes keep the shared residual alive
+        c_again, _ = lanes[0].cost_grad(xs[0])
+        assert c_again == c_after
+        for e in lanes:
+            e.close()
+
+
+def test_multistart_scheduler_over_lanes(mb, lib):
+    """mambo_multistart_run over lanes of one GPU: same minima as running every start alone, and the reported best
+    start is the arg-min (multistart precedent: orbitals.jl:39-67)."""
+    n = 6
+    x_true = o.random_x(n, 5)
+    T = o.reconstruct_factored(x_true, n)[1]
+    cL, uL = o.cartan_2b_num_params(n), o.real_orbital_rotation_num_params(n)
+    rng = np.random.default_rng(7)
+    K = 5
+    x0s = np.stack([np.concatenate([np.zeros(cL), 2 * np.pi * rng.random(uL)]) for _ in range(K)])
+    with mb.CSAEngine(T) as e:
+        lanes = [e, e.lane(), e.lane()]
+        xm, res, best = mb.multistart(lanes, x0s, max_iter=200)
+        alone = [e.optimize(x0, max_iter=200) for x0 in x0s]
+        for k in range(K):
+            assert abs(res[k]["minimum"] - alone[k][1]["minimum"]) <= 1e-9 * max(1.0, abs(alone[k][1]["minimum"]))
+            c, _ = e.cost_grad(xm[k])
+            assert abs(c - res[k]["minimum"]) <= 1e-9 * max(1.0, abs(c))
+        assert best == int(np.argmin([r["minimum"] for r in res]))
+        for ln in lanes[1:]:
+            ln.close()
+
+
 def test_device_entry_points_match_host_closures(mb, lib):
     import torch
     n = 11
