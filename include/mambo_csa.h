@@ -106,6 +106,20 @@ int  mambo_csa_residual_cost(mambo_csa* h, double* cost);
 int  mambo_csa_get_residual(mambo_csa* h, double* tbt_out, double* obt_out);
 int  mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double* obt_out);
 
+/* --- initial guess (guesses.jl:51-84) ------------------------------------------------------------------- */
+/* The eigenpair of largest |eigenvalue| of Symmetric(reshape(tbt_residual, (N^2, N^2))) -- what tbt_svd_1st keeps of
+ * its O(N^6) `eigen` (guesses.jl:55-63) -- by Lanczos with full re-orthogonalisation on the device-resident residual
+ * (HBM-bound matrix-vector products).  vec receives the eigenvector as the N x N column-major operator
+ * `reshape(U[:,1], (n,n))`, unit Frobenius norm, largest-magnitude entry positive.  tol <= 0: 1e-13 (relative Ritz
+ * residual); max_iter <= 0: 600 Krylov vectors.  The O(N^3) remainder of tbt_svd_1st (eigen of the N x N operator,
+ * SVD_to_CSA, log of the rotation) stays with the caller.                                                       */
+int  mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval, double* vec,
+                           int* iterations, double* residual);
+
+/* Host half of the Lanczos driver (no GPU): largest-|eigenvalue| Ritz pair of the m x m symmetric tridiagonal with
+ * diagonal alpha[0..m) and off-diagonal beta[0..m-1) (bisection + inverse iteration); z receives the unit vector.   */
+int  mambo_debug_tridiag_leading(const double* alpha, const double* beta, int m, double* theta, double* z);
+
 /* --- device-resident entry points (no host synchronisation; used by the multi-GPU host and bench) -------- */
 /* Run all engine work on `stream` (a cudaStream_t); NULL restores the handle's own stream (so the legacy
  * default stream, whose handle is 0, cannot be selected: pass a created stream). */

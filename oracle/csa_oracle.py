@@ -415,7 +415,7 @@ def SOn_unitary_to_params(U):
     return np.array([Ulog[i, j] for i in range(n) for j in range(i + 1, n)])
 
 
-def tbt_svd_1st(tbt, tiny: float = 1e-12):
+def tbt_svd_1st(tbt, tiny: float = 1e-12, fix_sign: bool = False):
     """guesses.jl:51-84 + SVD_to_CSA (:3-49).  Returns (lambda (cL), theta (uL)).  Note K1 of SURVEY.md:
     SVD_to_CSA fills lambda in *upper*-triangular order (guesses.jl:12-18) although every consumer reads it
     lower-triangular -- reproduced on purpose."""
@@ -429,6 +429,13 @@ def tbt_svd_1st(tbt, tiny: float = 1e-12):
     lamv = lamv[ind]
     Uv = Uv[:, ind]
     full_l = np.reshape(Uv[:, 0], (n, n), order="F")
+    if fix_sign:
+        # The sign of a LAPACK eigenvector is a convention, and through K1 (coefficients filled in upper- but read in
+        # lower-triangular order) the resulting fragment depends on it.  fix_sign pins the convention the CUDA library
+        # documents (largest-magnitude entry positive) so that the two can be compared entry by entry.
+        big = np.argmax(np.abs(full_l.reshape(-1, order="F")))
+        if full_l.reshape(-1, order="F")[big] < 0:
+            full_l = -full_l
     cur_l = np.triu(full_l) + np.triu(full_l, 1).T
     lead = lamv[0]
     if np.sum(np.abs(cur_l - full_l)) > tiny:

@@ -17,6 +17,7 @@
 #include "small_kernels.cuh"
 #include "chain_kernels.cuh"
 #include "panel_kernels.cuh"
+#include "lanczos_kernels.cuh"
 
 namespace {
 
@@ -1207,6 +1208,199 @@ int mambo_csa_eval_sharded_finish_device(mambo_csa* h, double* d_out) {
 int mambo_csa_eval_sharded_device(mambo_csa* h, const double* d_x, double* d_out) {
     TRY(mambo_csa_eval_sharded_push_device(h, d_x));
     return mambo_csa_eval_sharded_finish_device(h, d_out);
+}
+
+// ---- leading eigenpair of the residual (initial guess of a greedy step, guesses.jl:51-84) ---------------------------
+namespace {
+
+// number of eigenvalues of the symmetric tridiagonal (a, b) strictly below x (Sturm sequence)
+int sturm_count(const std::vector<double>& a, const std::vector<double>& b, int m, double x) {
+    int cnt = 0;
+    double d = 1.0;
+    for (int i = 0; i < m; ++i) {
+        const double off = i ? b[i - 1] * b[i - 1] : 0.0;
+        d = a[i] - x - (i ? off / d : 0.0);
+        if (d == 0.0) d = -1e-300;
+        if (d < 0.0) ++cnt;
+    }
+    return cnt;
+}
+// k-th smallest eigenvalue (0-based) of the m x m tridiagonal by bisection
+double tridiag_eigval(const std::vector<double>& a, const std::vector<double>& b, int m, int k) {
+    double lo = a[0], hi = a[0];
+    for (int i = 0; i < m; ++i) {
+        const double r = (i ? std::fabs(b[i - 1]) : 0.0) + (i + 1 < m ? std::fabs(b[i]) : 0.0);
+        lo = std::min(lo, a[i] - r);
+        hi = std::max(hi, a[i] + r);
+    }
+    for (int it = 0; it < 200 && hi - lo > 4e-16 * std::max(std::fabs(lo), std::fabs(hi)); ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (mid <= lo || mid >= hi) break;
+        if (sturm_count(a, b, m, mid) > k) hi = mid;
+        else lo = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+// unit eigenvector of the tridiagonal for eigenvalue theta: inverse iteration; each solve is Gaussian elimination with
+// partial pivoting on the shifted tridiagonal (second super-diagonal kept in dl)
+void tridiag_eigvec(const std::vector<double>& a, const std::vector<double>& b, int m, double theta, std::vector<double>& z) {
+    z.assign(m, 1.0 / std::sqrt((double)m));
+    if (m == 1) { z[0] = 1.0; return; }
+    double scale = 0.0;
+    for (int i = 0; i < m; ++i) scale = std::max(scale, std::fabs(a[i]) + (i + 1 < m ? std::fabs(b[i]) : 0.0));
+    const double shift = theta + 1e-15 * std::max(scale, 1e-300);   // keeps the elimination away from an exact zero pivot
+    std::vector<double> d(m), du(m), dl(m);
+    auto nz = [](double v) { return v == 0.0 ? 1e-300 : v; };
+    for (int rep = 0; rep < 4; ++rep) {
+        for (int i = 0; i < m; ++i) { d[i] = a[i] - shift; du[i] = i + 1 < m ? b[i] : 0.0; dl[i] = i + 1 < m ? b[i] : 0.0; }
+        for (int i = 0; i + 1 < m; ++i) {
+            if (std::fabs(d[i]) >= std::fabs(dl[i])) {
+                const double mult = dl[i] / nz(d[i]);
+                d[i + 1] -= mult * du[i];
+                z[i + 1] -= mult * z[i];
+                dl[i] = 0.0;
+            } else {
+                const double mult = d[i] / dl[i];
+                d[i] = dl[i];
+                const double tmp = d[i + 1];
+                d[i + 1] = du[i] - mult * tmp;
+                if (i + 2 < m) {
+                    dl[i] = du[i + 1];
+                    du[i + 1] = -mult * dl[i];
+                } else {
+                    dl[i] = 0.0;
+                }
+                du[i] = tmp;
+                const double t = z[i];
+                z[i] = z[i + 1];
+                z[i + 1] = t - mult * z[i + 1];
+            }
+        }
+        z[m - 1] /= nz(d[m - 1]);
+        z[m - 2] = (z[m - 2] - du[m - 2] * z[m - 1]) / nz(d[m - 2]);
+        for (int i = m - 3; i >= 0; --i) z[i] = (z[i] - du[i] * z[i + 1] - dl[i] * z[i + 2]) / nz(d[i]);
+        double nrm = 0.0, big = 0.0;
+        for (double v : z) big = std::max(big, std::fabs(v));
+        if (!(big > 0.0) || std::isinf(big) || big != big) { z.assign(m, 0.0); z[0] = 1.0; big = 1.0; }
+        for (double& v : z) { v /= big; nrm += v * v; }
+        nrm = std::sqrt(nrm);
+        for (double& v : z) v /= nrm;
+    }
+}
+
+}  // namespace
+
+// Host half of the Lanczos driver on its own (no GPU involved): extremal Ritz value of largest magnitude of the m x m
+// tridiagonal (alpha, beta) and its unit eigenvector.  Exposed so that the CPU test-suite can pin it against LAPACK.
+int mambo_debug_tridiag_leading(const double* alpha, const double* beta, int m, double* theta, double* z) {
+    if (!alpha || !beta || m < 1 || !theta || !z) return fail(MAMBO_EINVAL, "bad arguments");
+    std::vector<double> a(alpha, alpha + m), b(beta, beta + m), v;
+    const double lo = tridiag_eigval(a, b, m, 0), hi = tridiag_eigval(a, b, m, m - 1);
+    *theta = std::fabs(lo) > std::fabs(hi) ? lo : hi;
+    tridiag_eigvec(a, b, m, *theta, v);
+    std::memcpy(z, v.data(), sizeof(double) * m);
+    return MAMBO_OK;
+}
+
+// Largest-|eigenvalue| eigenpair of Symmetric(reshape(residual tbt, (N^2, N^2))): Lanczos with full (twice-applied
+// classical Gram-Schmidt) re-orthogonalisation on the device-resident T~.  vec: N x N column-major, unit Frobenius norm.
+int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval, double* vec, int* iterations, double* residual) {
+    if (!h || !eigval || !vec) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "leading_eig needs an unsharded handle");
+    CU(cudaSetDevice(h->device));
+    const int n = h->N, R = h->nR;
+    const long long ldv = h->ldT;
+    if (!(tol > 0.0)) tol = 1e-13;
+    int mmax = max_iter > 0 ? max_iter : 600;
+    mmax = std::min(mmax, R);
+    cudaStream_t st = h->stream;
+    double *V = nullptr, *w = nullptr, *c = nullptr, *ab = nullptr, *d_s = nullptr, *d_vec = nullptr;
+    auto cleanup = [&]() {
+        for (double* b : {V, w, c, ab, d_s, d_vec})
+            if (b) cudaFree(b);
+    };
+#define LCU(call)                          \
+    do {                                   \
+        cudaError_t le__ = (call);         \
+        if (le__ != cudaSuccess) {         \
+            cleanup();                     \
+            CU(le__);                      \
+        }                                  \
+    } while (0)
+    LCU(cudaMalloc((void**)&V, sizeof(double) * (size_t)(mmax + 1) * ldv));
+    LCU(cudaMalloc((void**)&w, sizeof(double) * ldv));
+    LCU(cudaMalloc((void**)&c, sizeof(double) * (mmax + 1)));
+    LCU(cudaMalloc((void**)&ab, sizeof(double) * 2 * (mmax + 1)));
+    LCU(cudaMalloc((void**)&d_s, sizeof(double) * (mmax + 1)));
+    LCU(cudaMalloc((void**)&d_vec, sizeof(double) * (size_t)n * n));
+    LCU(cudaMemsetAsync(w, 0, sizeof(double) * ldv, st));
+    LCU(cudaMemsetAsync(ab, 0, sizeof(double) * 2 * (mmax + 1), st));
+    double* alpha = ab;
+    double* beta = ab + (mmax + 1);
+    const int vblocks = (R + 255) / 256;
+    const int mv_grid = std::max(1, std::min((R + 7) / 8, h->num_sms * 8));
+    const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
+    lanczos::k_start<<<vblocks, 256, 0, st>>>(w, R, h->pa, h->pq, n);
+    lanczos::k_normalise<<<1, 1024, 0, st>>>(w, R, (int)ldv, V, beta, mmax);   // beta[mmax] is scratch
+    h->launches += 2;
+    std::vector<double> ha(mmax + 1), hb(mmax + 1), z;
+    double theta = 0.0, res = 0.0;
+    int m = 0;
+    bool done = false;
+    while (!done) {
+        const int stop = std::min(mmax, m + (m < 16 ? 4 : 12));
+        for (; m < stop; ++m) {
+            const double* vj = V + (size_t)m * ldv;
+            if (general) lanczos::k_symv<1><<<mv_grid, 256, 0, st>>>(h->T2, h->T1, h->ldT, R, vj, w);   // T1 holds M^T, T2 holds M (k_pack)
+            else lanczos::k_symv<0><<<mv_grid, 256, 0, st>>>(h->T1, nullptr, h->ldT, R, vj, w);
+            for (int pass = 0; pass < 2; ++pass) {
+                lanczos::k_dots<<<m + 1, 256, 0, st>>>(V, ldv, R, w, c);
+                lanczos::k_project<<<vblocks, 256, sizeof(double) * (m + 1), st>>>(V, ldv, R, m + 1, c, w, alpha, m, pass);
+            }
+            lanczos::k_normalise<<<1, 1024, 0, st>>>(w, R, (int)ldv, V + (size_t)(m + 1) * ldv, beta, m);
+            h->launches += 6;
+        }
+        LCU(cudaGetLastError());
+        LCU(cudaMemcpyAsync(ha.data(), alpha, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        LCU(cudaMemcpyAsync(hb.data(), beta, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
+        LCU(cudaStreamSynchronize(st));
+        // an invariant subspace was reached at step k (beta_k ~ 0): the Krylov space is exhausted there
+        double bscale = 0.0;
+        for (int i = 0; i < m; ++i) bscale = std::max(bscale, std::max(std::fabs(ha[i]), std::fabs(hb[i])));
+        int meff = m;
+        for (int i = 0; i < m; ++i)
+            if (!(hb[i] > 1e-14 * std::max(bscale, 1e-300))) { meff = i + 1; break; }
+        const double lo = tridiag_eigval(ha, hb, meff, 0), hi = tridiag_eigval(ha, hb, meff, meff - 1);
+        theta = std::fabs(lo) > std::fabs(hi) ? lo : hi;       // sortperm(abs.(L))[end] (guesses.jl:61)
+        tridiag_eigvec(ha, hb, meff, theta, z);
+        res = std::fabs(hb[meff - 1] * z[meff - 1]);
+        if (meff < m || res <= tol * std::max(std::fabs(theta), 1e-300) || m >= mmax || theta == 0.0) {
+            if (meff < m) res = 0.0;
+            m = meff;
+            done = true;
+        }
+    }
+    LCU(cudaMemcpyAsync(d_s, z.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
+    LCU(cudaMemsetAsync(d_vec, 0, sizeof(double) * (size_t)n * n, st));
+    lanczos::k_combine<<<vblocks, 256, sizeof(double) * m, st>>>(V, ldv, R, m, d_s, h->pa, h->pq, h->sw, n, h->packed ? 1 : 0, d_vec);
+    h->launches++;
+    LCU(cudaGetLastError());
+    LCU(cudaMemcpyAsync(vec, d_vec, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, st));
+    LCU(cudaStreamSynchronize(st));
+#undef LCU
+    cleanup();
+    // fix the sign so that the result does not depend on the start vector: largest-magnitude entry positive
+    {
+        size_t big = 0;
+        for (size_t i = 1; i < (size_t)n * n; ++i)
+            if (std::fabs(vec[i]) > std::fabs(vec[big]) * (1.0 + 1e-12)) big = i;
+        if (vec[big] < 0.0)
+            for (size_t i = 0; i < (size_t)n * n; ++i) vec[i] = -vec[i];
+    }
+    *eigval = theta;
+    if (iterations) *iterations = m;
+    if (residual) *residual = res;
+    return MAMBO_OK;
 }
 
 int mambo_csa_subtract_fragment(mambo_csa* h, const double* x, double* new_cost) {

@@ -18,6 +18,7 @@ from typing import Optional
 import numpy as np
 
 from .engine import CSAEngine, CSA as _CSA, CSA_SD as _CSA_SD
+from .guesses import tbt_svd_1st
 from .structures import (F_OP, F_FRAG, CSA_x_to_F_FRAG, CSA_SD_x_to_F_FRAG, cartan_2b_num_params,
                          real_orbital_rotation_num_params)
 
@@ -47,6 +48,17 @@ def _bfgs(engine: CSAEngine, x0, g_tol: float = 1e-8, maxiter: int = 1000, nativ
     return OptimResult(np.asarray(r.x), float(r.fun), int(r.nit), int(r.nfev), bool(r.success))
 
 
+def _x0_svd(engine: CSAEngine, offset: int) -> np.ndarray:
+    """decompose.jl:87-92 / 212-217: x0 from the largest SVD fragment of the (device-resident) residual."""
+    N = engine.N
+    cL, uL = cartan_2b_num_params(N), real_orbital_rotation_num_params(N)
+    lam, theta = tbt_svd_1st(engine)
+    x0 = np.zeros(offset + cL + uL)
+    x0[offset:offset + cL] = lam
+    x0[offset + cL:] = theta
+    return x0
+
+
 def _x0_random(N: int, offset: int, rng) -> np.ndarray:
     """decompose.jl:86-94: lambda = 0, theta = 2*pi*rand (the reference draws from the unseeded global RNG)."""
     cL, uL = cartan_2b_num_params(N), real_orbital_rotation_num_params(N)
@@ -64,8 +76,9 @@ def CSA_greedy_step(F, do_svd: bool = SVD_for_CSA, x0=None, rng=None, engine: Op
     try:
         if x0 is None:
             if do_svd:
-                raise NotImplementedError("tbt_svd_1st initial guess (guesses.jl:51-84) stays on the Julia side; pass x0")
-            x0 = _x0_random(engine.N, 0, np.random.default_rng() if rng is None else rng)
+                x0 = _x0_svd(engine, 0)
+            else:
+                x0 = _x0_random(engine.N, 0, np.random.default_rng() if rng is None else rng)
         return _bfgs(engine, x0, native=native, **opt)
     finally:
         if own:
@@ -81,8 +94,9 @@ def CSA_SD_greedy_step(F, do_svd: bool = SVD_for_CSA_SD, x0=None, rng=None, engi
     try:
         if x0 is None:
             if do_svd:
-                raise NotImplementedError("tbt_svd_1st initial guess (guesses.jl:51-84) stays on the Julia side; pass x0")
-            x0 = _x0_random(engine.N, engine.N, np.random.default_rng() if rng is None else rng)
+                x0 = _x0_svd(engine, engine.N)
+            else:
+                x0 = _x0_random(engine.N, engine.N, np.random.default_rng() if rng is None else rng)
         return _bfgs(engine, x0, native=native, **opt)
     finally:
         if own:
@@ -90,7 +104,7 @@ def CSA_SD_greedy_step(F, do_svd: bool = SVD_for_CSA_SD, x0=None, rng=None, engi
 
 
 def _greedy(H: F_OP, alpha_max: int, flavour: str, decomp_tol: float, verbose: bool, SAVELOAD: bool, SAVENAME: str,
-            x0s, rng, native: bool, device: int, **opt):
+            x0s, rng, native: bool, device: int, do_svd: Optional[bool] = None, **opt):
     N = H.N
     cL, uL = cartan_2b_num_params(N), real_orbital_rotation_num_params(N)
     sd = flavour == "CSA_SD"
@@ -101,6 +115,8 @@ def _greedy(H: F_OP, alpha_max: int, flavour: str, decomp_tol: float, verbose: b
     to_frag = CSA_SD_x_to_F_FRAG if sd else CSA_x_to_F_FRAG
     step = CSA_SD_greedy_step if sd else CSA_greedy_step
     rng = np.random.default_rng() if rng is None else rng
+    if do_svd is None:
+        do_svd = SVD_for_CSA_SD if sd else SVD_for_CSA          # config.jl:9-10, the steps' defaults
 
     Farr: list[F_FRAG] = []
     X = np.zeros((tot_L, alpha_max))
@@ -123,7 +139,7 @@ def _greedy(H: F_OP, alpha_max: int, flavour: str, decomp_tol: float, verbose: b
             print(f"Initial L2 cost is {curr_cost}")
         while curr_cost > decomp_tol and a_curr < alpha_max:
             x0 = None if x0s is None else x0s[a_curr]
-            sol = step(None, do_svd=False, x0=x0, rng=rng, engine=eng, native=native, **opt)
+            sol = step(None, do_svd=do_svd, x0=x0, rng=rng, engine=eng, native=native, **opt)
             a_curr += 1
             if verbose:
                 print(f"Current L2 cost after {a_curr} fragments is {sol.minimum}")
@@ -142,15 +158,18 @@ def _greedy(H: F_OP, alpha_max: int, flavour: str, decomp_tol: float, verbose: b
 
 
 def CSA_greedy_decomposition(H: F_OP, alpha_max: int, decomp_tol: float = EPS, verbose: bool = False, SAVELOAD: bool = False,
-                             SAVENAME: str = "CSA.npz", x0s=None, rng=None, native: bool = False, device: int = 0, **opt):
+                             SAVENAME: str = "CSA.npz", x0s=None, rng=None, native: bool = False, device: int = 0,
+                             do_svd: Optional[bool] = None, **opt):
     """decompose.jl:1-80: only the two-body tensor is optimised (filled[1:2] = false)."""
-    return _greedy(H, alpha_max, "CSA", decomp_tol, verbose, SAVELOAD, SAVENAME, x0s, rng, native, device, **opt)
+    return _greedy(H, alpha_max, "CSA", decomp_tol, verbose, SAVELOAD, SAVENAME, x0s, rng, native, device, do_svd, **opt)
 
 
 def CSA_SD_greedy_decomposition(H: F_OP, alpha_max: int, decomp_tol: float = EPS, verbose: bool = False, SAVELOAD: bool = False,
-                                SAVENAME: str = "CSA_SD.npz", x0s=None, rng=None, native: bool = False, device: int = 0, **opt):
-    """decompose.jl:122-205: one- and two-body tensors are optimised together."""
-    return _greedy(H, alpha_max, "CSA_SD", decomp_tol, verbose, SAVELOAD, SAVENAME, x0s, rng, native, device, **opt)
+                                SAVENAME: str = "CSA_SD.npz", x0s=None, rng=None, native: bool = False, device: int = 0,
+                                do_svd: Optional[bool] = None, **opt):
+    """decompose.jl:122-205: one- and two-body tensors are optimised together; every step starts from the largest SVD
+    fragment of the residual (SVD_for_CSA_SD = true, config.jl:10)."""
+    return _greedy(H, alpha_max, "CSA_SD", decomp_tol, verbose, SAVELOAD, SAVENAME, x0s, rng, native, device, do_svd, **opt)
 
 
 def to_OP(frag: F_FRAG, device: int = 0) -> F_OP:

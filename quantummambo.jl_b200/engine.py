@@ -148,6 +148,15 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_reconstruct(self._h, x.ctypes.data, t.ctypes.data, None if o is None else o.ctypes.data))
         return t, o
 
+    def leading_eig(self, tol: float = 0.0, max_iter: int = 0):
+        """(eigenvalue, N x N operator, info) of largest |eigenvalue| of the residual's N^2 x N^2 matrix view
+        (mambo_csa_leading_eig: device Lanczos; replaces the full `eigen` of guesses.jl:55-63)."""
+        n = self.N
+        lam, it, res = C.c_double(), C.c_int(), C.c_double()
+        vec = np.empty((n, n), order="F")
+        _lib.check(self._lib.mambo_csa_leading_eig(self._h, tol, max_iter, C.byref(lam), vec.ctypes.data, C.byref(it), C.byref(res)))
+        return lam.value, vec, {"iterations": it.value, "residual": res.value}
+
     # -- native optimiser / multistart ---------------------------------------------------------------------------
     def optimize(self, x0, g_tol: float = 1e-8, max_iter: int = 1000, lbfgs_memory: int = 0, verbose: int = 0):
         """Minimise cost(x) from x0 with the library's BFGS (mambo_csa_optimize)."""

@@ -305,6 +305,80 @@ def test_multistart_scheduler_over_lanes(mb, lib):
             ln.close()
 
 
+def _sym_matrix_view(T):
+    """Symmetric(reshape(tbt, (N^2, N^2))) as Julia builds it (guesses.jl:57): upper triangle of the column-major view."""
+    n = T.shape[0]
+    M = np.reshape(np.asfortranarray(T), (n * n, n * n), order="F")
+    return np.triu(M) + np.triu(M, 1).T
+
+
+@pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
+@pytest.mark.parametrize("n", [1, 2, 3, 6, 10, 17])
+def test_leading_eigenpair_matches_dense_eigen(mb, lib, n, kind):
+    """mambo_csa_leading_eig (device Lanczos) against the full `eigen` the reference runs (guesses.jl:57-63)."""
+    T = KINDS[kind](n, 30 + n)
+    M = _sym_matrix_view(T)
+    w, v = np.linalg.eigh(M)
+    k = int(np.argmax(np.abs(w)))
+    with mb.CSAEngine(T) as e:
+        lam, vec, info = e.leading_eig()
+    assert abs(lam - w[k]) <= 1e-11 * abs(w[k])
+    got = vec.reshape(-1, order="F")
+    assert abs(np.linalg.norm(got) - 1.0) <= 1e-12
+    ref = v[:, k]
+    gap = np.min(np.abs(np.delete(w, k) - w[k])) if len(w) > 1 else 1.0
+    # rank-one projector: independent of the sign convention; accuracy limited by residual / gap
+    assert rel(np.outer(got, got), np.outer(ref, ref)) <= 1e-9 * max(1.0, abs(w[k]) / gap)
+    assert np.linalg.norm(M @ got - lam * got) <= 1e-10 * abs(lam)
+
+
+def test_svd_initial_guess_matches_oracle(mb, lib):
+    """tbt_svd_1st on the device-resident residual (guesses.jl:51-84): same fragment as the oracle's dense-eigen port.
+    The sign of the leading eigenvector is a LAPACK convention that the fragment depends on, so the oracle
+    is asked for the library's documented convention (largest-magnitude entry positive); the n x n `eigen` may still flip
+    the columns of the rotation, hence the comparison on the operator W(x0)."""
+    for n in (4, 7, 12):
+        T = o.dense_sym_tbt(n, 40 + n)
+        lam_o, th_o = o.tbt_svd_1st(T, fix_sign=True)
+        with mb.CSAEngine(T) as e:
+            lam_g, th_g = mb.tbt_svd_1st(e)
+        W_o = o.reconstruct_factored(np.concatenate([lam_o, th_o]), n)[1]
+        W_g = o.reconstruct_factored(np.concatenate([lam_g, th_g]), n)[1]
+        assert rel(W_g, W_o) <= 1e-8
+    with mb.CSAEngine(o.pairsym_tbt(5, 1)) as e:        # no p<->q symmetry: the reference refuses (guesses.jl:69-71)
+        with pytest.raises(ValueError):
+            mb.tbt_svd_1st(e)
+
+
+def test_leading_eigenpair_full_size(mb, lib):
+    """N = 50 (R = 1275 packed rows): eigen-residual and eigenvalue against LAPACK on the 2500 x 2500 view."""
+    n = 50
+    T = o.dense_sym_tbt(n, 0)
+    M = _sym_matrix_view(T)
+    with mb.CSAEngine(T) as e:
+        lam, vec, info = e.leading_eig()
+    got = vec.reshape(-1, order="F")
+    w = np.linalg.eigvalsh(M)
+    top = w[np.argmax(np.abs(w))]
+    assert abs(lam - top) <= 1e-11 * abs(top)
+    assert np.linalg.norm(M @ got - lam * got) <= 1e-9 * abs(lam)
+    assert np.abs(vec - vec.T).max() <= 1e-14
+
+
+def test_csa_sd_greedy_uses_the_svd_guess_by_default(mb, lib):
+    """CSA_SD_greedy_step starts from tbt_svd_1st unless told otherwise (SVD_for_CSA_SD = true, config.jl:10): on a
+    tensor that IS one CSA_SD fragment the guess is already the two-body solution and the step converges to ~0."""
+    n = 6
+    x_true = o.random_x(n, 9, "CSA_SD")
+    h_t, W_t = o.reconstruct_factored(x_true, n, "CSA_SD")
+    H = mb.F_OP(([0.0], h_t, W_t))
+    frags = mb.CSA_SD_greedy_decomposition(H, 1, decomp_tol=1e-10)
+    assert len(frags) == 1
+    with mb.CSAEngine(W_t, h_t, "CSA_SD") as e:
+        c = e.subtract_fragment(frags[0].x())
+    assert c <= 1e-8 * (np.sum(W_t ** 2) + np.sum(h_t ** 2))
+
+
 def test_device_entry_points_match_host_closures(mb, lib):
     import torch
     n = 11
