@@ -116,6 +116,9 @@ int  mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, doubl
 int  mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval, double* vec,
                            int* iterations, double* residual);
 
+/* y = T~ v in the engine's row space (device pointers, rows_padded doubles each, see mambo_csa_get_info; in the packed
+ * mode row (p<=q) carries sqrt(2 - delta_pq) v[p,q]).  One pass over the resident residual: 8 rows^2 bytes, HBM-bound. */
+int  mambo_csa_symv_device(mambo_csa* h, const double* d_v, double* d_y);
 /* Host half of the Lanczos driver (no GPU): largest-|eigenvalue| Ritz pair of the m x m symmetric tridiagonal with
  * diagonal alpha[0..m) and off-diagonal beta[0..m-1) (bisection + inverse iteration); z receives the unit vector.   */
 int  mambo_debug_tridiag_leading(const double* alpha, const double* beta, int m, double* theta, double* z);

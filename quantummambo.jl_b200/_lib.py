@@ -77,6 +77,7 @@ SIGNATURES = {
     "mambo_csa_get_residual": (C.c_int, [_P, _P, _P]),
     "mambo_csa_reconstruct": (C.c_int, [_P, _P, _P, _P]),
     "mambo_csa_leading_eig": (C.c_int, [_P, C.c_double, C.c_int, _D, _P, C.POINTER(C.c_int), _D]),
+    "mambo_csa_symv_device": (C.c_int, [_P, _P, _P]),
     "mambo_debug_tridiag_leading": (C.c_int, [_P, _P, C.c_int, _D, _P]),
     "mambo_csa_set_stream": (C.c_int, [_P, _P]),
     "mambo_csa_get_stream": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),

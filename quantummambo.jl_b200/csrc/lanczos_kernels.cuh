@@ -7,7 +7,7 @@
 // mode, N^2 x N^2 otherwise).  The only O(R^2) work per step is the symmetric matrix-vector product below, an
 // HBM-bound stream over T~ (8 R^2 bytes, 2 R^2 flop -> 0.25 flop/B); everything else is O(R m).
 //
-//   k_symv     : y = T~ v            one warp per row, 16-byte streaming loads, v through L1/L2 (HBM roofline)
+//   k_symv     : y = T~ v            one CTA per row, 16-byte streaming loads, v through L1/L2 (HBM roofline)
 //   k_dots     : c[k] = V[k] . w     one CTA per Krylov vector (classical Gram-Schmidt, applied twice)
 //   k_project  : w -= sum_k c[k] V[k]  (and accumulates the coefficients: alpha_j is c[j])
 //   k_normalise: beta = ||w||, V[j+1] = w / beta
@@ -19,42 +19,42 @@
 namespace lanczos {
 
 // y[r] = sum_j T[r][j] v[j] for r in [0, rows).  T row-major with pitch ldT (multiple of 64, zero padded), v has ldT
-// entries (zero padded).  GENERAL != 0: the matrix is Symmetric(upper triangle) of a non-symmetric tensor view; T2 holds
-// the transpose, so element (r, j<r) is taken from T2 (== T[j][r]).
+// entries (zero padded).  One CTA per row (grid-stride): the 8 warps take interleaved 512-byte segments of the row, up to
+// four 16-byte streaming loads in flight per thread, partial sums combined in a fixed order (bit-reproducible).
+// GENERAL != 0: the matrix is Symmetric(upper triangle) of a non-symmetric tensor view; T2 holds the transpose, so
+// element (r, j<r) is taken from T2 (== T[j][r]).
 template <int GENERAL>
 __global__ void __launch_bounds__(256) k_symv(const double* __restrict__ T, const double* __restrict__ T2, long long ldT, int rows,
                                               const double* __restrict__ v, double* __restrict__ y) {
-    const int lane = threadIdx.x & 31;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    __shared__ double red[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npair = (int)(ldT >> 1);
     const double2* v2 = reinterpret_cast<const double2*>(v);
-    for (int r = warp_global; r < rows; r += nwarps) {
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
         const double2* t = reinterpret_cast<const double2*>(T + (long long)r * ldT);
         const double2* u = GENERAL ? reinterpret_cast<const double2*>(T2 + (long long)r * ldT) : nullptr;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int j = lane;
-        // ldT is a multiple of 64 doubles -> npair is a multiple of 32: every lane runs the same trip count
-        for (; j + 96 < npair; j += 128) {
-            double2 x0 = __ldcs(t + j), x1 = __ldcs(t + j + 32), x2 = __ldcs(t + j + 64), x3 = __ldcs(t + j + 96);
+        int j = threadIdx.x;
+        for (; j + 768 < npair; j += 1024) {
+            double2 x0 = __ldcs(t + j), x1 = __ldcs(t + j + 256), x2 = __ldcs(t + j + 512), x3 = __ldcs(t + j + 768);
             if (GENERAL) {
-                const double2 z0 = __ldcs(u + j), z1 = __ldcs(u + j + 32), z2 = __ldcs(u + j + 64), z3 = __ldcs(u + j + 96);
+                const double2 z0 = __ldcs(u + j), z1 = __ldcs(u + j + 256), z2 = __ldcs(u + j + 512), z3 = __ldcs(u + j + 768);
                 if (2 * j < r) x0.x = z0.x;
                 if (2 * j + 1 < r) x0.y = z0.y;
-                if (2 * (j + 32) < r) x1.x = z1.x;
-                if (2 * (j + 32) + 1 < r) x1.y = z1.y;
-                if (2 * (j + 64) < r) x2.x = z2.x;
-                if (2 * (j + 64) + 1 < r) x2.y = z2.y;
-                if (2 * (j + 96) < r) x3.x = z3.x;
-                if (2 * (j + 96) + 1 < r) x3.y = z3.y;
+                if (2 * (j + 256) < r) x1.x = z1.x;
+                if (2 * (j + 256) + 1 < r) x1.y = z1.y;
+                if (2 * (j + 512) < r) x2.x = z2.x;
+                if (2 * (j + 512) + 1 < r) x2.y = z2.y;
+                if (2 * (j + 768) < r) x3.x = z3.x;
+                if (2 * (j + 768) + 1 < r) x3.y = z3.y;
             }
-            const double2 w0 = __ldg(v2 + j), w1 = __ldg(v2 + j + 32), w2 = __ldg(v2 + j + 64), w3 = __ldg(v2 + j + 96);
+            const double2 w0 = __ldg(v2 + j), w1 = __ldg(v2 + j + 256), w2 = __ldg(v2 + j + 512), w3 = __ldg(v2 + j + 768);
             a0 = fma(x0.x, w0.x, fma(x0.y, w0.y, a0));
             a1 = fma(x1.x, w1.x, fma(x1.y, w1.y, a1));
             a2 = fma(x2.x, w2.x, fma(x2.y, w2.y, a2));
             a3 = fma(x3.x, w3.x, fma(x3.y, w3.y, a3));
         }
-        for (; j < npair; j += 32) {
+        for (; j < npair; j += 256) {
             double2 x0 = __ldcs(t + j);
             if (GENERAL) {
                 const double2 z0 = __ldcs(u + j);
@@ -67,7 +67,15 @@ __global__ void __launch_bounds__(256) k_symv(const double* __restrict__ T, cons
         double a = (a0 + a1) + (a2 + a3);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) y[r] = a;
+        if (lane == 0) red[warp] = a;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += red[q];
+            y[r] = s;
+        }
+        __syncthreads();
     }
 }
 

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -123,6 +124,10 @@ struct mambo_csa {
     int peer_attached = 0;
     int plen_pad = 0;
     unsigned long long peer_epoch = 0;
+    // Lanczos workspace of mambo_csa_leading_eig (allocated on first use, kept: cudaMalloc/cudaFree of tens of MB cost more
+    // than the iteration itself)
+    double* eig_ws = nullptr;
+    size_t eig_ws_doubles = 0;
     // CUDA-graph segments of the small-kernel sequences
     bool use_graphs = true;
     std::vector<GraphSeg> g_pre, g_fin;   // index 0: device-decided s; 1+s: s squarings
@@ -936,7 +941,7 @@ void mambo_csa_destroy(mambo_csa* h) {
         delete h->sh;
     }
     void* bufs[] = {h->At, h->Bt, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
-                    h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
+                    h->eig_ws, h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_x) cudaFreeHost(h->h_x);
@@ -1290,6 +1295,20 @@ void tridiag_eigvec(const std::vector<double>& a, const std::vector<double>& b, 
 
 }  // namespace
 
+// y = T~ v on the device, in the engine's row space (rows_padded entries each; rows beyond `rows` must be zero in v and
+// are left untouched in y): the HBM-bound building block of the Lanczos driver, exported for callers that bring their
+// own Krylov method and for bandwidth measurements.
+int mambo_csa_symv_device(mambo_csa* h, const double* d_v, double* d_y) {
+    if (!h || !d_v || !d_y) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "symv needs an unsharded handle");
+    CU(cudaSetDevice(h->device));
+    if (h->mode == (int)MAMBO_SYM_GENERAL) lanczos::k_symv<1><<<h->nR, 256, 0, h->stream>>>(h->T2, h->T1, h->ldT, h->nR, d_v, d_y);
+    else lanczos::k_symv<0><<<h->nR, 256, 0, h->stream>>>(h->T1, nullptr, h->ldT, h->nR, d_v, d_y);
+    h->launches++;
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
 // Host half of the Lanczos driver on its own (no GPU involved): extremal Ritz value of largest magnitude of the m x m
 // tridiagonal (alpha, beta) and its unit eigenvector.  Exposed so that the CPU test-suite can pin it against LAPACK.
 int mambo_debug_tridiag_leading(const double* alpha, const double* beta, int m, double* theta, double* z) {
@@ -1314,11 +1333,27 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
     int mmax = max_iter > 0 ? max_iter : 600;
     mmax = std::min(mmax, R);
     cudaStream_t st = h->stream;
-    double *V = nullptr, *w = nullptr, *c = nullptr, *ab = nullptr, *d_s = nullptr, *d_vec = nullptr;
-    auto cleanup = [&]() {
-        for (double* b : {V, w, c, ab, d_s, d_vec})
-            if (b) cudaFree(b);
-    };
+    const bool dbg = std::getenv("MAMBO_EIG_DEBUG") != nullptr;
+    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; };
+    const double t_begin = now();
+    // workspace: V [(mmax+1)][ldv] | w [ldv] | c [mmax+1] | alpha, beta [2 (mmax+1)] | s [mmax+1] | vec [n n]
+    // sized for the default Krylov dimension at least, so that a short first call does not force a re-allocation later
+    const int mcap = std::max(mmax, std::min(600, R));
+    const size_t need = (size_t)(mcap + 2) * ldv + 4 * (size_t)(mcap + 1) + (size_t)n * n;
+    if (h->eig_ws_doubles < need) {
+        if (h->eig_ws) CU(cudaFree(h->eig_ws));
+        h->eig_ws = nullptr;
+        h->eig_ws_doubles = 0;
+        CU(cudaMalloc((void**)&h->eig_ws, sizeof(double) * need));
+        h->eig_ws_doubles = need;
+    }
+    double* V = h->eig_ws;
+    double* w = V + (size_t)(mcap + 1) * ldv;
+    double* c = w + ldv;
+    double* ab = c + (mcap + 1);
+    double* d_s = ab + 2 * (mcap + 1);
+    double* d_vec = d_s + (mcap + 1);
+    auto cleanup = [&]() {};
 #define LCU(call)                          \
     do {                                   \
         cudaError_t le__ = (call);         \
@@ -1327,18 +1362,12 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
             CU(le__);                      \
         }                                  \
     } while (0)
-    LCU(cudaMalloc((void**)&V, sizeof(double) * (size_t)(mmax + 1) * ldv));
-    LCU(cudaMalloc((void**)&w, sizeof(double) * ldv));
-    LCU(cudaMalloc((void**)&c, sizeof(double) * (mmax + 1)));
-    LCU(cudaMalloc((void**)&ab, sizeof(double) * 2 * (mmax + 1)));
-    LCU(cudaMalloc((void**)&d_s, sizeof(double) * (mmax + 1)));
-    LCU(cudaMalloc((void**)&d_vec, sizeof(double) * (size_t)n * n));
     LCU(cudaMemsetAsync(w, 0, sizeof(double) * ldv, st));
     LCU(cudaMemsetAsync(ab, 0, sizeof(double) * 2 * (mmax + 1), st));
     double* alpha = ab;
     double* beta = ab + (mmax + 1);
     const int vblocks = (R + 255) / 256;
-    const int mv_grid = std::max(1, std::min((R + 7) / 8, h->num_sms * 8));
+    const int mv_grid = R;                               // one CTA per row, scheduled dynamically: the tail is one row long
     const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
     lanczos::k_start<<<vblocks, 256, 0, st>>>(w, R, h->pa, h->pq, n);
     lanczos::k_normalise<<<1, 1024, 0, st>>>(w, R, (int)ldv, V, beta, mmax);   // beta[mmax] is scratch
@@ -1347,7 +1376,10 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
     double theta = 0.0, res = 0.0;
     int m = 0;
     bool done = false;
+    const double t_alloc = now() - t_begin;
+    double t_enq = 0, t_sync = 0, t_host = 0, tq = now();
     while (!done) {
+        tq = now();
         const int stop = std::min(mmax, m + (m < 16 ? 4 : 12));
         for (; m < stop; ++m) {
             const double* vj = V + (size_t)m * ldv;
@@ -1361,9 +1393,11 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
             h->launches += 6;
         }
         LCU(cudaGetLastError());
+        t_enq += now() - tq; tq = now();
         LCU(cudaMemcpyAsync(ha.data(), alpha, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
         LCU(cudaMemcpyAsync(hb.data(), beta, sizeof(double) * m, cudaMemcpyDeviceToHost, st));
         LCU(cudaStreamSynchronize(st));
+        t_sync += now() - tq; tq = now();
         // an invariant subspace was reached at step k (beta_k ~ 0): the Krylov space is exhausted there
         double bscale = 0.0;
         for (int i = 0; i < m; ++i) bscale = std::max(bscale, std::max(std::fabs(ha[i]), std::fabs(hb[i])));
@@ -1379,7 +1413,9 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
             m = meff;
             done = true;
         }
+        t_host += now() - tq;
     }
+    const double t_loop_end = now();
     LCU(cudaMemcpyAsync(d_s, z.data(), sizeof(double) * m, cudaMemcpyHostToDevice, st));
     LCU(cudaMemsetAsync(d_vec, 0, sizeof(double) * (size_t)n * n, st));
     lanczos::k_combine<<<vblocks, 256, sizeof(double) * m, st>>>(V, ldv, R, m, d_s, h->pa, h->pq, h->sw, n, h->packed ? 1 : 0, d_vec);
@@ -1388,7 +1424,9 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
     LCU(cudaMemcpyAsync(vec, d_vec, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, st));
     LCU(cudaStreamSynchronize(st));
 #undef LCU
-    cleanup();
+    if (dbg)
+        fprintf(stderr, "[mambo eig] m=%d setup %.3f ms, enqueue %.3f ms, sync %.3f ms, host tridiagonal %.3f ms, Ritz vector + D2H %.3f ms\n", m,
+                t_alloc * 1e3, t_enq * 1e3, t_sync * 1e3, t_host * 1e3, (now() - t_loop_end) * 1e3);
     // fix the sign so that the result does not depend on the start vector: largest-magnitude entry positive
     {
         size_t big = 0;

@@ -157,6 +157,10 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_leading_eig(self._h, tol, max_iter, C.byref(lam), vec.ctypes.data, C.byref(it), C.byref(res)))
         return lam.value, vec, {"iterations": it.value, "residual": res.value}
 
+    def symv_device(self, d_v_ptr: int, d_y_ptr: int):
+        """y = T~ v on the device (rows_padded doubles each): one HBM pass over the resident residual."""
+        _lib.check(self._lib.mambo_csa_symv_device(self._h, d_v_ptr, d_y_ptr))
+
     # -- native optimiser / multistart ---------------------------------------------------------------------------
     def optimize(self, x0, g_tol: float = 1e-8, max_iter: int = 1000, lbfgs_memory: int = 0, verbose: int = 0):
         """Minimise cost(x) from x0 with the library's BFGS (mambo_csa_optimize)."""

@@ -332,6 +332,38 @@ def test_leading_eigenpair_matches_dense_eigen(mb, lib, n, kind):
     assert np.linalg.norm(M @ got - lam * got) <= 1e-10 * abs(lam)
 
 
+@pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
+def test_symv_matches_the_matrix_view(mb, lib, kind):
+    """mambo_csa_symv_device: y = Symmetric(reshape(tbt)) v for an operator v (N x N), through the engine's row space."""
+    import torch
+    n = 9
+    T = KINDS[kind](n, 3)
+    M = _sym_matrix_view(T)
+    rng = np.random.default_rng(0)
+    v = rng.standard_normal((n, n))
+    if kind == "dense_sym":
+        v = v + v.T                                                   # the packed mode carries symmetric operators
+    want = (M @ v.reshape(-1, order="F")).reshape(n, n, order="F")
+    with mb.CSAEngine(T) as e:
+        info = e.info()
+        rows, rp = info["rows"], info["rows_padded"]
+        if info["mode_name"] == "fullsym-packed":
+            idx = [(a, q) for q in range(n) for a in range(q + 1)]
+            sw = np.array([1.0 if a == q else np.sqrt(2.0) for a, q in idx])
+        else:
+            idx = [(r % n, r // n) for r in range(n * n)]
+            sw = np.ones(n * n)
+        hv = np.zeros(rp)
+        hv[:rows] = sw * np.array([v[a, q] for a, q in idx])
+        d_v = torch.from_numpy(hv).cuda()
+        d_y = torch.zeros(rp, dtype=torch.float64, device="cuda")
+        e.symv_device(d_v.data_ptr(), d_y.data_ptr())
+        e.synchronize()
+        y = d_y.cpu().numpy()[:rows] / sw
+    got = np.array([want[a, q] for a, q in idx])
+    assert rel(y, got) <= 1e-12
+
+
 def test_svd_initial_guess_matches_oracle(mb, lib):
     """tbt_svd_1st on the device-resident residual (guesses.jl:51-84): same fragment as the oracle's dense-eigen port.
     The sign of the leading eigenvector is a LAPACK convention that the fragment depends on, so the oracle
