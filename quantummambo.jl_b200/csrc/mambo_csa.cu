@@ -128,6 +128,9 @@ struct mambo_csa {
     // than the iteration itself)
     double* eig_ws = nullptr;
     size_t eig_ws_doubles = 0;
+    // scratch of the built-in optimiser (vectors + dense inverse Hessian or L-BFGS ring), kept between runs for the same reason
+    void* opt_ws = nullptr;
+    size_t opt_ws_bytes = 0;
     // CUDA-graph segments of the small-kernel sequences
     bool use_graphs = true;
     std::vector<GraphSeg> g_pre, g_fin;   // index 0: device-decided s; 1+s: s squarings
@@ -860,6 +863,23 @@ int subtract_impl(mambo_csa* h, const double* d_x, int s_host) {
 extern "C" {
 
 const char* mambo_last_error(void) { return g_err.c_str(); }
+
+// Library-internal (used by optimizer.cu, not declared in the public header): a device scratch area owned by the handle,
+// grown on demand and released with it.  cudaMalloc / cudaFree per optimisation run would synchronise the whole device
+// and stall sibling lanes.
+int mambo_csa_scratch(mambo_csa* h, size_t bytes, void** ptr) {
+    if (!h || !ptr) return fail(MAMBO_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    if (h->opt_ws_bytes < bytes) {
+        if (h->opt_ws) CU(cudaFree(h->opt_ws));
+        h->opt_ws = nullptr;
+        h->opt_ws_bytes = 0;
+        CU(cudaMalloc(&h->opt_ws, bytes));
+        h->opt_ws_bytes = bytes;
+    }
+    *ptr = h->opt_ws;
+    return MAMBO_OK;
+}
 void mambo_set_error(const char* msg) { g_err = msg ? msg : ""; }
 
 int mambo_csa_get_stream(mambo_csa* h, void** stream, int* device) {
@@ -941,7 +961,7 @@ void mambo_csa_destroy(mambo_csa* h) {
         delete h->sh;
     }
     void* bufs[] = {h->At, h->Bt, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
-                    h->eig_ws, h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
+                    h->eig_ws, h->opt_ws, h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
     if (h->h_x) cudaFreeHost(h->h_x);

@@ -14,6 +14,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <initializer_list>
 #include <string>
 #include <thread>
 #include <utility>
@@ -24,6 +25,7 @@
 #include "../../include/mambo_csa.h"
 
 extern "C" void mambo_set_error(const char* msg);   // defined in mambo_csa.cu (thread-local message)
+extern "C" int mambo_csa_scratch(mambo_csa* h, size_t bytes, void** ptr);   // handle-owned device scratch (mambo_csa.cu)
 
 namespace {
 
@@ -116,12 +118,129 @@ __global__ void k_direction(double* __restrict__ p, const double* __restrict__ u
     if (i < n) p[i] = -(u[i] - rho * (s[i] * a + Hy[i] * b) + c * s[i] * b);
 }
 
+// Up to 6 dot products a_k.b_k and max|m| in ONE single-CTA pass (one host round trip instead of one per scalar):
+// res[k] = a_k.b_k, res[6] = max|m|.  Fixed-order reductions (bit-reproducible).
+struct DotSet {
+    const double* a[6];
+    const double* b[6];
+    const double* m;
+    int nd;
+};
+__global__ void __launch_bounds__(1024) k_multi_dot(DotSet ds, int n, double* __restrict__ res) {
+    __shared__ double sd[7][32];
+    double acc[6] = {0, 0, 0, 0, 0, 0}, mx = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            if (k < ds.nd) acc[k] = fma(ds.a[k][i], ds.b[k][i], acc[k]);
+        if (ds.m) mx = fmax(mx, fabs(ds.m[i]));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) sd[k][threadIdx.x >> 5] = acc[k];
+        sd[6][threadIdx.x >> 5] = mx;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double r = 0.0;
+        if (threadIdx.x < 6) {
+            for (int w = 0; w < 32; ++w) r += sd[threadIdx.x][w];
+        } else {
+            for (int w = 0; w < 32; ++w) r = fmax(r, sd[6][w]);
+        }
+        res[threadIdx.x] = r;
+    }
+}
+
+// L-BFGS two-loop recursion in one single-CTA kernel (Nocedal & Wright alg. 7.4): p = -H_k g from the `used` newest
+// pairs of the ring (S, Y: [mem][n]; rho[mem]); `head` is the slot of the newest pair; H_0 = gamma I.
+// Also returns res[0] = g.p and res[1] = max|g| so that the host needs one round trip per iteration.
+__global__ void __launch_bounds__(1024) k_lbfgs_direction(const double* __restrict__ g, const double* __restrict__ S, const double* __restrict__ Y,
+                                                          const double* __restrict__ rho, int mem, int used, int head, double gamma, int n,
+                                                          double* __restrict__ p, double* __restrict__ res) {
+    __shared__ double sred[32];
+    __shared__ double s_val;
+    __shared__ double s_alpha[64];
+    auto block_sum = [&](double v) -> double {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < 32; ++w) t += sred[w];
+            s_val = t;
+        }
+        __syncthreads();
+        const double out = s_val;
+        __syncthreads();
+        return out;
+    };
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = g[i];          // q = g
+    __syncthreads();
+    for (int k = 0; k < used; ++k) {                                        // newest -> oldest
+        const int slot = (head - k + mem) % mem;
+        const double* s = S + (size_t)slot * n;
+        const double* y = Y + (size_t)slot * n;
+        double d = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) d = fma(s[i], p[i], d);
+        const double a = rho[slot] * block_sum(d);
+        if (threadIdx.x == 0) s_alpha[k] = a;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = fma(-a, y[i], p[i]);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] *= gamma;        // r = H_0 q
+    __syncthreads();
+    for (int k = used - 1; k >= 0; --k) {                                   // oldest -> newest
+        const int slot = (head - k + mem) % mem;
+        const double* s = S + (size_t)slot * n;
+        const double* y = Y + (size_t)slot * n;
+        double d = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) d = fma(y[i], p[i], d);
+        const double b = rho[slot] * block_sum(d);
+        const double a = s_alpha[k];
+        for (int i = threadIdx.x; i < n; i += blockDim.x) p[i] = fma(a - b, s[i], p[i]);
+        __syncthreads();
+    }
+    double gp = 0.0, gm = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = -p[i];
+        p[i] = v;
+        gp = fma(g[i], v, gp);
+        gm = fmax(gm, fabs(g[i]));
+    }
+    const double tot = block_sum(gp);
+    for (int o = 16; o > 0; o >>= 1) gm = fmax(gm, __shfl_xor_sync(0xffffffffu, gm, o));
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = gm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < 32; ++w) m = fmax(m, sred[w]);
+        res[0] = tot;
+        res[1] = m;
+    }
+}
+__global__ void k_store_pair(double* __restrict__ Sslot, double* __restrict__ Yslot, const double* __restrict__ s, const double* __restrict__ y,
+                             double* __restrict__ rho_slot, double rho, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        Sslot[i] = s[i];
+        Yslot[i] = y[i];
+    }
+    if (i == 0) *rho_slot = rho;
+}
+
 struct Opt {
     mambo_csa* h = nullptr;
     int L = 0, device = 0;
     cudaStream_t stream = nullptr;
     double *x = nullptr, *g = nullptr, *p = nullptr, *xt = nullptr, *out = nullptr, *s = nullptr, *y = nullptr, *Hy = nullptr,
            *s2 = nullptr, *Hy2 = nullptr, *u = nullptr, *H = nullptr, *scal = nullptr;
+    double *LS = nullptr, *LY = nullptr, *Lrho = nullptr;   // L-BFGS ring (lbfgs_memory > 0)
     double* h_scal = nullptr;  // pinned
     int evals = 0;
     char err[256] = {0};
@@ -129,21 +248,28 @@ struct Opt {
 
 int blocks(int n) { return (n + 255) / 256; }
 
-int opt_free(Opt* o) {
-    double* bufs[] = {o->x, o->g, o->p, o->xt, o->out, o->s, o->y, o->Hy, o->s2, o->Hy2, o->u, o->H, o->scal};
-    for (double* b : bufs)
-        if (b) cudaFree(b);
+int opt_free(Opt* o) {   // device buffers live in the handle's scratch area; only the pinned scalars are ours
     if (o->h_scal) cudaFreeHost(o->h_scal);
+    o->h_scal = nullptr;
     return 0;
 }
 
-// (a.b, max|a|) -> host
-int dot_host(Opt* o, const double* a, const double* b, double* dot, double* amax) {
-    k_dot_absmax<<<1, 1024, 0, o->stream>>>(a, b, o->L, o->scal);
-    OCU(cudaMemcpyAsync(o->h_scal, o->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+// several dot products and max|m| in one kernel + one host round trip; out[k] = a_k.b_k, *amax = max|m|
+int dots_host(Opt* o, std::initializer_list<std::pair<const double*, const double*>> pairs, const double* m, double* out, double* amax) {
+    DotSet ds;
+    ds.nd = 0;
+    for (auto& pr : pairs) {
+        ds.a[ds.nd] = pr.first;
+        ds.b[ds.nd] = pr.second;
+        ++ds.nd;
+    }
+    for (int k = ds.nd; k < 6; ++k) ds.a[k] = ds.b[k] = nullptr;
+    ds.m = m;
+    k_multi_dot<<<1, 1024, 0, o->stream>>>(ds, o->L, o->scal);
+    OCU(cudaMemcpyAsync(o->h_scal, o->scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
     OCU(cudaStreamSynchronize(o->stream));
-    if (dot) *dot = o->h_scal[0];
-    if (amax) *amax = o->h_scal[1];
+    for (int k = 0; k < ds.nd; ++k) out[k] = o->h_scal[k];
+    if (amax) *amax = o->h_scal[6];
     return MAMBO_OK;
 }
 
@@ -158,10 +284,10 @@ int phi(Opt* o, double alpha, double* f, double* df) {
     o->evals++;
     k_dot_absmax<<<1, 1024, 0, o->stream>>>(o->out + 1, o->p, o->L, o->scal);
     OCU(cudaMemcpyAsync(o->h_scal, o->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
-    OCU(cudaMemcpyAsync(o->h_scal + 2, o->out, sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    OCU(cudaMemcpyAsync(o->h_scal + 8, o->out, sizeof(double), cudaMemcpyDeviceToHost, o->stream));
     OCU(cudaStreamSynchronize(o->stream));
     *df = o->h_scal[0];
-    *f = o->h_scal[2];
+    *f = o->h_scal[8];
     return MAMBO_OK;
 }
 
@@ -282,20 +408,38 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         return code;
     };
     if (cudaSetDevice(o->device) != cudaSuccess) return finish(MAMBO_ECUDA);
-    double** vecs[] = {&o->x, &o->g, &o->p, &o->xt, &o->s, &o->y, &o->Hy, &o->s2, &o->Hy2, &o->u};
-    for (double** v : vecs)
-        if (cudaMalloc((void**)v, sizeof(double) * L) != cudaSuccess) {
-            snprintf(o->err, sizeof(o->err), "cudaMalloc of optimiser vectors failed");
+    const int mem = std::min(std::max(opt.lbfgs_memory, 0), 64);
+    const bool lbfgs = mem > 0;
+    {
+        // one carve-up of the handle's scratch: 10 vectors, out (L+1), 8 scalars, then H (L x L) or the L-BFGS ring
+        const size_t Lp = ((size_t)L + 1 + 15) & ~(size_t)15;     // keeps every piece 128-byte aligned
+        const size_t big = lbfgs ? (2 * (size_t)mem * L + 64) : (size_t)L * L;
+        const size_t total = 11 * Lp + 16 + big;
+        void* base = nullptr;
+        rc = mambo_csa_scratch(h, total * sizeof(double), &base);
+        if (rc) {
+            snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+            return finish(rc);
+        }
+        double* q = static_cast<double*>(base);
+        double** vecs[] = {&o->x, &o->g, &o->p, &o->xt, &o->s, &o->y, &o->Hy, &o->s2, &o->Hy2, &o->u, &o->out};
+        for (double** v : vecs) {
+            *v = q;
+            q += Lp;
+        }
+        o->scal = q;
+        q += 16;
+        if (lbfgs) {
+            o->LS = q;
+            o->LY = q + (size_t)mem * L;
+            o->Lrho = q + 2 * (size_t)mem * L;
+        } else {
+            o->H = q;
+        }
+        if (cudaMallocHost((void**)&o->h_scal, 12 * sizeof(double)) != cudaSuccess) {
+            snprintf(o->err, sizeof(o->err), "cudaMallocHost of optimiser scalars failed");
             return finish(MAMBO_ENOMEM);
         }
-    if (cudaMalloc((void**)&o->out, sizeof(double) * (L + 1)) != cudaSuccess || cudaMalloc((void**)&o->scal, 4 * sizeof(double)) != cudaSuccess ||
-        cudaMallocHost((void**)&o->h_scal, 4 * sizeof(double)) != cudaSuccess) {
-        snprintf(o->err, sizeof(o->err), "cudaMalloc of optimiser scratch failed");
-        return finish(MAMBO_ENOMEM);
-    }
-    if (cudaMalloc((void**)&o->H, sizeof(double) * (size_t)L * L) != cudaSuccess) {
-        snprintf(o->err, sizeof(o->err), "cudaMalloc of the dense %d x %d inverse Hessian failed", L, L);
-        return finish(MAMBO_ENOMEM);
     }
     auto CK = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess) {
@@ -305,7 +449,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         return false;
     };
     if (CK(cudaMemcpyAsync(o->x, x0, sizeof(double) * L, cudaMemcpyHostToDevice, o->stream), "H2D x0")) return finish(MAMBO_ECUDA);
-    k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
+    if (!lbfgs) k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
 
     // f, g at x0
     double f = 0, dfdummy = 0;
@@ -313,33 +457,38 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     rc = phi(o, 0.0, &f, &dfdummy);
     if (rc) return finish(rc);
     cudaMemcpyAsync(o->g, o->out + 1, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
-    double gnorm = 0;
-    rc = dot_host(o, o->g, o->g, nullptr, &gnorm);
+    double gnorm = 0, gg = 0;
+    rc = dots_host(o, {{o->g, o->g}}, o->g, &gg, &gnorm);
     if (rc) return finish(rc);
     k_scale_neg<<<blocks(L), 256, 0, o->stream>>>(o->p, o->g, L);   // H = I
+    double df0 = -gg;                                                // g.p of the current direction, kept up to date below
 
     int it = 0, converged = 0;
-    // The rank-2 update of iteration k is applied to H in memory during iteration k+1, in the same pass that
-    // forms u = H g_new: (s_prev, Hy_prev, rho, cc) describe that pending update.
+    // Dense mode: the rank-2 update of iteration k is applied to H in memory during iteration k+1, in the same pass that
+    // forms u = H g_new: (s_prev, Hy_prev, rho, cc) describe that pending update.  Host round trips per iteration: one
+    // per line-search evaluation plus two fused multi-dot reads (was seven single dots).
     bool pending = false;
     bool fresh = true;             // H is still the (re)start identity: rescale it by s.y / y.y before the first update
     double rho = 0, cc = 0;
     double *s_cur = o->s, *Hy_cur = o->Hy, *s_prev = o->s2, *Hy_prev = o->Hy2;
+    int l_used = 0, l_head = -1;   // L-BFGS ring state
+    double l_gamma = 1.0;
     for (; it < opt.max_iter; ++it) {
         if (gnorm <= opt.g_tol) {
             converged = 1;
             break;
         }
-        double df0 = 0;
-        rc = dot_host(o, o->g, o->p, &df0, nullptr);
-        if (rc) return finish(rc);
         if (!(df0 < 0)) {  // not a descent direction: restart from steepest descent
-            k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
+            if (!lbfgs) k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
             pending = false;
             fresh = true;
+            l_used = 0;
+            l_head = -1;
+            l_gamma = 1.0;
             k_scale_neg<<<blocks(L), 256, 0, o->stream>>>(o->p, o->g, L);
-            rc = dot_host(o, o->g, o->p, &df0, nullptr);
+            rc = dots_host(o, {{o->g, o->g}}, nullptr, &gg, nullptr);
             if (rc) return finish(rc);
+            df0 = -gg;
             if (!(df0 < 0)) break;
         }
         double alpha = 0, fnew = f;
@@ -354,47 +503,61 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         // accepted point = last evaluated: xt, out.  s = xt - x, y = g_new - g
         k_sub<<<blocks(L), 256, 0, o->stream>>>(s_cur, o->xt, o->x, L);
         k_sub<<<blocks(L), 256, 0, o->stream>>>(o->y, o->out + 1, o->g, L);
-        double sy = 0, yHy = 0, hyg = 0, sg = 0;
-        rc = dot_host(o, s_cur, o->y, &sy, nullptr);
+        double d2[2] = {0, 0};
+        rc = dots_host(o, {{s_cur, o->y}, {o->y, o->y}}, nullptr, d2, nullptr);
         if (rc) return finish(rc);
-        if (fresh && sy > 1e-300) {
-            // Nocedal & Wright (6.20): H0 <- (s.y / y.y) I before the first update, so the first curvature pair sets the scale
-            double yy = 0;
-            rc = dot_host(o, o->y, o->y, &yy, nullptr);
-            if (rc) return finish(rc);
-            const double gamma = sy / yy;
-            k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, gamma);
-            k_scale<<<blocks(L), 256, 0, o->stream>>>(o->u, o->out + 1, gamma, L);     // u  = H g_new
-            k_scale<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->y, gamma, L);          // Hy = H y
-            fresh = false;
-        } else {
-            // one pass over H: fold in the pending update of the previous iteration and form u = H g_new
-            k_update_gemv<<<(L + 7) / 8, 256, 0, o->stream>>>(o->H, L, s_prev, Hy_prev, rho, cc, pending ? 1 : 0, o->out + 1, o->u);
-            // Hy = H y = H g_new - H g = u + p   (p = -H g)
-            k_axpy<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->u, o->p, 1.0, L);
-        }
-        pending = false;
-        cudaMemcpyAsync(o->x, o->xt, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
-        cudaMemcpyAsync(o->g, o->out + 1, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
+        const double sy = d2[0], yy = d2[1];
         f = fnew;
-        rc = dot_host(o, o->g, o->g, nullptr, &gnorm);
-        if (rc) return finish(rc);
-        if (sy > 1e-300) {
-            rc = dot_host(o, o->y, Hy_cur, &yHy, nullptr);
-            if (rc) return finish(rc);
-            rc = dot_host(o, Hy_cur, o->g, &hyg, nullptr);
-            if (rc) return finish(rc);
-            rc = dot_host(o, s_cur, o->g, &sg, nullptr);
-            if (rc) return finish(rc);
-            rho = 1.0 / sy;
-            cc = rho * (1.0 + rho * yHy);
-            // direction of the updated matrix from vectors only; the matrix itself is updated next iteration
-            k_direction<<<blocks(L), 256, 0, o->stream>>>(o->p, o->u, s_cur, Hy_cur, rho, cc, hyg, sg, L);
-            pending = true;
-            std::swap(s_cur, s_prev);
-            std::swap(Hy_cur, Hy_prev);
+        if (lbfgs) {
+            if (sy > 1e-300) {
+                l_head = (l_head + 1) % mem;
+                l_used = std::min(l_used + 1, mem);
+                k_store_pair<<<blocks(L), 256, 0, o->stream>>>(o->LS + (size_t)l_head * L, o->LY + (size_t)l_head * L, s_cur, o->y,
+                                                               o->Lrho + l_head, 1.0 / sy, L);
+                l_gamma = sy / yy;
+            }
+            cudaMemcpyAsync(o->x, o->xt, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
+            cudaMemcpyAsync(o->g, o->out + 1, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
+            k_lbfgs_direction<<<1, 1024, 0, o->stream>>>(o->g, o->LS, o->LY, o->Lrho, mem, l_used, std::max(l_head, 0), l_gamma, L, o->p, o->scal);
+            if (CK(cudaMemcpyAsync(o->h_scal, o->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, o->stream), "D2H scalars") ||
+                CK(cudaStreamSynchronize(o->stream), "sync"))
+                return finish(MAMBO_ECUDA);
+            df0 = o->h_scal[0];
+            gnorm = o->h_scal[1];
         } else {
-            k_scale_neg<<<blocks(L), 256, 0, o->stream>>>(o->p, o->u, L);
+            if (fresh && sy > 1e-300) {
+                // Nocedal & Wright (6.20): H0 <- (s.y / y.y) I before the first update, so the first curvature pair sets the scale
+                const double gamma = sy / yy;
+                k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, gamma);
+                k_scale<<<blocks(L), 256, 0, o->stream>>>(o->u, o->out + 1, gamma, L);     // u  = H g_new
+                k_scale<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->y, gamma, L);          // Hy = H y
+                fresh = false;
+            } else {
+                // one pass over H: fold in the pending update of the previous iteration and form u = H g_new
+                k_update_gemv<<<(L + 7) / 8, 256, 0, o->stream>>>(o->H, L, s_prev, Hy_prev, rho, cc, pending ? 1 : 0, o->out + 1, o->u);
+                // Hy = H y = H g_new - H g = u + p   (p = -H g)
+                k_axpy<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->u, o->p, 1.0, L);
+            }
+            pending = false;
+            cudaMemcpyAsync(o->x, o->xt, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
+            cudaMemcpyAsync(o->g, o->out + 1, sizeof(double) * L, cudaMemcpyDeviceToDevice, o->stream);
+            double d4[4] = {0, 0, 0, 0};   // y.Hy, Hy.g, s.g, u.g
+            rc = dots_host(o, {{o->y, Hy_cur}, {Hy_cur, o->g}, {s_cur, o->g}, {o->u, o->g}}, o->g, d4, &gnorm);
+            if (rc) return finish(rc);
+            const double yHy = d4[0], hyg = d4[1], sg = d4[2], ug = d4[3];
+            if (sy > 1e-300) {
+                rho = 1.0 / sy;
+                cc = rho * (1.0 + rho * yHy);
+                // direction of the updated matrix from vectors only; the matrix itself is updated next iteration
+                k_direction<<<blocks(L), 256, 0, o->stream>>>(o->p, o->u, s_cur, Hy_cur, rho, cc, hyg, sg, L);
+                df0 = -(ug - rho * (sg * hyg + hyg * sg) + cc * sg * sg);
+                pending = true;
+                std::swap(s_cur, s_prev);
+                std::swap(Hy_cur, Hy_prev);
+            } else {
+                k_scale_neg<<<blocks(L), 256, 0, o->stream>>>(o->p, o->u, L);
+                df0 = -ug;
+            }
         }
         if (opt.verbose && (it % opt.verbose == 0))
             fprintf(stderr, "[mambo bfgs] it %d f=%.10e |g|inf=%.3e alpha=%.3e evals=%d\n", it, f, gnorm, alpha, o->evals);

@@ -448,6 +448,24 @@ def test_native_bfgs_finds_planted_fragment(mb, lib):
         assert e.cost(xm) == pytest.approx(res["minimum"], abs=1e-14)
 
 
+def test_native_lbfgs_mode_finds_planted_fragment(mb, lib):
+    """lbfgs_memory > 0 (mambo_opt_options_t): limited-memory two-loop direction instead of the dense inverse Hessian;
+    same minimum as the dense mode on a planted fragment, and against the oracle's cost at the returned point."""
+    n = 7
+    T, xs = o.planted_tbt(n, 1, 4)
+    rng = np.random.default_rng(1)
+    x0 = xs[0] + 0.02 * rng.standard_normal(xs[0].shape)
+    with mb.CSAEngine(T) as e:
+        xd, rd = e.optimize(x0, g_tol=1e-9, max_iter=500)
+        xl, rl = e.optimize(x0, g_tol=1e-9, max_iter=500, lbfgs_memory=12)
+        tt = float(np.sum(T * T))
+        assert rd["minimum"] < 1e-12 * tt and rl["minimum"] < 1e-12 * tt
+        assert rl["iterations"] > 0 and rl["evaluations"] >= rl["iterations"]
+        c_l = o.cost_grad_factored(xl, T, need_grad=False)
+        c_l = c_l[0] if isinstance(c_l, tuple) else c_l
+        assert abs(c_l - rl["minimum"]) <= 1e-12 * tt
+
+
 def test_greedy_decomposition_matches_oracle_driver(mb, lib):
     """decompose.jl:1-80 end to end at LiH size (N=6 stand-in: planted R=2 + small symmetric noise): same x0s, same
     BFGS (scipy) on both sides -> same fragments' cost trail and final 1-norm."""
