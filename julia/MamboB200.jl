@@ -12,9 +12,10 @@ module MamboB200
 
 using QuantumMAMBO
 import QuantumMAMBO: F_OP, F_FRAG, CSA_x_to_F_FRAG, CSA_SD_x_to_F_FRAG, cartan_2b_num_params,
-                     real_orbital_rotation_num_params, tbt_svd_1st, SVD_for_CSA, SVD_for_CSA_SD,
+                     real_orbital_rotation_num_params, tbt_svd_1st, SVD_to_CSA, SVD_for_CSA, SVD_for_CSA_SD, SVD_tiny,
                      DECOMPOSITION_PRINT, ϵ
 using Optim
+using LinearAlgebra
 
 const LIB = get(ENV, "MAMBO_B200_LIB", joinpath(@__DIR__, "..", "quantummambo.jl_b200", "csrc", "libmambo_b200.so"))
 
@@ -75,6 +76,43 @@ function residual_cost(e::Engine)
     return c[]
 end
 
+"Another evaluation context on the same GPU sharing the device-resident residual of `e` (mambo_csa_create_lane)."
+function lane(e::Engine)
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:mambo_csa_create_lane, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), e.h, href))
+    l = Engine(href[], e.L)
+    finalizer(x -> (x.h != C_NULL && ccall((:mambo_csa_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), l)
+    return l
+end
+
+"""
+    tbt_svd_1st(e::Engine, n)
+
+guesses.jl:51-84 on the device-resident residual: the O(N^6) `eigen(Symmetric(reshape(tbt,(N^2,N^2))))` of :55-63 is
+replaced by `mambo_csa_leading_eig` (device Lanczos, only the eigenpair of largest |eigenvalue| is ever used); the
+N x N `eigen` and `SVD_to_CSA` (:3-49) stay as they are.
+"""
+function QuantumMAMBO.tbt_svd_1st(e::Engine, n::Integer; tiny = SVD_tiny)
+    Λ1 = Ref{Float64}(0.0)
+    full_l = Matrix{Float64}(undef, n, n)
+    iters = Ref{Cint}(0)
+    resid = Ref{Float64}(0.0)
+    GC.@preserve full_l check(ccall((:mambo_csa_leading_eig, LIB), Cint,
+        (Ptr{Cvoid}, Cdouble, Cint, Ref{Float64}, Ptr{Float64}, Ref{Cint}, Ref{Float64}),
+        e.h, 0.0, 0, Λ1, full_l, iters, resid))
+    cur_l = Symmetric(full_l)
+    lead = Λ1[]
+    if sum(abs.(cur_l - full_l)) > tiny                                   # guesses.jl:67-75
+        if sum(abs.(full_l + full_l')) > tiny
+            error("SVD operator is neither Hermitian or anti-Hermitian, cannot do double factorization into Hermitian fragment!")
+        end
+        cur_l = Hermitian(1im * full_l)
+        lead *= -1
+    end
+    ωl, Ul = eigen(cur_l)
+    return SVD_to_CSA(lead, ωl, Ul)
+end
+
 # ---- drop-in greedy steps (same signatures as decompose.jl:82, :207) ---------------------------------------------
 function _optimize(e::Engine, x0, print)
     c(x) = cost(e, x)                                       # decompose.jl:96-99   / :221-224
@@ -90,14 +128,14 @@ function QuantumMAMBO.CSA_greedy_step(F::F_OP, do_svd = SVD_for_CSA, print = DEC
     cartan_L = cartan_2b_num_params(F.N)
     unitary_L = real_orbital_rotation_num_params(F.N)
     x0 = zeros(cartan_L + unitary_L)
+    e = engine === nothing ? Engine(F, MAMBO_CSA) : engine       # with `engine`, F_rem is the engine's residual
     if do_svd
-        frag = tbt_svd_1st(F.mbts[3])
+        frag = tbt_svd_1st(e, F.N)                                 # largest SVD fragment of the *residual*
         x0[1:cartan_L] = frag.C.λ
         x0[cartan_L+1:end] = frag.U[1].θs
     else
         x0[cartan_L+1:end] = 2π * rand(unitary_L)
     end
-    e = engine === nothing ? Engine(F, MAMBO_CSA) : engine
     return _optimize(e, x0, print)
 end
 
@@ -105,14 +143,14 @@ function QuantumMAMBO.CSA_SD_greedy_step(F::F_OP, do_svd = SVD_for_CSA_SD, print
     cartan_L = cartan_2b_num_params(F.N)
     unitary_L = real_orbital_rotation_num_params(F.N)
     x0 = zeros(cartan_L + unitary_L + F.N)
+    e = engine === nothing ? Engine(F, MAMBO_CSA_SD) : engine
     if do_svd
-        frag = tbt_svd_1st(F.mbts[3])
+        frag = tbt_svd_1st(e, F.N)
         x0[F.N+1:F.N+cartan_L] = frag.C.λ
         x0[F.N+cartan_L+1:end] = frag.U[1].θs
     else
         x0[F.N+cartan_L+1:end] = 2π * rand(unitary_L)
     end
-    e = engine === nothing ? Engine(F, MAMBO_CSA_SD) : engine
     return _optimize(e, x0, print)
 end
 
@@ -131,7 +169,7 @@ function CSA_greedy_decomposition_b200(H::F_OP, α_max; decomp_tol = ϵ, verbose
     α = 0
     while curr_cost > decomp_tol && α < α_max
         α += 1
-        sol = flavour == MAMBO_CSA ? QuantumMAMBO.CSA_greedy_step(H; engine = e) : QuantumMAMBO.CSA_SD_greedy_step(H, false; engine = e)
+        sol = flavour == MAMBO_CSA ? QuantumMAMBO.CSA_greedy_step(H; engine = e) : QuantumMAMBO.CSA_SD_greedy_step(H; engine = e)
         frag = flavour == MAMBO_CSA ? CSA_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L) :
                                       CSA_SD_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L)
         push!(Farr, frag)

@@ -43,6 +43,7 @@ struct Params {
     const int* visit_start; // [gridDim.x]
     long long ldT;
     int P, Q, ld, Np, S;
+    const int* run_if;      // optional device flag: the kernel returns at once when *run_if == 0 (exact-cost fallback)
     int dephase;            // cycles by which column group 1 starts late (0 = off)
     int lookahead;          // sub-tiles requested ahead of the current step (0 = default)
 };
@@ -87,6 +88,7 @@ template <int NB, bool DO_E, bool STORE, bool TPREF>
 __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ld = 8 * NB + 4;   // == p.ld: compile-time pitch turns the fragment addressing into immediates
+    if (p.run_if && *p.run_if == 0) return;
     const int S = p.S, Q = p.Q;
     double* sB = reinterpret_cast<double*>(smem_raw);
     double* sA = sB + ROWS * ld;
@@ -353,6 +355,205 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
 #pragma unroll
         for (int w = 0; w < NCONS; ++w) s += sred[w];
         p.cost_part[blockIdx.x] = s;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k_ty -- the hot kernel of the single-GEMM formulation:  Y_I = sum_J T~_IJ A~_J   (pieces per visit, as above).
+//
+// With G = A~^T A~ (= (U^T U) o (U^T U), the identity up to rounding) the contraction shared by every gradient term is
+//      E = D A~ = (B~ A~^T - T~) A~ = B~ G - T~ A~ = C~ - Y,          C~ = A~ (Lambda G)   (O(R N^2), panel kernels)
+// and the cost follows from N x N quantities (cost = |T~|^2 - <B~, C~> + 2 <Lambda, A~^T E>), so one evaluation needs ONE
+// R x R x N product instead of two: the T~ tile is loaded straight into DMMA A fragments (same perm8 layout as the
+// accumulators of k_fused) and multiplied with the A~ sub-tile streamed through the TMA ring.  Half the DMMA work of
+// k_fused for the same single pass over T~.  k_fused remains the kernel for the residual update (STORE), the cost-only
+// evaluation and the exact-cost fallback when the residual is tiny against the tensor (cancellation in the expansion).
+// ---------------------------------------------------------------------------------------------------------------------
+struct YParams {
+    const double* T;        // [P*64][ldT] local rows of T~
+    const double* Acol;     // A~ rows of all columns [Q*64][ld]
+    double* Ypiece;         // [visits][2][64][Np]
+    const int* visit_start; // [gridDim.x]
+    long long ldT;
+    int P, Q, ld, Np, S;
+    int lookahead;
+};
+
+inline size_t smem_bytes_y(int ld, int S) { return (size_t)(S * SUB) * ld * 8 + (2 * S) * 8 + 64; }
+
+template <int NB, bool TPREF>
+__global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int ld = 8 * NB + 4;
+    const int S = p.S, Q = p.Q;
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(sA + (size_t)S * SUB * ld);
+    uint64_t* empty = full + S;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long total = (long long)p.P * Q;
+    const long long tbeg = total * blockIdx.x / gridDim.x;
+    const long long tend = total * (blockIdx.x + 1) / gridDim.x;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NCONS / 2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int t0 = lane & 3, t1 = lane >> 2;
+    const int wc = (warp >> 2) & 1, wr = warp & 3;
+    const int prow = perm8(t1);
+    const int pc0 = t0, pc1 = 4 + ((t0 + 2) & 3);
+
+    double e[2][NB][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int b = 0; b < NB; ++b) e[mb][b][0] = e[mb][b][1] = 0.0;
+    double acc[2][4][2];
+    double tn[2][4][2];
+
+    const long long lane_off = (long long)(16 * wr + prow) * p.ldT + 32 * wc;
+    auto loadT = [&](double(&dst)[2][4][2], int panel_, int ct_) {
+        const double* base = p.T + (long long)panel_ * ROWS * p.ldT + (long long)ct_ * COLS + lane_off;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 4; ++nb) {
+                dst[mb][nb][0] = __ldcs(base + (long long)mb * 8 * p.ldT + nb * 8 + pc0);
+                dst[mb][nb][1] = __ldcs(base + (long long)mb * 8 * p.ldT + nb * 8 + pc1);
+            }
+    };
+
+    int panel = (int)(tbeg / Q), ct = (int)(tbeg % Q);
+    int gi = 0, pv = 0;
+    if (TPREF && tbeg < tend) loadT(tn, panel, ct);
+
+    const int g_total = 2 * (int)(tend - tbeg);
+    const int lookahead = p.lookahead > 0 ? min(p.lookahead, S - 2) : ((S >= 6) ? 4 : (S - 2));
+    int g_issued = 0, ct_p = ct;
+    const uint32_t sub_bytes = (uint32_t)(SUB * ld * 8);
+    auto produce_upto = [&](int g_hi) {
+        while (g_issued < g_total && g_issued <= g_hi) {
+            const int slot = g_issued % S, use = g_issued / S, c = g_issued & 1;
+            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+            mbar_expect_tx(&full[slot], sub_bytes);
+            bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ct_p * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
+            ++g_issued;
+            if (c == 1 && ++ct_p == Q) ct_p = 0;
+        }
+    };
+
+    for (long long t = tbeg; t < tend; ++t, ++gi) {
+        if (t == tbeg || ct == 0) ++pv;
+        if (warp == 0) {
+            if (lane == 0) produce_upto(2 * gi + 1 + lookahead);
+            __syncwarp();
+        }
+        int npanel = panel, nct = ct + 1;
+        if (nct == Q) { nct = 0; ++npanel; }
+        if (TPREF) {
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 4; ++nb) {
+                    acc[mb][nb][0] = tn[mb][nb][0];
+                    acc[mb][nb][1] = tn[mb][nb][1];
+                }
+            if (t + 1 < tend) loadT(tn, npanel, nct);     // next tile's loads fly during this step's DMMAs
+        } else {
+            loadT(acc, panel, ct);                        // large N: no register room for the look-ahead tile
+        }
+
+        const int g = 2 * gi + wc;
+        const int slot = g % S;
+        mbar_wait(&full[slot], (g / S) & 1);
+        const double* sAs = sA + (size_t)slot * SUB * ld;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {
+            const double* r0 = sAs + (8 * kb + pc0) * ld + 2 * t1;
+            const double* r1 = sAs + (8 * kb + pc1) * ld + 2 * t1;
+#pragma unroll
+            for (int pr = 0; pr + 1 < NB / 2; pr += 2) {
+                const double2 b00 = *reinterpret_cast<const double2*>(r0 + 16 * pr);
+                const double2 b01 = *reinterpret_cast<const double2*>(r0 + 16 * (pr + 1));
+                const double2 b10 = *reinterpret_cast<const double2*>(r1 + 16 * pr);
+                const double2 b11 = *reinterpret_cast<const double2*>(r1 + 16 * (pr + 1));
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][0], b00.x);
+                    dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][0], b00.y);
+                    dmma(e[mb][2 * pr + 2][0], e[mb][2 * pr + 2][1], acc[mb][kb][0], b01.x);
+                    dmma(e[mb][2 * pr + 3][0], e[mb][2 * pr + 3][1], acc[mb][kb][0], b01.y);
+                }
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b10.x);
+                    dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b10.y);
+                    dmma(e[mb][2 * pr + 2][0], e[mb][2 * pr + 2][1], acc[mb][kb][1], b11.x);
+                    dmma(e[mb][2 * pr + 3][0], e[mb][2 * pr + 3][1], acc[mb][kb][1], b11.y);
+                }
+            }
+            if ((NB / 2) & 1) {
+                constexpr int pr = (NB / 2) - 1;
+                const double2 b0 = *reinterpret_cast<const double2*>(r0 + 16 * pr);
+                const double2 b1 = *reinterpret_cast<const double2*>(r1 + 16 * pr);
+                double t0v = 0.0, t1v = 0.0;
+                if (NB & 1) {
+                    t0v = (r0 - 2 * t1)[8 * (NB - 1) + t1];
+                    t1v = (r1 - 2 * t1)[8 * (NB - 1) + t1];
+                }
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][0], b0.x);
+                    dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][0], b0.y);
+                    if (NB & 1) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], t0v);
+                }
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) {
+                    dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b1.x);
+                    dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b1.y);
+                    if (NB & 1) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
+                }
+            } else if (NB & 1) {
+                const double t0v = (r0 - 2 * t1)[8 * (NB - 1) + t1];
+                const double t1v = (r1 - 2 * t1)[8 * (NB - 1) + t1];
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], t0v);
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[slot]);
+
+        const bool lastp = (ct == Q - 1) || (t == tend - 1);
+        if (lastp) {
+            const int visit = p.visit_start[blockIdx.x] + (pv - 1);
+            double* dst = p.Ypiece + ((size_t)(visit * 2 + wc) * ROWS + 16 * wr + prow) * p.Np;
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+#pragma unroll
+                for (int b = 0; b < NB; ++b) {
+                    int n0, n1;
+                    if (b < 2 * (NB / 2)) {
+                        n0 = 16 * (b >> 1) + 2 * (2 * t0) + (b & 1);
+                        n1 = n0 + 2;
+                    } else {
+                        n0 = 8 * (NB - 1) + 2 * t0;
+                        n1 = n0 + 1;
+                    }
+                    dst[(size_t)mb * 8 * p.Np + n0] = e[mb][b][0];
+                    dst[(size_t)mb * 8 * p.Np + n1] = e[mb][b][1];
+                    e[mb][b][0] = e[mb][b][1] = 0.0;
+                }
+            }
+        }
+        panel = npanel;
+        ct = nct;
     }
 }
 

@@ -1,6 +1,8 @@
 // panel_kernels.cuh -- the O(N^4) operand build and gradient epilogues as FP64 tensor-core panel GEMMs (sm_100a).
 //
+//   k_gram     : G = A~^T A~ = (U^T U) o (U^T U) and the staged product G Lambda (single-GEMM formulation, see k_ty)
 //   k_prep_mma : A~ panel (64 rows, gathered from U) -> global; B~_I = A~_I Lambda            (fermionic.jl:74-83 operands)
+//                and, for the single-GEMM formulation, C~_I = A~_I (Lambda G) with the partial <B~_I, C~_I> = |W~_I|^2
 //   k_post_mma : E~_I = fixed-order sum of the fused kernel's pieces; F_I = E~_I Lambda (theta gradient, gradient.jl:57-74);
 //                Spart_I = A~_I^T E~_I (lambda gradient, gradient.jl:13-41)
 //
@@ -95,10 +97,12 @@ __device__ __forceinline__ void gemm_kk(const double* __restrict__ sA, const dou
 template <int NB, int CS>
 __global__ void __launch_bounds__(NTHR, 1) k_prep_mma(const double* __restrict__ U, const double* __restrict__ LamP,
                                                       const int* __restrict__ pa, const int* __restrict__ pq, const double* __restrict__ sw,
-                                                      int n, int prow_begin, int prow_end, double* __restrict__ At, double* __restrict__ Bt) {
+                                                      int n, int prow_begin, int prow_end, double* __restrict__ At, double* __restrict__ Bt,
+                                                      const double* __restrict__ GLP, double* __restrict__ Ct, double* __restrict__ wpart) {
     using G = Geo<NB, CS>;
     constexpr int LD = G::LD, NBW = G::NBW, NBC = G::NBC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_wred[NTHR / 32];
     double* sA = reinterpret_cast<double*>(smem_raw);
     double* sL = sA + G::panel_elems;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(sL + G::lam_elems);
@@ -144,13 +148,91 @@ __global__ void __launch_bounds__(NTHR, 1) k_prep_mma(const double* __restrict__
             if (blk < nblk)
                 *reinterpret_cast<double2*>(out + (size_t)mb * 8 * LD + 8 * (nb_lo + blk) + 2 * t0) = make_double2(acc[mb][nb][0], acc[mb][nb][1]);
         }
+    if (!GLP) return;
+    // ---- single-GEMM formulation: C~ = A~ (Lambda G) (the staged matrix is G Lambda = (Lambda G)^T), <B~, C~> ----------
+    __syncthreads();                                        // every warp is done reading Lambda from sL
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bytes = (uint32_t)((size_t)8 * nblk * LD * 8);
+        mbar_expect(mbar, bytes);
+        bulk(sL, GLP + (size_t)8 * nb_lo * LD, bytes, mbar);
+    }
+    mbar_wait(mbar, 1);
+    double acc2[2][NBW][2];
+    gemm_kk<NB, CS>(sA, sL, nblk, acc2);
+    double* outc = Ct + (size_t)((panel - prow_begin) * ROWS + 16 * wr + t1) * LD;
+    double wsum = 0.0;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NBW; ++nb) {
+            const int blk = wc * NBW + nb;
+            if (blk < nblk) {
+                *reinterpret_cast<double2*>(outc + (size_t)mb * 8 * LD + 8 * (nb_lo + blk) + 2 * t0) = make_double2(acc2[mb][nb][0], acc2[mb][nb][1]);
+                wsum = fma(acc[mb][nb][0], acc2[mb][nb][0], fma(acc[mb][nb][1], acc2[mb][nb][1], wsum));
+            }
+        }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if (lane == 0) s_wred[warp] = wsum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < NTHR / 32; ++w) t += s_wred[w];
+        wpart[(size_t)(panel - prow_begin) * CS + cs] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// k_gram: G[l][m] = (sum_p U[p][l] U[p][m])^2 (= A~^T A~ over all N^2 rows; the identity up to the rounding of exp(K)) and
+//         GLP[m][k] = (G Lambda)[m][k], padded pitch LD: the [column][k] staging of Lambda G for k_prep_mma's second GEMM.
+//   one CTA per row m; U and Lambda are dense n x n, row-major.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gram(const double* __restrict__ U, const double* __restrict__ Lam, int n, int LD,
+                                              double* __restrict__ GLP) {
+    __shared__ double um[256];     // column m of U
+    __shared__ double g[256];      // row m of G
+    const int m = blockIdx.x, j = threadIdx.x;
+    if (j < n) um[j] = U[(size_t)j * n + m];
+    __syncthreads();
+    // the loads below do not depend on each other: four accumulators and an 8-deep unroll keep them in flight together
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    if (j < n) {
+        int p = 0;
+#pragma unroll 2
+        for (; p + 3 < n; p += 4) {
+            d0 = fma(um[p], U[(size_t)p * n + j], d0);
+            d1 = fma(um[p + 1], U[(size_t)(p + 1) * n + j], d1);
+            d2 = fma(um[p + 2], U[(size_t)(p + 2) * n + j], d2);
+            d3 = fma(um[p + 3], U[(size_t)(p + 3) * n + j], d3);
+        }
+        for (; p < n; ++p) d0 = fma(um[p], U[(size_t)p * n + j], d0);
+    }
+    const double d = (d0 + d1) + (d2 + d3);
+    g[j] = d * d;
+    __syncthreads();
+    if (j < n) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = 0;
+#pragma unroll 2
+        for (; i + 3 < n; i += 4) {
+            a0 = fma(g[i], Lam[(size_t)i * n + j], a0);
+            a1 = fma(g[i + 1], Lam[(size_t)(i + 1) * n + j], a1);
+            a2 = fma(g[i + 2], Lam[(size_t)(i + 2) * n + j], a2);
+            a3 = fma(g[i + 3], Lam[(size_t)(i + 3) * n + j], a3);
+        }
+        for (; i < n; ++i) a0 = fma(g[i], Lam[(size_t)i * n + j], a0);
+        GLP[(size_t)m * LD + j] = (a0 + a1) + (a2 + a3);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // k_esum: E~[row][LD] = fixed-order sum of the fused kernel's pieces (two warp-column partials per visit)
 // ------------------------------------------------------------------------------------------------------------
+//         single-GEMM formulation (Ct != null): the pieces hold Y = T~ A~ and E~ = C~ - Y
 __global__ void __launch_bounds__(256) k_esum(const double* __restrict__ Epiece, const int* __restrict__ piece_first, int Np, int LD,
-                                              double* __restrict__ Et) {
+                                              double* __restrict__ Et, const double* __restrict__ Ct) {
     const int panel = blockIdx.x;
     const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
     const int total = ROWS * Np;
@@ -168,7 +250,10 @@ __global__ void __launch_bounds__(256) k_esum(const double* __restrict__ Epiece,
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int idx = base + u * 256;
-            if (idx < total) Et[(size_t)(panel * ROWS + idx / Np) * LD + (idx % Np)] = acc4[u];
+            if (idx < total) {
+                const size_t o = (size_t)(panel * ROWS + idx / Np) * LD + (idx % Np);
+                Et[o] = Ct ? Ct[o] - acc4[u] : acc4[u];
+            }
         }
     }
 }

@@ -515,8 +515,14 @@ __global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__
                                                       int npanels, const double* __restrict__ F1, const double* __restrict__ F2,
                                                       const double* __restrict__ sw, const double* __restrict__ Rchain,
                                                       const int* __restrict__ s_ptr, int n, int Np, int packed, double gcoef,
-                                                      int row_begin, int row_end, double* __restrict__ part) {
+                                                      int row_begin, int row_end, double* __restrict__ part,
+                                                      // single-GEMM formulation (Lam != null): cost from N x N quantities, see below
+                                                      const double* __restrict__ Lam, double* __restrict__ ls_part, unsigned* __restrict__ done,
+                                                      const double* __restrict__ wpart, int nw, const double* __restrict__ tnorm2, double tau,
+                                                      int* __restrict__ flag) {
     __shared__ double redS[8][128], redG[8][128];
+    __shared__ double redL[4];
+    double ldot = 0.0;
     const int a = blockIdx.x, tx = threadIdx.x & 127, grp = threadIdx.x >> 7;
     const double* U = Rchain + (size_t)(*s_ptr) * n * n;
     if (a == 0 && threadIdx.x == 0) {
@@ -577,8 +583,36 @@ __global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__
             }
             part[1 + (size_t)a * n + b] = ss;
             part[1 + (size_t)n * n + (size_t)a * n + b] = gcoef * gg;
+            if (Lam) ldot = fma(Lam[(size_t)a * n + b], ss, ldot);
         }
         __syncthreads();
+    }
+    if (!Lam) return;
+    // Two-body cost of the single-GEMM formulation (fused::k_ty), every term additive over row shards:
+    //     cost = |T~|^2 - <B~, C~> + 2 <Lambda, S>,   S = A~^T E (this shard's partial, just reduced above).
+    // The expansion cancels when the residual is tiny against the tensor: `flag` is raised when cost < tau * max(|T~|^2,
+    // |W~|^2), and the exact-cost pass queued behind this kernel (fused::k_fused, cost only) then runs instead of returning
+    // at once.  Row partials are combined by the last CTA to finish, in row order: deterministic.
+    if (grp == 0) {
+        for (int o = 16; o > 0; o >>= 1) ldot += __shfl_xor_sync(0xffffffffu, ldot, o);
+        if ((tx & 31) == 0) redL[tx >> 5] = ldot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ls_part[a] = (redL[0] + redL[1]) + (redL[2] + redL[3]);
+        __threadfence();
+        const unsigned old = atomicAdd(done, 1u);
+        if (old == gridDim.x - 1) {
+            *done = 0;
+            __threadfence();
+            double ls = 0.0, w = 0.0;
+            for (int i = 0; i < n; ++i) ls += __ldcg(ls_part + i);
+            for (int i = 0; i < nw; ++i) w += wpart[i];
+            const double t2 = *tnorm2;
+            const double c = (t2 - w) + 2.0 * ls;
+            part[0] = c;
+            *flag = (c < tau * fmax(t2, w)) ? 1 : 0;     // also catches a (rounding-)negative value
+        }
     }
 }
 
@@ -786,6 +820,39 @@ __global__ void k_sumsq_add(const double* __restrict__ v, int len, const double*
         for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) t += red[w];
         for (int i = 0; i < ncost; ++i) t += cost_part[i];
         dst[0] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Exact-cost fallback of the single-GEMM formulation: take the sum of fused::k_fused's partials when `flag` is up.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_cost_select(const int* __restrict__ flag, const double* __restrict__ cost_part, int ncost, double* __restrict__ part) {
+    if (threadIdx.x == 0 && *flag) {
+        double c = 0.0;
+        for (int i = 0; i < ncost; ++i) c += cost_part[i];
+        part[0] = c;
+    }
+}
+// per-CTA partial sums of squares of a (zero padded) array -> out[blockIdx.x]; fixed order within a CTA
+__global__ void __launch_bounds__(256) k_sumsq_partial(const double* __restrict__ v, long long len, double* __restrict__ out) {
+    __shared__ double red[8];
+    double a0 = 0.0, a1 = 0.0;
+    const long long stride = (long long)gridDim.x * 256;
+    long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+    for (; i + stride < len; i += 2 * stride) {
+        const double x = v[i], y = v[i + stride];
+        a0 = fma(x, x, a0);
+        a1 = fma(y, y, a1);
+    }
+    if (i < len) a0 = fma(v[i], v[i], a0);
+    double a = a0 + a1;
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += red[q];
+        out[blockIdx.x] = s;
     }
 }
 
