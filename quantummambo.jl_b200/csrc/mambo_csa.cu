@@ -408,7 +408,7 @@ const int* u_sptr(const mambo_csa* h) { return h->use_chain ? h->d_zero : h->d_s
 int enqueue_prep(mambo_csa* h) {
     if (h->use_panel) {
         if (h->fast) {
-            panel::k_gram<<<h->N, 256, 0, h->stream>>>(u_base(h), h->Lam, h->N, h->ld, h->GLP);
+            panel::k_gram<<<h->N, 1024, 0, h->stream>>>(u_base(h), h->Lam, h->N, h->ld, h->GLP);
             h->launches++;
         }
         NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT, CST><<<dim3(h->nRpad / panel::ROWS, CST), panel::NTHR, panel::prep_smem<NBT, CST>(), h->stream>>>(
@@ -429,11 +429,10 @@ int enqueue_prep(mambo_csa* h) {
 
 int enqueue_post_f(mambo_csa* h, double* F, bool with_S = false) {
     if (h->use_panel) {
-        const int ysplit = std::max(1, std::min(8, (2 * h->num_sms) / std::max(h->P, 1)));
-        panel::k_esum<<<dim3(h->P, ysplit), 256, 0, h->stream>>>(h->Epiece, h->piece_first, h->Np, h->ld, h->EtP, h->fast ? h->Ct : nullptr);
         NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT, CST><<<dim3(h->P, CST), panel::NTHR, panel::post_smem<NBT, CST>(), h->stream>>>(
-                                     h->EtP, h->LamP, h->At, h->N, h->row_begin, F, h->Spart, with_S ? 1 : 0)));
-        h->launches += 2;
+                                     h->Epiece, h->piece_first, h->fast ? h->Ct : nullptr, h->LamP, h->At, h->N, h->row_begin, F, h->Spart,
+                                     with_S ? 1 : 0)));
+        h->launches += 1;
         CU(cudaGetLastError());
         return MAMBO_OK;
     }

@@ -189,41 +189,49 @@ __global__ void __launch_bounds__(NTHR, 1) k_prep_mma(const double* __restrict__
 //         GLP[m][k] = (G Lambda)[m][k], padded pitch LD: the [column][k] staging of Lambda G for k_prep_mma's second GEMM.
 //   one CTA per row m; U and Lambda are dense n x n, row-major.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gram(const double* __restrict__ U, const double* __restrict__ Lam, int n, int LD,
-                                              double* __restrict__ GLP) {
-    __shared__ double um[256];     // column m of U
-    __shared__ double g[256];      // row m of G
-    const int m = blockIdx.x, j = threadIdx.x;
-    if (j < n) um[j] = U[(size_t)j * n + m];
+__global__ void __launch_bounds__(1024) k_gram(const double* __restrict__ U, const double* __restrict__ Lam, int n, int LD,
+                                               double* __restrict__ GLP) {
+    // 1024 threads = 8 row groups x 128 columns: every thread issues its <= ceil(n/8) independent loads back to back, so a
+    // phase costs about one memory round trip instead of n of them; group partials are combined in a fixed order.
+    __shared__ double um[256];        // column m of U
+    __shared__ double g[256];         // row m of G
+    __shared__ double red[8][128];
+    const int m = blockIdx.x, tx = threadIdx.x & 127, grp = threadIdx.x >> 7;
+    for (int p = threadIdx.x; p < n; p += 1024) um[p] = U[(size_t)p * n + m];
     __syncthreads();
-    // the loads below do not depend on each other: four accumulators and an 8-deep unroll keep them in flight together
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-    if (j < n) {
-        int p = 0;
-#pragma unroll 2
-        for (; p + 3 < n; p += 4) {
-            d0 = fma(um[p], U[(size_t)p * n + j], d0);
-            d1 = fma(um[p + 1], U[(size_t)(p + 1) * n + j], d1);
-            d2 = fma(um[p + 2], U[(size_t)(p + 2) * n + j], d2);
-            d3 = fma(um[p + 3], U[(size_t)(p + 3) * n + j], d3);
+    for (int j0 = 0; j0 < n; j0 += 128) {
+        const int j = j0 + tx;
+        double d = 0.0;
+        if (j < n) {
+#pragma unroll 8
+            for (int p = grp; p < n; p += 8) d = fma(um[p], U[(size_t)p * n + j], d);
         }
-        for (; p < n; ++p) d0 = fma(um[p], U[(size_t)p * n + j], d0);
+        red[grp][tx] = d;
+        __syncthreads();
+        if (grp == 0 && j < n) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += red[k][tx];
+            g[j] = t * t;
+        }
+        __syncthreads();
     }
-    const double d = (d0 + d1) + (d2 + d3);
-    g[j] = d * d;
-    __syncthreads();
-    if (j < n) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int i = 0;
-#pragma unroll 2
-        for (; i + 3 < n; i += 4) {
-            a0 = fma(g[i], Lam[(size_t)i * n + j], a0);
-            a1 = fma(g[i + 1], Lam[(size_t)(i + 1) * n + j], a1);
-            a2 = fma(g[i + 2], Lam[(size_t)(i + 2) * n + j], a2);
-            a3 = fma(g[i + 3], Lam[(size_t)(i + 3) * n + j], a3);
+    for (int j0 = 0; j0 < n; j0 += 128) {
+        const int j = j0 + tx;
+        double a = 0.0;
+        if (j < n) {
+#pragma unroll 8
+            for (int i = grp; i < n; i += 8) a = fma(g[i], Lam[(size_t)i * n + j], a);
         }
-        for (; i < n; ++i) a0 = fma(g[i], Lam[(size_t)i * n + j], a0);
-        GLP[(size_t)m * LD + j] = (a0 + a1) + (a2 + a3);
+        red[grp][tx] = a;
+        __syncthreads();
+        if (grp == 0 && j < n) {
+            double t = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) t += red[k][tx];
+            GLP[(size_t)m * LD + j] = t;
+        }
+        __syncthreads();
     }
 }
 
@@ -261,8 +269,11 @@ __global__ void __launch_bounds__(256) k_esum(const double* __restrict__ Epiece,
 // ------------------------------------------------------------------------------------------------------------
 // k_post_mma: per local panel and column split: F[:, cols] = E~ Lambda[:, cols] ; Spart[:, cols] = A~_panel^T E~[:, cols]
 // ------------------------------------------------------------------------------------------------------------
+//   The E~ panel itself is assembled in shared memory first: fixed-order sum of the hot kernel's pieces (two warp-column
+//   partials per visit), subtracted from C~ in the single-GEMM formulation (E~ = C~ - Y), so it never round-trips HBM.
 template <int NB, int CS>
-__global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__ Et, const double* __restrict__ LamP,
+__global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
+                                                      const double* __restrict__ Ct, const double* __restrict__ LamP,
                                                       const double* __restrict__ At, int n, int row_begin, double* __restrict__ F,
                                                       double* __restrict__ Spart, int do_S) {
     using G = Geo<NB, CS>;
@@ -280,10 +291,31 @@ __global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__
     if (threadIdx.x == 0) {
         mbar_init(mbar);
         const uint32_t lbytes = (uint32_t)((size_t)8 * nblk * LD * 8), pbytes = (uint32_t)(G::panel_elems * 8);
-        mbar_expect(mbar, lbytes + pbytes + (do_S ? pbytes : 0u));
-        bulk(sE, Et + (size_t)panel * ROWS * LD, pbytes, mbar);
+        mbar_expect(mbar, lbytes + (do_S ? pbytes : 0u));
         bulk(sL, LamP + (size_t)8 * nb_lo * LD, lbytes, mbar);
         if (do_S) bulk(sAp, At + (size_t)(row_begin + panel * ROWS) * LD, pbytes, mbar);
+    }
+    {   // E~ panel -> shared memory while the TMA copies are in flight; every load below is independent of the others
+        const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
+        const double* cpanel = Ct ? Ct + (size_t)panel * ROWS * LD : nullptr;
+        for (int idx = threadIdx.x; idx < ROWS * (LD / 2); idx += NTHR) {
+            const int row = idx / (LD / 2), c2 = 2 * (idx % (LD / 2));
+            double2 a = make_double2(0.0, 0.0);
+            if (c2 < Np) {
+                for (int v = v0; v < v1; ++v) {
+                    const double2 y0 = __ldcs(reinterpret_cast<const double2*>(Epiece + ((size_t)(v * 2 + 0) * ROWS + row) * Np + c2));
+                    const double2 y1 = __ldcs(reinterpret_cast<const double2*>(Epiece + ((size_t)(v * 2 + 1) * ROWS + row) * Np + c2));
+                    a.x += y0.x + y1.x;
+                    a.y += y0.y + y1.y;
+                }
+                if (cpanel) {
+                    const double2 cc = *reinterpret_cast<const double2*>(cpanel + (size_t)row * LD + c2);
+                    a.x = cc.x - a.x;
+                    a.y = cc.y - a.y;
+                }
+            }
+            *reinterpret_cast<double2*>(sE + (size_t)row * LD + c2) = a;
+        }
     }
     __syncthreads();
     mbar_wait(mbar, 0);
