@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations timed for the CPU baseline (0 = auto)")
     ap.add_argument("--no-greedy", action="store_true", help="skip the greedy-CSA time-to-tolerance leg")
     ap.add_argument("--lanes", type=int, default=0,
-                    help="evaluation lanes per GPU (mambo_csa_create_lane); 0 = floor(SMs / orbital-rotation CTAs), 1..8")
+                    help="evaluation lanes per GPU (mambo_csa_create_lane); 0 = auto (see main), 1..8")
     return ap.parse_args()
 
 
@@ -287,8 +287,13 @@ def main():
 
     # ---- evaluation lanes: independent evaluations of the step overlap on the device (mambo_csa_create_lane) ----------
     tiles = (n + 15) // 16
-    nl = args.lanes if args.lanes > 0 else max(1, min(8, info["num_sms"] // (tiles * tiles)))
+    # default: as many lanes as orbital-rotation chains fit on the device at two CTAs per SM, rounded down to a divisor
+    # of the step's BATCH points so that every lane carries the same number of evaluations
+    nl = args.lanes if args.lanes > 0 else max(1, min(8, (2 * info["num_sms"]) // (tiles * tiles)))
     nl = min(nl, BATCH)
+    if args.lanes <= 0:
+        while BATCH % nl:
+            nl -= 1
     group = [eng] + [eng.lane() for _ in range(nl - 1)]
     main_stream = torch.cuda.Stream(dev)      # real side streams: handle 0 (legacy default) would mean "own stream"
     torch.cuda.set_stream(main_stream)

@@ -5,24 +5,33 @@
 //   k_chain_d : Lt = Dexp(K)[G^T] by the product rule over the same sequence, then the gradient in x order
 //               (reference: del_u_theta gradient.jl:76-129 contracted as in grad_theta :131-146; `vcat` :148-151).
 //
-// One CTA owns one 16x16 tile of every N x N matrix of the chain; the ~5+s dependent products are separated by a
-// grid-wide barrier (one counter in global memory) instead of kernel boundaries.  Every matrix that is later a
+// One CTA owns one CT x CT tile of every N x N matrix of the chain; the ~5+s dependent products are separated by a
+// barrier instead of kernel boundaries.  CT = 16 (16 warps = 4 (8x8 blocks) x 4 (k quarters)) in two flavours:
+//   CLUSTER : N <= 64.  At most 4 x 4 tiles, so the whole chain runs in ONE thread-block cluster (<= 16 CTAs) and the
+//             steps are separated by the hardware cluster barrier (barrier.cluster release/acquire) instead of a round
+//             trip through a global-memory counter (~1.2 us).
+//   grid    : larger N.  Cooperative launch, grid-wide barrier on one counter in global memory.
+// (CT = 32 also compiles -- 16 warps = 16 blocks, full k -- and would put N <= 128 into one cluster, but a step is then
+// bound by the DMMA rate of 16 SMs: measured slower than 49 CTAs with the global barrier at N = 100.)  Every matrix that is later a
 // right-hand operand is stored twice (M and M^T), and every matrix has a padded pitch ldm (== 4 mod 16, zero pad), so
 // that each operand of a tile product is ONE contiguous 16 x ldm block: it is fetched by the TMA engine with a single
-// cp.async.bulk (completion on an mbarrier) and lands in shared memory already in a bank-conflict-free layout.  Products run on the FP64 tensor pipe (DMMA.8x8x4) with 16 warps = 4 (8x8 blocks) x 4 (k
-// quarters) and two accumulators per product, which keeps the dependent DMMA chains at ~3.
-// Launched cooperatively (all CTAs co-resident; grid <= 121 CTAs for N <= 168).
+// cp.async.bulk (completion on an mbarrier) and lands in shared memory already in a bank-conflict-free layout.  Products run
+// on the FP64 tensor pipe (DMMA.8x8x4) with two accumulators per product term.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
 namespace chain {
 
-constexpr int CT = 16;       // tile edge
-constexpr int KQ = 4;        // k split across warps
-constexpr int NTHR = 4 * KQ * 32;
+constexpr int NTHR = 512;    // 16 warps = (CT/8)^2 blocks x KQ k-slices
 constexpr int SMAXC = 14;
 constexpr int NSTRIP = 6;
+template <int CT>
+struct Geo {
+    static constexpr int BW = CT / 8;           // 8x8 blocks per tile edge
+    static constexpr int NBLK = BW * BW;        // blocks per tile (4 or 16)
+    static constexpr int KQ = 16 / NBLK;        // k split across warps (4 or 1)
+};
 
 __constant__ double c_t[17] = {1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880,
                                1.0 / 3628800, 1.0 / 39916800, 1.0 / 479001600, 1.0 / 6227020800.0, 1.0 / 87178291200.0,
@@ -57,10 +66,13 @@ struct DParams {
 // pitch of every chain matrix: smallest ldm >= n with ldm == 4 (mod 16)  (100 -> 100, 152 -> 164)
 __host__ __device__ inline int ldm_for(int n) { return ((n + 11) / 16) * 16 + 4; }
 __host__ __device__ inline int lda_for(int n) { return ldm_for(n); }
-__host__ __device__ inline int rows_pad(int n) { return ((n + CT - 1) / CT) * CT; }
-__host__ __device__ inline size_t mat_stride(int n) { return (size_t)rows_pad(n) * ldm_for(n); }
+__host__ __device__ inline int rows_pad(int n, int ct) { return ((n + ct - 1) / ct) * ct; }
+__host__ __device__ inline size_t mat_stride(int n, int ct) { return (size_t)rows_pad(n, ct) * ldm_for(n); }
 __host__ __device__ inline int kpad(int n) { return ((n + 3) / 4) * 4; }
-inline size_t smem_bytes(int n) { return ((size_t)NSTRIP * CT * lda_for(n) + (size_t)(KQ - 1) * 4 * 32 * 4) * sizeof(double) + 64; }
+inline size_t smem_bytes(int n, int ct) {
+    const int kq = 16 / ((ct / 8) * (ct / 8));
+    return ((size_t)NSTRIP * ct * lda_for(n) + (size_t)(kq - 1) * 4 * 32 * 4) * sizeof(double) + 64;
+}
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -106,7 +118,25 @@ __device__ __forceinline__ void grid_exit(unsigned* bar) {
     }
 }
 
-// ---- strip loader: rows [r0, r0+16) of a chain matrix (pitch ldm, zero padded) -> S, one TMA bulk copy ---------------
+// Step barrier of the chain.  CLUSTER: every CTA of the chain is in one thread-block cluster; the hardware barrier orders
+// the peers' global stores (release / acquire at cluster scope) and the proxy fence hands them to the TMA engine.
+template <bool CLUSTER>
+__device__ __forceinline__ void step_barrier(unsigned* ctr, unsigned& target, long long* stamps = nullptr) {
+    if (CLUSTER) {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    } else {
+        grid_barrier(ctr, target, stamps);
+    }
+}
+template <bool CLUSTER>
+__device__ __forceinline__ void chain_exit(unsigned* bar) {
+    if (!CLUSTER) grid_exit(bar);
+}
+
+// ---- strip loader: rows [r0, r0+CT) of a chain matrix (pitch ldm, zero padded) -> S, one TMA bulk copy ---------------
+template <int CT>
 struct Loader {
     uint64_t* mbar;
     uint32_t parity;
@@ -148,11 +178,13 @@ struct Loader {
 
 // this warp's k quarter of an 8x8 block product, two accumulators: (c, d) += SA[block rows] . SB[block cols]^T
 // SA: [16 rows i][lda] (k contiguous), SB: [16 cols j][lda] (k contiguous)
+template <int CT>
 __device__ __forceinline__ void mm_q(const double* SA, const double* SB, int lda, int ks, double (&c)[2], double (&d)[2]) {
+    constexpr int KQ = Geo<CT>::KQ, NBLK = Geo<CT>::NBLK, BW = Geo<CT>::BW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int t0 = lane & 3, t1 = lane >> 2, b = warp & 3, kq = warp >> 2;
-    const double* a = SA + (8 * (b >> 1) + t1) * lda + t0;
-    const double* bb = SB + (8 * (b & 1) + t1) * lda + t0;
+    const int t0 = lane & 3, t1 = lane >> 2, b = warp % NBLK, kq = warp / NBLK;
+    const double* a = SA + (8 * (b / BW) + t1) * lda + t0;
+    const double* bb = SB + (8 * (b % BW) + t1) * lda + t0;
     int kk = kq;
     for (; kk + KQ < ks; kk += 2 * KQ) {
         dmma(c[0], c[1], a[4 * kk], bb[4 * kk]);
@@ -160,8 +192,11 @@ __device__ __forceinline__ void mm_q(const double* SA, const double* SB, int lda
     }
     if (kk < ks) dmma(c[0], c[1], a[4 * kk], bb[4 * kk]);
 }
-// combine the k quarters; afterwards warps 0..3 hold the full sums
+// combine the k quarters; afterwards warps 0..NBLK-1 hold the full sums (nothing to do when every warp owns its block)
+template <int CT>
 __device__ __forceinline__ void combine(double* red, double* v, int nv) {
+    constexpr int KQ = Geo<CT>::KQ;
+    if (KQ == 1) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (warp >= 4)
         for (int i = 0; i < nv; ++i) red[(((warp >> 2) - 1) * 128 + (warp & 3) * 32 + lane) * 4 + i] = v[i];
@@ -177,7 +212,9 @@ struct Ctx {
     int n, lda, ks, i0, j0, ei, ej;
 };
 
+template <int CT>
 __device__ __forceinline__ Ctx make_ctx(double* sm, int n, uint64_t** mbar) {
+    constexpr int KQ = Geo<CT>::KQ, NBLK = Geo<CT>::NBLK, BW = Geo<CT>::BW;
     Ctx c;
     c.n = n;
     c.lda = lda_for(n);
@@ -187,9 +224,9 @@ __device__ __forceinline__ Ctx make_ctx(double* sm, int n, uint64_t** mbar) {
     *mbar = reinterpret_cast<uint64_t*>(c.red + (KQ - 1) * 4 * 32 * 4);
     c.i0 = blockIdx.y * CT;
     c.j0 = blockIdx.x * CT;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = warp & 3;
-    c.ei = c.i0 + 8 * (b >> 1) + (lane >> 2);
-    c.ej = c.j0 + 8 * (b & 1) + 2 * (lane & 3);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, b = warp % NBLK;
+    c.ei = c.i0 + 8 * (b / BW) + (lane >> 2);
+    c.ej = c.j0 + 8 * (b % BW) + 2 * (lane & 3);
     for (int idx = threadIdx.x; idx < NSTRIP * CT * c.lda; idx += NTHR) sm[idx] = 0.0;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(s32(*mbar)));
@@ -200,13 +237,15 @@ __device__ __forceinline__ Ctx make_ctx(double* sm, int n, uint64_t** mbar) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
+template <int CT, bool CLUSTER>
+__global__ void __launch_bounds__(NTHR, 2) k_chain_u(UParams p) {
+    constexpr int NBLK = Geo<CT>::NBLK;
     extern __shared__ __align__(128) double sm[];
     const int n = p.n;
-    const size_t nn = mat_stride(n);
+    const size_t nn = mat_stride(n, CT);
     uint64_t* mbar;
-    Ctx c = make_ctx(sm, n, &mbar);
-    Loader ld{mbar, 0u, c.lda, 0u, 0};
+    Ctx c = make_ctx<CT>(sm, n, &mbar);
+    Loader<CT> ld{mbar, 0u, c.lda, 0u, 0};
     __shared__ double s_red[NTHR / 32];
     __shared__ double s_scale;
     __shared__ int s_s;
@@ -257,8 +296,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
         return (i < j ? th[(size_t)i * n - (size_t)i * (i + 1) / 2 + (j - i - 1)] : -th[(size_t)j * n - (size_t)j * (j + 1) / 2 + (i - j - 1)]) * sc;
     };
     // ---- step 1: X2 = X.X; rows I of X -> S0, columns J of X (as rows of X^T) -> S1, built straight from theta ----
-    {
-        const int r = threadIdx.x >> 5;
+    for (int r = threadIdx.x >> 5; r < CT; r += NTHR / 32) {
 #pragma unroll 4
         for (int k = lane; k < n; k += 32) {
             c.S[0][r * lda + k] = kval(i0 + r, k);
@@ -269,13 +307,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
     double v[4] = {0, 0, 0, 0};
     {
         double a2[2] = {0, 0}, b2[2] = {0, 0};
-        mm_q(c.S[0], c.S[1], lda, ks, a2, b2);
+        mm_q<CT>(c.S[0], c.S[1], lda, ks, a2, b2);
         v[0] = a2[0] + b2[0];
         v[1] = a2[1] + b2[1];
     }
-    combine(c.red, v, 2);
+    combine<CT>(c.red, v, 2);
     double x1[2] = {0, 0}, x2[2] = {0, 0};
-    if (warp < 4) {
+    if (warp < NBLK) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = ei, j = ej + e;
@@ -294,7 +332,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
             }
         }
     }
-    grid_barrier(p.bar, target);
+    step_barrier<CLUSTER>(p.bar, target);
     // ---- step 2: X3 = X2.X, X4 = X2.X2; P0..P2, Q3 (S1 still holds the columns of X) -----------------------------
     ld.begin(true);
     ld.rows(c.S[0], p.X2, i0);
@@ -302,15 +340,15 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
     ld.wait();
     {
         double a3[2] = {0, 0}, b3[2] = {0, 0}, a4[2] = {0, 0}, b4[2] = {0, 0};
-        mm_q(c.S[0], c.S[1], lda, ks, a3, b3);
-        mm_q(c.S[0], c.S[2], lda, ks, a4, b4);
+        mm_q<CT>(c.S[0], c.S[1], lda, ks, a3, b3);
+        mm_q<CT>(c.S[0], c.S[2], lda, ks, a4, b4);
         v[0] = a3[0] + b3[0];
         v[1] = a3[1] + b3[1];
         v[2] = a4[0] + b4[0];
         v[3] = a4[1] + b4[1];
     }
-    combine(c.red, v, 4);
-    if (warp < 4) {
+    combine<CT>(c.red, v, 4);
+    if (warp < NBLK) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = ei, j = ej + e;
@@ -325,7 +363,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
             }
         }
     }
-    grid_barrier(p.bar, target);
+    step_barrier<CLUSTER>(p.bar, target);
     // ---- steps 3-5: Q2 = P2 + X4.Q3, Q1 = P1 + X4.Q2, R0 = P0 + X4.Q1 (rows of X4 loaded once) ---------------------
     {
         const double* Bsrc[3] = {p.Q3t, p.Q2t, p.Q1t};
@@ -335,18 +373,18 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
             if (st == 0) ld.rows(c.S[0], p.X4, i0);
             ld.rows(c.S[1], Bsrc[st], j0);
             double cin[2] = {0, 0};
-            if (warp < 4) {
+            if (warp < NBLK) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     if (ei < n && ej + e < n) cin[e] = Csrc[st][ei * lda + ej + e];
             }
             ld.wait();
             double a2[2] = {0, 0}, b2[2] = {0, 0};
-            mm_q(c.S[0], c.S[1], lda, ks, a2, b2);
+            mm_q<CT>(c.S[0], c.S[1], lda, ks, a2, b2);
             v[0] = a2[0] + b2[0];
             v[1] = a2[1] + b2[1];
-            combine(c.red, v, 2);
-            if (warp < 4) {
+            combine<CT>(c.red, v, 2);
+            if (warp < NBLK) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int i = ei, j = ej + e;
@@ -362,7 +400,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
                     }
                 }
             }
-            grid_barrier(p.bar, target);
+            step_barrier<CLUSTER>(p.bar, target);
         }
     }
     // ---- s squarings: R[q+1] = R[q].R[q] -------------------------------------------------------------------------
@@ -372,11 +410,11 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
         ld.rows(c.S[1], p.Rt + (size_t)q * nn, j0);
         ld.wait();
         double a2[2] = {0, 0}, b2[2] = {0, 0};
-        mm_q(c.S[0], c.S[1], lda, ks, a2, b2);
+        mm_q<CT>(c.S[0], c.S[1], lda, ks, a2, b2);
         v[0] = a2[0] + b2[0];
         v[1] = a2[1] + b2[1];
-        combine(c.red, v, 2);
-        if (warp < 4) {
+        combine<CT>(c.red, v, 2);
+        if (warp < NBLK) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int i = ei, j = ej + e;
@@ -387,19 +425,21 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_u(UParams p) {
                 }
             }
         }
-        grid_barrier(p.bar, target);
+        step_barrier<CLUSTER>(p.bar, target);
     }
-    grid_exit(p.bar);
+    chain_exit<CLUSTER>(p.bar);
 }
 
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
+template <int CT, bool CLUSTER>
+__global__ void __launch_bounds__(NTHR, 2) k_chain_d(DParams p) {
+    constexpr int NBLK = Geo<CT>::NBLK;
     extern __shared__ __align__(128) double sm[];
     const int n = p.n;
-    const size_t nn = mat_stride(n);
+    const size_t nn = mat_stride(n, CT);
     uint64_t* mbar;
-    Ctx c = make_ctx(sm, n, &mbar);
-    Loader ld{mbar, 0u, c.lda, 0u, 0};
+    Ctx c = make_ctx<CT>(sm, n, &mbar);
+    Loader<CT> ld{mbar, 0u, c.lda, 0u, 0};
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[91] = clock64();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = c.i0, j0 = c.j0, lda = c.lda, ks = c.ks, ei = c.ei, ej = c.ej;
@@ -414,8 +454,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
     ld.begin(true);
     ld.rows(c.S[1], p.X, i0);
     ld.rows(c.S[2], p.Xt, j0);
-    {
-        const int r = threadIdx.x >> 5;
+    for (int r = threadIdx.x >> 5; r < CT; r += NTHR / 32) {
 #pragma unroll 4
         for (int k = lane; k < n; k += 32) {
             c.S[0][r * lda + k] = dxval(i0 + r, k);
@@ -426,14 +465,14 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
     ld.wait();
     {
         double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
-        mm_q(c.S[0], c.S[2], lda, ks, a1, b1);   // dX.X
-        mm_q(c.S[1], c.S[3], lda, ks, a2, b2);   // X.dX
+        mm_q<CT>(c.S[0], c.S[2], lda, ks, a1, b1);   // dX.X
+        mm_q<CT>(c.S[1], c.S[3], lda, ks, a2, b2);   // X.dX
         v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
         v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
     }
-    combine(c.red, v, 2);
+    combine<CT>(c.red, v, 2);
     double d1[2] = {0, 0}, d2[2] = {0, 0};
-    if (warp < 4) {
+    if (warp < NBLK) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = ei, j = ej + e;
@@ -445,7 +484,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
             }
         }
     }
-    grid_barrier(p.bar, target);
+    step_barrier<CLUSTER>(p.bar, target);
     // ---- step 2: dX3 = dX2.X + X2.dX ; dX4 = dX2.X2 + X2.dX2 ; dP0..dP2, dQ3 -----------------------------------------
     // kept: S2 = cols X, S3 = cols dX.  S0 <- rows dX2, S1 <- rows X2, S4 <- cols X2, S5 <- cols dX2
     ld.begin(true);
@@ -456,18 +495,18 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
     ld.wait();
     {
         double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
-        mm_q(c.S[0], c.S[2], lda, ks, a1, b1);   // dX2.X
-        mm_q(c.S[1], c.S[3], lda, ks, a2, b2);   // X2.dX
+        mm_q<CT>(c.S[0], c.S[2], lda, ks, a1, b1);   // dX2.X
+        mm_q<CT>(c.S[1], c.S[3], lda, ks, a2, b2);   // X2.dX
         v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
         v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
         double a3[2] = {0, 0}, b3[2] = {0, 0}, a4[2] = {0, 0}, b4[2] = {0, 0};
-        mm_q(c.S[0], c.S[4], lda, ks, a3, b3);   // dX2.X2
-        mm_q(c.S[1], c.S[5], lda, ks, a4, b4);   // X2.dX2
+        mm_q<CT>(c.S[0], c.S[4], lda, ks, a3, b3);   // dX2.X2
+        mm_q<CT>(c.S[1], c.S[5], lda, ks, a4, b4);   // X2.dX2
         v[2] = (a3[0] + b3[0]) + (a4[0] + b4[0]);
         v[3] = (a3[1] + b3[1]) + (a4[1] + b4[1]);
     }
-    combine(c.red, v, 4);
-    if (warp < 4) {
+    combine<CT>(c.red, v, 4);
+    if (warp < NBLK) {
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const int i = ei, j = ej + e;
@@ -482,7 +521,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
             }
         }
     }
-    grid_barrier(p.bar, target);
+    step_barrier<CLUSTER>(p.bar, target);
     // ---- steps 3-5: dQ2 = dP2 + dX4.Q3 + X4.dQ3 ; dQ1 = dP1 + dX4.Q2 + X4.dQ2 ; dR0 = dP0 + dX4.Q1 + X4.dQ1 ----------
     {
         const double* B1[3] = {p.Q3t, p.Q2t, p.Q1t};
@@ -497,19 +536,19 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
             ld.rows(c.S[2], B1[st], j0);
             ld.rows(c.S[3], B2[st], j0);
             double cin[2] = {0, 0};
-            if (warp < 4) {
+            if (warp < NBLK) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e)
                     if (ei < n && ej + e < n) cin[e] = Csrc[st][ei * lda + ej + e];
             }
             ld.wait();
             double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
-            mm_q(c.S[0], c.S[2], lda, ks, a1, b1);
-            mm_q(c.S[1], c.S[3], lda, ks, a2, b2);
+            mm_q<CT>(c.S[0], c.S[2], lda, ks, a1, b1);
+            mm_q<CT>(c.S[1], c.S[3], lda, ks, a2, b2);
             v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
             v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
-            combine(c.red, v, 2);
-            if (warp < 4) {
+            combine<CT>(c.red, v, 2);
+            if (warp < NBLK) {
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
                     const int i = ei, j = ej + e;
@@ -524,7 +563,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
                     }
                 }
             }
-            grid_barrier(p.bar, target);
+            step_barrier<CLUSTER>(p.bar, target);
         }
     }
     // ---- s squarings: dR[q+1] = dR[q].R[q] + R[q].dR[q] ---------------------------------------------------------------
@@ -541,13 +580,13 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
         ld.wait();
         if (dbg) p.dbg[q * 6 + 2] = clock64();
         double a1[2] = {0, 0}, b1[2] = {0, 0}, a2[2] = {0, 0}, b2[2] = {0, 0};
-        mm_q(c.S[0], c.S[2], lda, ks, a1, b1);
-        mm_q(c.S[1], c.S[3], lda, ks, a2, b2);
+        mm_q<CT>(c.S[0], c.S[2], lda, ks, a1, b1);
+        mm_q<CT>(c.S[1], c.S[3], lda, ks, a2, b2);
         v[0] = (a1[0] + b1[0]) + (a2[0] + b2[0]);
         v[1] = (a1[1] + b1[1]) + (a2[1] + b2[1]);
         if (dbg) p.dbg[q * 6 + 3] = clock64();
-        combine(c.red, v, 2);
-        if (warp < 4) {
+        combine<CT>(c.red, v, 2);
+        if (warp < NBLK) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int i = ei, j = ej + e;
@@ -558,7 +597,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
             }
         }
         if (dbg) p.dbg[q * 6 + 4] = clock64();
-        grid_barrier(p.bar, target, dbg ? p.dbg + 56 + 4 * q : nullptr);
+        step_barrier<CLUSTER>(p.bar, target, dbg ? p.dbg + 56 + 4 * q : nullptr);
         if (dbg) p.dbg[q * 6 + 5] = clock64();
     }
     // ---- gradient in x order (gradient.jl:148-151, 287-290): out = [cost, (g1), g_lambda, g_theta] -------------------
@@ -566,8 +605,8 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
         const double* Lt = p.dR + (size_t)s * nn;
         const double* Ltt = p.dRt + (size_t)s * nn;
         const int cL = n * (n + 1) / 2, off = p.sd ? n : 0;
-        if (threadIdx.x < CT * CT) {
-            const int i = i0 + threadIdx.x / CT, j = j0 + threadIdx.x % CT;
+        for (int idx = threadIdx.x; idx < CT * CT; idx += NTHR) {
+            const int i = i0 + idx / CT, j = j0 + idx % CT;
             if (i < n && j < n) {
                 if (j <= i) p.out[1 + off + i * (i + 1) / 2 + j] = 2.0 * p.part[1 + i * n + j] * (i != j ? 2.0 : 1.0);
                 else p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (__ldcg(Ltt + i * lda + j) - __ldcg(Lt + i * lda + j));
@@ -580,7 +619,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_chain_d(DParams p) {
         }
     }
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[92] = clock64();
-    grid_exit(p.bar);
+    chain_exit<CLUSTER>(p.bar);
 }
 
 }  // namespace chain

@@ -100,6 +100,8 @@ struct mambo_csa {
     unsigned* d_bar = nullptr;                 // grid-barrier counters of the persistent chain kernels
     long long* d_dbg = nullptr;                // MAMBO_CHAIN_DEBUG=1: clock64 stamps of the derivative chain
     bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
+    int chain_ct = 16;                         // tile edge of the chain kernels
+    bool chain_cluster = false;                // N <= 64: the <= 4 x 4 tiles form ONE thread-block cluster (hardware barrier)
     bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
     int dephase = 0;                           // fused kernel: start offset (cycles) of column group 1
     int lookahead = 0;                         // fused kernel: operand sub-tiles requested ahead (0 = default)
@@ -344,17 +346,48 @@ int launch_coop(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream
     return MAMBO_OK;
 }
 
+// One thread-block cluster holding the whole grid (the chain kernels for N <= 128): co-scheduling is guaranteed by the
+// cluster launch itself, the steps synchronise on the hardware cluster barrier.
+int launch_cluster(const void* func, dim3 grid, dim3 block, size_t smem, cudaStream_t st, void** args) {
+    cudaLaunchConfig_t cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = grid.x;
+    attr[0].val.clusterDim.y = grid.y;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelExC(&cfg, func, args));
+    return MAMBO_OK;
+}
+
+int launch_chain(mambo_csa* h, bool deriv, void** args) {
+    const int n = h->N, ct = h->chain_ct, tiles = (n + ct - 1) / ct;
+    const size_t smem = chain::smem_bytes(n, ct);
+    if (h->chain_cluster) {
+        const void* f = deriv ? (const void*)chain::k_chain_d<16, true> : (const void*)chain::k_chain_u<16, true>;
+        return launch_cluster(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);
+    }
+    const void* f = deriv ? (const void*)chain::k_chain_d<16, false> : (const void*)chain::k_chain_u<16, false>;
+    return launch_coop(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);
+}
+
 int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host);
 
 // U = exp(K) in ONE persistent kernel (chain::k_chain_u): grid barriers instead of kernel boundaries.
 int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
     if (!h->use_chain) return enqueue_unitary_legacy(h, d_x, s_host);
-    const int n = h->N, tiles = (n + chain::CT - 1) / chain::CT;
+    const int n = h->N;
     chain::UParams p = h->cu;
     p.x = d_x; p.n = n; p.lam_off = h->lam_off; p.s_override = s_host;
     p.Lam = h->Lam; p.U = h->U; p.LamP = h->use_panel ? h->LamP : nullptr; p.ldl = h->ld; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
     void* args[] = {&p};
-    TRY(launch_coop((const void*)chain::k_chain_u, dim3(tiles, tiles), dim3(chain::NTHR), chain::smem_bytes(n), h->stream, args));
+    TRY(launch_chain(h, false, args));
     h->launches++;
     return MAMBO_OK;
 }
@@ -482,12 +515,11 @@ int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
         h->launches++;
     }
     if (h->use_chain) {
-        const int tiles = (n + chain::CT - 1) / chain::CT;
         chain::DParams p = h->cd;
         p.part = h->d_part; p.g1 = h->g1; p.n = n; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0;
         p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar; p.dbg = h->d_dbg;
         void* args[] = {&p};
-        TRY(launch_coop((const void*)chain::k_chain_d, dim3(tiles, tiles), dim3(chain::NTHR), chain::smem_bytes(n), h->stream, args));
+        TRY(launch_chain(h, true, args));
         h->launches++;
         return MAMBO_OK;
     }
@@ -854,7 +886,37 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     TRY(dalloc(&h->U, nn));
     TRY(dalloc(&h->d_zero, 1));
     {
-        const size_t ms = chain::mat_stride(n);
+        // N <= 64: the <= 4 x 4 tiles of the chain run as ONE thread-block cluster and synchronise on the hardware cluster
+        // barrier.  (A 32 x 32 tiling would bring N <= 128 under the 16-CTA limit too, but was measured slower: a step is
+        // then bound by the DMMA rate of 16 SMs instead of the barrier.)
+        h->chain_ct = 16;
+        h->chain_cluster = false;
+        if (n <= 64 && std::getenv("MAMBO_CHAIN_GRID") == nullptr) {
+            // only if the device can actually place one such cluster (<= 16 CTAs with this much shared memory in one GPC)
+            const int tiles = (n + 15) / 16, sm_chain = (int)chain::smem_bytes(n, 16);
+            bool ok = true;
+            for (const void* f : {(const void*)chain::k_chain_u<16, true>, (const void*)chain::k_chain_d<16, true>}) {
+                ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_chain) == cudaSuccess;
+                ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+                cudaLaunchConfig_t cfg;
+                std::memset(&cfg, 0, sizeof(cfg));
+                cfg.gridDim = dim3(tiles, tiles);
+                cfg.blockDim = dim3(chain::NTHR);
+                cfg.dynamicSmemBytes = sm_chain;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = tiles;
+                attr[0].val.clusterDim.y = tiles;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                int nclusters = 0;
+                ok = ok && cudaOccupancyMaxActiveClusters(&nclusters, f, &cfg) == cudaSuccess && nclusters >= 1;
+            }
+            cudaGetLastError();
+            h->chain_cluster = ok;
+        }
+        const size_t ms = chain::mat_stride(n, h->chain_ct);
         const size_t ncm = 11 + 11 + 4 * (size_t)(chain::SMAXC + 1);
         TRY(dalloc(&h->cmats, ncm * ms));
         double* cm = h->cmats;
@@ -894,7 +956,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         NB_PANEL_DISPATCH(h->NB, need_post = (panel::post_smem<NBT, CST>()));
         h->use_panel = need_post <= prop.sharedMemPerBlockOptin;
     }
-    if (chain::smem_bytes(n) > prop.sharedMemPerBlockOptin) h->use_chain = false;
+    if (chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin) h->use_chain = false;
     h->use_panel = h->use_panel && h->use_chain;          // Lambda's padded copy is written by k_chain_u
     h->fast = h->use_panel && std::getenv("MAMBO_TWO_GEMM") == nullptr;
     if (const char* e = std::getenv("MAMBO_TAU")) h->tau = std::atof(e);
@@ -922,10 +984,18 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_post_mma<NBT, CST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)(panel::post_smem<NBT, CST>()))));
     }
-    if (chain::smem_bytes(n) > prop.sharedMemPerBlockOptin) h->use_chain = false;
+    if (chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin) h->use_chain = false;
     if (h->use_chain) {
-        CU(cudaFuncSetAttribute(chain::k_chain_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::smem_bytes(n)));
-        CU(cudaFuncSetAttribute(chain::k_chain_d, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chain::smem_bytes(n)));
+        const int sm_chain = (int)chain::smem_bytes(n, h->chain_ct);
+        if (h->chain_cluster) {
+            for (const void* f : {(const void*)chain::k_chain_u<16, true>, (const void*)chain::k_chain_d<16, true>}) {
+                CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_chain));
+                CU(cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            }
+        } else {
+            for (const void* f : {(const void*)chain::k_chain_u<16, false>, (const void*)chain::k_chain_d<16, false>})
+                CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_chain));
+        }
     }
 
     // opt-in shared-memory sizes, set once per handle
