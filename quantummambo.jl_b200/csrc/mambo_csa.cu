@@ -462,9 +462,15 @@ int enqueue_prep(mambo_csa* h) {
 
 int enqueue_post_f(mambo_csa* h, double* F, bool with_S = false) {
     if (h->use_panel) {
+        const bool split = h->NB >= 16;           // column-split panel kernels (NB_PANEL_DISPATCH): sum the pieces once, up front
+        if (split) {
+            const int ysplit = std::max(1, std::min(8, (2 * h->num_sms) / std::max(h->P, 1)));
+            panel::k_esum<<<dim3(h->P, ysplit), 256, 0, h->stream>>>(h->Epiece, h->piece_first, h->Np, h->ld, h->EtP, h->fast ? h->Ct : nullptr);
+            h->launches++;
+        }
         NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT, CST><<<dim3(h->P, CST), panel::NTHR, panel::post_smem<NBT, CST>(), h->stream>>>(
-                                     h->Epiece, h->piece_first, h->fast ? h->Ct : nullptr, h->LamP, h->At, h->N, h->row_begin, F, h->Spart,
-                                     with_S ? 1 : 0)));
+                                     h->Epiece, h->piece_first, h->fast ? h->Ct : nullptr, split ? h->EtP : nullptr, h->LamP, h->At, h->N,
+                                     h->row_begin, F, h->Spart, with_S ? 1 : 0)));
         h->launches += 1;
         CU(cudaGetLastError());
         return MAMBO_OK;

@@ -269,13 +269,14 @@ __global__ void __launch_bounds__(256) k_esum(const double* __restrict__ Epiece,
 // ------------------------------------------------------------------------------------------------------------
 // k_post_mma: per local panel and column split: F[:, cols] = E~ Lambda[:, cols] ; Spart[:, cols] = A~_panel^T E~[:, cols]
 // ------------------------------------------------------------------------------------------------------------
-//   The E~ panel itself is assembled in shared memory first: fixed-order sum of the hot kernel's pieces (two warp-column
-//   partials per visit), subtracted from C~ in the single-GEMM formulation (E~ = C~ - Y), so it never round-trips HBM.
+//   Without column split (CS = 1) the E~ panel itself is assembled in shared memory first: fixed-order sum of the hot
+//   kernel's pieces (two warp-column partials per visit), subtracted from C~ in the single-GEMM formulation (E~ = C~ - Y),
+//   so it never round-trips HBM.  With CS > 1 the CS CTAs of a panel would each repeat that sum: k_esum does it once.
 template <int NB, int CS>
 __global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
-                                                      const double* __restrict__ Ct, const double* __restrict__ LamP,
-                                                      const double* __restrict__ At, int n, int row_begin, double* __restrict__ F,
-                                                      double* __restrict__ Spart, int do_S) {
+                                                      const double* __restrict__ Ct, const double* __restrict__ Et,
+                                                      const double* __restrict__ LamP, const double* __restrict__ At, int n,
+                                                      int row_begin, double* __restrict__ F, double* __restrict__ Spart, int do_S) {
     using G = Geo<NB, CS>;
     constexpr int Np = G::Np, LD = G::LD, NBW = G::NBW, NBC = G::NBC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -291,30 +292,54 @@ __global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__
     if (threadIdx.x == 0) {
         mbar_init(mbar);
         const uint32_t lbytes = (uint32_t)((size_t)8 * nblk * LD * 8), pbytes = (uint32_t)(G::panel_elems * 8);
-        mbar_expect(mbar, lbytes + (do_S ? pbytes : 0u));
+        mbar_expect(mbar, lbytes + (do_S ? pbytes : 0u) + (Et ? pbytes : 0u));
+        if (Et) bulk(sE, Et + (size_t)panel * ROWS * LD, pbytes, mbar);   // column-split launches: E~ was summed once by k_esum
         bulk(sL, LamP + (size_t)8 * nb_lo * LD, lbytes, mbar);
         if (do_S) bulk(sAp, At + (size_t)(row_begin + panel * ROWS) * LD, pbytes, mbar);
     }
-    {   // E~ panel -> shared memory while the TMA copies are in flight; every load below is independent of the others
+    if (!Et) {   // E~ panel -> shared memory while the TMA copies are in flight.  Four elements per thread and trip so that the
+        // 4 x (2 visits x 2 + 1) independent loads are in flight together (one memory round trip per trip, not per load).
         const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
         const double* cpanel = Ct ? Ct + (size_t)panel * ROWS * LD : nullptr;
-        for (int idx = threadIdx.x; idx < ROWS * (LD / 2); idx += NTHR) {
-            const int row = idx / (LD / 2), c2 = 2 * (idx % (LD / 2));
-            double2 a = make_double2(0.0, 0.0);
-            if (c2 < Np) {
-                for (int v = v0; v < v1; ++v) {
-                    const double2 y0 = __ldcs(reinterpret_cast<const double2*>(Epiece + ((size_t)(v * 2 + 0) * ROWS + row) * Np + c2));
-                    const double2 y1 = __ldcs(reinterpret_cast<const double2*>(Epiece + ((size_t)(v * 2 + 1) * ROWS + row) * Np + c2));
-                    a.x += y0.x + y1.x;
-                    a.y += y0.y + y1.y;
+        constexpr int HALF = LD / 2, TOTAL = ROWS * HALF, UN = 4;
+        for (int base = threadIdx.x; base < TOTAL; base += UN * NTHR) {
+            double2 a[UN];
+            int row[UN], c2[UN];
+            bool live[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int idx = base + u * NTHR;
+                row[u] = idx / HALF;
+                c2[u] = 2 * (idx % HALF);
+                live[u] = idx < TOTAL && c2[u] < Np;
+                a[u] = make_double2(0.0, 0.0);
+            }
+            for (int v = v0; v < v1; ++v) {
+                double2 y0[UN], y1[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    y0[u] = y1[u] = make_double2(0.0, 0.0);
+                    if (live[u]) {
+                        y0[u] = __ldcs(reinterpret_cast<const double2*>(Epiece + ((size_t)(v * 2 + 0) * ROWS + row[u]) * Np + c2[u]));
+                        y1[u] = __ldcs(reinterpret_cast<const double2*>(Epiece + ((size_t)(v * 2 + 1) * ROWS + row[u]) * Np + c2[u]));
+                    }
                 }
-                if (cpanel) {
-                    const double2 cc = *reinterpret_cast<const double2*>(cpanel + (size_t)row * LD + c2);
-                    a.x = cc.x - a.x;
-                    a.y = cc.y - a.y;
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    a[u].x += y0[u].x + y1[u].x;
+                    a[u].y += y0[u].y + y1[u].y;
                 }
             }
-            *reinterpret_cast<double2*>(sE + (size_t)row * LD + c2) = a;
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                if (base + u * NTHR >= TOTAL) continue;
+                if (cpanel && live[u]) {
+                    const double2 cc = *reinterpret_cast<const double2*>(cpanel + (size_t)row[u] * LD + c2[u]);
+                    a[u].x = cc.x - a[u].x;
+                    a[u].y = cc.y - a[u].y;
+                }
+                *reinterpret_cast<double2*>(sE + (size_t)row[u] * LD + c2[u]) = a[u];
+            }
         }
     }
     __syncthreads();
