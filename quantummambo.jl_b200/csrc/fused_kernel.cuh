@@ -377,6 +377,8 @@ struct YParams {
     long long ldT;
     int P, Q, ld, Np, S;
     int lookahead;
+    int split;              // bulk copies per 32-row sub-tile
+    int dephase;            // cycles by which column group 1 starts late (0 = off)
 };
 
 inline size_t smem_bytes_y(int ld, int S) { return (size_t)(S * SUB) * ld * 8 + (2 * S) * 8 + 64; }
@@ -407,6 +409,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
     const int wc = (warp >> 2) & 1, wr = warp & 3;
     const int prow = perm8(t1);
     const int pc0 = t0, pc1 = 4 + ((t0 + 2) & 3);
+    // Warps w and w+4 share a scheduler (one of each column group).  Starting column group 1 half a step late keeps the
+    // two out of phase, so the DMMA-free stretch at every step boundary of one warp (ring wait, T~ fragment moves, first
+    // operand loads) falls into the DMMA stream of the other instead of leaving the tensor pipe idle.
+    if (p.dephase && wc == 1) {
+        const long long t_start = clock64();
+        while (clock64() - t_start < (long long)p.dephase) { }
+    }
 
     double e[2][NB][2];
 #pragma unroll
@@ -441,7 +450,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
             const int slot = g_issued % S, use = g_issued / S, c = g_issued & 1;
             if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
             mbar_expect_tx(&full[slot], sub_bytes);
-            bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ct_p * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
+            {   // p.split bulk copies per sub-tile (1, 2, 4 or 8; measured: one copy is fastest, 191 / 199 / 211 / 227 us at N = 100)
+                const int nsp = p.split;
+                const uint32_t part = sub_bytes / (uint32_t)nsp;
+                const char* src = reinterpret_cast<const char*>(p.Acol + ((size_t)ct_p * COLS + c * SUB) * ld);
+                char* dst = reinterpret_cast<char*>(sA + (size_t)slot * SUB * ld);
+                for (int q = 0; q < nsp; ++q) bulk_g2s(dst + (size_t)q * part, src + (size_t)q * part, part, &full[slot]);
+            }
             ++g_issued;
             if (c == 1 && ++ct_p == Q) ct_p = 0;
         }

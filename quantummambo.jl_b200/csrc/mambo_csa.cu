@@ -116,6 +116,8 @@ struct mambo_csa {
     unsigned* d_done = nullptr;                // last-CTA-out counter of k_post_reduce
     double* tnorm2 = nullptr;                  // == sh->tnorm2
     int Sy = 0;                                // ring depth of k_ty
+    int ty_dephase = 0;                        // start offset (cycles) of column group 1 in k_ty
+    int ty_split = 1;                          // bulk copies per operand sub-tile (32 rows x ld doubles; rows are 16-byte multiples)
     size_t smem_y = 0;
     double tau = 1e-4;                         // fallback threshold: relative error of the expanded cost ~ 1e-15 / tau
     double* LamP = nullptr;                    // Lambda with the panel pitch [Np][ld] (written by k_chain_u)
@@ -273,6 +275,8 @@ YParams make_yparams(mambo_csa* h, const double* T) {
     p.Np = h->Np;
     p.S = h->Sy;
     p.lookahead = h->lookahead;
+    p.split = h->ty_split;
+    p.dephase = h->ty_dephase;
     return p;
 }
 
@@ -966,6 +970,11 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->use_panel = h->use_panel && h->use_chain;          // Lambda's padded copy is written by k_chain_u
     h->fast = h->use_panel && std::getenv("MAMBO_TWO_GEMM") == nullptr;
     if (const char* e = std::getenv("MAMBO_TAU")) h->tau = std::atof(e);
+    if (const char* e = std::getenv("MAMBO_TY_DEPHASE")) h->ty_dephase = std::atoi(e);
+    if (const char* e = std::getenv("MAMBO_TY_SPLIT")) {
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2 || v == 4 || v == 8) h->ty_split = v;
+    }
     if (h->fast) {
         TRY(dalloc(&h->Ct, (size_t)h->P * ROWS * h->ld));
         TRY(dalloc(&h->GLP, (size_t)h->Np * h->ld));
