@@ -383,8 +383,11 @@ struct YParams {
 
 inline size_t smem_bytes_y(int ld, int S) { return (size_t)(S * SUB) * ld * 8 + (2 * S) * 8 + 64; }
 
-template <int NB, bool TPREF>
-__global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
+// MB = m-blocks (8 rows) per warp: 2 -> 8 warps (4 row groups x 2 column groups, 2 warps per scheduler), 1 -> 16 warps
+// (8 x 2, 4 warps per scheduler, <= 128 registers): more warps to cover ring waits and operand loads at every step boundary.
+template <int NB, bool TPREF, int MB>
+__global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
+    constexpr int NWR = 8 / MB;            // row groups (warps per column group)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ld = 8 * NB + 4;
     const int S = p.S, Q = p.Q;
@@ -399,14 +402,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < S; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NCONS / 2);
+            mbar_init(&empty[s], NWR);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     const int t0 = lane & 3, t1 = lane >> 2;
-    const int wc = (warp >> 2) & 1, wr = warp & 3;
+    const int wc = (warp / NWR) & 1, wr = warp % NWR;
     const int prow = perm8(t1);
     const int pc0 = t0, pc1 = 4 + ((t0 + 2) & 3);
     // Warps w and w+4 share a scheduler (one of each column group).  Starting column group 1 half a step late keeps the
@@ -417,19 +420,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
         while (clock64() - t_start < (long long)p.dephase) { }
     }
 
-    double e[2][NB][2];
+    double e[MB][NB][2];
 #pragma unroll
-    for (int mb = 0; mb < 2; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int b = 0; b < NB; ++b) e[mb][b][0] = e[mb][b][1] = 0.0;
-    double acc[2][4][2];
-    double tn[2][4][2];
+    double acc[MB][4][2];
+    double tn[MB][4][2];
 
-    const long long lane_off = (long long)(16 * wr + prow) * p.ldT + 32 * wc;
-    auto loadT = [&](double(&dst)[2][4][2], int panel_, int ct_) {
+    const long long lane_off = (long long)(8 * MB * wr + prow) * p.ldT + 32 * wc;
+    auto loadT = [&](double(&dst)[MB][4][2], int panel_, int ct_) {
         const double* base = p.T + (long long)panel_ * ROWS * p.ldT + (long long)ct_ * COLS + lane_off;
 #pragma unroll
-        for (int mb = 0; mb < 2; ++mb)
+        for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
             for (int nb = 0; nb < 4; ++nb) {
                 dst[mb][nb][0] = __ldcs(base + (long long)mb * 8 * p.ldT + nb * 8 + pc0);
@@ -472,7 +475,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
         if (nct == Q) { nct = 0; ++npanel; }
         if (TPREF) {
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb)
+            for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                 for (int nb = 0; nb < 4; ++nb) {
                     acc[mb][nb][0] = tn[mb][nb][0];
@@ -498,14 +501,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
                 const double2 b10 = *reinterpret_cast<const double2*>(r1 + 16 * pr);
                 const double2 b11 = *reinterpret_cast<const double2*>(r1 + 16 * (pr + 1));
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
+                for (int mb = 0; mb < MB; ++mb) {
                     dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][0], b00.x);
                     dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][0], b00.y);
                     dmma(e[mb][2 * pr + 2][0], e[mb][2 * pr + 2][1], acc[mb][kb][0], b01.x);
                     dmma(e[mb][2 * pr + 3][0], e[mb][2 * pr + 3][1], acc[mb][kb][0], b01.y);
                 }
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
+                for (int mb = 0; mb < MB; ++mb) {
                     dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b10.x);
                     dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b10.y);
                     dmma(e[mb][2 * pr + 2][0], e[mb][2 * pr + 2][1], acc[mb][kb][1], b11.x);
@@ -522,13 +525,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
                     t1v = (r1 - 2 * t1)[8 * (NB - 1) + t1];
                 }
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
+                for (int mb = 0; mb < MB; ++mb) {
                     dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][0], b0.x);
                     dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][0], b0.y);
                     if (NB & 1) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], t0v);
                 }
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) {
+                for (int mb = 0; mb < MB; ++mb) {
                     dmma(e[mb][2 * pr][0], e[mb][2 * pr][1], acc[mb][kb][1], b1.x);
                     dmma(e[mb][2 * pr + 1][0], e[mb][2 * pr + 1][1], acc[mb][kb][1], b1.y);
                     if (NB & 1) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
@@ -537,9 +540,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
                 const double t0v = (r0 - 2 * t1)[8 * (NB - 1) + t1];
                 const double t1v = (r1 - 2 * t1)[8 * (NB - 1) + t1];
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], t0v);
+                for (int mb = 0; mb < MB; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][0], t0v);
 #pragma unroll
-                for (int mb = 0; mb < 2; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
+                for (int mb = 0; mb < MB; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
             }
         }
         __syncwarp();
@@ -548,9 +551,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_ty(YParams p) {
         const bool lastp = (ct == Q - 1) || (t == tend - 1);
         if (lastp) {
             const int visit = p.visit_start[blockIdx.x] + (pv - 1);
-            double* dst = p.Ypiece + ((size_t)(visit * 2 + wc) * ROWS + 16 * wr + prow) * p.Np;
+            double* dst = p.Ypiece + ((size_t)(visit * 2 + wc) * ROWS + 8 * MB * wr + prow) * p.Np;
 #pragma unroll
-            for (int mb = 0; mb < 2; ++mb) {
+            for (int mb = 0; mb < MB; ++mb) {
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
                     int n0, n1;

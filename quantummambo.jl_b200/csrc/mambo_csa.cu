@@ -116,6 +116,7 @@ struct mambo_csa {
     unsigned* d_done = nullptr;                // last-CTA-out counter of k_post_reduce
     double* tnorm2 = nullptr;                  // == sh->tnorm2
     int Sy = 0;                                // ring depth of k_ty
+    int ty_mb = 2;                             // k_ty: m-blocks per warp (2: 8 warps, 1: 16 warps)
     int ty_dephase = 0;                        // start offset (cycles) of column group 1 in k_ty
     int ty_split = 1;                          // bulk copies per operand sub-tile (32 rows x ld doubles; rows are 16-byte multiples)
     size_t smem_y = 0;
@@ -219,10 +220,10 @@ int launch_fused(mambo_csa* h, const Params& p) {
     return fail(MAMBO_EINVAL, "unsupported NB bucket");
 }
 
-template <int NB>
-int launch_ty_nb(mambo_csa* h, const YParams& p) {
+template <int NB, int MB>
+int launch_ty_mb(mambo_csa* h, const YParams& p) {
     constexpr bool TPREF = (NB <= 16);
-    auto kern = k_ty<NB, TPREF>;
+    auto kern = k_ty<NB, TPREF, MB>;
     if (p.P < 0) {   // configuration call from create
         CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_y));
         return MAMBO_OK;
@@ -240,11 +241,20 @@ int launch_ty_nb(mambo_csa* h, const YParams& p) {
         e1 = h->ev_pool[h->ev_used++];
         CU(cudaEventRecord(e0, h->stream));
     }
-    kern<<<h->G, NTHREADS, h->smem_y, h->stream>>>(p);
+    kern<<<h->G, 64 * (8 / MB), h->smem_y, h->stream>>>(p);
     if (e1) CU(cudaEventRecord(e1, h->stream));
     CU(cudaGetLastError());
     h->launches++;
     return MAMBO_OK;
+}
+
+template <int NB>
+int launch_ty_nb(mambo_csa* h, const YParams& p) {
+    if (p.P < 0) {
+        TRY((launch_ty_mb<NB, 1>(h, p)));
+        return launch_ty_mb<NB, 2>(h, p);
+    }
+    return h->ty_mb == 1 ? launch_ty_mb<NB, 1>(h, p) : launch_ty_mb<NB, 2>(h, p);
 }
 
 int launch_ty(mambo_csa* h, const YParams& p) {
@@ -971,6 +981,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->fast = h->use_panel && std::getenv("MAMBO_TWO_GEMM") == nullptr;
     if (const char* e = std::getenv("MAMBO_TAU")) h->tau = std::atof(e);
     if (const char* e = std::getenv("MAMBO_TY_DEPHASE")) h->ty_dephase = std::atoi(e);
+    if (const char* e = std::getenv("MAMBO_TY_MB")) h->ty_mb = (std::atoi(e) == 1) ? 1 : 2;
     if (const char* e = std::getenv("MAMBO_TY_SPLIT")) {
         const int v = std::atoi(e);
         if (v == 1 || v == 2 || v == 4 || v == 8) h->ty_split = v;

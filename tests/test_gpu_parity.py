@@ -236,6 +236,41 @@ def test_peer_exchange_of_shards_on_one_gpu(mb, lib):
                 e.close()
 
 
+def test_single_gemm_formulation_matches_two_gemm_kernel_and_falls_back(mb, lib, monkeypatch):
+    """The default evaluation (fused::k_ty: E = C~ - T~ A~, cost from N x N quantities) against the two-GEMM kernel
+    (MAMBO_TWO_GEMM=1: D = B~ A~^T - T~ explicitly) on the same handle inputs, including the regime where the expanded
+    cost cancels (x at / near a planted fragment) and the exact-cost pass must take over."""
+    n = 13
+    T, xs = o.planted_tbt(n, 1, 7)
+    x_true = xs[0]
+    rng = np.random.default_rng(2)
+    probes = [o.random_x(n, 1), x_true, x_true + 1e-7 * rng.standard_normal(x_true.shape),
+              x_true + 1e-3 * rng.standard_normal(x_true.shape)]
+    fast = mb.CSAEngine(T)
+    monkeypatch.setenv("MAMBO_TWO_GEMM", "1")
+    slow = mb.CSAEngine(T)
+    monkeypatch.delenv("MAMBO_TWO_GEMM")
+    tt = float(np.sum(T * T))
+    try:
+        for x in probes:
+            cf, gf = fast.cost_grad(x)
+            cs, gs = slow.cost_grad(x)
+            c0, g0 = o.cost_grad_factored(x, T)
+            assert cf >= 0.0
+            # cost: 1e-10 relative, down to what FP64 resolves: every element of D = W - T carries eps |T|, so
+            # |D|^2 carries ~ eps |D| |T| (and eps^2 |T|^2 at the exact solution)
+            ctol = 1e-10 * abs(c0) + 1e-14 * np.sqrt(abs(c0) * tt) + 1e-26 * tt
+            assert abs(cf - cs) <= ctol
+            assert abs(cf - c0) <= ctol
+            # gradient: 1e-10 of its size, down to the FP64 floor of D itself (each element of D = W - T carries eps |T|)
+            gtol = 1e-10 * float(np.max(np.abs(g0))) + 1e-13 * np.sqrt(tt)
+            assert float(np.max(np.abs(gf - gs))) <= gtol
+            assert float(np.max(np.abs(gf - g0))) <= gtol
+    finally:
+        fast.close()
+        slow.close()
+
+
 def test_lanes_share_the_residual_and_run_concurrently(mb, lib):
     """mambo_csa_create_lane: lanes evaluate independently (one host thread each, overlapping on the device), give the
     parent's bits, see residual updates made through a sibling, and keep the residual alive after the parent is closed."""
