@@ -74,6 +74,9 @@ typedef struct mambo_csa_info_t {
     double flops_per_eval;            /* DMMA flops executed by the fused kernel(s) per evaluation          */
     double tensor_bytes;              /* bytes of residual tensor resident on this GPU                      */
     double asym_pair, asym_pq;        /* measured relative asymmetries of the input tensor                  */
+    int    hot_gemms;                 /* R x R x N products per pass of the hot kernel: 1 (single-GEMM formulation,
+                                         fused::k_ty) or 2 (fused::k_fused, MAMBO_TWO_GEMM=1 / legacy paths)   */
+    int    lanes_hint;                /* evaluation lanes that fit side by side: floor(2 SMs / chain CTAs), >= 1 */
 } mambo_csa_info_t;
 
 /* --- lifetime ------------------------------------------------------------------------------------------ */

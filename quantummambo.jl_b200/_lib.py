@@ -45,6 +45,7 @@ class MamboInfo(C.Structure):
         ("num_sms", C.c_int), ("launches_per_eval", C.c_int),
         ("flops_per_eval", C.c_double), ("tensor_bytes", C.c_double),
         ("asym_pair", C.c_double), ("asym_pq", C.c_double),
+        ("hot_gemms", C.c_int), ("lanes_hint", C.c_int),
     ]
 
 

@@ -1229,6 +1229,11 @@ int mambo_csa_get_info(const mambo_csa* h, mambo_csa_info_t* info) {
     info->tensor_bytes = passes * (double)h->P * ROWS * (double)h->ldT * 8.0;
     info->asym_pair = h->asym_pair;
     info->asym_pq = h->asym_pq;
+    info->hot_gemms = h->fast ? 1 : 2;
+    {
+        const int tiles = (h->N + h->chain_ct - 1) / h->chain_ct;
+        info->lanes_hint = std::max(1, (2 * h->num_sms) / (tiles * tiles));
+    }
     return MAMBO_OK;
 }
 
