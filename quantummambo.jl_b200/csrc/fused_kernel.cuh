@@ -79,6 +79,11 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+__device__ __forceinline__ long long gtime() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 // slot -> position inside an 8-group.  Even slots 2j -> j, odd slots 2j+1 -> 4 + (j+2)%4.
 __host__ __device__ __forceinline__ int perm8(int m) { return (m & 1) ? (4 + (((m >> 1) + 2) & 3)) : (m >> 1); }
 
@@ -154,34 +159,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
     int gi = 0, pv = 0;
     if (TPREF && tbeg < tend) loadT(tn, panel, ct);
 
-    // ---- producer state (used by lane 0 of warp 0 only): sub-tile g = 2*step + column group ----------------
+    // ---- operand ring: sub-tile g = 2*step + column group lives in slot g % S; the producer role rotates over the warps
+    // (sub-tile g is requested by lane 0 of warp g % NCONS) so that no single warp carries the ~650 cycles per request
+    // and paces the CTA (see k_ty below).  The B~ panel (once per row panel) stays with warp 0.
     const int g_total = 2 * (int)(tend - tbeg);
-    const int lookahead = p.lookahead > 0 ? min(p.lookahead, S - 2) : ((S >= 6) ? 2 : (S - 2));   // sub-tiles issued beyond the current step
-    int g_issued = 0, ct_p = ct;
+    int lookahead = p.lookahead > 0 ? min(p.lookahead, S - 2) : ((S >= 6) ? 2 : (S - 2));   // sub-tiles requested ahead of use
+    lookahead &= ~1;
+    const int ct0 = ct;
     const uint32_t panel_bytes = (uint32_t)(ROWS * ld * 8), sub_bytes = (uint32_t)(SUB * ld * 8);
-    auto produce_upto = [&](int g_hi) {
-        while (g_issued < g_total && g_issued <= g_hi) {
-            const int slot = g_issued % S, use = g_issued / S, c = g_issued & 1;
-            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
-            mbar_expect_tx(&full[slot], sub_bytes);
-            bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ct_p * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
-            ++g_issued;
-            if (c == 1 && ++ct_p == Q) ct_p = 0;
-        }
+    auto request = [&](int g) {
+        const int slot = g % S, use = g / S, c = g & 1;
+        const int ctg = (ct0 + (g >> 1)) % Q;
+        if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+        mbar_expect_tx(&full[slot], sub_bytes);
+        bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ctg * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
     };
+    if (lane == 0)
+        for (int g = warp; g < lookahead && g < g_total; g += NCONS) request(g);
+    __syncwarp();
 
     const double* sBrow = sB + (16 * wr + prow) * ld + 2 * t0;
 
     for (long long t = tbeg; t < tend; ++t, ++gi) {
         const bool newpanel = (t == tbeg || ct == 0);
-        if (warp == 0) {
+        {
+            const int g1 = 2 * gi + lookahead;         // the sub-tiles of step gi + lookahead/2
             if (lane == 0) {
-                if (newpanel) {
+                if (warp == 0 && newpanel) {
                     if (pv > 0) mbar_wait(bempty, (pv - 1) & 1);   // every warp is done with the old B~ panel
                     mbar_expect_tx(bfull, panel_bytes);
                     bulk_g2s(sB, p.Brow + (size_t)panel * ROWS * ld, panel_bytes, bfull);
                 }
-                produce_upto(2 * gi + 1 + lookahead);
+                if (g1 < g_total && g1 % NCONS == warp) request(g1);
+                if (g1 + 1 < g_total && (g1 + 1) % NCONS == warp) request(g1 + 1);
             }
             __syncwarp();
         }
@@ -377,8 +387,8 @@ struct YParams {
     long long ldT;
     int P, Q, ld, Np, S;
     int lookahead;
-    int split;              // bulk copies per 32-row sub-tile
     int dephase;            // cycles by which column group 1 starts late (0 = off)
+    long long* dbg;         // development aid (MAMBO_TY_DEBUG=1): clock64 stamps of CTA 0, [warp][step][4]
 };
 
 inline size_t smem_bytes_y(int ld, int S) { return (size_t)(S * SUB) * ld * 8 + (2 * S) * 8 + 64; }
@@ -388,6 +398,7 @@ inline size_t smem_bytes_y(int ld, int S) { return (size_t)(S * SUB) * ld * 8 + 
 template <int NB, bool TPREF, int MB>
 __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
     constexpr int NWR = 8 / MB;            // row groups (warps per column group)
+    if (p.dbg && threadIdx.x == 0) p.dbg[16 * 64 * 4 + blockIdx.x * 4 + 0] = gtime();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ld = 8 * NB + 4;
     const int S = p.S, Q = p.Q;
@@ -444,31 +455,39 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
     int gi = 0, pv = 0;
     if (TPREF && tbeg < tend) loadT(tn, panel, ct);
 
+    // ---- operand ring: sub-tile g = 2*step + column group lives in slot g % S.  The producer role ROTATES over the
+    // warps: sub-tile g is requested by lane 0 of warp g % (number of warps), `lookahead` sub-tiles ahead of its use.  One
+    // request (empty-slot wait + expect_tx + UBLKCP) costs ~650 cycles of the issuing warp; with a fixed producer warp
+    // those 2 x 650 cycles per step made that warp 17 % slower than the others, and because every other warp can only
+    // run as far ahead as the ring holds, the whole CTA ran at its pace (clock64 stamps, tools/ty_stamps.py).
+    constexpr int NWARPS = 2 * NWR;
     const int g_total = 2 * (int)(tend - tbeg);
-    const int lookahead = p.lookahead > 0 ? min(p.lookahead, S - 2) : ((S >= 6) ? 4 : (S - 2));
-    int g_issued = 0, ct_p = ct;
+    int lookahead = p.lookahead > 0 ? min(p.lookahead, S - 2) : ((S >= 6) ? 4 : (S - 2));
+    lookahead &= ~1;                                   // even: both sub-tiles of a step are requested in the same step
+    const int ct0 = ct;
     const uint32_t sub_bytes = (uint32_t)(SUB * ld * 8);
-    auto produce_upto = [&](int g_hi) {
-        while (g_issued < g_total && g_issued <= g_hi) {
-            const int slot = g_issued % S, use = g_issued / S, c = g_issued & 1;
-            if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
-            mbar_expect_tx(&full[slot], sub_bytes);
-            {   // p.split bulk copies per sub-tile (1, 2, 4 or 8; measured: one copy is fastest, 191 / 199 / 211 / 227 us at N = 100)
-                const int nsp = p.split;
-                const uint32_t part = sub_bytes / (uint32_t)nsp;
-                const char* src = reinterpret_cast<const char*>(p.Acol + ((size_t)ct_p * COLS + c * SUB) * ld);
-                char* dst = reinterpret_cast<char*>(sA + (size_t)slot * SUB * ld);
-                for (int q = 0; q < nsp; ++q) bulk_g2s(dst + (size_t)q * part, src + (size_t)q * part, part, &full[slot]);
-            }
-            ++g_issued;
-            if (c == 1 && ++ct_p == Q) ct_p = 0;
-        }
+    auto request = [&](int g) {                        // called by lane 0 of warp g % NWARPS
+        const int slot = g % S, use = g / S, c = g & 1;
+        const int ctg = (ct0 + (g >> 1)) % Q;
+        if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
+        mbar_expect_tx(&full[slot], sub_bytes);
+        bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ctg * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
     };
+    if (lane == 0)
+        for (int g = warp; g < lookahead && g < g_total; g += NWARPS) request(g);
+    __syncwarp();
 
+    const bool dbg = p.dbg && blockIdx.x == 0 && lane == 0;
+    if (p.dbg && threadIdx.x == 0) p.dbg[16 * 64 * 4 + blockIdx.x * 4 + 1] = gtime();
     for (long long t = tbeg; t < tend; ++t, ++gi) {
         if (t == tbeg || ct == 0) ++pv;
-        if (warp == 0) {
-            if (lane == 0) produce_upto(2 * gi + 1 + lookahead);
+        if (dbg && gi < 64) p.dbg[(warp * 64 + gi) * 4 + 0] = clock64();
+        {
+            const int g1 = 2 * gi + lookahead;
+            if (lane == 0) {
+                if (g1 < g_total && g1 % NWARPS == warp) request(g1);
+                if (g1 + 1 < g_total && (g1 + 1) % NWARPS == warp) request(g1 + 1);
+            }
             __syncwarp();
         }
         int npanel = panel, nct = ct + 1;
@@ -488,7 +507,9 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
 
         const int g = 2 * gi + wc;
         const int slot = g % S;
+        if (dbg && gi < 64) p.dbg[(warp * 64 + gi) * 4 + 1] = clock64();
         mbar_wait(&full[slot], (g / S) & 1);
+        if (dbg && gi < 64) p.dbg[(warp * 64 + gi) * 4 + 2] = clock64();
         const double* sAs = sA + (size_t)slot * SUB * ld;
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) {
@@ -547,6 +568,7 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);
+        if (dbg && gi < 64) p.dbg[(warp * 64 + gi) * 4 + 3] = clock64();
 
         const bool lastp = (ct == Q - 1) || (t == tend - 1);
         if (lastp) {
@@ -572,6 +594,10 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
         }
         panel = npanel;
         ct = nct;
+    }
+    if (p.dbg && threadIdx.x == 0) {
+        p.dbg[16 * 64 * 4 + blockIdx.x * 4 + 2] = gtime();
+        p.dbg[16 * 64 * 4 + blockIdx.x * 4 + 3] = (long long)(tend - tbeg);
     }
 }
 

@@ -116,9 +116,9 @@ struct mambo_csa {
     unsigned* d_done = nullptr;                // last-CTA-out counter of k_post_reduce
     double* tnorm2 = nullptr;                  // == sh->tnorm2
     int Sy = 0;                                // ring depth of k_ty
+    long long* ty_dbg = nullptr;               // MAMBO_TY_DEBUG=1: clock64 stamps of CTA 0 of k_ty
     int ty_mb = 2;                             // k_ty: m-blocks per warp (2: 8 warps, 1: 16 warps)
     int ty_dephase = 0;                        // start offset (cycles) of column group 1 in k_ty
-    int ty_split = 1;                          // bulk copies per operand sub-tile (32 rows x ld doubles; rows are 16-byte multiples)
     size_t smem_y = 0;
     double tau = 1e-4;                         // fallback threshold: relative error of the expanded cost ~ 1e-15 / tau
     double* LamP = nullptr;                    // Lambda with the panel pitch [Np][ld] (written by k_chain_u)
@@ -285,8 +285,8 @@ YParams make_yparams(mambo_csa* h, const double* T) {
     p.Np = h->Np;
     p.S = h->Sy;
     p.lookahead = h->lookahead;
-    p.split = h->ty_split;
     p.dephase = h->ty_dephase;
+    p.dbg = h->ty_dbg;
     return p;
 }
 
@@ -980,12 +980,10 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->use_panel = h->use_panel && h->use_chain;          // Lambda's padded copy is written by k_chain_u
     h->fast = h->use_panel && std::getenv("MAMBO_TWO_GEMM") == nullptr;
     if (const char* e = std::getenv("MAMBO_TAU")) h->tau = std::atof(e);
+    if (std::getenv("MAMBO_TY_DEBUG") && h->fast) TRY(dalloc(&h->ty_dbg, (size_t)16 * 64 * 4 + 160 * 4));
+    h->ty_dephase = 256 * h->NB;                // half a step (16 NB DMMAs of 16 cycles per warp and step): measured 1 % faster than 0
     if (const char* e = std::getenv("MAMBO_TY_DEPHASE")) h->ty_dephase = std::atoi(e);
     if (const char* e = std::getenv("MAMBO_TY_MB")) h->ty_mb = (std::atoi(e) == 1) ? 1 : 2;
-    if (const char* e = std::getenv("MAMBO_TY_SPLIT")) {
-        const int v = std::atoi(e);
-        if (v == 1 || v == 2 || v == 4 || v == 8) h->ty_split = v;
-    }
     if (h->fast) {
         TRY(dalloc(&h->Ct, (size_t)h->P * ROWS * h->ld));
         TRY(dalloc(&h->GLP, (size_t)h->Np * h->ld));
@@ -1190,7 +1188,7 @@ void mambo_csa_destroy(mambo_csa* h) {
             if (b) cudaFree(b);
         delete h->sh;
     }
-    void* bufs[] = {h->Ct, h->GLP, h->wpart, h->d_flag, h->ls_part, h->d_done, h->At, h->Bt, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
+    void* bufs[] = {h->ty_dbg, h->Ct, h->GLP, h->wpart, h->d_flag, h->ls_part, h->d_done, h->At, h->Bt, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
                     h->eig_ws, h->opt_ws, h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -1305,6 +1303,12 @@ int mambo_csa_get_segments(mambo_csa* h, double* seg_ms, int* evals) {
         }
     if (evals) *evals = n;
     h->seg_used = 0;
+    return MAMBO_OK;
+}
+
+int mambo_csa_debug_ty_stamps(mambo_csa* h, long long* out4096) {
+    if (!h || !h->ty_dbg) return fail(MAMBO_ESTATE, "set MAMBO_TY_DEBUG=1 before create");
+    CU(cudaMemcpy(out4096, h->ty_dbg, sizeof(long long) * (16 * 64 * 4 + 160 * 4), cudaMemcpyDeviceToHost));
     return MAMBO_OK;
 }
 
