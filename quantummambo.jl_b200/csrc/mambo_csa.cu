@@ -115,6 +115,7 @@ struct mambo_csa {
     double* ls_part = nullptr;                 // per output row <Lambda_a, S_a> (k_post_reduce)
     unsigned* d_done = nullptr;                // last-CTA-out counter of k_post_reduce
     double* tnorm2 = nullptr;                  // == sh->tnorm2
+    int prep_cs = 1;                           // column split of k_prep_mma (NB_PANEL_DISPATCH)
     int Sy = 0;                                // ring depth of k_ty
     long long* ty_dbg = nullptr;               // MAMBO_TY_DEBUG=1: clock64 stamps of CTA 0 of k_ty
     int ty_mb = 2;                             // k_ty: m-blocks per warp (2: 8 warps, 1: 16 warps)
@@ -437,19 +438,20 @@ int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host) {
 const double* u_base(const mambo_csa* h) { return h->use_chain ? h->U : h->R; }
 const int* u_sptr(const mambo_csa* h) { return h->use_chain ? h->d_zero : h->d_s; }
 
-// NB bucket -> (NBT, CST): panel-kernel instantiation and its column split (CST = 4 above N = 104 so that the
-// panels plus the Lambda slice fit in shared memory)
+// NB bucket -> (NBT, CST, CSP): panel-kernel instantiation, column split of k_post_mma (CST = 4 above N = 104 so that the
+// panels plus the Lambda slice fit in shared memory) and of k_prep_mma (CSP; a split of 2 for 72 < N <= 104 -- two 100 KB
+// CTAs per SM, twice as many CTAs as panels -- was measured 2 us slower than 1: the kernel is not GEMM-bound)
 #define NB_PANEL_DISPATCH(nb, CALL)                 \
     switch (nb) {                                   \
-        case 1: { constexpr int NBT = 1, CST = 1; CALL; break; }   \
-        case 2: { constexpr int NBT = 2, CST = 1; CALL; break; }   \
-        case 4: { constexpr int NBT = 4, CST = 1; CALL; break; }   \
-        case 7: { constexpr int NBT = 7, CST = 1; CALL; break; }   \
-        case 10: { constexpr int NBT = 10, CST = 1; CALL; break; } \
-        case 13: { constexpr int NBT = 13, CST = 1; CALL; break; } \
-        case 16: { constexpr int NBT = 16, CST = 4; CALL; break; } \
-        case 19: { constexpr int NBT = 19, CST = 4; CALL; break; } \
-        default: { constexpr int NBT = 21, CST = 4; CALL; break; } \
+        case 1: { constexpr int NBT = 1, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 2: { constexpr int NBT = 2, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 4: { constexpr int NBT = 4, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 7: { constexpr int NBT = 7, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 10: { constexpr int NBT = 10, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; } \
+        case 13: { constexpr int NBT = 13, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; } \
+        case 16: { constexpr int NBT = 16, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
+        case 19: { constexpr int NBT = 19, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
+        default: { constexpr int NBT = 21, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
     }
 
 int enqueue_prep(mambo_csa* h) {
@@ -458,7 +460,7 @@ int enqueue_prep(mambo_csa* h) {
             panel::k_gram<<<h->N, 1024, 0, h->stream>>>(u_base(h), h->Lam, h->N, h->ld, h->GLP);
             h->launches++;
         }
-        NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT, CST><<<dim3(h->nRpad / panel::ROWS, CST), panel::NTHR, panel::prep_smem<NBT, CST>(), h->stream>>>(
+        NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT, CSP><<<dim3(h->nRpad / panel::ROWS, CSP), panel::NTHR, panel::prep_smem<NBT, CSP>(), h->stream>>>(
                                      u_base(h), h->LamP, h->pa, h->pq, h->sw, h->N, h->prow_begin, h->prow_end, h->At, h->Bt,
                                      h->fast ? h->GLP : nullptr, h->Ct, h->wpart)));
         h->launches++;
@@ -512,7 +514,7 @@ int enqueue_post_sr(mambo_csa* h) {
                                                                  h->sw, u_base(h), u_sptr(h), n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
                                                                  h->row_begin, std::min(h->row_end, h->nR), h->d_part,
                                                                  h->fast ? h->Lam : nullptr, h->ls_part, h->d_done, h->wpart,
-                                                                 h->P * (h->NB >= 16 ? 4 : 1) /* column split of the panel kernels */,
+                                                                 h->P * h->prep_cs /* partial <B~,C~> per (panel, column split of k_prep_mma) */,
                                                                  h->tnorm2, h->tau, h->d_flag);
     h->launches += 1;
     if (h->fast) {
@@ -1003,8 +1005,9 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     if (h->use_panel) {
         TRY(dalloc(&h->LamP, (size_t)h->Np * h->ld));
         TRY(dalloc(&h->EtP, (size_t)h->P * ROWS * h->ld));
-        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_prep_mma<NBT, CST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)(panel::prep_smem<NBT, CST>()))));
+        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_prep_mma<NBT, CSP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                         (int)(panel::prep_smem<NBT, CSP>()))));
+        h->prep_cs = h->NB >= 16 ? 4 : 1;                          // == CSP of NB_PANEL_DISPATCH
         NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_post_mma<NBT, CST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)(panel::post_smem<NBT, CST>()))));
     }
