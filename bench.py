@@ -204,19 +204,29 @@ def greedy_time_to_tolerance(mb, syn, device: int, n: int = 50, R: int = 2, frag
         for _ in range(R):
             W, _ = e.reconstruct(np.concatenate([rng.standard_normal(cL), 2 * np.pi * rng.random(uL)]))
             T += W
-    trail, evals = [], 0
-    with mb.CSAEngine(T, device=device) as e:
-        c0 = e.residual_cost()
-        t0 = time.perf_counter()
-        for _ in range(frags):
-            x0 = np.concatenate([np.zeros(cL), 2 * np.pi * rng.random(uL)])      # decompose.jl:86-94
-            xm, res = e.optimize(x0, g_tol=1e-8, max_iter=max_iter)
-            trail.append(e.subtract_fragment(xm))
-            evals += res["evaluations"]
-        dt = time.perf_counter() - t0
-    out = {"workload": f"planted N={n} R={R}, {frags} greedy fragments x <= {max_iter} BFGS iterations (native optimiser)",
+
+    def run(lbfgs_memory: int):
+        trail, evals = [], 0
+        rng_x = np.random.default_rng(2001)
+        with mb.CSAEngine(T, device=device) as e:
+            c_init = e.residual_cost()
+            t0 = time.perf_counter()
+            for _ in range(frags):
+                x0 = np.concatenate([np.zeros(cL), 2 * np.pi * rng_x.random(uL)])      # decompose.jl:86-94
+                xm, res = e.optimize(x0, g_tol=1e-8, max_iter=max_iter, lbfgs_memory=lbfgs_memory)
+                trail.append(e.subtract_fragment(xm))
+                evals += res["evaluations"]
+            dt = time.perf_counter() - t0
+        return c_init, dt, evals, trail
+
+    c0, dt, evals, trail = run(0)
+    out = {"workload": f"planted N={n} R={R}, {frags} greedy fragments x <= {max_iter} BFGS iterations (native optimiser, dense "
+                       "inverse Hessian like Optim.jl's BFGS)",
            "seconds": dt, "evaluations": evals, "initial_cost": c0, "cost_trail": trail,
            "ms_per_evaluation_incl_optimizer": dt / max(evals, 1) * 1e3}
+    _, dt_l, evals_l, trail_l = run(10)
+    out["lbfgs_memory_10"] = {"seconds": dt_l, "evaluations": evals_l, "cost_trail": trail_l,
+                              "ms_per_evaluation_incl_optimizer": dt_l / max(evals_l, 1) * 1e3}
     # BASELINE.json configs[2]: 8-way multistart of the first greedy step (random theta guesses), here on ONE GPU:
     # the 8 runs one after the other on one handle versus spread over evaluation lanes that share the residual
     K = 8

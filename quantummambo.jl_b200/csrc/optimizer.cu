@@ -13,6 +13,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <initializer_list>
 #include <string>
@@ -84,11 +85,11 @@ __global__ void k_scale(double* __restrict__ out, const double* __restrict__ a, 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = f * a[i];
 }
-// One pass over the dense inverse Hessian: (optionally) apply the pending BFGS update
-//     H <- H - rho (s Hy^T + Hy s^T) + c s s^T
+// One pass over the dense inverse Hessian: (optionally) apply the pending (self-scaled) BFGS update
+//     H <- tau H - rho (s Hy^T + Hy s^T) + c s s^T          (rho already carries the factor tau)
 // and form u = H g with the updated matrix.  One warp per row, fixed-order shuffle reduction.
 __global__ void __launch_bounds__(256) k_update_gemv(double* __restrict__ H, int n, const double* __restrict__ s,
-                                                     const double* __restrict__ Hy, double rho, double c, int apply,
+                                                     const double* __restrict__ Hy, double tau, double rho, double c, int apply,
                                                      const double* __restrict__ g, double* __restrict__ u) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + warp;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) k_update_gemv(double* __restrict__ H, int
     for (int j = lane; j < n; j += 32) {
         double h = hr[j];
         if (apply) {
-            h = h - rho * (si * Hy[j] + hyi * s[j]) + c * si * s[j];
+            h = tau * h - rho * (si * Hy[j] + hyi * s[j]) + c * si * s[j];
             hr[j] = h;
         }
         acc = fma(h, g[j], acc);
@@ -111,11 +112,11 @@ __global__ void k_scale_neg(double* __restrict__ out, const double* __restrict__
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = -a[i];
 }
-// p = -(u - rho (s a + Hy b) + c s b)   with a = Hy.g, b = s.g   (the search direction of the *updated* H)
+// p = -(tau u - rho (s a + Hy b) + c s b)   with a = Hy.g, b = s.g   (the search direction of the *updated* H)
 __global__ void k_direction(double* __restrict__ p, const double* __restrict__ u, const double* __restrict__ s,
-                            const double* __restrict__ Hy, double rho, double c, double a, double b, int n) {
+                            const double* __restrict__ Hy, double tau, double rho, double c, double a, double b, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) p[i] = -(u[i] - rho * (s[i] * a + Hy[i] * b) + c * s[i] * b);
+    if (i < n) p[i] = -(tau * u[i] - rho * (s[i] * a + Hy[i] * b) + c * s[i] * b);
 }
 
 // Up to 6 dot products a_k.b_k and max|m| in ONE single-CTA pass (one host round trip instead of one per scalar):
@@ -469,8 +470,15 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     // per line-search evaluation plus two fused multi-dot reads (was seven single dots).
     bool pending = false;
     bool fresh = true;             // H is still the (re)start identity: rescale it by s.y / y.y before the first update
-    double rho = 0, cc = 0;
+    double rho = 0, cc = 0, tau = 1.0;
+    // Optional self-scaling (Oren-Luenberger with Al-Baali's cap, MAMBO_BFGS_SELFSCALE=1): H is multiplied by
+    // tau = min(1, s.y / y.Hy) before each update.  Off by default: on the CSA landscape the factors compound and the
+    // metric collapses (N=100 planted fragment, 1000 iterations: cost 8.5e3 with, 3.6e2 without).  The limited-memory mode
+    // (lbfgs_memory > 0), which re-scales gamma = s.y / y.y every iteration, reaches 1.4e2 in the same budget.
+    const bool selfscale = std::getenv("MAMBO_BFGS_SELFSCALE") != nullptr;
     double *s_cur = o->s, *Hy_cur = o->Hy, *s_prev = o->s2, *Hy_prev = o->Hy2;
+    double alpha_prev = 1.0;       // step length accepted by the previous line search
+    double df0_prev = -1.0;        // directional derivative at the start of the previous line search
     int l_used = 0, l_head = -1;   // L-BFGS ring state
     double l_gamma = 1.0;
     for (; it < opt.max_iter; ++it) {
@@ -493,7 +501,14 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         }
         double alpha = 0, fnew = f;
         bool ok = false;
-        const double a1 = (it == 0) ? std::min(1.0, 1.0 / std::max(gnorm, 1e-300)) : 1.0;
+        // First trial step: the unit step once the metric is learnt, otherwise twice the step accepted last time.  With
+        // L ~ N^2 parameters of very different curvature (lambda vs theta) and H = gamma I in every direction not yet
+        // explored, the unit step is ~30x too long for hundreds of iterations; starting every search there costs 3-4
+        // evaluations per iteration in the zoom phase.
+        // (Nocedal & Wright (3.60): alpha_prev * phi'_prev(0) / phi'(0), the step that would give the same first-order change.)
+        double a1 = (it == 0) ? std::min(1.0, 1.0 / std::max(gnorm, 1e-300)) : alpha_prev * (df0_prev / df0);
+        if (it > 0) a1 = std::min(1.0, std::max(0.5 * alpha_prev, std::min(a1, 2.0 * alpha_prev)));
+        df0_prev = df0;
         rc = line_search(o, f, df0, a1, &alpha, &fnew, &ok);
         if (rc) return finish(rc);
         if (!ok || !(fnew <= f)) {
@@ -508,6 +523,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         if (rc) return finish(rc);
         const double sy = d2[0], yy = d2[1];
         f = fnew;
+        alpha_prev = alpha;
         if (lbfgs) {
             if (sy > 1e-300) {
                 l_head = (l_head + 1) % mem;
@@ -534,7 +550,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
                 fresh = false;
             } else {
                 // one pass over H: fold in the pending update of the previous iteration and form u = H g_new
-                k_update_gemv<<<(L + 7) / 8, 256, 0, o->stream>>>(o->H, L, s_prev, Hy_prev, rho, cc, pending ? 1 : 0, o->out + 1, o->u);
+                k_update_gemv<<<(L + 7) / 8, 256, 0, o->stream>>>(o->H, L, s_prev, Hy_prev, tau, rho, cc, pending ? 1 : 0, o->out + 1, o->u);
                 // Hy = H y = H g_new - H g = u + p   (p = -H g)
                 k_axpy<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->u, o->p, 1.0, L);
             }
@@ -546,11 +562,13 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
             if (rc) return finish(rc);
             const double yHy = d4[0], hyg = d4[1], sg = d4[2], ug = d4[3];
             if (sy > 1e-300) {
-                rho = 1.0 / sy;
-                cc = rho * (1.0 + rho * yHy);
+                const double r1 = 1.0 / sy;
+                tau = (selfscale && yHy > 0.0) ? std::min(1.0, sy / yHy) : 1.0;
+                rho = tau * r1;                          // coefficient of the cross terms
+                cc = r1 * (1.0 + tau * r1 * yHy);        // coefficient of s s^T
                 // direction of the updated matrix from vectors only; the matrix itself is updated next iteration
-                k_direction<<<blocks(L), 256, 0, o->stream>>>(o->p, o->u, s_cur, Hy_cur, rho, cc, hyg, sg, L);
-                df0 = -(ug - rho * (sg * hyg + hyg * sg) + cc * sg * sg);
+                k_direction<<<blocks(L), 256, 0, o->stream>>>(o->p, o->u, s_cur, Hy_cur, tau, rho, cc, hyg, sg, L);
+                df0 = -(tau * ug - rho * (sg * hyg + hyg * sg) + cc * sg * sg);
                 pending = true;
                 std::swap(s_cur, s_prev);
                 std::swap(Hy_cur, Hy_prev);

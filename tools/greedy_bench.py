@@ -35,7 +35,8 @@ if __name__ == "__main__":
                 break
             x0 = np.concatenate([np.zeros(cL), 2 * np.pi * rng.random(uL)])
             t1 = time.perf_counter()
-            xm, res = e.optimize(x0, g_tol=1e-8, max_iter=maxit, verbose=int(os.environ.get('VERB', '0')))
+            xm, res = e.optimize(x0, g_tol=1e-8, max_iter=maxit, verbose=int(os.environ.get('VERB', '0')),
+                                 lbfgs_memory=int(os.environ.get('LBFGS', '0')))
             c = e.subtract_fragment(xm)
             tot_evals += res["evaluations"]
             print(f"  frag {a + 1}: cost {c:.6e} iters {res['iterations']} evals {res['evaluations']} conv {res['converged']} "
