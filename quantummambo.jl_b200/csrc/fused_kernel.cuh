@@ -1,6 +1,7 @@
-// fused_kernel.cuh -- the hot kernel of the CSA engine (sm_100a).
+// fused_kernel.cuh -- the hot kernels of the CSA engine (sm_100a): k_ty (one R x R x N product per evaluation, further
+// down) and k_fused (two chained products; residual update, cost-only evaluation, exact-cost fallback).
 //
-// For a residual matrix T~ (rows i, cols j; j contiguous) and operand matrices A~ (rows x Np) and
+// k_fused: for a residual matrix T~ (rows i, cols j; j contiguous) and operand matrices A~ (rows x Np) and
 // B~ = A~ Lambda it computes, per 64x64 tile,
 //      D   = B~_I A~_J^T - T~_IJ            (GEMM #1, K = Np, FP64 DMMA.8x8x4)
 //      cost += sum D^2
@@ -9,9 +10,9 @@
 // contraction shared by every gradient term (gradient.jl:13-28, 57-74) in one pass over T~.
 //
 // Layout / schedule
-//   * persistent CTAs (one per SM), 8 warps (4 row groups x 2 column groups, warp tile 16 x 32); lane 0 of
-//     warp 0 doubles as the TMA producer (a ninth warp would cap every thread at 168 registers);
-//     the flattened (row panel, column tile) steps are split evenly over CTAs.
+//   * persistent CTAs (one per SM), 8 warps (4 row groups x 2 column groups, warp tile 16 x 32); the TMA producer
+//     role rotates over lane 0 of the eight warps (a ninth warp would cap every thread at 168 registers, a fixed
+//     producer warp paces the whole CTA); the flattened (row panel, column tile) steps are split evenly over CTAs.
 //   * B~ panel (64 x ld) resident in shared memory per row panel; A~ column sub-tiles (32 x ld) stream
 //     through an S-slot ring filled by the TMA engine (cp.async.bulk, SASS UBLKCP) and handed over with
 //     mbarrier full/empty pairs.
