@@ -104,6 +104,8 @@ int  mambo_csa_grad(mambo_csa* h, const double* x, double* grad);
 int  mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* grad);
 
 /* --- greedy driver state (device-resident residual) ------------------------------------------------------ */
+/* On a row-panel shard both return the shard-local part of the cost (the caller sums over shards; the replicated
+ * one-body term of CSA_SD is counted by shard 0 only).                                                          */
 int  mambo_csa_subtract_fragment(mambo_csa* h, const double* x, double* new_cost);
 int  mambo_csa_residual_cost(mambo_csa* h, double* cost);
 int  mambo_csa_get_residual(mambo_csa* h, double* tbt_out, double* obt_out);
@@ -175,9 +177,16 @@ typedef struct mambo_opt_result_t {
     int    iterations, evaluations, converged, device;
 } mambo_opt_result_t;
 
-/* Minimise cost(x) from x0 on one handle with the built-in BFGS (Hager-Zhang-style line search). */
+/* Minimise cost(x) from x0 on one handle with the built-in BFGS (strong-Wolfe line search).  On a row-panel shard
+ * (after the peer exchange has been set up) every rank calls this with the same x0 on its own shard handle: the
+ * evaluations exchange their partial vectors inside the library and return identical bits on every rank, so the
+ * replicated optimiser states stay in lock-step without any host collective.                                   */
 int  mambo_csa_optimize(mambo_csa* h, const double* x0, double* x_min, const mambo_opt_options_t* opt,
                         mambo_opt_result_t* res);
+/* Allocate up front what mambo_csa_optimize needs on this handle for the given mode (device scratch, pinned scalars).
+ * Allocation synchronises the device, so with several handles on one GPU (lanes, or shards driven from one process) do
+ * this before the runs start: a shard spinning for its peers must never be waited for by a peer's cudaMalloc.       */
+int  mambo_csa_optimize_reserve(mambo_csa* h, int lbfgs_memory);
 /* K starts x0[k*L .. (k+1)*L) distributed over the given handles (one worker thread per handle);
  * x_min receives the K minimisers, res the K results; *best receives argmin_k res[k].minimum. */
 int  mambo_multistart_run(mambo_csa** handles, int nhandles, int K, const double* x0, double* x_min,

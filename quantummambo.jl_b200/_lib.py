@@ -97,6 +97,7 @@ SIGNATURES = {
     "mambo_csa_get_segments": (C.c_int, [_P, _D, C.POINTER(C.c_int)]),
     "mambo_csa_get_profile": (C.c_int, [_P, _D, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "mambo_csa_optimize": (C.c_int, [_P, _P, _P, C.POINTER(OptOptions), C.POINTER(OptResult)]),
+    "mambo_csa_optimize_reserve": (C.c_int, [_P, C.c_int]),
     "mambo_multistart_run": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.POINTER(OptOptions),
                                        C.POINTER(OptResult), C.POINTER(C.c_int)]),
 }

@@ -150,6 +150,7 @@ struct mambo_csa {
     // scratch of the built-in optimiser (vectors + dense inverse Hessian or L-BFGS ring), kept between runs for the same reason
     void* opt_ws = nullptr;
     size_t opt_ws_bytes = 0;
+    void* opt_hs = nullptr;                    // pinned host scalars of the optimiser (128 bytes)
     // CUDA-graph segments of the small-kernel sequences
     bool use_graphs = true;
     std::vector<GraphSeg> g_pre, g_fin;   // index 0: device-decided s; 1+s: s squarings
@@ -620,7 +621,7 @@ int enqueue_partial(mambo_csa* h, int s_host, bool need_grad) {
         return run_segment(h, h->g_costonly, [&]() -> int {
             if (h->flavour == MAMBO_CSA_SD) {
                 small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, u_base(h), u_sptr(h), h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
-                small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->N * h->N, h->cost_part, h->G, h->d_part);
+                small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->shard == 0 ? h->N * h->N : 0, h->cost_part, h->G, h->d_part);
                 h->launches += 2;
             } else {
                 small::k_sumsq_add<<<1, 256, 0, h->stream>>>(nullptr, 0, h->cost_part, h->G, h->d_part);
@@ -1076,7 +1077,8 @@ int subtract_impl(mambo_csa* h, const double* d_x, int s_host) {
     if (h->flavour == MAMBO_CSA_SD) {
         small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, u_base(h), u_sptr(h), n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
         small::k_obt_sub<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->hT, h->hfrag, n);
-        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, nn, h->cost_part, h->G, h->d_part);
+        // sharded handles return shard-local costs that the caller sums: the (replicated) one-body term counts once
+        small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->shard == 0 ? nn : 0, h->cost_part, h->G, h->d_part);
         h->launches += 3;
     } else {
         small::k_sumsq_add<<<1, 256, 0, h->stream>>>(nullptr, 0, h->cost_part, h->G, h->d_part);
@@ -1109,6 +1111,13 @@ int mambo_csa_scratch(mambo_csa* h, size_t bytes, void** ptr) {
         h->opt_ws_bytes = bytes;
     }
     *ptr = h->opt_ws;
+    return MAMBO_OK;
+}
+int mambo_csa_scratch_host(mambo_csa* h, void** ptr) {   // 128 bytes of pinned host memory owned by the handle
+    if (!h || !ptr) return fail(MAMBO_EINVAL, "null argument");
+    CU(cudaSetDevice(h->device));
+    if (!h->opt_hs) CU(cudaMallocHost(&h->opt_hs, 128));
+    *ptr = h->opt_hs;
     return MAMBO_OK;
 }
 void mambo_set_error(const char* msg) { g_err = msg ? msg : ""; }
@@ -1195,6 +1204,7 @@ void mambo_csa_destroy(mambo_csa* h) {
                     h->eig_ws, h->opt_ws, h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
+    if (h->opt_hs) cudaFreeHost(h->opt_hs);
     if (h->h_x) cudaFreeHost(h->h_x);
     if (h->h_out) cudaFreeHost(h->h_out);
     if (h->h_status) cudaFreeHost(h->h_status);

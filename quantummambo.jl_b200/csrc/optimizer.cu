@@ -27,6 +27,7 @@
 
 extern "C" void mambo_set_error(const char* msg);   // defined in mambo_csa.cu (thread-local message)
 extern "C" int mambo_csa_scratch(mambo_csa* h, size_t bytes, void** ptr);   // handle-owned device scratch (mambo_csa.cu)
+extern "C" int mambo_csa_scratch_host(mambo_csa* h, void** ptr);            // handle-owned pinned scalars (128 bytes)
 
 namespace {
 
@@ -244,15 +245,22 @@ struct Opt {
     double *LS = nullptr, *LY = nullptr, *Lrho = nullptr;   // L-BFGS ring (lbfgs_memory > 0)
     double* h_scal = nullptr;  // pinned
     int evals = 0;
+    bool sharded = false;
     char err[256] = {0};
 };
 
 int blocks(int n) { return (n + 255) / 256; }
 
-int opt_free(Opt* o) {   // device buffers live in the handle's scratch area; only the pinned scalars are ours
-    if (o->h_scal) cudaFreeHost(o->h_scal);
+int opt_free(Opt* o) {   // device buffers and pinned scalars live in the handle's scratch areas: nothing to release
     o->h_scal = nullptr;
     return 0;
+}
+
+// doubles of device scratch one optimisation run needs (layout: optimize_impl)
+size_t opt_scratch_doubles(int L, int mem) {
+    const size_t Lp = ((size_t)L + 1 + 15) & ~(size_t)15;
+    const size_t big = mem > 0 ? (2 * (size_t)mem * L + 64) : (size_t)L * L;
+    return 11 * Lp + 16 + big;
 }
 
 // several dot products and max|m| in one kernel + one host round trip; out[k] = a_k.b_k, *amax = max|m|
@@ -277,7 +285,10 @@ int dots_host(Opt* o, std::initializer_list<std::pair<const double*, const doubl
 // phi(alpha) = cost(x + alpha p), dphi = grad(x + alpha p).p ; leaves [cost, grad] in o->out and the point in o->xt
 int phi(Opt* o, double alpha, double* f, double* df) {
     k_axpy<<<blocks(o->L), 256, 0, o->stream>>>(o->xt, o->x, o->p, alpha, o->L);
-    int rc = mambo_csa_eval_device(o->h, o->xt, o->out);
+    // Row-panel shard: every rank runs this same optimiser on its own shard handle; the evaluation exchanges the partial
+    // vectors over NVLink peer memory inside the library and returns identical bits on every rank, so the replicated
+    // BFGS states never diverge and no host collective is needed.
+    int rc = o->sharded ? mambo_csa_eval_sharded_device(o->h, o->xt, o->out) : mambo_csa_eval_device(o->h, o->xt, o->out);
     if (rc) {
         snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
         return rc;
@@ -398,6 +409,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     Opt ob, *o = &ob;
     o->h = h;
     o->L = info.num_params;
+    o->sharded = info.nshards > 1;
     void* st = nullptr;
     rc = mambo_csa_get_stream(h, &st, &o->device);
     if (rc) return rc;
@@ -414,8 +426,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     {
         // one carve-up of the handle's scratch: 10 vectors, out (L+1), 8 scalars, then H (L x L) or the L-BFGS ring
         const size_t Lp = ((size_t)L + 1 + 15) & ~(size_t)15;     // keeps every piece 128-byte aligned
-        const size_t big = lbfgs ? (2 * (size_t)mem * L + 64) : (size_t)L * L;
-        const size_t total = 11 * Lp + 16 + big;
+        const size_t total = opt_scratch_doubles(L, mem);
         void* base = nullptr;
         rc = mambo_csa_scratch(h, total * sizeof(double), &base);
         if (rc) {
@@ -437,10 +448,13 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         } else {
             o->H = q;
         }
-        if (cudaMallocHost((void**)&o->h_scal, 12 * sizeof(double)) != cudaSuccess) {
-            snprintf(o->err, sizeof(o->err), "cudaMallocHost of optimiser scalars failed");
-            return finish(MAMBO_ENOMEM);
+        void* hs = nullptr;
+        rc = mambo_csa_scratch_host(h, &hs);
+        if (rc) {
+            snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+            return finish(rc);
         }
+        o->h_scal = static_cast<double*>(hs);
     }
     auto CK = [&](cudaError_t e, const char* what) {
         if (e != cudaSuccess) {
@@ -584,6 +598,13 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     if (CK(cudaMemcpyAsync(x_min, o->x, sizeof(double) * L, cudaMemcpyDeviceToHost, o->stream), "D2H x") ||
         CK(cudaStreamSynchronize(o->stream), "sync"))
         return finish(MAMBO_ECUDA);
+    if (o->sharded) {   // a peer that never published its partial vector shows up as a status flag, not as a CUDA error
+        rc = mambo_csa_synchronize(h);
+        if (rc) {
+            snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+            return finish(rc);
+        }
+    }
     if (res) {
         res->minimum = f;
         res->iterations = it;
@@ -600,6 +621,20 @@ thread_local std::string g_opt_err;
 
 extern "C" {
 
+// Allocate everything mambo_csa_optimize will need on this handle (device scratch for the given mode, pinned scalars) so
+// that the run itself allocates nothing.  cudaMalloc / cudaMallocHost synchronise the whole device: with several handles
+// on one GPU (lanes, shards in one process) an allocation in one thread would otherwise wait for kernels of another.
+int mambo_csa_optimize_reserve(mambo_csa* h, int lbfgs_memory) {
+    if (!h) return MAMBO_EINVAL;
+    const int L = mambo_csa_num_params(h);
+    if (L <= 0) return MAMBO_EINVAL;
+    const int mem = std::min(std::max(lbfgs_memory, 0), 64);
+    void* p = nullptr;
+    int rc = mambo_csa_scratch(h, opt_scratch_doubles(L, mem) * sizeof(double), &p);
+    if (rc) return rc;
+    return mambo_csa_scratch_host(h, &p);
+}
+
 int mambo_csa_optimize(mambo_csa* h, const double* x0, double* x_min, const mambo_opt_options_t* opt, mambo_opt_result_t* res) {
     if (!h || !x0 || !x_min) return MAMBO_EINVAL;
     std::string err;
@@ -615,6 +650,10 @@ int mambo_multistart_run(mambo_csa** handles, int nhandles, int K, const double*
     if (L <= 0) return MAMBO_EINVAL;
     for (int i = 1; i < nhandles; ++i)
         if (mambo_csa_num_params(handles[i]) != L) return MAMBO_EINVAL;
+    for (int i = 0; i < nhandles; ++i) {   // allocate before any worker starts: an allocation stalls every handle of that GPU
+        int rc = mambo_csa_optimize_reserve(handles[i], opt ? opt->lbfgs_memory : 0);
+        if (rc) return rc;
+    }
     std::atomic<int> next(0), failed(0);
     std::vector<std::string> errs(nhandles);
     std::vector<std::thread> workers;

@@ -162,6 +162,11 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_symv_device(self._h, d_v_ptr, d_y_ptr))
 
     # -- native optimiser / multistart ---------------------------------------------------------------------------
+    def optimize_reserve(self, lbfgs_memory: int = 0):
+        """Pre-allocate the optimiser's workspaces (mambo_csa_optimize_reserve): call on every lane / shard sharing a
+        GPU before concurrent `optimize` runs start."""
+        _lib.check(self._lib.mambo_csa_optimize_reserve(self._h, lbfgs_memory))
+
     def optimize(self, x0, g_tol: float = 1e-8, max_iter: int = 1000, lbfgs_memory: int = 0, verbose: int = 0):
         """Minimise cost(x) from x0 with the library's BFGS (mambo_csa_optimize)."""
         x0 = _f64(x0, self.L)

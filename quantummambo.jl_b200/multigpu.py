@@ -114,6 +114,23 @@ class ShardedEngine:
         out = self.d_out.cpu().numpy()
         return float(out[0]), out[1:].copy()
 
+    # -- sharded greedy step: the library's BFGS replicated on every rank, evaluations exchanged over peer memory --------
+    def optimize(self, x0, **opt):
+        """mambo_csa_optimize on this shard (call on every rank with the same x0 after setup_peers): returns the same
+        (x_min, result) on every rank."""
+        return self.eng.optimize(x0, **opt)
+
+    def subtract_fragment(self, x) -> float:
+        """F_rem -= to_OP(frag) on this rank's rows; returns the new residual cost summed over the shards."""
+        c = self.torch.tensor([self.eng.subtract_fragment(x)], dtype=self.torch.float64, device=self.dev)
+        allreduce_sum(c)
+        return float(c.item())
+
+    def residual_cost(self) -> float:
+        c = self.torch.tensor([self.eng.residual_cost()], dtype=self.torch.float64, device=self.dev)
+        allreduce_sum(c)
+        return float(c.item())
+
     def eval_partial(self, x):
         torch = self.torch
         with torch.cuda.stream(self.stream):

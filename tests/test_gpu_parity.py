@@ -446,6 +446,52 @@ def test_csa_sd_greedy_uses_the_svd_guess_by_default(mb, lib):
     assert c <= 1e-8 * (np.sum(W_t ** 2) + np.sum(h_t ** 2))
 
 
+def test_sharded_greedy_step_runs_in_lock_step(mb, lib):
+    """The library's BFGS on row-panel shards (BASELINE configs[4]): every shard runs the same optimiser on its own handle,
+    the evaluations exchange partial vectors over peer memory; all shards must return identical bits, agree with the
+    unsharded run over a short trajectory, and the residual update must leave shard-local costs that sum to the total."""
+    import threading
+    n, world = 20, 3                      # 210 packed rows = 4 panels of 64 over 3 shards
+    T, xs = o.planted_tbt(n, 1, 11)
+    rng = np.random.default_rng(4)
+    x0 = xs[0] + 0.05 * rng.standard_normal(xs[0].shape)
+    shards = [mb.CSAEngine(T, shard=r, nshards=world) for r in range(world)]
+    try:
+        for e in shards:
+            e.peer_export()
+        for r, e in enumerate(shards):
+            for q, peer in enumerate(shards):
+                if q != r:
+                    e.peer_attach_local(q, peer)
+        for e in shards:                   # one process drives all shards here: no allocation once a shard can spin for its peers
+            e.optimize_reserve()
+        out = [None] * world
+
+        def work(r):
+            out[r] = shards[r].optimize(x0, g_tol=1e-9, max_iter=12)
+
+        th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        with mb.CSAEngine(T) as whole:
+            xw, rw = whole.optimize(x0, g_tol=1e-9, max_iter=12)
+            for r in range(world):
+                assert np.array_equal(out[r][0], out[0][0]) and out[r][1]["minimum"] == out[0][1]["minimum"]
+            assert out[0][1]["iterations"] == rw["iterations"]
+            assert abs(out[0][1]["minimum"] - rw["minimum"]) <= 1e-8 * abs(rw["minimum"]) + 1e-20
+            assert rel(out[0][0], xw) <= 1e-8
+            # residual update: shard-local costs add up to the unsharded one
+            total = sum(e.subtract_fragment(out[0][0]) for e in shards)
+            cw = whole.subtract_fragment(out[0][0])
+            assert abs(total - cw) <= 1e-10 * abs(cw) + 1e-22 * float(np.sum(T * T))
+            assert abs(sum(e.residual_cost() for e in shards) - cw) <= 1e-10 * abs(cw) + 1e-22 * float(np.sum(T * T))
+    finally:
+        for e in shards:
+            e.close()
+
+
 def test_device_entry_points_match_host_closures(mb, lib):
     import torch
     n = 11
