@@ -153,7 +153,9 @@ struct mambo_csa {
     void* opt_hs = nullptr;                    // pinned host scalars of the optimiser (128 bytes)
     // CUDA-graph segments of the small-kernel sequences
     bool use_graphs = true;
+    bool capturing = false;               // a graph segment is being captured: nested segments run inline
     std::vector<GraphSeg> g_pre, g_fin;   // index 0: device-decided s; 1+s: s squarings
+    std::vector<GraphSeg> g_host;         // the WHOLE host-API evaluation (H2D of x ... D2H of cost+grad) as one graph per s
     GraphSeg g_mid, g_post, g_costonly;
     // optional live profiling of the fused kernel (CUDA events on the launching stream)
     bool profiling = false;
@@ -571,20 +573,23 @@ int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
 // be bracketed by profiling events.  All pointers inside a segment are handle-internal and therefore fixed.
 template <class F>
 int run_segment(mambo_csa* h, GraphSeg& seg, F&& body) {
-    if (!h->use_graphs) return body();
+    if (!h->use_graphs || h->capturing) return body();      // inside an enclosing capture: the kernels join that graph
     if (!seg.exec) {
+        h->capturing = true;
         cudaStream_t saved = h->stream;
         h->stream = h->own_stream;
         const long long l0 = h->launches;
         cudaError_t e = cudaStreamBeginCapture(h->own_stream, cudaStreamCaptureModeThreadLocal);
         if (e != cudaSuccess) {
             h->stream = saved;
+            h->capturing = false;
             CU(e);
         }
         int rc = body();
         cudaGraph_t graph = nullptr;
         e = cudaStreamEndCapture(h->own_stream, &graph);
         h->stream = saved;
+        h->capturing = false;
         seg.kernels = (int)(h->launches - l0);
         h->launches = l0;
         if (rc) {
@@ -693,6 +698,21 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad) {
     if (s_host < -1 || s_host > small::SMAX) return fail(MAMBO_ERANGE, "||K||_1 exceeds 2^14 (or x contains NaN)");
     std::memcpy(h->h_x, x, sizeof(double) * h->L);
     const long long l0 = h->launches;
+    if (need_grad && h->use_graphs && !h->profiling && s_host >= 0) {
+        // one graph launch for the whole closure: H2D of x, every kernel, D2H of [cost, grad] and of the status word (all
+        // addresses are handle-owned and fixed; the hot kernel needs no event bracket when profiling is off)
+        TRY(run_segment(h, seg_for(h->g_host, s_host), [&]() -> int {
+            CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
+            TRY(enqueue_partial(h, s_host, true));
+            TRY(enqueue_finish_seg(h, s_host));
+            CU(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            return MAMBO_OK;
+        }));
+        CU(cudaStreamSynchronize(h->stream));
+        h->launches_last_eval = (int)(h->launches - l0);
+        return check_status(h);
+    }
     CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
     int rc = enqueue_partial(h, s_host, need_grad);
     if (rc) return rc;
@@ -1189,7 +1209,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    for (auto* v : {&h->g_pre, &h->g_fin})
+    for (auto* v : {&h->g_pre, &h->g_fin, &h->g_host})
         for (GraphSeg& g : *v)
             if (g.exec) cudaGraphExecDestroy(g.exec);
     for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})

@@ -50,3 +50,4 @@ dur = cta[:, 2] - cta[:, 1]
 order = np.argsort(dur)
 print("slowest CTAs:", [(int(b), int(dur[b]), int(cta[b, 3])) for b in order[-6:]], " fastest:", [(int(b), int(dur[b]), int(cta[b, 3])) for b in order[:4]])
 print("ns per step: min/median/max", float((dur / cta[:, 3]).min()), float(np.median(dur / cta[:, 3])), float((dur / cta[:, 3]).max()))
+np.save(os.environ.get("TY_SAVE", "/tmp/ty_cta.npy"), (dur / cta[:, 3]))
