@@ -602,6 +602,15 @@ def test_full_size_properties(mb, lib, n):
                 e.cost_device(d_x.data_ptr(), d_c.data_ptr())
                 e.synchronize()
                 assert abs(float(d_c.item()) - res[name][0]) <= 1e-13 * abs(c0)
+                # (5) lanes give the parent's bits; (6) leading eigenpair (initial guess): eigen-residual on the host matrix view
+                with e.lane() as ln:
+                    cl, gl = ln.cost_grad(x)
+                    assert cl == res[name][0] and np.array_equal(gl, res[name][1])
+                lam, vec, st = e.leading_eig(max_iter=400)
+                v = vec.reshape(-1, order="F")
+                Mv = np.reshape(np.asfortranarray(T), (n * n, n * n), order="F") @ v
+                assert np.linalg.norm(Mv - lam * v) <= max(10 * st["residual"], 1e-9 * abs(lam)) + 1e-12 * abs(lam)
+                assert abs(float(v @ Mv) - lam) <= 1e-10 * abs(lam)
                 nc = e.subtract_fragment(x)
                 assert abs(nc - c0) <= RTOL * abs(c0)
                 assert e.residual_cost() == pytest.approx(c0, rel=1e-11)
