@@ -45,6 +45,18 @@ int fail(int code, const std::string& msg) {
 
 const int kNBBuckets[] = {1, 2, 4, 7, 10, 13, 16, 19, 21};
 
+// Opt-in dynamic shared memory of a kernel is a per-function (per-process) attribute: handles of different N share the
+// non-templated kernels, so the limit is only ever RAISED -- a later, smaller problem must not lower it under an
+// earlier handle that is still in use.
+template <class K>
+cudaError_t raise_smem(K kernel, int bytes) {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, (const void*)kernel);
+    if (e != cudaSuccess) return e;
+    if (a.maxDynamicSharedSizeBytes >= bytes) return cudaSuccess;
+    return cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
 struct GraphSeg {
     cudaGraphExec_t exec = nullptr;
     int kernels = 0;
@@ -185,7 +197,7 @@ int launch_fused_nb(mambo_csa* h, const Params& p) {
     constexpr bool TPREF = (NB <= 13);
     auto kern = k_fused<NB, DO_E, STORE, TPREF>;
     if (p.P < 0) {   // configuration call from create
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+        CU(raise_smem(kern, (int)h->smem));
         return MAMBO_OK;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -229,7 +241,7 @@ int launch_ty_mb(mambo_csa* h, const YParams& p) {
     constexpr bool TPREF = (NB <= 16);
     auto kern = k_ty<NB, TPREF, MB>;
     if (p.P < 0) {   // configuration call from create
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_y));
+        CU(raise_smem(kern, (int)h->smem_y));
         return MAMBO_OK;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -939,7 +951,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
             const int tiles = (n + 15) / 16, sm_chain = (int)chain::smem_bytes(n, 16);
             bool ok = true;
             for (const void* f : {(const void*)chain::k_chain_u<16, true>, (const void*)chain::k_chain_d<16, true>}) {
-                ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_chain) == cudaSuccess;
+                ok = ok && raise_smem(f, sm_chain) == cudaSuccess;
                 ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
                 cudaLaunchConfig_t cfg;
                 std::memset(&cfg, 0, sizeof(cfg));
@@ -1026,23 +1038,21 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     if (h->use_panel) {
         TRY(dalloc(&h->LamP, (size_t)h->Np * h->ld));
         TRY(dalloc(&h->EtP, (size_t)h->P * ROWS * h->ld));
-        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_prep_mma<NBT, CSP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)(panel::prep_smem<NBT, CSP>()))));
+        NB_PANEL_DISPATCH(h->NB, CU(raise_smem(panel::k_prep_mma<NBT, CSP>, (int)(panel::prep_smem<NBT, CSP>()))));
         h->prep_cs = h->NB >= 16 ? 4 : 1;                          // == CSP of NB_PANEL_DISPATCH
-        NB_PANEL_DISPATCH(h->NB, CU(cudaFuncSetAttribute(panel::k_post_mma<NBT, CST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                         (int)(panel::post_smem<NBT, CST>()))));
+        NB_PANEL_DISPATCH(h->NB, CU(raise_smem(panel::k_post_mma<NBT, CST>, (int)(panel::post_smem<NBT, CST>()))));
     }
     if (chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin) h->use_chain = false;
     if (h->use_chain) {
         const int sm_chain = (int)chain::smem_bytes(n, h->chain_ct);
         if (h->chain_cluster) {
             for (const void* f : {(const void*)chain::k_chain_u<16, true>, (const void*)chain::k_chain_d<16, true>}) {
-                CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_chain));
+                CU(raise_smem(f, sm_chain));
                 CU(cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
             }
         } else {
             for (const void* f : {(const void*)chain::k_chain_u<16, false>, (const void*)chain::k_chain_d<16, false>})
-                CU(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_chain));
+                CU(raise_smem(f, sm_chain));
         }
     }
 
@@ -1058,18 +1068,16 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
                                small::posts_smem(h->Np)};
         for (size_t b : need)
             if (b > lim) return fail(MAMBO_EINVAL, "N too large for the shared-memory resident small kernels");
-        CU(cudaFuncSetAttribute(small::k_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(nn * 8)));
-        CU(cudaFuncSetAttribute(small::k_mm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 2, 2)));
-        CU(cudaFuncSetAttribute(small::k_pow34, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 1, 2)));
-        CU(cudaFuncSetAttribute(small::k_dpow34, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::strip_bytes(n, 2, 4)));
-        NCH_DISPATCH((h->Np + 31) / 32, CU(cudaFuncSetAttribute(small::k_prep<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                                (int)small::prep_smem(n, h->Np))));
-        CU(cudaFuncSetAttribute(small::k_post_f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::postf_smem(h->Np)));
+        CU(raise_smem(small::k_build, (int)(nn * 8)));
+        CU(raise_smem(small::k_mm, (int)small::strip_bytes(n, 2, 2)));
+        CU(raise_smem(small::k_pow34, (int)small::strip_bytes(n, 1, 2)));
+        CU(raise_smem(small::k_dpow34, (int)small::strip_bytes(n, 2, 4)));
+        NCH_DISPATCH((h->Np + 31) / 32, CU(raise_smem(small::k_prep<NCH>, (int)small::prep_smem(n, h->Np))));
+        CU(raise_smem(small::k_post_f, (int)small::postf_smem(h->Np)));
         h->postf32 = small::postf32_smem(n, h->Np) <= 113 * 1024;   // two CTAs per SM
         if (h->postf32)
-            NCH_DISPATCH((h->Np + 31) / 32, CU(cudaFuncSetAttribute(small::k_post_f32<NCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                                    (int)small::postf32_smem(n, h->Np))));
-        CU(cudaFuncSetAttribute(small::k_post_s, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small::posts_smem(h->Np)));
+            NCH_DISPATCH((h->Np + 31) / 32, CU(raise_smem(small::k_post_f32<NCH>, (int)small::postf32_smem(n, h->Np))));
+        CU(raise_smem(small::k_post_s, (int)small::posts_smem(h->Np)));
     }
     if (!parent) {
         // |T~|^2 of the local rows (zero padding contributes nothing); kept current by subtract_impl

@@ -271,6 +271,24 @@ def test_single_gemm_formulation_matches_two_gemm_kernel_and_falls_back(mb, lib,
         slow.close()
 
 
+def test_handles_of_different_sizes_coexist(mb, lib):
+    """Opt-in shared-memory limits are per kernel function, not per handle: creating a smaller problem afterwards must not
+    take them away from a larger handle that is still in use."""
+    big_n, small_n = 40, 5
+    Tb, Ts = o.dense_sym_tbt(big_n, 1), o.dense_sym_tbt(small_n, 2)
+    xb, xs = o.random_x(big_n, 3), o.random_x(small_n, 4)
+    with mb.CSAEngine(Tb) as big:
+        c1, g1 = big.cost_grad(xb)
+        with mb.CSAEngine(Ts) as small:
+            cs, gs = small.cost_grad(xs)
+            c2, g2 = big.cost_grad(xb + 0.0)
+            xm, res = big.optimize(xb, max_iter=3)
+            lam, vec, _ = big.leading_eig()
+        c0, g0 = o.cost_grad_factored(xs, Ts)
+        assert abs(cs - c0) <= RTOL * abs(c0) and rel(gs, g0) <= RTOL
+        assert c1 == c2 and np.array_equal(g1, g2) and res["minimum"] <= c1
+
+
 def test_lanes_share_the_residual_and_run_concurrently(mb, lib):
     """mambo_csa_create_lane: lanes evaluate independently (one host thread each, overlapping on the device), give the
     parent's bits, see residual updates made through a sibling, and keep the residual alive after the parent is closed."""
