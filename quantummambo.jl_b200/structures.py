@@ -127,3 +127,18 @@ def CSA_L1(F: F_FRAG) -> float:
                 l1 += (2.0 if i != j else 0.5) * abs(lam[idx])
             idx += 1
     return l1
+
+
+def ob_correction(tbt, spin_orb: bool = False) -> np.ndarray:
+    """fermionic.jl:457-479: one-body correction carried by the two-body tensor, (2x) sum_r tbt[:, :, r, r]."""
+    tbt = np.asarray(tbt, dtype=np.float64)
+    obt = np.einsum("pqrr->pq", tbt)
+    return obt if spin_orb else 2.0 * obt
+
+
+def one_body_L1(H: F_OP) -> float:
+    """lcu.jl:262-267: 1-norm of the corrected one-body term, sum |eigenvalues| of obt + ob_correction (to_OBF,
+    fermionic.jl:527-538; OBF_L1, lcu.jl:239-260).  O(N^3) post-processing, stays on the host as in the reference."""
+    M = np.asarray(H.obt if H.obt is not None else np.zeros((H.N, H.N))) + ob_correction(H.tbt, H.spin_orb)
+    D = np.linalg.eigvalsh(M) if np.allclose(M, M.T) else np.real(np.linalg.eigvals(M))
+    return float(np.sum(np.abs(D))) * (0.5 if H.spin_orb else 1.0)

@@ -30,3 +30,14 @@ def test_svd_to_csa_fills_upper_triangular_order_like_the_reference(mb):
     assert np.allclose(coeffs, want, rtol=0, atol=1e-15)
     assert theta.shape == (n * (n - 1) // 2,)
     assert np.allclose(sla.expm(o.construct_anti_symmetric(n, theta)), Q, atol=1e-10)
+
+
+def test_one_body_l1_and_correction_match_the_oracle(mb):
+    """lcu.jl:262-267 / fermionic.jl:457-479 host mirrors (post-processing of the final 1-norms)."""
+    n = 6
+    T = o.dense_sym_tbt(n, 3)
+    h = np.random.default_rng(1).standard_normal((n, n))
+    h = h + h.T
+    H = mb.F_OP(([0.0], h, T))
+    assert np.allclose(mb.ob_correction(T), o.ob_correction(T), atol=1e-15)
+    assert abs(mb.one_body_L1(H) - o.one_body_L1(h, T)) <= 1e-12 * o.one_body_L1(h, T)
