@@ -19,61 +19,78 @@
 namespace lanczos {
 
 // y[r] = sum_j T[r][j] v[j] for r in [0, rows).  T row-major with pitch ldT (multiple of 64, zero padded), v has ldT
-// entries (zero padded).  One CTA per row (grid-stride): the 8 warps take interleaved 512-byte segments of the row, up to
-// four 16-byte streaming loads in flight per thread, partial sums combined in a fixed order (bit-reproducible).
+// entries (zero padded).  One CTA per group of RPC = 4 consecutive rows (grid-stride over groups): the 8 warps take
+// interleaved 512-byte segments of each row, up to four 16-byte streaming loads in flight per thread; the four row sums go
+// through ONE shuffle + shared-memory combine per group (fixed order: bit-reproducible), so the reduction epilogue and its
+// two block barriers are paid once per 160 KB instead of once per 40 KB row.
 // GENERAL != 0: the matrix is Symmetric(upper triangle) of a non-symmetric tensor view; T2 holds the transpose, so
 // element (r, j<r) is taken from T2 (== T[j][r]).
+constexpr int SYMV_RPC = 4;
 template <int GENERAL>
 __global__ void __launch_bounds__(256) k_symv(const double* __restrict__ T, const double* __restrict__ T2, long long ldT, int rows,
                                               const double* __restrict__ v, double* __restrict__ y) {
-    __shared__ double red[8];
+    __shared__ double red[SYMV_RPC][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int npair = (int)(ldT >> 1);
     const double2* v2 = reinterpret_cast<const double2*>(v);
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-        const double2* t = reinterpret_cast<const double2*>(T + (long long)r * ldT);
-        const double2* u = GENERAL ? reinterpret_cast<const double2*>(T2 + (long long)r * ldT) : nullptr;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int j = threadIdx.x;
-        for (; j + 768 < npair; j += 1024) {
-            double2 x0 = __ldcs(t + j), x1 = __ldcs(t + j + 256), x2 = __ldcs(t + j + 512), x3 = __ldcs(t + j + 768);
-            if (GENERAL) {
-                const double2 z0 = __ldcs(u + j), z1 = __ldcs(u + j + 256), z2 = __ldcs(u + j + 512), z3 = __ldcs(u + j + 768);
-                if (2 * j < r) x0.x = z0.x;
-                if (2 * j + 1 < r) x0.y = z0.y;
-                if (2 * (j + 256) < r) x1.x = z1.x;
-                if (2 * (j + 256) + 1 < r) x1.y = z1.y;
-                if (2 * (j + 512) < r) x2.x = z2.x;
-                if (2 * (j + 512) + 1 < r) x2.y = z2.y;
-                if (2 * (j + 768) < r) x3.x = z3.x;
-                if (2 * (j + 768) + 1 < r) x3.y = z3.y;
-            }
-            const double2 w0 = __ldg(v2 + j), w1 = __ldg(v2 + j + 256), w2 = __ldg(v2 + j + 512), w3 = __ldg(v2 + j + 768);
-            a0 = fma(x0.x, w0.x, fma(x0.y, w0.y, a0));
-            a1 = fma(x1.x, w1.x, fma(x1.y, w1.y, a1));
-            a2 = fma(x2.x, w2.x, fma(x2.y, w2.y, a2));
-            a3 = fma(x3.x, w3.x, fma(x3.y, w3.y, a3));
-        }
-        for (; j < npair; j += 256) {
-            double2 x0 = __ldcs(t + j);
-            if (GENERAL) {
-                const double2 z0 = __ldcs(u + j);
-                if (2 * j < r) x0.x = z0.x;
-                if (2 * j + 1 < r) x0.y = z0.y;
-            }
-            const double2 w0 = __ldg(v2 + j);
-            a0 = fma(x0.x, w0.x, fma(x0.y, w0.y, a0));
-        }
-        double a = (a0 + a1) + (a2 + a3);
+    const int ngroups = (rows + SYMV_RPC - 1) / SYMV_RPC;
+    for (int grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+        double sum[SYMV_RPC];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) red[warp] = a;
+        for (int rr = 0; rr < SYMV_RPC; ++rr) {
+            const int r = grp * SYMV_RPC + rr;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (r < rows) {
+                const double2* t = reinterpret_cast<const double2*>(T + (long long)r * ldT);
+                const double2* u = GENERAL ? reinterpret_cast<const double2*>(T2 + (long long)r * ldT) : nullptr;
+                int j = threadIdx.x;
+                for (; j + 768 < npair; j += 1024) {
+                    double2 x0 = __ldcs(t + j), x1 = __ldcs(t + j + 256), x2 = __ldcs(t + j + 512), x3 = __ldcs(t + j + 768);
+                    if (GENERAL) {
+                        const double2 z0 = __ldcs(u + j), z1 = __ldcs(u + j + 256), z2 = __ldcs(u + j + 512), z3 = __ldcs(u + j + 768);
+                        if (2 * j < r) x0.x = z0.x;
+                        if (2 * j + 1 < r) x0.y = z0.y;
+                        if (2 * (j + 256) < r) x1.x = z1.x;
+                        if (2 * (j + 256) + 1 < r) x1.y = z1.y;
+                        if (2 * (j + 512) < r) x2.x = z2.x;
+                        if (2 * (j + 512) + 1 < r) x2.y = z2.y;
+                        if (2 * (j + 768) < r) x3.x = z3.x;
+                        if (2 * (j + 768) + 1 < r) x3.y = z3.y;
+                    }
+                    const double2 w0 = __ldg(v2 + j), w1 = __ldg(v2 + j + 256), w2 = __ldg(v2 + j + 512), w3 = __ldg(v2 + j + 768);
+                    a0 = fma(x0.x, w0.x, fma(x0.y, w0.y, a0));
+                    a1 = fma(x1.x, w1.x, fma(x1.y, w1.y, a1));
+                    a2 = fma(x2.x, w2.x, fma(x2.y, w2.y, a2));
+                    a3 = fma(x3.x, w3.x, fma(x3.y, w3.y, a3));
+                }
+                for (; j < npair; j += 256) {
+                    double2 x0 = __ldcs(t + j);
+                    if (GENERAL) {
+                        const double2 z0 = __ldcs(u + j);
+                        if (2 * j < r) x0.x = z0.x;
+                        if (2 * j + 1 < r) x0.y = z0.y;
+                    }
+                    const double2 w0 = __ldg(v2 + j);
+                    a0 = fma(x0.x, w0.x, fma(x0.y, w0.y, a0));
+                }
+            }
+            sum[rr] = (a0 + a1) + (a2 + a3);
+        }
+#pragma unroll
+        for (int rr = 0; rr < SYMV_RPC; ++rr) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum[rr] += __shfl_xor_sync(0xffffffffu, sum[rr], o);
+            if (lane == 0) red[rr][warp] = sum[rr];
+        }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = 0.0;
+        if (threadIdx.x < SYMV_RPC) {
+            const int r = grp * SYMV_RPC + threadIdx.x;
+            if (r < rows) {
+                double s = 0.0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) s += red[q];
-            y[r] = s;
+                for (int q = 0; q < 8; ++q) s += red[threadIdx.x][q];
+                y[r] = s;
+            }
         }
         __syncthreads();
     }

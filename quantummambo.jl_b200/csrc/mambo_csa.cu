@@ -1602,8 +1602,8 @@ int mambo_csa_symv_device(mambo_csa* h, const double* d_v, double* d_y) {
     if (!h || !d_v || !d_y) return fail(MAMBO_EINVAL, "null argument");
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "symv needs an unsharded handle");
     CU(cudaSetDevice(h->device));
-    if (h->mode == (int)MAMBO_SYM_GENERAL) lanczos::k_symv<1><<<h->nR, 256, 0, h->stream>>>(h->T2, h->T1, h->ldT, h->nR, d_v, d_y);
-    else lanczos::k_symv<0><<<h->nR, 256, 0, h->stream>>>(h->T1, nullptr, h->ldT, h->nR, d_v, d_y);
+    if (h->mode == (int)MAMBO_SYM_GENERAL) lanczos::k_symv<1><<<(h->nR + lanczos::SYMV_RPC - 1) / lanczos::SYMV_RPC, 256, 0, h->stream>>>(h->T2, h->T1, h->ldT, h->nR, d_v, d_y);
+    else lanczos::k_symv<0><<<(h->nR + lanczos::SYMV_RPC - 1) / lanczos::SYMV_RPC, 256, 0, h->stream>>>(h->T1, nullptr, h->ldT, h->nR, d_v, d_y);
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
@@ -1667,7 +1667,7 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
     double* alpha = ab;
     double* beta = ab + (mmax + 1);
     const int vblocks = (R + 255) / 256;
-    const int mv_grid = R;                               // one CTA per row, scheduled dynamically: the tail is one row long
+    const int mv_grid = (R + lanczos::SYMV_RPC - 1) / lanczos::SYMV_RPC;   // one CTA per group of rows, scheduled dynamically
     const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
     lanczos::k_start<<<vblocks, 256, 0, st>>>(w, R, h->pa, h->pq, n);
     lanczos::k_normalise<<<1, 1024, 0, st>>>(w, R, (int)ldv, V, beta, mmax);   // beta[mmax] is scratch
