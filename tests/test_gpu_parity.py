@@ -599,6 +599,23 @@ def test_csa_sd_greedy_step_molecule_sizes(mb, lib):
 
 
 # ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [70, 110, 130])
+def test_large_kernel_buckets_match_oracle(mb, lib, n):
+    """The kernel instantiations between the benchmark sizes: n = 70 (10 n-blocks), 110 (16 n-blocks: column-split panel
+    kernels, k_esum, shallower operand ring) and 130 (19 n-blocks: no T~ look-ahead registers) -- the code path of the
+    N = 152 configuration at a size whose host tensor stays small."""
+    T = o.dense_sym_tbt(n, 5)
+    x = o.random_x(n, 6)
+    c0, g0 = o.cost_grad_factored(x, T)
+    with mb.CSAEngine(T) as e:
+        c, g = e.cost_grad(x)
+        assert e.info()["mode_name"] == "fullsym-packed"
+        nc = e.subtract_fragment(x)
+    assert abs(c - c0) <= RTOL * abs(c0) and rel(g, g0) <= RTOL
+    assert abs(nc - c0) <= RTOL * abs(c0)
+
+
+# ------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [50, 100])
 def test_full_size_properties(mb, lib, n):
     """BASELINE.json sizes.  (1) pointwise parity with the factored oracle at one x; (2) the three symmetry modes of
