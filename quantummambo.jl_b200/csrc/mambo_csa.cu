@@ -114,6 +114,8 @@ struct mambo_csa {
     bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
     int chain_ct = 16;                         // tile edge of the chain kernels
     bool chain_cluster = false;                // N <= 64: the <= 4 x 4 tiles form ONE thread-block cluster (hardware barrier)
+    bool chain_data = false;                   // data-driven chain (sentinel polling, no step barriers): MAMBO_CHAIN_DATA=1 (experimental)
+    int chain_nmats = 0;                       // matrices in cmats (reset to the sentinel by k_chain_u in the data-driven mode)
     bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
     int dephase = 0;                           // fused kernel: start offset (cycles) of column group 1
     int lookahead = 0;                         // fused kernel: operand sub-tiles requested ahead (0 = default)
@@ -399,11 +401,15 @@ int launch_cluster(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
 int launch_chain(mambo_csa* h, bool deriv, void** args) {
     const int n = h->N, ct = h->chain_ct, tiles = (n + ct - 1) / ct;
     const size_t smem = chain::smem_bytes(n, ct);
+    if (h->chain_data) {
+        const void* f = deriv ? (const void*)chain::k_chain_d<16, chain::SYNC_DATA> : (const void*)chain::k_chain_u<16, chain::SYNC_DATA>;
+        return launch_coop(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);   // CTAs poll each other: co-residency required
+    }
     if (h->chain_cluster) {
-        const void* f = deriv ? (const void*)chain::k_chain_d<16, true> : (const void*)chain::k_chain_u<16, true>;
+        const void* f = deriv ? (const void*)chain::k_chain_d<16, chain::SYNC_CLUSTER> : (const void*)chain::k_chain_u<16, chain::SYNC_CLUSTER>;
         return launch_cluster(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);
     }
-    const void* f = deriv ? (const void*)chain::k_chain_d<16, false> : (const void*)chain::k_chain_u<16, false>;
+    const void* f = deriv ? (const void*)chain::k_chain_d<16, chain::SYNC_GRID> : (const void*)chain::k_chain_u<16, chain::SYNC_GRID>;
     return launch_coop(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);
 }
 
@@ -416,6 +422,7 @@ int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
     chain::UParams p = h->cu;
     p.x = d_x; p.n = n; p.lam_off = h->lam_off; p.s_override = s_host;
     p.Lam = h->Lam; p.U = h->U; p.LamP = h->use_panel ? h->LamP : nullptr; p.ldl = h->ld; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
+    p.cm_base = h->cmats; p.cm_count = h->chain_nmats;
     void* args[] = {&p};
     TRY(launch_chain(h, false, args));
     h->launches++;
@@ -554,7 +561,7 @@ int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
     if (h->use_chain) {
         chain::DParams p = h->cd;
         p.part = h->d_part; p.g1 = h->g1; p.n = n; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0;
-        p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar; p.dbg = h->d_dbg;
+        p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar; p.status = h->d_status; p.dbg = h->d_dbg;
         void* args[] = {&p};
         TRY(launch_chain(h, true, args));
         h->launches++;
@@ -950,7 +957,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
             // only if the device can actually place one such cluster (<= 16 CTAs with this much shared memory in one GPC)
             const int tiles = (n + 15) / 16, sm_chain = (int)chain::smem_bytes(n, 16);
             bool ok = true;
-            for (const void* f : {(const void*)chain::k_chain_u<16, true>, (const void*)chain::k_chain_d<16, true>}) {
+            for (const void* f : {(const void*)chain::k_chain_u<16, chain::SYNC_CLUSTER>, (const void*)chain::k_chain_d<16, chain::SYNC_CLUSTER>}) {
                 ok = ok && raise_smem(f, sm_chain) == cudaSuccess;
                 ok = ok && cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
                 cudaLaunchConfig_t cfg;
@@ -973,6 +980,12 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         }
         const size_t ms = chain::mat_stride(n, h->chain_ct);
         const size_t ncm = 11 + 11 + 4 * (size_t)(chain::SMAXC + 1);
+        h->chain_nmats = (int)ncm;
+        // Data-driven variant (chain::SYNC_DATA): correct, but measured SLOWER than barrier + TMA reload at N = 100 (finish
+        // 62 vs 48 us, pre 84 vs 76 us): copying the four 12.8 KB strips with ordinary loads costs ~2800 cycles against
+        // ~1250 for the TMA engine, which eats the ~2300 cycles saved on the barrier.  Kept opt-in for further work
+        // (poll only the strips produced in the previous step, TMA for the rest).
+        h->chain_data = std::getenv("MAMBO_CHAIN_DATA") != nullptr;
         TRY(dalloc(&h->cmats, ncm * ms));
         double* cm = h->cmats;
         auto ctake = [&](size_t k) { double* r = cm; cm += k * ms; return r; };
@@ -988,7 +1001,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     }
     TRY(dalloc(&h->g1, (size_t)n));
     TRY(dalloc(&h->d_s, 1));
-    TRY(dalloc(&h->d_bar, 2));
+    TRY(dalloc(&h->d_bar, 4));                  // [0] barrier counter, [1] exit counter, [2] scratch target of release operations
     if (std::getenv("MAMBO_CHAIN_DEBUG")) TRY(dalloc(&h->d_dbg, 6 * 16));
     TRY(dalloc(&h->d_scale, 1));
     TRY(dalloc(&h->d_status, 1));
@@ -1045,15 +1058,13 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     if (chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin) h->use_chain = false;
     if (h->use_chain) {
         const int sm_chain = (int)chain::smem_bytes(n, h->chain_ct);
-        if (h->chain_cluster) {
-            for (const void* f : {(const void*)chain::k_chain_u<16, true>, (const void*)chain::k_chain_d<16, true>}) {
-                CU(raise_smem(f, sm_chain));
+        for (const void* f : {(const void*)chain::k_chain_u<16, chain::SYNC_GRID>, (const void*)chain::k_chain_d<16, chain::SYNC_GRID>,
+                              (const void*)chain::k_chain_u<16, chain::SYNC_DATA>, (const void*)chain::k_chain_d<16, chain::SYNC_DATA>,
+                              (const void*)chain::k_chain_u<16, chain::SYNC_CLUSTER>, (const void*)chain::k_chain_d<16, chain::SYNC_CLUSTER>})
+            CU(raise_smem(f, sm_chain));
+        if (h->chain_cluster)
+            for (const void* f : {(const void*)chain::k_chain_u<16, chain::SYNC_CLUSTER>, (const void*)chain::k_chain_d<16, chain::SYNC_CLUSTER>})
                 CU(cudaFuncSetAttribute(f, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            }
-        } else {
-            for (const void* f : {(const void*)chain::k_chain_u<16, false>, (const void*)chain::k_chain_d<16, false>})
-                CU(raise_smem(f, sm_chain));
-        }
     }
 
     // opt-in shared-memory sizes, set once per handle

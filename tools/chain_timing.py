@@ -20,3 +20,4 @@ with mb.CSAEngine(T) as e:
         b = flat[56 + 4 * q: 60 + 4 * q]
         print("barrier", q, "red issue", b[1] - b[0], "poll phase", b[2] - b[1], "polls", b[3])
     print("kernel start->squarings", flat[90] - flat[91], "squarings", a[8, 5] - flat[90], "tail", flat[92] - a[8, 5], "total", flat[92] - flat[91])
+    print("poll loader (thread 0, last call): first pass", flat[56], "retry rounds", flat[57], "own total", flat[58], "incl. CTA sync", flat[59])
