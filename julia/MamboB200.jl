@@ -113,6 +113,45 @@ function QuantumMAMBO.tbt_svd_1st(e::Engine, n::Integer; tiny = SVD_tiny)
     return SVD_to_CSA(lead, ωl, Ul)
 end
 
+# ---- optional: the library's own optimiser (dense BFGS / L-BFGS with all vectors on the device) ---------------------------
+struct OptOptions            # mambo_opt_options_t
+    max_iter::Cint
+    g_tol::Cdouble
+    lbfgs_memory::Cint
+    verbose::Cint
+end
+struct OptResult             # mambo_opt_result_t
+    minimum::Cdouble
+    iterations::Cint
+    evaluations::Cint
+    converged::Cint
+    device::Cint
+end
+
+"Minimise cost(x) from x0 on the GPU (stands in for `optimize(cost, grad!, x0, BFGS())`, decompose.jl:107-119)."
+function optimize_native(e::Engine, x0::Vector{Float64}; max_iter = 1000, g_tol = 1e-8, lbfgs_memory = 0)
+    xmin = similar(x0)
+    opt = Ref(OptOptions(max_iter, g_tol, lbfgs_memory, 0))
+    res = Ref(OptResult(0.0, 0, 0, 0, 0))
+    GC.@preserve x0 xmin check(ccall((:mambo_csa_optimize, LIB), Cint,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ref{OptOptions}, Ref{OptResult}), e.h, x0, xmin, opt, res))
+    return xmin, res[]
+end
+
+"K independent starts (columns of X0) scheduled over `engines` (lanes of one GPU and/or engines on several GPUs)."
+function multistart(engines::Vector{Engine}, X0::Matrix{Float64}; max_iter = 1000, g_tol = 1e-8, lbfgs_memory = 0)
+    L, K = size(X0)
+    Xmin = similar(X0)
+    hs = [e.h for e in engines]
+    opt = Ref(OptOptions(max_iter, g_tol, lbfgs_memory, 0))
+    res = Vector{OptResult}(undef, K)
+    best = Ref{Cint}(-1)
+    GC.@preserve X0 Xmin hs res check(ccall((:mambo_multistart_run, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ref{OptOptions}, Ptr{OptResult}, Ref{Cint}),
+        hs, length(hs), K, X0, Xmin, opt, res, best))
+    return Xmin, res, Int(best[]) + 1
+end
+
 # ---- drop-in greedy steps (same signatures as decompose.jl:82, :207) ---------------------------------------------
 function _optimize(e::Engine, x0, print)
     c(x) = cost(e, x)                                       # decompose.jl:96-99   / :221-224
