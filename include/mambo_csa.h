@@ -76,7 +76,7 @@ typedef struct mambo_csa_info_t {
     double asym_pair, asym_pq;        /* measured relative asymmetries of the input tensor                  */
     int    hot_gemms;                 /* R x R x N products per pass of the hot kernel: 1 (single-GEMM formulation,
                                          fused::k_ty) or 2 (fused::k_fused, MAMBO_TWO_GEMM=1 / legacy paths)   */
-    int    lanes_hint;                /* evaluation lanes that fit side by side: floor(2 SMs / chain CTAs), >= 1 */
+    int    lanes_hint;                /* useful number of evaluation lanes: min(8, floor(4 SMs / chain CTAs)), >= 1 */
 } mambo_csa_info_t;
 
 /* --- lifetime ------------------------------------------------------------------------------------------ */
@@ -91,7 +91,7 @@ int  mambo_csa_create_sharded(mambo_csa** h, int N, int flavour, const double* t
  * chains / epilogues of one lane fill the SMs while another lane's are waiting at a grid barrier.  A residual update
  * (mambo_csa_subtract_fragment) through any handle of the group is seen by all of them; the caller must not run it
  * concurrently with evaluations on sibling lanes.  The residual is freed when the last handle of the group is
- * destroyed.  Useful lane counts: floor(148 / ceil(N/16)^2) -- 3 at N=100, 9 at N=50, 1 at N=152.                 */
+ * destroyed.  Useful lane counts (mambo_csa_info_t.lanes_hint): 8 at N <= 100, 4 at N = 152.                       */
 int  mambo_csa_create_lane(mambo_csa* parent, mambo_csa** lane);
 void mambo_csa_destroy(mambo_csa* h);
 int  mambo_csa_get_info(const mambo_csa* h, mambo_csa_info_t* info);
