@@ -458,11 +458,34 @@ def main():
     host_nl = max(1, min(nl, (2 * (os.cpu_count() or 1)) // max(world, 1)))
     while BATCH % host_nl:
         host_nl -= 1
+    def batch_leg():
+        """The step's BATCH points through ONE C-ABI call per step (mambo_csa_cost_grad_batch over the lanes): host x in,
+        H2D, kernels, D2H of every cost+grad inside the timed region, a single caller thread."""
+        xb = np.stack(xs)
+        mb.cost_grad_batch(group, xb)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        acc_ = 0.0
+        for s_ in range(args.steps):
+            xb[:, 0] += 1e-9
+            c_, g_ = mb.cost_grad_batch(group, xb)
+            acc_ += float(c_[0])
+        dt_ = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_ = float(t.item())
+        return dt_
+
     t_e2e1 = host_leg(1)
     t_e2e = host_leg(host_nl) if host_nl > 1 else t_e2e1
+    t_batch = batch_leg()
     sampler.stop()
     e2e_value = evals_total / t_e2e
     e2e_value1 = evals_total / t_e2e1
+    e2e_batch = evals_total / t_batch
     for e in group[1:]:
         e.close()
     stream = main_stream
@@ -593,7 +616,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": BATCH * L * 8,
                     "d2h_bytes_per_step": BATCH * (L + 1) * 8,
                     "timer": "host perf_counter around synchronous C-ABI calls (mambo_csa_cost_grad), one caller thread per lane",
-                    "caller_threads_per_gpu": host_nl, "single_caller": e2e_value1},
+                    "caller_threads_per_gpu": host_nl, "single_caller": e2e_value1,
+                    "batch_call": {"value": e2e_batch, "what": "one mambo_csa_cost_grad_batch call per step from a single caller "
+                                   "thread (the step's points in one wave over the lanes; waves do not overlap)"}},
             "single_lane": {"value": value1, "ms_per_step": ms1 / args.steps,
                             "note": "one evaluation in flight at a time (the sequential BFGS case)"},
             "gpu_launches": int(launches), "launches_per_eval": launches / (BATCH * args.steps),

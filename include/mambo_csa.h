@@ -102,6 +102,10 @@ const char* mambo_last_error(void);
 int  mambo_csa_cost(mambo_csa* h, const double* x, double* cost);
 int  mambo_csa_grad(mambo_csa* h, const double* x, double* grad);
 int  mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* grad);
+/* The same closure at K points x[k*L .. (k+1)*L) in one call (K independent runs of a multistart): point k is evaluated on
+ * lanes[k mod nlanes] (a handle and lanes created from it, see mambo_csa_create_lane); the evaluations of a wave overlap
+ * on the device.  costs: K doubles, grads: K*L doubles (either may be NULL).                                          */
+int  mambo_csa_cost_grad_batch(mambo_csa** lanes, int nlanes, int K, const double* x, double* costs, double* grads);
 
 /* --- greedy driver state (device-resident residual) ------------------------------------------------------ */
 /* On a row-panel shard both return the shard-local part of the cost (the caller sums over shards; the replicated

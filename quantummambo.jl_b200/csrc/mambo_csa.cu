@@ -710,7 +710,14 @@ int check_status(mambo_csa* h) {
 }
 
 // full evaluation from a host x; results land in h->h_out (pinned) after synchronisation
-int eval_host(mambo_csa* h, const double* x, bool need_grad) {
+int eval_host_wait(mambo_csa* h) {   // second half of eval_host: results are in h->h_out afterwards
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return check_status(h);
+}
+
+// nowait: enqueue only (H2D, kernels, D2H into the pinned staging); the caller finishes with eval_host_wait
+int eval_host(mambo_csa* h, const double* x, bool need_grad, bool nowait = false) {
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "host closures need an unsharded handle (use the *_device entry points)");
     CU(cudaSetDevice(h->device));
     const int s_host = host_s_for(h, x);
@@ -728,8 +735,9 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad) {
             CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             return MAMBO_OK;
         }));
-        CU(cudaStreamSynchronize(h->stream));
         h->launches_last_eval = (int)(h->launches - l0);
+        if (nowait) return MAMBO_OK;
+        CU(cudaStreamSynchronize(h->stream));
         return check_status(h);
     }
     CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
@@ -743,8 +751,9 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad) {
         CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
     h->launches_last_eval = (int)(h->launches - l0);
+    if (nowait) return MAMBO_OK;
+    CU(cudaStreamSynchronize(h->stream));
     return check_status(h);
 }
 
@@ -1306,6 +1315,34 @@ int mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* gra
 // search): one fused evaluation serves both.
 int mambo_csa_cost(mambo_csa* h, const double* x, double* cost) { return mambo_csa_cost_grad(h, x, cost, nullptr); }
 int mambo_csa_grad(mambo_csa* h, const double* x, double* grad) { return mambo_csa_cost_grad(h, x, nullptr, grad); }
+
+// K independent evaluations (multistart: one point per run) in ONE call: point k goes to lane k mod nlanes; each wave
+// enqueues one evaluation per lane without waiting (H2D from the lane's pinned staging, kernels, D2H), then collects them
+// in lane order.  The lanes overlap on the device as they do under one caller thread each, without needing those threads.
+int mambo_csa_cost_grad_batch(mambo_csa** lanes, int nlanes, int K, const double* xs, double* costs, double* grads) {
+    if (!lanes || nlanes < 1 || K < 0 || !xs) return fail(MAMBO_EINVAL, "bad arguments");
+    const int L = lanes[0] ? lanes[0]->L : 0;
+    for (int i = 0; i < nlanes; ++i)
+        if (!lanes[i] || lanes[i]->L != L) return fail(MAMBO_EINVAL, "lanes must be handles of the same problem");
+    for (int k0 = 0; k0 < K; k0 += nlanes) {
+        const int nw = std::min(nlanes, K - k0);
+        for (int i = 0; i < nw; ++i) {
+            lanes[i]->memo_valid = false;
+            TRY(eval_host(lanes[i], xs + (size_t)(k0 + i) * L, true, true));
+        }
+        int rc_first = MAMBO_OK;
+        for (int i = 0; i < nw; ++i) {
+            const int rc = eval_host_wait(lanes[i]);      // every lane is drained even after a failure
+            if (rc && !rc_first) rc_first = rc;
+            if (!rc) {
+                if (costs) costs[k0 + i] = lanes[i]->h_out[0];
+                if (grads) std::memcpy(grads + (size_t)(k0 + i) * L, lanes[i]->h_out + 1, sizeof(double) * L);
+            }
+        }
+        if (rc_first) return rc_first;
+    }
+    return MAMBO_OK;
+}
 
 int mambo_csa_set_stream(mambo_csa* h, void* stream) {
     if (!h) return fail(MAMBO_EINVAL, "null handle");

@@ -233,6 +233,20 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_synchronize(self._h))
 
 
+def cost_grad_batch(engines, xs):
+    """cost and gradient at the K rows of `xs` in one library call (mambo_csa_cost_grad_batch): point k runs on
+    engines[k % len(engines)] (an engine and lanes created from it); returns (costs [K], grads [K, L])."""
+    engines = list(engines)
+    lib = engines[0]._lib
+    L = engines[0].L
+    xs = np.ascontiguousarray(xs, dtype=np.float64).reshape(-1, L)
+    K = xs.shape[0]
+    costs, grads = np.empty(K), np.empty((K, L))
+    hs = (C.c_void_p * len(engines))(*[e._h.value for e in engines])
+    _lib.check(lib.mambo_csa_cost_grad_batch(hs, len(engines), K, xs.ctypes.data, costs.ctypes.data, grads.ctypes.data))
+    return costs, grads
+
+
 def multistart(engines, x0s, g_tol: float = 1e-8, max_iter: int = 1000, lbfgs_memory: int = 0, verbose: int = 0):
     """K independent BFGS runs from the rows of `x0s`, scheduled over `engines` by the library
     (mambo_multistart_run: one worker thread per handle pulling starts from a shared counter; precedent

@@ -271,6 +271,26 @@ def test_single_gemm_formulation_matches_two_gemm_kernel_and_falls_back(mb, lib,
         slow.close()
 
 
+def test_batch_closure_over_lanes_matches_single_closures(mb, lib):
+    """mambo_csa_cost_grad_batch: K points in one call, spread over lanes in waves -- the same bits as K single closures."""
+    for n, flavour in ((11, "CSA"), (8, "CSA_SD")):
+        T = o.dense_sym_tbt(n, 6)
+        obt = _obt(n, 6) if flavour == "CSA_SD" else None
+        with mb.CSAEngine(T, obt, flavour) as e:
+            lanes = [e, e.lane(), e.lane()]
+            xs = np.stack([o.random_x(n, 30 + k, flavour) for k in range(7)])       # 7 points over 3 lanes: ragged last wave
+            costs, grads = mb.cost_grad_batch(lanes, xs)
+            for k in range(len(xs)):
+                c, g = e.cost_grad(xs[k])
+                assert costs[k] == c and np.array_equal(grads[k], g)
+                c0, g0 = o.cost_grad_factored(xs[k], T, obt, flavour)
+                assert abs(c - c0) <= RTOL * abs(c0) and rel(g, g0) <= RTOL
+            c1, g1 = mb.cost_grad_batch(lanes[:1], xs[:2])                           # a single lane is allowed
+            assert c1[1] == costs[1] and np.array_equal(g1[0], grads[0])
+            for ln in lanes[1:]:
+                ln.close()
+
+
 def test_handles_of_different_sizes_coexist(mb, lib):
     """Opt-in shared-memory limits are per kernel function, not per handle: creating a smaller problem afterwards must not
     take them away from a larger handle that is still in use."""
