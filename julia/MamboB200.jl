@@ -113,6 +113,17 @@ function QuantumMAMBO.tbt_svd_1st(e::Engine, n::Integer; tiny = SVD_tiny)
     return SVD_to_CSA(lead, ωl, Ul)
 end
 
+"cost and gradient at the K columns of X in one call, spread over `engines` (an Engine and lanes of it)."
+function cost_grad_batch(engines::Vector{Engine}, X::Matrix{Float64})
+    L, K = size(X)
+    costs = Vector{Float64}(undef, K)
+    grads = Matrix{Float64}(undef, L, K)
+    hs = [e.h for e in engines]
+    GC.@preserve X costs grads hs check(ccall((:mambo_csa_cost_grad_batch, LIB), Cint,
+        (Ptr{Ptr{Cvoid}}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), hs, length(hs), K, X, costs, grads))
+    return costs, grads
+end
+
 # ---- optional: the library's own optimiser (dense BFGS / L-BFGS with all vectors on the device) ---------------------------
 struct OptOptions            # mambo_opt_options_t
     max_iter::Cint
