@@ -49,8 +49,6 @@ struct UParams {
     double* scale_out;
     int* status;
     unsigned* bar;  // [0] barrier counter, [1] exit counter (both zero between launches)
-    double* cm_base;   // SYNC_DATA: first of the cm_count chain matrices (contiguous, mat_stride each) reset to the sentinel
-    int cm_count;
 };
 struct DParams {
     const double* part;   // [cost, S, G]
@@ -64,6 +62,8 @@ struct DParams {
     unsigned* bar;
     int* status;
     long long* dbg;       // optional clock64 stamps of CTA 0 (development aid; MAMBO_CHAIN_DEBUG=1)
+    int write_cost;       // 1: out[0] = part[0]; 0: the cost is written by small::k_cost_select running beside this kernel
+    int write_lambda;     // 1: lambda gradient from part's S; 0: small::k_reduce_s (side stream) writes it
 };
 
 // pitch of every chain matrix: smallest ldm >= n with ldm == 4 (mod 16)  (100 -> 100, 152 -> 164)
@@ -124,15 +124,7 @@ __device__ __forceinline__ void grid_exit(unsigned* bar) {
 // How the dependent steps of a chain are ordered across CTAs:
 //   SYNC_GRID     grid-wide barrier on a global counter (cooperative launch), operands re-read by TMA afterwards;
 //   SYNC_CLUSTER  hardware cluster barrier (N <= 64: all tiles in one thread-block cluster), TMA afterwards;
-//   SYNC_DATA     no barrier at all: every matrix element is reset to a sentinel bit pattern (a NaN no arithmetic
-//                 produces) at the start of k_chain_u, producers store their tiles with plain stores, and consumers poll
-//                 the operand strips themselves until no sentinel is left -- the arrival of the data IS the
-//                 synchronisation (the LL protocol of collective libraries).  Saves the store drain of the release, the
-//                 counter round trip and the separate reload per step -- but the strips then have to be copied by the
-//                 threads themselves, which measured slower than the TMA reload by more than the barrier costs
-//                 (N = 100: 62 vs 48 us for k_chain_d).  Opt-in (MAMBO_CHAIN_DATA=1), not the default.
-constexpr int SYNC_GRID = 0, SYNC_CLUSTER = 1, SYNC_DATA = 2;
-constexpr unsigned long long SENTINEL = 0xFFFFFFFFFFFFFFFFull;
+constexpr int SYNC_GRID = 0, SYNC_CLUSTER = 1;
 
 template <int SYNC>
 __device__ __forceinline__ void step_barrier(unsigned* ctr, unsigned& target, long long* stamps = nullptr) {
@@ -140,42 +132,13 @@ __device__ __forceinline__ void step_barrier(unsigned* ctr, unsigned& target, lo
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         asm volatile("fence.proxy.async;" ::: "memory");
-    } else if (SYNC == SYNC_GRID) {
-        grid_barrier(ctr, target, stamps);
     } else {
-        // No barrier -- but the tile just stored must LEAVE this SM promptly: plain stores may linger in the SM's write
-        // path for thousands of cycles when nothing forces them out (measured: consumers polled ~6700 cycles per step).
-        // bar.sync + a release operation by one thread is cumulative over the CTA's stores; its target is a scratch word.
-        __syncthreads();      // also: shared-memory strips are about to be overwritten by the next step's loader
-        if (threadIdx.x == 0) asm volatile("red.release.gpu.global.add.u32 [%0], 0;" ::"l"(ctr + 2) : "memory");
+        grid_barrier(ctr, target, stamps);
     }
-}
-// a real barrier in every mode (start of k_chain_u in SYNC_DATA: the sentinel reset must be visible before anyone polls)
-template <int SYNC>
-__device__ __forceinline__ void hard_barrier(unsigned* ctr, unsigned& target) {
-    if (SYNC == SYNC_CLUSTER) step_barrier<SYNC_CLUSTER>(ctr, target);
-    else grid_barrier(ctr, target);
 }
 template <int SYNC>
 __device__ __forceinline__ void chain_exit(unsigned* bar) {
     if (SYNC != SYNC_CLUSTER) grid_exit(bar);
-}
-
-// one element produced by another CTA (or another thread): poll until it is no longer the sentinel
-__device__ __forceinline__ double poll_ld(const double* p, int* status) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    if (v == SENTINEL) {
-        const long long t0 = clock64();
-        do {
-            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-            if (clock64() - t0 > 4000000000ll) {   // ~2 s: a producer died
-                *status = 3;
-                break;
-            }
-        } while (v == SENTINEL);
-    }
-    return __longlong_as_double((long long)v);
 }
 
 // ---- strip loader: rows [r0, r0+CT) of a chain matrix (pitch ldm, zero padded) -> S, one TMA bulk copy ---------------
@@ -219,111 +182,6 @@ struct Loader {
     }
 };
 
-// ---- SYNC_DATA strip loader: the same interface, but the strips are copied by all threads with L2-coherent 16-byte loads
-// that are repeated until no valid element carries the sentinel; padding (rows / columns beyond n) is written as zero
-// whatever global memory holds there.  Up to 8 chunks per thread are in flight together.
-template <int CT>
-struct PollLoader {
-    int lda, n;
-    int* status;
-    double* S_[4];
-    const double* M_[4];
-    int r0_[4];
-    int nreq;
-    long long* dbg = nullptr;   // development aid: [0] first-pass cycles, [1] retry rounds, [2] total cycles (thread 0, last call)
-
-    __device__ __forceinline__ void begin(bool = false) { nreq = 0; }
-    __device__ __forceinline__ void rows(double* S, const double* M, int r0) {
-        S_[nreq] = S;
-        M_[nreq] = M + (size_t)r0 * lda;
-        r0_[nreq] = r0;
-        ++nreq;
-    }
-    // Warp w copies row w (and w + 16, ... for taller tiles) of every requested strip; lane l takes the 16-byte chunks
-    // l, l + 32, ... of the row: no index arithmetic beyond adds (runtime divisions cost more than the loads here).  All
-    // loads of a thread are issued before the first is tested.
-    __device__ __forceinline__ void wait() {
-        static_assert(CT % 16 == 0, "one warp per row group");
-        constexpr int RPW = CT / 16;                       // rows per warp
-        constexpr int MAXIT = 3;                           // ceil((lda / 2) / 32) for lda <= 192
-        constexpr int B = 4 * RPW * MAXIT;
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const int half = lda >> 1;
-        const long long tdbg0 = dbg ? clock64() : 0;
-        long long tdbg1 = 0;
-        int rounds = 0;
-        unsigned long long lo[B], hi[B];
-        bool v0[B], v1[B];
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int rr = 0; rr < RPW; ++rr)
-#pragma unroll
-                for (int it = 0; it < MAXIT; ++it) {
-                    const int u = (q * RPW + rr) * MAXIT + it;
-                    const int row = warp + 16 * rr, c2 = lane + 32 * it;
-                    const bool live = q < nreq && c2 < half;
-                    const bool rv = live && (r0_[q < nreq ? q : 0] + row < n);
-                    v0[u] = rv && 2 * c2 < n;
-                    v1[u] = rv && 2 * c2 + 1 < n;
-                    lo[u] = hi[u] = 0ull;
-                    if (v0[u]) {
-                        const double* src = M_[q] + (size_t)row * lda + 2 * c2;
-                        asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(lo[u]), "=l"(hi[u]) : "l"(src) : "memory");
-                    }
-                }
-        bool again = false;
-#pragma unroll
-        for (int u = 0; u < B; ++u) again = again || (v0[u] && lo[u] == SENTINEL) || (v1[u] && hi[u] == SENTINEL);
-        if (dbg) tdbg1 = clock64();
-        if (again) {
-            const long long t0 = clock64();
-            do {
-                // issue every outstanding reload first, test afterwards: the loads stay in flight together
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-#pragma unroll
-                    for (int rr = 0; rr < RPW; ++rr)
-#pragma unroll
-                        for (int it = 0; it < MAXIT; ++it) {
-                            const int u = (q * RPW + rr) * MAXIT + it;
-                            if ((v0[u] && lo[u] == SENTINEL) || (v1[u] && hi[u] == SENTINEL)) {
-                                const double* src = M_[q] + (size_t)(warp + 16 * rr) * lda + 2 * (lane + 32 * it);
-                                asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(lo[u]), "=l"(hi[u]) : "l"(src) : "memory");
-                            }
-                        }
-                again = false;
-                ++rounds;
-#pragma unroll
-                for (int u = 0; u < B; ++u) again = again || (v0[u] && lo[u] == SENTINEL) || (v1[u] && hi[u] == SENTINEL);
-                if (again && clock64() - t0 > 4000000000ll) {
-                    *status = 3;
-                    break;
-                }
-            } while (again);
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int rr = 0; rr < RPW; ++rr)
-#pragma unroll
-                for (int it = 0; it < MAXIT; ++it) {
-                    const int u = (q * RPW + rr) * MAXIT + it;
-                    const int row = warp + 16 * rr, c2 = lane + 32 * it;
-                    if (q < nreq && c2 < half)
-                        *reinterpret_cast<double2*>(S_[q] + (size_t)row * lda + 2 * c2) =
-                            make_double2(v0[u] ? __longlong_as_double((long long)lo[u]) : 0.0, v1[u] ? __longlong_as_double((long long)hi[u]) : 0.0);
-                }
-        if (dbg && threadIdx.x == 0) {
-            dbg[0] = tdbg1 - tdbg0;
-            dbg[1] = rounds;
-            dbg[2] = clock64() - tdbg0;
-        }
-        __syncthreads();
-        if (dbg && threadIdx.x == 0) dbg[3] = clock64() - tdbg0;
-    }
-};
-
 // this warp's k quarter of an 8x8 block product, two accumulators: (c, d) += SA[block rows] . SB[block cols]^T
 // SA: [16 rows i][lda] (k contiguous), SB: [16 cols j][lda] (k contiguous)
 template <int CT>
@@ -353,27 +211,6 @@ __device__ __forceinline__ void combine(double* red, double* v, int nv) {
         for (int q = 0; q < KQ - 1; ++q)
             for (int i = 0; i < nv; ++i) v[i] += red[((q * 128) + warp * 32 + lane) * 4 + i];
 }
-
-template <int CT, int SYNC>
-struct LoaderSel {
-    using type = Loader<CT>;
-    static __device__ __forceinline__ type make(uint64_t* mbar, int lda, int, int*) { return type{mbar, 0u, lda, 0u, 0}; }
-};
-template <int CT>
-struct LoaderSel<CT, SYNC_DATA> {
-    using type = PollLoader<CT>;
-    static __device__ __forceinline__ type make(uint64_t*, int lda, int n, int* status) {
-        type l;
-        l.lda = lda;
-        l.n = n;
-        l.status = status;
-        l.nreq = 0;
-        return l;
-    }
-};
-
-template <int CT> __device__ __forceinline__ void set_dbg(PollLoader<CT>& l, long long* d) { l.dbg = d; }
-template <int CT> __device__ __forceinline__ void set_dbg(Loader<CT>&, long long*) {}
 
 struct Ctx {
     double* S[NSTRIP];
@@ -407,14 +244,14 @@ __device__ __forceinline__ Ctx make_ctx(double* sm, int n, uint64_t** mbar) {
 
 // ------------------------------------------------------------------------------------------------------------
 template <int CT, int SYNC>
-__global__ void __launch_bounds__(NTHR, SYNC == SYNC_DATA ? 1 : 2) k_chain_u(UParams p) {
+__global__ void __launch_bounds__(NTHR, 2) k_chain_u(UParams p) {
     constexpr int NBLK = Geo<CT>::NBLK;
     extern __shared__ __align__(128) double sm[];
     const int n = p.n;
     const size_t nn = mat_stride(n, CT);
     uint64_t* mbar;
     Ctx c = make_ctx<CT>(sm, n, &mbar);
-    typename LoaderSel<CT, SYNC>::type ld = LoaderSel<CT, SYNC>::make(mbar, c.lda, n, p.status);
+    Loader<CT> ld{mbar, 0u, c.lda, 0u, 0};
     __shared__ double s_red[NTHR / 32];
     __shared__ double s_scale;
     __shared__ int s_s;
@@ -424,20 +261,6 @@ __global__ void __launch_bounds__(NTHR, SYNC == SYNC_DATA ? 1 : 2) k_chain_u(UPa
     const double* lam = p.x + p.lam_off;
     const double* th = p.x + p.lam_off + cL;
     unsigned target = 0;
-
-    // SYNC_DATA: every element of every chain matrix (this tile position of each of them; the CTAs together cover all)
-    // goes back to the sentinel, and ONE real barrier makes that visible before any CTA starts to poll.
-    if (SYNC == SYNC_DATA) {
-        const unsigned long long sent = SENTINEL;
-        for (int m = 0; m < p.cm_count; ++m) {
-            double* base = p.cm_base + (size_t)m * nn;
-            for (int idx = threadIdx.x; idx < CT * CT; idx += NTHR) {
-                const int i = c.i0 + idx / CT, j = c.j0 + idx % CT;
-                if (j < c.lda) base[(size_t)i * c.lda + j] = __longlong_as_double((long long)sent);
-            }
-        }
-        hard_barrier<SYNC>(p.bar, target);
-    }
 
     // ---- ||K||_1 (== max row sum; every CTA computes the same number in the same order) and s ---------------
     {
@@ -615,16 +438,15 @@ __global__ void __launch_bounds__(NTHR, SYNC == SYNC_DATA ? 1 : 2) k_chain_u(UPa
 
 // ------------------------------------------------------------------------------------------------------------
 template <int CT, int SYNC>
-__global__ void __launch_bounds__(NTHR, SYNC == SYNC_DATA ? 1 : 2) k_chain_d(DParams p) {
+__global__ void __launch_bounds__(NTHR, 2) k_chain_d(DParams p) {
     constexpr int NBLK = Geo<CT>::NBLK;
     extern __shared__ __align__(128) double sm[];
     const int n = p.n;
     const size_t nn = mat_stride(n, CT);
     uint64_t* mbar;
     Ctx c = make_ctx<CT>(sm, n, &mbar);
-    typename LoaderSel<CT, SYNC>::type ld = LoaderSel<CT, SYNC>::make(mbar, c.lda, n, p.status);
+    Loader<CT> ld{mbar, 0u, c.lda, 0u, 0};
     if (p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.dbg[91] = clock64();
-    if (SYNC == SYNC_DATA && p.dbg && blockIdx.x == 0 && blockIdx.y == 0) set_dbg(ld, p.dbg + 56);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int i0 = c.i0, j0 = c.j0, lda = c.lda, ks = c.ks, ei = c.ei, ej = c.ej;
     const int s = *p.s_in;
@@ -792,14 +614,13 @@ __global__ void __launch_bounds__(NTHR, SYNC == SYNC_DATA ? 1 : 2) k_chain_d(DPa
         for (int idx = threadIdx.x; idx < CT * CT; idx += NTHR) {
             const int i = i0 + idx / CT, j = j0 + idx % CT;
             if (i < n && j < n) {
-                if (j <= i) p.out[1 + off + i * (i + 1) / 2 + j] = 2.0 * p.part[1 + i * n + j] * (i != j ? 2.0 : 1.0);
-                else if (SYNC == SYNC_DATA)
-                    p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (poll_ld(Ltt + i * lda + j, p.status) - poll_ld(Lt + i * lda + j, p.status));
-                else p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (__ldcg(Ltt + i * lda + j) - __ldcg(Lt + i * lda + j));
+                if (j <= i) {
+                    if (p.write_lambda) p.out[1 + off + i * (i + 1) / 2 + j] = 2.0 * p.part[1 + i * n + j] * (i != j ? 2.0 : 1.0);
+                } else p.out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (__ldcg(Ltt + i * lda + j) - __ldcg(Lt + i * lda + j));
             }
         }
         if (blockIdx.x == 0 && blockIdx.y == 0) {
-            if (threadIdx.x == 0) p.out[0] = p.part[0];
+            if (threadIdx.x == 0 && p.write_cost) p.out[0] = p.part[0];
             if (p.sd)
                 for (int k = threadIdx.x; k < n; k += NTHR) p.out[1 + k] = p.g1[k];
         }

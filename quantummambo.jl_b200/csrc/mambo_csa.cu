@@ -98,9 +98,7 @@ struct mambo_csa {
     double* sw = nullptr;
     double *Epiece = nullptr, *Et = nullptr, *F1 = nullptr, *F2 = nullptr, *Spart = nullptr, *cost_part = nullptr;
     int *visit_start = nullptr, *piece_first = nullptr;
-    double* mats = nullptr;                    // all N x N matrices of the expm chains
-    double *X, *X2, *X3, *X4, *P0, *P1, *P2, *Q3, *Q2, *Q1, *R;      // R: (SMAX+1) matrices
-    double *dX, *dX2, *dX4, *dP0, *dP1, *dP2, *dQ3, *dQ2, *dQ1, *dR; // dR: (SMAX+1) matrices
+    double* mats = nullptr;                    // Lam, Dh, DU, hfrag (dense n x n each)
     // persistent-chain kernels: padded-pitch matrices (chain::mat_stride each) and their transposed copies
     double* cmats = nullptr;
     chain::UParams cu;
@@ -111,17 +109,19 @@ struct mambo_csa {
     int* d_s = nullptr;
     unsigned* d_bar = nullptr;                 // grid-barrier counters of the persistent chain kernels
     long long* d_dbg = nullptr;                // MAMBO_CHAIN_DEBUG=1: clock64 stamps of the derivative chain
-    bool use_chain = true;                     // persistent chain kernels (false: one launch per product)
     int chain_ct = 16;                         // tile edge of the chain kernels
     bool chain_cluster = false;                // N <= 64: the <= 4 x 4 tiles form ONE thread-block cluster (hardware barrier)
-    bool chain_data = false;                   // data-driven chain (sentinel polling, no step barriers): MAMBO_CHAIN_DATA=1 (experimental)
-    int chain_nmats = 0;                       // matrices in cmats (reset to the sentinel by k_chain_u in the data-driven mode)
-    bool postf32 = false;                      // Lambda-resident half-panel variant of the F epilogue
     int dephase = 0;                           // fused kernel: start offset (cycles) of column group 1
     int lookahead = 0;                         // fused kernel: operand sub-tiles requested ahead (0 = default)
-    bool use_panel = false;                    // tensor-core panel GEMMs for the operand build and the epilogues
     // single-GEMM formulation (fused::k_ty): E = C~ - T~ A~, cost from N x N quantities, exact-cost fallback behind a flag
     bool fast = false;
+    // lean single-GEMM path (unsharded handles): no B~/C~ panel GEMMs and no Gram kernel -- the N x N closed forms of
+    // panel::k_build_a replace them; B~ is only built for the two-GEMM kernel (residual update, cost-only, exact-cost pass)
+    bool lean = false;
+    double* aux = nullptr;                     // [o | d | t | wn] of k_build_a (3 N + 1)
+    double* obc = nullptr;                     // one-body cost of the last evaluation (CSA_SD), 0 for CSA
+    cudaStream_t side_stream = nullptr;        // the flagged exact-cost pass runs beside the derivative chain
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double* Ct = nullptr;                      // C~ = A~ (Lambda G) rows of the local panels [P*64][ld]
     double* GLP = nullptr;                     // G Lambda with the panel pitch [Np][ld] (k_gram)
     double* wpart = nullptr;                   // per (panel, column split) <B~, C~>
@@ -169,6 +169,9 @@ struct mambo_csa {
     bool use_graphs = true;
     bool capturing = false;               // a graph segment is being captured: nested segments run inline
     std::vector<GraphSeg> g_pre, g_fin;   // index 0: device-decided s; 1+s: s squarings
+    std::vector<GraphSeg> g_pre_b;        // lean handles: chain + full operand build (A~ and B~) for the two-GEMM kernel
+    std::vector<GraphSeg> g_fin_seq;      // finish half without the side branch (two-call evaluations: partial / finish)
+    GraphSeg g_post_seq;
     std::vector<GraphSeg> g_host;         // the WHOLE host-API evaluation (H2D of x ... D2H of cost+grad) as one graph per s
     GraphSeg g_mid, g_post, g_costonly;
     // optional live profiling of the fused kernel (CUDA events on the launching stream)
@@ -349,16 +352,6 @@ int host_s_for(const mambo_csa* h, const double* x) {
     return s;
 }
 
-dim3 mm_grid(int n) { return dim3((n + small::TS - 1) / small::TS, (n + small::TS - 1) / small::TS); }
-dim3 mm_block() { return dim3(small::TS, small::TS); }
-
-void mm(mambo_csa* h, double* C, const double* Cin, const double* A1, const double* B1, const double* A2, const double* B2,
-        const int* s_ptr, int step) {
-    const int n = h->N;
-    small::k_mm<<<mm_grid(n), mm_block(), small::strip_bytes(n, A2 ? 2 : 1, A2 ? 2 : 1), h->stream>>>(C, Cin, A1, B1, A2, B2, n, s_ptr, step);
-    h->launches++;
-}
-
 // U = exp(K): Taylor-16 (Paterson-Stockmeyer, 6 GEMMs) + s squarings; every intermediate is kept for the
 // derivative chain.  s_host >= 0: number of squarings (known when x came from the host; passed down so that
 // host and device agree); s_host < 0: the device decides and SMAX guarded launches are enqueued.
@@ -401,10 +394,6 @@ int launch_cluster(const void* func, dim3 grid, dim3 block, size_t smem, cudaStr
 int launch_chain(mambo_csa* h, bool deriv, void** args) {
     const int n = h->N, ct = h->chain_ct, tiles = (n + ct - 1) / ct;
     const size_t smem = chain::smem_bytes(n, ct);
-    if (h->chain_data) {
-        const void* f = deriv ? (const void*)chain::k_chain_d<16, chain::SYNC_DATA> : (const void*)chain::k_chain_u<16, chain::SYNC_DATA>;
-        return launch_coop(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);   // CTAs poll each other: co-residency required
-    }
     if (h->chain_cluster) {
         const void* f = deriv ? (const void*)chain::k_chain_d<16, chain::SYNC_CLUSTER> : (const void*)chain::k_chain_u<16, chain::SYNC_CLUSTER>;
         return launch_cluster(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);
@@ -413,56 +402,21 @@ int launch_chain(mambo_csa* h, bool deriv, void** args) {
     return launch_coop(f, dim3(tiles, tiles), dim3(chain::NTHR), smem, h->stream, args);
 }
 
-int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host);
-
 // U = exp(K) in ONE persistent kernel (chain::k_chain_u): grid barriers instead of kernel boundaries.
 int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
-    if (!h->use_chain) return enqueue_unitary_legacy(h, d_x, s_host);
     const int n = h->N;
     chain::UParams p = h->cu;
     p.x = d_x; p.n = n; p.lam_off = h->lam_off; p.s_override = s_host;
-    p.Lam = h->Lam; p.U = h->U; p.LamP = h->use_panel ? h->LamP : nullptr; p.ldl = h->ld; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
-    p.cm_base = h->cmats; p.cm_count = h->chain_nmats;
+    p.Lam = h->Lam; p.U = h->U; p.LamP = h->LamP; p.ldl = h->ld; p.s_out = h->d_s; p.scale_out = h->d_scale; p.status = h->d_status; p.bar = h->d_bar;
     void* args[] = {&p};
     TRY(launch_chain(h, false, args));
     h->launches++;
     return MAMBO_OK;
 }
 
-int enqueue_unitary_legacy(mambo_csa* h, const double* d_x, int s_host) {
-    const int n = h->N, nn = n * n;
-    small::k_build<<<1, 1024, (size_t)nn * 8, h->stream>>>(d_x, n, h->lam_off, h->X, h->Lam, h->d_s, h->d_scale, h->d_status, s_host);
-    h->launches++;
-    mm(h, h->X2, nullptr, h->X, h->X, nullptr, nullptr, nullptr, 0);
-    small::k_pow34<<<mm_grid(n), mm_block(), small::strip_bytes(n, 1, 2), h->stream>>>(h->X, h->X2, h->X3, h->X4, h->P0, h->P1, h->P2, h->Q3, n);
-    h->launches++;
-    mm(h, h->Q2, h->P2, h->X4, h->Q3, nullptr, nullptr, nullptr, 0);
-    mm(h, h->Q1, h->P1, h->X4, h->Q2, nullptr, nullptr, nullptr, 0);
-    mm(h, h->R, h->P0, h->X4, h->Q1, nullptr, nullptr, nullptr, 0);
-    const int nsq = s_host >= 0 ? std::min(s_host, small::SMAX) : small::SMAX;
-    for (int i = 0; i < nsq; ++i)
-        mm(h, h->R + (size_t)(i + 1) * nn, nullptr, h->R + (size_t)i * nn, h->R + (size_t)i * nn, nullptr, nullptr, h->d_s, i);
-    CU(cudaGetLastError());
-    return MAMBO_OK;
-}
-
-#define NCH_DISPATCH(nch, CALL)                \
-    switch (nch) {                             \
-        case 1: { constexpr int NCH = 1; CALL; break; } \
-        case 2: { constexpr int NCH = 2; CALL; break; } \
-        case 3: { constexpr int NCH = 3; CALL; break; } \
-        case 4: { constexpr int NCH = 4; CALL; break; } \
-        case 5: { constexpr int NCH = 5; CALL; break; } \
-        default: { constexpr int NCH = 6; CALL; break; } \
-    }
-
-// exp(K) for the kernels outside the chain: dense copy (chain kernels) or R[s] of the legacy launch-per-product chain
-const double* u_base(const mambo_csa* h) { return h->use_chain ? h->U : h->R; }
-const int* u_sptr(const mambo_csa* h) { return h->use_chain ? h->d_zero : h->d_s; }
-
-// NB bucket -> (NBT, CST, CSP): panel-kernel instantiation, column split of k_post_mma (CST = 4 above N = 104 so that the
-// panels plus the Lambda slice fit in shared memory) and of k_prep_mma (CSP; a split of 2 for 72 < N <= 104 -- two 100 KB
-// CTAs per SM, twice as many CTAs as panels -- was measured 2 us slower than 1: the kernel is not GEMM-bound)
+// NB bucket -> (NBT, CST, CSP): panel-kernel instantiation, column split of k_post_mma (CST = 4 above N = 104, 6 above N = 152,
+// so that the panels plus the Lambda slice fit in shared memory) and of k_prep_mma (CSP; a split of 2 for 72 < N <= 104 -- two
+// 100 KB CTAs per SM, twice as many CTAs as panels -- was measured 2 us slower than 1: the kernel is not GEMM-bound)
 #define NB_PANEL_DISPATCH(nb, CALL)                 \
     switch (nb) {                                   \
         case 1: { constexpr int NBT = 1, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
@@ -473,116 +427,131 @@ const int* u_sptr(const mambo_csa* h) { return h->use_chain ? h->d_zero : h->d_s
         case 13: { constexpr int NBT = 13, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; } \
         case 16: { constexpr int NBT = 16, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
         case 19: { constexpr int NBT = 19, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
-        default: { constexpr int NBT = 21, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
+        default: { constexpr int NBT = 21, CST = 6, CSP = 6; (void)CSP; (void)CST; CALL; break; } \
     }
+int panel_cs(int nb) { return nb >= 21 ? 6 : (nb >= 16 ? 4 : 1); }   // == CST / CSP of NB_PANEL_DISPATCH
 
-int enqueue_prep(mambo_csa* h) {
-    if (h->use_panel) {
-        if (h->fast) {
-            panel::k_gram<<<h->N, 1024, 0, h->stream>>>(u_base(h), h->Lam, h->N, h->ld, h->GLP);
-            h->launches++;
-        }
-        NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT, CSP><<<dim3(h->nRpad / panel::ROWS, CSP), panel::NTHR, panel::prep_smem<NBT, CSP>(), h->stream>>>(
-                                     u_base(h), h->LamP, h->pa, h->pq, h->sw, h->N, h->prow_begin, h->prow_end, h->At, h->Bt,
-                                     h->fast ? h->GLP : nullptr, h->Ct, h->wpart)));
+// Operand build after the orbital rotation.
+//   PREP_LEAN : A~ (all rows) and the N x N closed forms only (panel::k_build_a) -- the lean single-GEMM evaluation
+//   PREP_AB   : A~ and B~ = A~ Lambda (panel::k_prep_mma) -- the two-GEMM kernel (residual update, cost-only, exact-cost pass);
+//               run_if makes it conditional on the device flag
+//   PREP_ABC  : Gram kernel + A~, B~, C~ = A~ (Lambda G) and <B~, C~> -- the first single-GEMM formulation (row-panel shards)
+enum PrepKind { PREP_LEAN, PREP_AB, PREP_ABC };
+int enqueue_prep(mambo_csa* h, PrepKind kind, const int* run_if = nullptr) {
+    if (kind == PREP_LEAN) {
+        const int blocks = std::min(h->nRpad / 32, h->num_sms - 1) + 1;
+        panel::k_build_a<<<blocks, 1024, 0, h->stream>>>(h->U, h->Lam, h->pa, h->pq, h->sw, h->N, h->ld, h->nRpad, h->At, h->aux);
         h->launches++;
         CU(cudaGetLastError());
         return MAMBO_OK;
     }
-    const int blocks = h->nRpad / small::PREP_ROWS;
-    NCH_DISPATCH((h->Np + 31) / 32,
-                 (small::k_prep<NCH><<<blocks, 256, small::prep_smem(h->N, h->Np), h->stream>>>(
-                     u_base(h), u_sptr(h), h->Lam, h->pa, h->pq, h->sw, h->N, h->Np, h->ld, h->nRpad, h->row_begin, h->row_end, h->At, h->Bt)));
+    const bool with_c = (kind == PREP_ABC);
+    if (with_c) {
+        panel::k_gram<<<h->N, 1024, 0, h->stream>>>(h->U, h->Lam, h->N, h->ld, h->GLP);
+        h->launches++;
+    }
+    NB_PANEL_DISPATCH(h->NB, (panel::k_prep_mma<NBT, CSP><<<dim3(h->nRpad / panel::ROWS, CSP), panel::NTHR, panel::prep_smem<NBT, CSP>(), h->stream>>>(
+                                 h->U, h->LamP, h->pa, h->pq, h->sw, h->N, h->prow_begin, h->prow_end, h->At, h->Bt,
+                                 with_c ? h->GLP : nullptr, h->Ct, h->wpart, run_if)));
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
 }
+PrepKind eval_prep_kind(const mambo_csa* h) { return h->lean ? PREP_LEAN : (h->fast ? PREP_ABC : PREP_AB); }
 
+// Row epilogue of one pass of the hot kernel: F = E~ Lambda and Spart = A~^T E~ per panel, where E~ is assembled from the
+// hot kernel's pieces: E (two-GEMM kernel), C~ - Y (first single-GEMM formulation) or Y itself (lean path: F = Y Lambda,
+// Spart = A~^T Y; the closed-form terms are added by k_post_reduce).
 int enqueue_post_f(mambo_csa* h, double* F, bool with_S = false) {
-    if (h->use_panel) {
-        const bool split = h->NB >= 16;           // column-split panel kernels (NB_PANEL_DISPATCH): sum the pieces once, up front
-        if (split) {
-            const int ysplit = std::max(1, std::min(8, (2 * h->num_sms) / std::max(h->P, 1)));
-            panel::k_esum<<<dim3(h->P, ysplit), 256, 0, h->stream>>>(h->Epiece, h->piece_first, h->Np, h->ld, h->EtP, h->fast ? h->Ct : nullptr);
-            h->launches++;
-        }
-        NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT, CST><<<dim3(h->P, CST), panel::NTHR, panel::post_smem<NBT, CST>(), h->stream>>>(
-                                     h->Epiece, h->piece_first, h->fast ? h->Ct : nullptr, split ? h->EtP : nullptr, h->LamP, h->At, h->N,
-                                     h->row_begin, F, h->Spart, with_S ? 1 : 0)));
-        h->launches += 1;
-        CU(cudaGetLastError());
-        return MAMBO_OK;
+    const bool split = h->NB >= 16;           // column-split panel kernels (NB_PANEL_DISPATCH): sum the pieces once, up front
+    const double* ct = (h->fast && !h->lean) ? h->Ct : nullptr;
+    if (split) {
+        const int ysplit = std::max(1, std::min(8, (2 * h->num_sms) / std::max(h->P, 1)));
+        panel::k_esum<<<dim3(h->P, ysplit), 256, 0, h->stream>>>(h->Epiece, h->piece_first, h->Np, h->ld, h->EtP, ct);
+        h->launches++;
     }
-    if (h->postf32) {
-        NCH_DISPATCH((h->Np + 31) / 32, (small::k_post_f32<NCH><<<2 * h->P, 256, small::postf32_smem(h->N, h->Np), h->stream>>>(
-                                            h->Epiece, h->piece_first, h->Lam, h->N, h->Np, h->Et, F)));
-    } else
-        small::k_post_f<<<h->P, 256, small::postf_smem(h->Np), h->stream>>>(h->Epiece, h->piece_first, h->Lam, h->N, h->Np, h->Et, F);
+    NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT, CST><<<dim3(h->P, CST), panel::NTHR, panel::post_smem<NBT, CST>(), h->stream>>>(
+                                 h->Epiece, h->piece_first, ct, split ? h->EtP : nullptr, h->LamP, h->At, h->N,
+                                 h->row_begin, F, h->Spart, with_S ? 1 : 0)));
+    h->launches += 1;
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
+// The flagged exact-cost pass of the single-GEMM formulations: returns at once unless k_post_reduce raised d_flag.
+//   out == nullptr: the exact two-body cost replaces part[0] (sequential tail: shards, two-call evaluations)
+//   out != nullptr: k_cost_select writes the final cost of the evaluation to out[0] (lean tail, beside the derivative chain)
+int enqueue_exact_pass(mambo_csa* h, double* out) {
+    if (h->lean) TRY(enqueue_prep(h, PREP_AB, h->d_flag));     // the lean evaluation has not built B~
+    Params px = make_params(h, h->T1);
+    px.run_if = h->d_flag;
+    TRY((launch_fused<false, false>(h, px)));
+    small::k_cost_select<<<1, 32, 0, h->stream>>>(h->d_flag, h->cost_part, h->G, h->d_part, out, h->obc);
     h->launches++;
     CU(cudaGetLastError());
     return MAMBO_OK;
 }
 
-int enqueue_post_sr(mambo_csa* h) {
-    const int n = h->N, nn = n * n;
+// N x N reduction of the row epilogues into part = [cost, S, G]; seq_tail: the exact-cost pass follows at once (part[0] is
+// final when this returns); otherwise it is left to enqueue_finish, which runs it beside the derivative chain.
+bool split_tail(const mambo_csa* h) { return h->lean && h->flavour == MAMBO_CSA; }
+int enqueue_post_sr(mambo_csa* h, bool seq_tail) {
+    const int n = h->N;
     const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
-    const int nch = (n + 63) / 64;
-    if (!h->use_panel) {
-        small::k_post_s<<<dim3(h->P, nch * nch), 256, small::posts_smem(h->Np), h->stream>>>(h->Et, h->At, n, h->Np, h->ld, h->row_begin, h->Spart);
+    if (split_tail(h) && !seq_tail) {
+        // only G is needed by the derivative chain; S, the lambda gradient, the cost and the flag are produced beside it
+        small::k_gather_g<<<n, 1024, 0, h->stream>>>(h->F1, general ? h->F2 : nullptr, h->sw, h->U, n, h->Np, h->packed ? 1 : 0,
+                                                    general ? 1.0 : 2.0, h->row_begin, std::min(h->row_end, h->nR), h->aux, h->d_part);
         h->launches++;
+        CU(cudaGetLastError());
+        return MAMBO_OK;
     }
-    (void)nn;
     small::k_post_reduce<<<n, 1024, 0, h->stream>>>(h->cost_part, h->fast ? 0 : h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
-                                                                 h->sw, u_base(h), u_sptr(h), n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
-                                                                 h->row_begin, std::min(h->row_end, h->nR), h->d_part,
-                                                                 h->fast ? h->Lam : nullptr, h->ls_part, h->d_done, h->wpart,
-                                                                 h->P * h->prep_cs /* partial <B~,C~> per (panel, column split of k_prep_mma) */,
-                                                                 h->tnorm2, h->tau, h->d_flag);
+                                                   h->sw, h->U, h->d_zero, n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
+                                                   h->row_begin, std::min(h->row_end, h->nR), h->d_part,
+                                                   h->fast ? h->Lam : nullptr, h->ls_part, h->d_done, h->wpart,
+                                                   h->P * h->prep_cs /* partial <B~,C~> per (panel, column split of k_prep_mma) */,
+                                                   h->tnorm2, h->tau, h->d_flag, h->lean ? h->aux : nullptr);
     h->launches += 1;
-    if (h->fast) {
-        // when the expanded cost cancelled (flag), the exact pass below runs instead of returning at once
-        Params px = make_params(h, h->T1);
-        px.run_if = h->d_flag;
-        TRY((launch_fused<false, false>(h, px)));
-        small::k_cost_select<<<1, 32, 0, h->stream>>>(h->d_flag, h->cost_part, h->G, h->d_part);
-        h->launches++;
-    }
     CU(cudaGetLastError());
+    if (h->fast && seq_tail) TRY(enqueue_exact_pass(h, nullptr));
     return MAMBO_OK;
 }
 
 // stage B: one-body terms, adjoint Frechet derivative, gradient assembly.  part lives in h->d_part.
-int enqueue_finish(mambo_csa* h, const double* d_x, int s_host, double* d_out) {
-    const int n = h->N, nn = n * n;
+//   side_tail (single-GEMM formulations, one-call evaluations): the flagged exact-cost pass and the cost hand-over run on the
+//   handle's side stream beside the derivative chain instead of in front of it.
+int enqueue_finish(mambo_csa* h, const double* d_x, double* d_out, bool side_tail) {
+    const int n = h->N;
     if (h->flavour == MAMBO_CSA_SD) {
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, u_base(h), u_sptr(h), n, h->d_part, h->g1, h->Dh, h->DU, nullptr);
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->U, h->d_zero, n, h->d_part, h->g1, h->Dh, h->DU, nullptr, h->obc);
         h->launches++;
     }
-    if (h->use_chain) {
-        chain::DParams p = h->cd;
-        p.part = h->d_part; p.g1 = h->g1; p.n = n; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0;
-        p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar; p.status = h->d_status; p.dbg = h->d_dbg;
-        void* args[] = {&p};
-        TRY(launch_chain(h, true, args));
-        h->launches++;
-        return MAMBO_OK;
+    side_tail = side_tail && h->fast;
+    if (side_tail) {
+        CU(cudaEventRecord(h->ev_fork, h->stream));
+        CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+        cudaStream_t main_stream = h->stream;
+        h->stream = h->side_stream;
+        if (split_tail(h)) {
+            small::k_reduce_s<<<n, 1024, 0, h->stream>>>(h->Spart, h->P, h->Lam, h->aux, n, h->lam_off, h->d_part, d_out, h->ls_part, h->d_done,
+                                                        h->tnorm2, h->tau, h->d_flag);
+            h->launches++;
+        }
+        const int rc = enqueue_exact_pass(h, d_out);
+        h->stream = main_stream;
+        TRY(rc);
+        CU(cudaEventRecord(h->ev_join, h->side_stream));
     }
-    small::k_build_d<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->d_part, h->d_scale, n, h->dX);
+    chain::DParams p = h->cd;
+    p.part = h->d_part; p.g1 = h->g1; p.n = n; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0;
+    p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar; p.status = h->d_status; p.dbg = h->d_dbg;
+    p.write_cost = side_tail ? 0 : 1;
+    p.write_lambda = (side_tail && split_tail(h)) ? 0 : 1;
+    void* args[] = {&p};
+    TRY(launch_chain(h, true, args));
     h->launches++;
-    mm(h, h->dX2, nullptr, h->dX, h->X, h->X, h->dX, nullptr, 0);
-    small::k_dpow34<<<mm_grid(n), mm_block(), small::strip_bytes(n, 2, 4), h->stream>>>(h->X, h->X2, h->dX, h->dX2, h->dX4, h->dP0, h->dP1,
-                                                                                      h->dP2, h->dQ3, n);
-    h->launches++;
-    mm(h, h->dQ2, h->dP2, h->dX4, h->Q3, h->X4, h->dQ3, nullptr, 0);
-    mm(h, h->dQ1, h->dP1, h->dX4, h->Q2, h->X4, h->dQ2, nullptr, 0);
-    mm(h, h->dR, h->dP0, h->dX4, h->Q1, h->X4, h->dQ1, nullptr, 0);
-    const int nsq = s_host >= 0 ? std::min(s_host, small::SMAX) : small::SMAX;
-    for (int i = 0; i < nsq; ++i)
-        mm(h, h->dR + (size_t)(i + 1) * nn, nullptr, h->dR + (size_t)i * nn, h->R + (size_t)i * nn, h->R + (size_t)i * nn,
-           h->dR + (size_t)i * nn, h->d_s, i);
-    small::k_assemble<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->d_part, h->g1, h->dR, h->d_s, n, h->flavour == MAMBO_CSA_SD ? 1 : 0, d_out);
-    h->launches++;
-    CU(cudaGetLastError());
+    if (side_tail) CU(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
     return MAMBO_OK;
 }
 
@@ -631,20 +600,22 @@ GraphSeg& seg_for(std::vector<GraphSeg>& v, int s_host) {  // index 0: device-de
     return v[idx];
 }
 
-// stage A: everything up to the per-shard partial vector [cost, S, G] (x must already be in h->d_x)
-int enqueue_partial(mambo_csa* h, int s_host, bool need_grad) {
+// stage A: everything up to the per-shard partial vector [cost, S, G] (x must already be in h->d_x).
+//   one_call: the finish half follows in the same call (eval_device / host closures), so the flagged exact-cost pass may be
+//   left to it (it then runs beside the derivative chain); otherwise part[0] is final when this segment ends.
+int enqueue_partial(mambo_csa* h, int s_host, bool need_grad, bool one_call) {
     if (need_grad) TRY(seg_mark(h));
-    TRY(run_segment(h, seg_for(h->g_pre, s_host), [&]() -> int {
-        TRY(enqueue_unitary(h, h->d_x, s_host));
-        return enqueue_prep(h);
-    }));
-    if (need_grad) TRY(seg_mark(h));
-    Params p = make_params(h, h->T1);
     if (!need_grad) {
+        // cost only: reconstruction + residual norm with the two-GEMM kernel's first half (needs B~)
+        TRY(run_segment(h, seg_for(h->g_pre_b, s_host), [&]() -> int {
+            TRY(enqueue_unitary(h, h->d_x, s_host));
+            return enqueue_prep(h, PREP_AB);
+        }));
+        Params p = make_params(h, h->T1);
         TRY((launch_fused<false, false>(h, p)));
         return run_segment(h, h->g_costonly, [&]() -> int {
             if (h->flavour == MAMBO_CSA_SD) {
-                small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, u_base(h), u_sptr(h), h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
+                small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->U, h->d_zero, h->N, nullptr, nullptr, h->Dh, h->DU, nullptr);
                 small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->shard == 0 ? h->N * h->N : 0, h->cost_part, h->G, h->d_part);
                 h->launches += 2;
             } else {
@@ -655,43 +626,52 @@ int enqueue_partial(mambo_csa* h, int s_host, bool need_grad) {
             return MAMBO_OK;
         });
     }
+    TRY(run_segment(h, seg_for(h->g_pre, s_host), [&]() -> int {
+        TRY(enqueue_unitary(h, h->d_x, s_host));
+        return enqueue_prep(h, eval_prep_kind(h));
+    }));
+    TRY(seg_mark(h));
+    const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
+    GraphSeg& post = one_call ? h->g_post : h->g_post_seq;
     if (h->fast) {
-        // single-GEMM formulation: Y = T~ A~ (k_ty), E = C~ - Y in k_esum, cost in k_cost_fast (enqueue_post_sr)
+        // single-GEMM formulations: Y = T~ A~ (k_ty); E~ = C~ - Y or, lean, Y itself goes through the row epilogue
         TRY(launch_ty(h, make_yparams(h, h->T1)));
-        if (h->mode == (int)MAMBO_SYM_GENERAL) {
+        if (general) {
             TRY(run_segment(h, h->g_mid, [&]() -> int { return enqueue_post_f(h, h->F1); }));
             TRY(launch_ty(h, make_yparams(h, h->T2)));
-            return run_segment(h, h->g_post, [&]() -> int {
+            return run_segment(h, post, [&]() -> int {
                 TRY(enqueue_post_f(h, h->F2, true));
-                return enqueue_post_sr(h);
+                return enqueue_post_sr(h, !one_call);
             });
         }
-        return run_segment(h, h->g_post, [&]() -> int {
+        return run_segment(h, post, [&]() -> int {
             TRY(enqueue_post_f(h, h->F1, true));
-            return enqueue_post_sr(h);
+            return enqueue_post_sr(h, !one_call);
         });
     }
+    Params p = make_params(h, h->T1);
     TRY((launch_fused<true, false>(h, p)));
-    if (h->mode == (int)MAMBO_SYM_GENERAL) {
+    if (general) {
         // second pass over the transposed residual: E = D A (pass 1 gave E' = D^T A); S uses E only (gradient.jl:22-26)
         TRY(run_segment(h, h->g_mid, [&]() -> int { return enqueue_post_f(h, h->F1); }));
         Params p2 = make_params(h, h->T2);
         p2.cost_part = h->cost_part + h->G;  // discarded
         TRY((launch_fused<true, false>(h, p2)));
-        return run_segment(h, h->g_post, [&]() -> int {
+        return run_segment(h, post, [&]() -> int {
             TRY(enqueue_post_f(h, h->F2, true));
-            return enqueue_post_sr(h);
+            return enqueue_post_sr(h, !one_call);
         });
     }
-    return run_segment(h, h->g_post, [&]() -> int {
+    return run_segment(h, post, [&]() -> int {
         TRY(enqueue_post_f(h, h->F1, true));
-        return enqueue_post_sr(h);
+        return enqueue_post_sr(h, !one_call);
     });
 }
 
-int enqueue_finish_seg(mambo_csa* h, int s_host) {
+int enqueue_finish_seg(mambo_csa* h, int s_host, bool one_call) {
     TRY(seg_mark(h));
-    TRY(run_segment(h, seg_for(h->g_fin, s_host), [&]() -> int { return enqueue_finish(h, h->d_x, s_host, h->d_out); }));
+    TRY(run_segment(h, seg_for(one_call ? h->g_fin : h->g_fin_seq, s_host),
+                    [&]() -> int { return enqueue_finish(h, h->d_x, h->d_out, one_call); }));
     return seg_mark(h);
 }
 
@@ -729,8 +709,8 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad, bool nowait = false
         // addresses are handle-owned and fixed; the hot kernel needs no event bracket when profiling is off)
         TRY(run_segment(h, seg_for(h->g_host, s_host), [&]() -> int {
             CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
-            TRY(enqueue_partial(h, s_host, true));
-            TRY(enqueue_finish_seg(h, s_host));
+            TRY(enqueue_partial(h, s_host, true, true));
+            TRY(enqueue_finish_seg(h, s_host, true));
             CU(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             return MAMBO_OK;
@@ -741,10 +721,10 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad, bool nowait = false
         return check_status(h);
     }
     CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
-    int rc = enqueue_partial(h, s_host, need_grad);
+    int rc = enqueue_partial(h, s_host, need_grad, true);
     if (rc) return rc;
     if (need_grad) {
-        rc = enqueue_finish_seg(h, s_host);
+        rc = enqueue_finish_seg(h, s_host, true);
         if (rc) return rc;
         CU(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToHost, h->stream));
     } else {
@@ -941,19 +921,9 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->S = S;
     h->smem = smem_bytes(h->ld, S);
 
-    // expm chain storage
     const size_t nn = (size_t)n * n;
-    const size_t nm = 10 + (small::SMAX + 1) + 9 + (small::SMAX + 1) + 4;
-    TRY(dalloc(&h->mats, nm * nn));
-    double* m = h->mats;
-    auto take = [&](size_t k) { double* r = m; m += k * nn; return r; };
-    h->X = take(1); h->X2 = take(1); h->X3 = take(1); h->X4 = take(1);
-    h->P0 = take(1); h->P1 = take(1); h->P2 = take(1); h->Q3 = take(1); h->Q2 = take(1); h->Q1 = take(1);
-    h->R = take(small::SMAX + 1);
-    h->dX = take(1); h->dX2 = take(1); h->dX4 = take(1);
-    h->dP0 = take(1); h->dP1 = take(1); h->dP2 = take(1); h->dQ3 = take(1); h->dQ2 = take(1); h->dQ1 = take(1);
-    h->dR = take(small::SMAX + 1);
-    h->Lam = take(1); h->Dh = take(1); h->DU = take(1); h->hfrag = take(1);
+    TRY(dalloc(&h->mats, 4 * nn));
+    h->Lam = h->mats; h->Dh = h->mats + nn; h->DU = h->mats + 2 * nn; h->hfrag = h->mats + 3 * nn;
     TRY(dalloc(&h->U, nn));
     TRY(dalloc(&h->d_zero, 1));
     {
@@ -989,12 +959,6 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         }
         const size_t ms = chain::mat_stride(n, h->chain_ct);
         const size_t ncm = 11 + 11 + 4 * (size_t)(chain::SMAXC + 1);
-        h->chain_nmats = (int)ncm;
-        // Data-driven variant (chain::SYNC_DATA): correct, but measured SLOWER than barrier + TMA reload at N = 100 (finish
-        // 62 vs 48 us, pre 84 vs 76 us): copying the four 12.8 KB strips with ordinary loads costs ~2800 cycles against
-        // ~1250 for the TMA engine, which eats the ~2300 cycles saved on the barrier.  Kept opt-in for further work
-        // (poll only the strips produced in the previous step, TMA for the rest).
-        h->chain_data = std::getenv("MAMBO_CHAIN_DATA") != nullptr;
         TRY(dalloc(&h->cmats, ncm * ms));
         double* cm = h->cmats;
         auto ctake = [&](size_t k) { double* r = cm; cm += k * ms; return r; };
@@ -1009,6 +973,10 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         d.dR = ctake(chain::SMAXC + 1); d.dRt = ctake(chain::SMAXC + 1);
     }
     TRY(dalloc(&h->g1, (size_t)n));
+    TRY(dalloc(&h->obc, 1));
+    CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     TRY(dalloc(&h->d_s, 1));
     TRY(dalloc(&h->d_bar, 4));                  // [0] barrier counter, [1] exit counter, [2] scratch target of release operations
     if (std::getenv("MAMBO_CHAIN_DEBUG")) TRY(dalloc(&h->d_dbg, 6 * 16));
@@ -1026,16 +994,17 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     h->dephase = 0;                             // measured: no gain from offsetting the column groups (kept as a knob)
     if (const char* e = std::getenv("MAMBO_DEPHASE")) h->dephase = std::atoi(e);
     if (const char* e = std::getenv("MAMBO_LOOKAHEAD")) h->lookahead = std::atoi(e);
-    h->use_chain = (std::getenv("MAMBO_LEGACY_CHAIN") == nullptr);
-    h->use_panel = false;
-    if (std::getenv("MAMBO_NO_PANEL") == nullptr) {
-        size_t need_post = 0;
+    {
+        size_t need_post = 0, need_prep = 0;
         NB_PANEL_DISPATCH(h->NB, need_post = (panel::post_smem<NBT, CST>()));
-        h->use_panel = need_post <= prop.sharedMemPerBlockOptin;
+        NB_PANEL_DISPATCH(h->NB, need_prep = (panel::prep_smem<NBT, CSP>()));
+        if (std::max(need_post, need_prep) > prop.sharedMemPerBlockOptin || chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin)
+            return fail(MAMBO_EINVAL, "N too large for the shared-memory budget of the panel / chain kernels");
     }
-    if (chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin) h->use_chain = false;
-    h->use_panel = h->use_panel && h->use_chain;          // Lambda's padded copy is written by k_chain_u
-    h->fast = h->use_panel && std::getenv("MAMBO_TWO_GEMM") == nullptr;
+    h->fast = std::getenv("MAMBO_TWO_GEMM") == nullptr;
+    // lean path: unsharded handles only (a shard needs its own rows' |W~|^2, which has no N x N closed form); MAMBO_NO_LEAN=1
+    // keeps the first single-GEMM formulation (Gram kernel + B~/C~ panel GEMMs) as the A/B reference of the parity tests
+    h->lean = h->fast && h->nshards == 1 && std::getenv("MAMBO_NO_LEAN") == nullptr;
     if (const char* e = std::getenv("MAMBO_TAU")) h->tau = std::atof(e);
     if (std::getenv("MAMBO_TY_DEBUG") && h->fast) TRY(dalloc(&h->ty_dbg, (size_t)16 * 64 * 4 + 160 * 4));
     h->ty_dephase = 256 * h->NB;                // half a step (16 NB DMMAs of 16 cycles per warp and step): measured 1 % faster than 0
@@ -1044,7 +1013,8 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     if (h->fast) {
         TRY(dalloc(&h->Ct, (size_t)h->P * ROWS * h->ld));
         TRY(dalloc(&h->GLP, (size_t)h->Np * h->ld));
-        TRY(dalloc(&h->wpart, (size_t)h->P * 4));
+        TRY(dalloc(&h->wpart, (size_t)h->P * 8));
+        TRY(dalloc(&h->aux, (size_t)3 * n + 1));
         TRY(dalloc(&h->d_flag, 1));
         TRY(dalloc(&h->ls_part, (size_t)n));
         TRY(dalloc(&h->d_done, 1));
@@ -1057,18 +1027,16 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         cfgy.P = -1;
         TRY(launch_ty(h, cfgy));
     }
-    if (h->use_panel) {
+    {
         TRY(dalloc(&h->LamP, (size_t)h->Np * h->ld));
         TRY(dalloc(&h->EtP, (size_t)h->P * ROWS * h->ld));
         NB_PANEL_DISPATCH(h->NB, CU(raise_smem(panel::k_prep_mma<NBT, CSP>, (int)(panel::prep_smem<NBT, CSP>()))));
-        h->prep_cs = h->NB >= 16 ? 4 : 1;                          // == CSP of NB_PANEL_DISPATCH
+        h->prep_cs = panel_cs(h->NB);
         NB_PANEL_DISPATCH(h->NB, CU(raise_smem(panel::k_post_mma<NBT, CST>, (int)(panel::post_smem<NBT, CST>()))));
     }
-    if (chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin) h->use_chain = false;
-    if (h->use_chain) {
+    {
         const int sm_chain = (int)chain::smem_bytes(n, h->chain_ct);
         for (const void* f : {(const void*)chain::k_chain_u<16, chain::SYNC_GRID>, (const void*)chain::k_chain_d<16, chain::SYNC_GRID>,
-                              (const void*)chain::k_chain_u<16, chain::SYNC_DATA>, (const void*)chain::k_chain_d<16, chain::SYNC_DATA>,
                               (const void*)chain::k_chain_u<16, chain::SYNC_CLUSTER>, (const void*)chain::k_chain_d<16, chain::SYNC_CLUSTER>})
             CU(raise_smem(f, sm_chain));
         if (h->chain_cluster)
@@ -1083,21 +1051,6 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         TRY((launch_fused<true, false>(h, cfg)));
         TRY((launch_fused<false, false>(h, cfg)));
         TRY((launch_fused<false, true>(h, cfg)));
-        const size_t lim = prop.sharedMemPerBlockOptin;
-        const size_t need[] = {nn * 8, small::strip_bytes(n, 2, 4), small::prep_smem(n, h->Np), small::postf_smem(h->Np),
-                               small::posts_smem(h->Np)};
-        for (size_t b : need)
-            if (b > lim) return fail(MAMBO_EINVAL, "N too large for the shared-memory resident small kernels");
-        CU(raise_smem(small::k_build, (int)(nn * 8)));
-        CU(raise_smem(small::k_mm, (int)small::strip_bytes(n, 2, 2)));
-        CU(raise_smem(small::k_pow34, (int)small::strip_bytes(n, 1, 2)));
-        CU(raise_smem(small::k_dpow34, (int)small::strip_bytes(n, 2, 4)));
-        NCH_DISPATCH((h->Np + 31) / 32, CU(raise_smem(small::k_prep<NCH>, (int)small::prep_smem(n, h->Np))));
-        CU(raise_smem(small::k_post_f, (int)small::postf_smem(h->Np)));
-        h->postf32 = small::postf32_smem(n, h->Np) <= 113 * 1024;   // two CTAs per SM
-        if (h->postf32)
-            NCH_DISPATCH((h->Np + 31) / 32, CU(raise_smem(small::k_post_f32<NCH>, (int)small::postf32_smem(n, h->Np))));
-        CU(raise_smem(small::k_post_s, (int)small::posts_smem(h->Np)));
     }
     if (!parent) {
         // |T~|^2 of the local rows (zero padding contributes nothing); kept current by subtract_impl
@@ -1111,7 +1064,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
 
 int subtract_impl(mambo_csa* h, const double* d_x, int s_host) {
     TRY(enqueue_unitary(h, d_x, s_host));
-    TRY(enqueue_prep(h));
+    TRY(enqueue_prep(h, PREP_AB));
     Params p = make_params(h, h->T1);
     TRY((launch_fused<false, true>(h, p)));
     if (h->mode == (int)MAMBO_SYM_GENERAL) {
@@ -1123,7 +1076,7 @@ int subtract_impl(mambo_csa* h, const double* d_x, int s_host) {
     small::k_sumsq_add<<<1, 256, 0, h->stream>>>(nullptr, 0, h->cost_part, h->G, h->tnorm2);   // |T~_new|^2 (two-body part)
     h->launches++;
     if (h->flavour == MAMBO_CSA_SD) {
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, u_base(h), u_sptr(h), n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(d_x, h->hT, h->U, h->d_zero, n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
         small::k_obt_sub<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->hT, h->hfrag, n);
         // sharded handles return shard-local costs that the caller sums: the (replicated) one-body term counts once
         small::k_sumsq_add<<<1, 256, 0, h->stream>>>(h->Dh, h->shard == 0 ? nn : 0, h->cost_part, h->G, h->d_part);
@@ -1237,10 +1190,11 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
-    for (auto* v : {&h->g_pre, &h->g_fin, &h->g_host})
+    if (h->side_stream) cudaStreamSynchronize(h->side_stream);
+    for (auto* v : {&h->g_pre, &h->g_fin, &h->g_host, &h->g_pre_b, &h->g_fin_seq})
         for (GraphSeg& g : *v)
             if (g.exec) cudaGraphExecDestroy(g.exec);
-    for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_costonly})
+    for (GraphSeg* g : {&h->g_mid, &h->g_post, &h->g_post_seq, &h->g_costonly})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     if (!h->sh || h->sh->refs.fetch_sub(1) == 1) {
         void* shared[] = {h->T1, h->T2, h->hT, h->pa, h->pq, h->sw, h->tnorm2};
@@ -1248,7 +1202,7 @@ void mambo_csa_destroy(mambo_csa* h) {
             if (b) cudaFree(b);
         delete h->sh;
     }
-    void* bufs[] = {h->ty_dbg, h->Ct, h->GLP, h->wpart, h->d_flag, h->ls_part, h->d_done, h->At, h->Bt, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
+    void* bufs[] = {h->aux, h->obc, h->ty_dbg, h->Ct, h->GLP, h->wpart, h->d_flag, h->ls_part, h->d_done, h->At, h->Bt, h->Epiece, h->Et, h->F1, h->F2, h->Spart, h->cost_part,
                     h->eig_ws, h->opt_ws, h->visit_start, h->piece_first, h->mats, h->cmats, h->LamP, h->EtP, h->U, h->d_zero, h->g1, h->d_s, h->d_bar, h->d_dbg, h->d_scale, h->d_status, h->d_x, h->d_out, h->d_part};
     for (void* b : bufs)
         if (b) cudaFree(b);
@@ -1262,6 +1216,9 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (h->peer_done) cudaFree(h->peer_done);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->seg_pool) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
 }
@@ -1420,7 +1377,7 @@ int mambo_csa_eval_partial_device(mambo_csa* h, const double* d_x, double* d_par
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
     if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
-    TRY(enqueue_partial(h, -1, true));
+    TRY(enqueue_partial(h, -1, true, false));
     CU(cudaMemcpyAsync(d_partial, h->d_part, sizeof(double) * (1 + 2 * (size_t)h->N * h->N), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval = (int)(h->launches - l0);
     h->memo_valid = false;
@@ -1432,7 +1389,7 @@ int mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double* 
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
     CU(cudaMemcpyAsync(h->d_part, d_partial, sizeof(double) * (1 + 2 * (size_t)h->N * h->N), cudaMemcpyDeviceToDevice, h->stream));
-    TRY(enqueue_finish_seg(h, -1));
+    TRY(enqueue_finish_seg(h, -1, false));
     if (d_out != h->d_out) CU(cudaMemcpyAsync(d_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval += (int)(h->launches - l0);
     return MAMBO_OK;
@@ -1444,8 +1401,8 @@ int mambo_csa_eval_device(mambo_csa* h, const double* d_x, double* d_out) {
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
     if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
-    TRY(enqueue_partial(h, -1, true));
-    TRY(enqueue_finish_seg(h, -1));
+    TRY(enqueue_partial(h, -1, true, true));
+    TRY(enqueue_finish_seg(h, -1, true));
     if (d_out != h->d_out) CU(cudaMemcpyAsync(d_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval = (int)(h->launches - l0);
     h->memo_valid = false;
@@ -1457,7 +1414,7 @@ int mambo_csa_cost_device(mambo_csa* h, const double* d_x, double* d_cost) {
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "cost_device needs an unsharded handle");
     CU(cudaSetDevice(h->device));
     if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
-    TRY(enqueue_partial(h, -1, false));
+    TRY(enqueue_partial(h, -1, false, false));
     CU(cudaMemcpyAsync(d_cost, h->d_part, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
     h->memo_valid = false;
     return MAMBO_OK;
@@ -1531,7 +1488,7 @@ int mambo_csa_eval_sharded_push_device(mambo_csa* h, const double* d_x) {
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
     if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
-    TRY(enqueue_partial(h, -1, true));
+    TRY(enqueue_partial(h, -1, true, false));
     h->peer_epoch++;
     const int plen = 1 + 2 * h->N * h->N;
     small::k_peer_push<<<std::min(64, (plen + 255) / 256), 256, 0, h->stream>>>(h->d_part, plen, h->plen_pad, h->peer_tab, h->nshards, h->shard,
@@ -1552,7 +1509,7 @@ int mambo_csa_eval_sharded_finish_device(mambo_csa* h, double* d_out) {
     small::k_peer_sum<<<std::min(64, (plen + 255) / 256), 256, 0, h->stream>>>(h->peer_recv, h->peer_flags, plen, h->plen_pad, h->nshards,
                                                                              h->peer_epoch, h->d_part, h->d_status);
     h->launches++;
-    TRY(enqueue_finish_seg(h, -1));
+    TRY(enqueue_finish_seg(h, -1, false));
     if (d_out != h->d_out) CU(cudaMemcpyAsync(d_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval += (int)(h->launches - l0);
     return MAMBO_OK;
@@ -1811,7 +1768,7 @@ int mambo_csa_residual_cost(mambo_csa* h, double* cost) {
     // L2_partial_cost(F_rem): evaluate the residual against the zero fragment (lambda = 0 => W = 0), theta = 0
     CU(cudaMemsetAsync(h->d_x, 0, sizeof(double) * h->L, h->stream));
     h->memo_valid = false;
-    TRY(enqueue_partial(h, 0, false));
+    TRY(enqueue_partial(h, 0, false, false));
     CU(cudaMemcpyAsync(h->h_out, h->d_part, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     *cost = h->h_out[0];
@@ -1850,7 +1807,7 @@ int mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double
     std::memcpy(h->h_x, x, sizeof(double) * h->L);
     CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
     TRY(enqueue_unitary(h, h->d_x, s_host));
-    TRY(enqueue_prep(h));
+    TRY(enqueue_prep(h, PREP_AB));
     h->memo_valid = false;
     if (tbt_out) {
         const size_t n4 = (size_t)nn * nn;
@@ -1864,7 +1821,7 @@ int mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double
     }
     if (obt_out && h->flavour == MAMBO_CSA_SD) {
         // h = U diag(l1) U^T: reuse the one-body kernel against the stored target, keep h in hfrag
-        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, u_base(h), u_sptr(h), n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
+        small::k_sd_onebody<<<1, 1024, 0, h->stream>>>(h->d_x, h->hT, h->U, h->d_zero, n, nullptr, nullptr, h->Dh, h->DU, h->hfrag);
         small::k_obt_colmajor<<<(nn + 127) / 128, 128, 0, h->stream>>>(h->hfrag, n, h->Dh);
         CU(cudaMemcpyAsync(obt_out, h->Dh, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));

@@ -10,500 +10,6 @@ namespace small {
 constexpr int SMAX = 14;            // maximum number of squarings (||K||_1 <= 2^14)
 constexpr int TS = 16;              // tile of the small N x N GEMMs
 
-// Taylor coefficients 1/k!, k = 0..16
-__constant__ double c_tay[17] = {1.0,
-                                 1.0,
-                                 0.5,
-                                 1.0 / 6,
-                                 1.0 / 24,
-                                 1.0 / 120,
-                                 1.0 / 720,
-                                 1.0 / 5040,
-                                 1.0 / 40320,
-                                 1.0 / 362880,
-                                 1.0 / 3628800,
-                                 1.0 / 39916800,
-                                 1.0 / 479001600,
-                                 1.0 / 6227020800.0,
-                                 1.0 / 87178291200.0,
-                                 1.0 / 1307674368000.0,
-                                 1.0 / 20922789888000.0};
-
-// ------------------------------------------------------------------------------------------------------
-// async global -> shared copies (LDGSTS): every load of a strip is in flight at once, no register staging
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// ------------------------------------------------------------------------------------------------------
-// k_build: x -> Lambda (full symmetric), X = K / 2^s, s  (unitaries.jl:31-44, gradient.jl:43-55)
-//   one CTA, K staged in shared memory; the 1-norm of K picks s so that ||X||_1 <= 1 (Taylor degree 16 is
-//   then exact to ~3e-15).  s_override >= 0: the host already knows s (x came through the host API).
-// ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_build(const double* __restrict__ x, int n, int lam_off, double* __restrict__ X,
-                                                double* __restrict__ Lam, int* __restrict__ s_out, double* __restrict__ scale_out,
-                                                int* __restrict__ status, int s_override) {
-    extern __shared__ double Ks[];  // n*n
-    __shared__ double red[32];
-    __shared__ double s_scale;
-    const int cL = n * (n + 1) / 2;
-    const double* lam = x + lam_off;
-    const double* th = x + lam_off + cL;
-    const int tid = threadIdx.x, nt = blockDim.x;
-    for (int idx = tid; idx < n * n; idx += nt) {
-        const int i = idx / n, j = idx % n;
-        double k = 0.0;
-        if (i < j) k = th[i * n - i * (i + 1) / 2 + (j - i - 1)];
-        else if (i > j) k = -th[j * n - j * (j + 1) / 2 + (i - j - 1)];
-        Ks[idx] = k;
-        const int a = i > j ? i : j, b = i > j ? j : i;
-        Lam[idx] = lam[a * (a + 1) / 2 + b];
-    }
-    __syncthreads();
-    double mx = 0.0;
-    for (int j = tid; j < n; j += nt) {   // K antisymmetric: column sums == row sums; rows are contiguous
-        double s = 0.0;
-        for (int i = 0; i < n; ++i) s += fabs(Ks[j * n + i]);
-        if (!(s == s)) s = INFINITY;      // fmax would drop a NaN: force the out-of-range path
-        mx = fmax(mx, s);
-    }
-    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    __syncthreads();
-    if (tid == 0) {
-        double m = 0.0;
-        for (int w = 0; w < (nt + 31) / 32; ++w) m = fmax(m, red[w]);
-        int s = 0;
-        if (m > 1.0) s = (int)ceil(log2(m));
-        if (s_override >= 0) s = s_override;
-        if (!(m == m) || isinf(m) || s > SMAX || s < 0) {  // NaN / Inf or too large
-            *status = 1;
-            s = SMAX;
-        }
-        *s_out = s;
-        s_scale = ldexp(1.0, -s);
-        *scale_out = s_scale;
-    }
-    __syncthreads();
-    const double sc = s_scale;
-    for (int idx = tid; idx < n * n; idx += nt) X[idx] = Ks[idx] * sc;
-}
-
-// ------------------------------------------------------------------------------------------------------
-// small N x N GEMM building blocks.  One CTA = one 16x16 output tile; the full 16 x n strip of every A
-// operand and the n x 16 strip of every B operand are brought into shared memory with one wave of async
-// copies (one L2 latency per launch instead of one per k-chunk), then reduced from shared memory.
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int strip_lda(int n) { return n | 1; }
-__device__ __forceinline__ void load_a_strip(double* As, const double* __restrict__ A, int n) {
-    const int lda = strip_lda(n), i0 = blockIdx.y * TS, tid = threadIdx.y * TS + threadIdx.x;
-    for (int idx = tid; idx < TS * n; idx += TS * TS) {
-        const int r = idx / n, c = idx % n;
-        if (i0 + r < n) cp_async8(As + r * lda + c, A + (size_t)(i0 + r) * n + c);
-        else As[r * lda + c] = 0.0;
-    }
-}
-__device__ __forceinline__ void load_b_strip(double* Bs, const double* __restrict__ B, int n) {
-    const int j0 = blockIdx.x * TS, tid = threadIdx.y * TS + threadIdx.x;
-    for (int idx = tid; idx < TS * n; idx += TS * TS) {
-        const int k = idx / TS, c = idx % TS;
-        if (j0 + c < n) cp_async8(Bs + idx, B + (size_t)k * n + j0 + c);
-        else Bs[idx] = 0.0;
-    }
-}
-__device__ __forceinline__ double strip_dot(const double* As, const double* Bs, int n) {
-    const double* a = As + threadIdx.y * strip_lda(n);
-    const double* b = Bs + threadIdx.x;
-    double acc0 = 0.0, acc1 = 0.0;
-    int k = 0;
-    for (; k + 1 < n; k += 2) {
-        acc0 = fma(a[k], b[k * TS], acc0);
-        acc1 = fma(a[k + 1], b[(k + 1) * TS], acc1);
-    }
-    if (k < n) acc0 = fma(a[k], b[k * TS], acc0);
-    return acc0 + acc1;
-}
-inline size_t strip_bytes(int n, int na, int nb) { return ((size_t)na * TS * (n | 1) + (size_t)nb * TS * n) * sizeof(double); }
-
-// C = Cin + A1.B1 + A2.B2   (A2 == nullptr skips the second product).  step >= *s_ptr => no-op (squaring
-// chain past s).
-__global__ void __launch_bounds__(TS * TS) k_mm(double* __restrict__ C, const double* __restrict__ Cin, const double* __restrict__ A1,
-                                              const double* __restrict__ B1, const double* __restrict__ A2,
-                                              const double* __restrict__ B2, int n, const int* __restrict__ s_ptr, int step) {
-    if (s_ptr && step >= *s_ptr) return;
-    extern __shared__ double sm[];
-    const int sa = TS * strip_lda(n), sb = TS * n;
-    double* As1 = sm;
-    double* Bs1 = As1 + sa;
-    double* As2 = Bs1 + sb;
-    double* Bs2 = As2 + sa;
-    load_a_strip(As1, A1, n);
-    load_b_strip(Bs1, B1, n);
-    if (A2) {
-        load_a_strip(As2, A2, n);
-        load_b_strip(Bs2, B2, n);
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    double acc = strip_dot(As1, Bs1, n);
-    if (A2) acc += strip_dot(As2, Bs2, n);
-    const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
-    if (i < n && j < n) C[i * n + j] = acc + (Cin ? Cin[i * n + j] : 0.0);
-}
-
-// X3 = X2.X, X4 = X2.X2, then P0,P1,P2 (degree-3 pieces) and Q3 = P3 + c16 X4.
-__global__ void __launch_bounds__(TS * TS) k_pow34(const double* __restrict__ X, const double* __restrict__ X2, double* __restrict__ X3,
-                                                 double* __restrict__ X4, double* __restrict__ P0, double* __restrict__ P1,
-                                                 double* __restrict__ P2, double* __restrict__ Q3, int n) {
-    extern __shared__ double sm[];
-    const int sa = TS * strip_lda(n), sb = TS * n;
-    double* A2s = sm;            // rows of X2
-    double* B1s = A2s + sa;      // cols of X
-    double* B2s = B1s + sb;      // cols of X2
-    load_a_strip(A2s, X2, n);
-    load_b_strip(B1s, X, n);
-    load_b_strip(B2s, X2, n);
-    cp_async_wait_all();
-    __syncthreads();
-    const double x3 = strip_dot(A2s, B1s, n), x4 = strip_dot(A2s, B2s, n);
-    const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
-    if (i < n && j < n) {
-        const int o = i * n + j;
-        const double id = (i == j) ? 1.0 : 0.0, x1 = X[o], x2 = X2[o];
-        X3[o] = x3;
-        X4[o] = x4;
-        P0[o] = c_tay[0] * id + c_tay[1] * x1 + c_tay[2] * x2 + c_tay[3] * x3;
-        P1[o] = c_tay[4] * id + c_tay[5] * x1 + c_tay[6] * x2 + c_tay[7] * x3;
-        P2[o] = c_tay[8] * id + c_tay[9] * x1 + c_tay[10] * x2 + c_tay[11] * x3;
-        Q3[o] = c_tay[12] * id + c_tay[13] * x1 + c_tay[14] * x2 + c_tay[15] * x3 + c_tay[16] * x4;
-    }
-}
-
-// dX3 = dX2.X + X2.dX, dX4 = dX2.X2 + X2.dX2, then dP0..dP2, dQ3.
-__global__ void __launch_bounds__(TS * TS) k_dpow34(const double* __restrict__ X, const double* __restrict__ X2,
-                                                  const double* __restrict__ dX, const double* __restrict__ dX2,
-                                                  double* __restrict__ dX4, double* __restrict__ dP0, double* __restrict__ dP1,
-                                                  double* __restrict__ dP2, double* __restrict__ dQ3, int n) {
-    extern __shared__ double sm[];
-    const int sa = TS * strip_lda(n), sb = TS * n;
-    double* AdX2 = sm;
-    double* AX2 = AdX2 + sa;
-    double* BX = AX2 + sa;
-    double* BX2 = BX + sb;
-    double* BdX = BX2 + sb;
-    double* BdX2 = BdX + sb;
-    load_a_strip(AdX2, dX2, n);
-    load_a_strip(AX2, X2, n);
-    load_b_strip(BX, X, n);
-    load_b_strip(BX2, X2, n);
-    load_b_strip(BdX, dX, n);
-    load_b_strip(BdX2, dX2, n);
-    cp_async_wait_all();
-    __syncthreads();
-    const double d3 = strip_dot(AdX2, BX, n) + strip_dot(AX2, BdX, n);
-    const double d4 = strip_dot(AdX2, BX2, n) + strip_dot(AX2, BdX2, n);
-    const int i = blockIdx.y * TS + threadIdx.y, j = blockIdx.x * TS + threadIdx.x;
-    if (i < n && j < n) {
-        const int o = i * n + j;
-        const double d1 = dX[o], d2 = dX2[o];
-        dX4[o] = d4;
-        dP0[o] = c_tay[1] * d1 + c_tay[2] * d2 + c_tay[3] * d3;
-        dP1[o] = c_tay[5] * d1 + c_tay[6] * d2 + c_tay[7] * d3;
-        dP2[o] = c_tay[9] * d1 + c_tay[10] * d2 + c_tay[11] * d3;
-        dQ3[o] = c_tay[13] * d1 + c_tay[14] * d2 + c_tay[15] * d3 + c_tay[16] * d4;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// rows x Lambda core shared by k_prep (B~ = A~ Lambda) and k_post_f32 (F = E~ Lambda):
-//   this warp's 4 rows (shared memory, pitch Np) times Lambda (shared memory [n][Np]) -> acc[4][NCH], column
-//   32*c + lane.  NCH = ceil(Np/32) is a template parameter so the loop body is branch-free.
-// ------------------------------------------------------------------------------------------------------
-constexpr int CMAX = 6;   // column chunks of 32 covering Np <= 192
-template <int NCH>
-__device__ __forceinline__ void rows4_times_lambda(const double* __restrict__ rows, const double* __restrict__ sL, int n, int Np,
-                                                   double (&acc)[4][NCH]) {
-    const int lane = threadIdx.x & 31;
-    const bool last_ok = (32 * (NCH - 1) + lane) < Np;
-    const double* lrow = sL + lane;
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) acc[i][c] = 0.0;
-#pragma unroll 4
-    for (int l = 0; l < n; ++l) {
-        const double a0 = rows[l], a1 = rows[Np + l], a2 = rows[2 * Np + l], a3 = rows[3 * Np + l];
-        double lm[NCH];
-#pragma unroll
-        for (int c = 0; c < NCH - 1; ++c) lm[c] = lrow[(size_t)l * Np + 32 * c];
-        lm[NCH - 1] = last_ok ? lrow[(size_t)l * Np + 32 * (NCH - 1)] : 0.0;
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-            acc[0][c] = fma(a0, lm[c], acc[0][c]);
-            acc[1][c] = fma(a1, lm[c], acc[1][c]);
-            acc[2][c] = fma(a2, lm[c], acc[2][c]);
-            acc[3][c] = fma(a3, lm[c], acc[3][c]);
-        }
-    }
-}
-// Lambda (row-major n x n in global memory) -> shared [n][Np], columns >= n zero; one wave of async copies
-__device__ __forceinline__ void stage_lambda(double* sL, const double* __restrict__ Lam, int n, int Np) {
-    const int c0 = threadIdx.x & 31, r0 = threadIdx.x >> 5, nr = blockDim.x >> 5;
-    if ((n & 1) == 0) {   // 16-byte async copies (rows of Lambda are 16-byte aligned when n is even; Np is a multiple of 8)
-        for (int l = r0; l < n; l += nr)
-            for (int m = 2 * c0; m < Np; m += 64) {
-                if (m < n) cp_async16(sL + (size_t)l * Np + m, Lam + (size_t)l * n + m);
-                else sL[(size_t)l * Np + m] = sL[(size_t)l * Np + m + 1] = 0.0;
-            }
-        return;
-    }
-    for (int l = r0; l < n; l += nr)
-        for (int m = c0; m < Np; m += 32) {
-            if (m < n) cp_async8(sL + (size_t)l * Np + m, Lam + (size_t)l * n + m);
-            else sL[(size_t)l * Np + m] = 0.0;
-        }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// k_prep: A~[r][l] = sw_r U[pa_r][l] U[pq_r][l],  B~[r][m] = sum_l A~[r][l] Lambda[l][m]
-//   U = Rchain[s].  32 rows per CTA, 256 threads (8 threads gather one row), Lambda resident in shared memory.
-//   Rows >= nR (padding) have sw = 0.
-// ------------------------------------------------------------------------------------------------------
-constexpr int PREP_ROWS = 32;
-inline size_t prep_smem(int n, int Np) { return ((size_t)n * Np + (size_t)PREP_ROWS * Np) * sizeof(double); }
-
-template <int NCH>
-__global__ void __launch_bounds__(256) k_prep(const double* __restrict__ Rchain, const int* __restrict__ s_ptr,
-                                              const double* __restrict__ Lam, const int* __restrict__ pa, const int* __restrict__ pq,
-                                              const double* __restrict__ sw, int n, int Np, int ld, int rows_total, int brow_begin,
-                                              int brow_end, double* __restrict__ At, double* __restrict__ Bt) {
-    extern __shared__ double sm[];
-    double* sL = sm;                     // [n][Np]  (columns >= n are zero)
-    double* sAt = sm + (size_t)n * Np;   // [32][Np]
-    const double* U = Rchain + (size_t)(*s_ptr) * n * n;
-    const int r0 = blockIdx.x * PREP_ROWS;
-    const bool need_b = !(r0 + PREP_ROWS <= brow_begin || r0 >= brow_end);
-    if (need_b) stage_lambda(sL, Lam, n, Np);
-    {
-        const int rr = threadIdx.x >> 3, l0 = threadIdx.x & 7, r = r0 + rr;
-        const bool live = r < rows_total;
-        const double w = live ? sw[r] : 0.0;
-        const double* ua = U + (size_t)(live ? pa[r] : 0) * n;
-        const double* uq = U + (size_t)(live ? pq[r] : 0) * n;
-#pragma unroll 4
-        for (int l = l0; l < Np; l += 8) {
-            const double v = (l < n && w != 0.0) ? w * ua[l] * uq[l] : 0.0;
-            sAt[rr * Np + l] = v;
-            if (live) At[(size_t)r * ld + l] = v;
-        }
-    }
-    if (!need_b) return;  // B~ only for this shard's rows
-    cp_async_wait_all();
-    __syncthreads();
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;  // 8 warps x 4 rows
-    double acc[4][NCH];
-    rows4_times_lambda<NCH>(sAt + (size_t)(grp * 4) * Np, sL, n, Np, acc);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int m = 32 * c + lane;
-        if (m < Np) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int r = r0 + grp * 4 + i;
-                if (r >= brow_begin && r < brow_end) Bt[(size_t)(r - brow_begin) * ld + m] = acc[i][c];
-            }
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// k_post_f: per local 64-row panel: E~ = fixed-order sum of the fused kernel's pieces (also stored),
-//   F = E~ Lambda (rows of the F tensor of the theta gradient).  Lambda streams through shared memory
-//   in 32-row chunks (double-buffered async copies).
-// ------------------------------------------------------------------------------------------------------
-inline size_t postf_smem(int Np) { return ((size_t)64 * Np + 2 * (size_t)32 * Np) * sizeof(double); }
-
-__global__ void __launch_bounds__(256) k_post_f(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
-                                                const double* __restrict__ Lam, int n, int Np, double* __restrict__ Et,
-                                                double* __restrict__ F) {
-    extern __shared__ double sm[];
-    double* sE = sm;                         // [64][Np]
-    double* sL = sm + (size_t)64 * Np;       // [2][32][Np]
-    const int panel = blockIdx.x;
-    const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
-    const int nch = (n + 31) / 32;
-    auto load_chunk = [&](int ch, int buf) {
-        double* dst = sL + (size_t)buf * 32 * Np;
-        for (int idx = threadIdx.x; idx < 32 * Np; idx += blockDim.x) {
-            const int l = ch * 32 + idx / Np, m = idx % Np;
-            if (l < n && m < n) cp_async8(dst + idx, Lam + (size_t)l * n + m);
-            else dst[idx] = 0.0;
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    load_chunk(0, 0);
-    for (int idx = threadIdx.x; idx < 64 * Np; idx += blockDim.x) {
-        double s = 0.0;
-        for (int v = v0; v < v1; ++v) {
-            s += Epiece[(size_t)(v * 2 + 0) * 64 * Np + idx];
-            s += Epiece[(size_t)(v * 2 + 1) * 64 * Np + idx];
-        }
-        sE[idx] = s;
-        Et[(size_t)panel * 64 * Np + idx] = s;
-    }
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;   // 8 warps x 8 rows
-    const int nchunk = (Np + 31) / 32;
-    double acc[8][CMAX];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int c = 0; c < CMAX; ++c) acc[i][c] = 0.0;
-    const double* s0 = sE + (size_t)grp * 8 * Np;
-    for (int ch = 0; ch < nch; ++ch) {
-        if (ch + 1 < nch) {
-            load_chunk(ch + 1, (ch + 1) & 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const double* L = sL + (size_t)(ch & 1) * 32 * Np + lane;
-        const int mmax = min(32, n - ch * 32);
-        for (int mm = 0; mm < mmax; ++mm) {
-            const int m = ch * 32 + mm;
-            double ev[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) ev[i] = s0[i * Np + m];
-#pragma unroll
-            for (int c = 0; c < CMAX; ++c) {
-                if (c < nchunk) {
-                    const double lm = (32 * c + lane < Np) ? L[(size_t)mm * Np + 32 * c] : 0.0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i][c] = fma(ev[i], lm, acc[i][c]);
-                }
-            }
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
-        const int b = 32 * c + lane;
-        if (c < nchunk && b < Np) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) F[(size_t)(panel * 64 + grp * 8 + i) * Np + b] = acc[i][c];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// k_post_f32: same as k_post_f for N where Lambda fits in shared memory next to a 32-row half panel:
-//   grid = 2 x panels (158 CTAs at N=100 packed, two resident per SM), one wave of async copies, no chunk loop.
-// ------------------------------------------------------------------------------------------------------
-inline size_t postf32_smem(int n, int Np) { return ((size_t)n * Np + (size_t)32 * Np) * sizeof(double); }
-
-template <int NCH>
-__global__ void __launch_bounds__(256) k_post_f32(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
-                                                  const double* __restrict__ Lam, int n, int Np, double* __restrict__ Et,
-                                                  double* __restrict__ F) {
-    extern __shared__ double sm[];
-    double* sL = sm;                        // [n][Np]
-    double* sE = sm + (size_t)n * Np;       // [32][Np]
-    const int panel = blockIdx.x >> 1, half = blockIdx.x & 1;
-    const int v0 = piece_first[panel], v1 = piece_first[panel + 1];
-    stage_lambda(sL, Lam, n, Np);
-    const size_t hoff = (size_t)half * 32 * Np;
-    const int total = 32 * Np;
-    for (int base = threadIdx.x; base < total; base += 4 * 256) {
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int v = v0; v < v1; ++v) {
-            const double* p0 = Epiece + (size_t)(v * 2 + 0) * 64 * Np + hoff;
-            const double* p1 = Epiece + (size_t)(v * 2 + 1) * 64 * Np + hoff;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int idx = base + u * 256;
-                if (idx < total) acc[u] += p0[idx] + p1[idx];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * 256;
-            if (idx < total) {
-                sE[idx] = acc[u];
-                Et[(size_t)panel * 64 * Np + hoff + idx] = acc[u];
-            }
-        }
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;   // 8 warps x 4 rows
-    double acc[4][NCH];
-    rows4_times_lambda<NCH>(sE + (size_t)grp * 4 * Np, sL, n, Np, acc);
-#pragma unroll
-    for (int c = 0; c < NCH; ++c) {
-        const int b = 32 * c + lane;
-        if (b < Np) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) F[(size_t)(panel * 64 + half * 32 + grp * 4 + i) * Np + b] = acc[i][c];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------
-// k_post_s: Spart[panel] = A~_panel^T E~_panel  (lambda gradient, gradient.jl:13-41).  grid = (panels, chunks^2):
-//   one CTA = one 64 x 64 output chunk of one panel, 4 x 4 register tiles, operands in shared memory.
-// ------------------------------------------------------------------------------------------------------
-inline size_t posts_smem(int Np) { (void)Np; return (size_t)2 * 64 * 64 * sizeof(double); }
-
-__global__ void __launch_bounds__(256) k_post_s(const double* __restrict__ Et, const double* __restrict__ At, int n, int Np, int ld,
-                                                int row_begin, double* __restrict__ Spart) {
-    extern __shared__ double sm[];
-    double* sE = sm;                 // [64 rows][64 cols j]
-    double* sAp = sm + 64 * 64;      // [64 rows][64 cols i]
-    const int panel = blockIdx.x;
-    const int nch = (n + 63) / 64;
-    const int i0 = (blockIdx.y / nch) * 64, j0 = (blockIdx.y % nch) * 64;
-    for (int idx = threadIdx.x; idx < 64 * 32; idx += blockDim.x) {   // 16-byte chunks: Np, ld, i0, j0 are all even
-        const int rr = idx >> 5, c = (idx & 31) * 2;
-        if (j0 + c < Np) cp_async16(sE + rr * 64 + c, Et + (size_t)(panel * 64 + rr) * Np + j0 + c);
-        else sE[rr * 64 + c] = sE[rr * 64 + c + 1] = 0.0;
-        if (i0 + c < Np) cp_async16(sAp + rr * 64 + c, At + (size_t)(row_begin + panel * 64 + rr) * ld + i0 + c);
-        else sAp[rr * 64 + c] = sAp[rr * 64 + c + 1] = 0.0;
-    }
-    cp_async_wait_all();
-    __syncthreads();
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double acc[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
-#pragma unroll 4
-    for (int r = 0; r < 64; ++r) {
-        double av[4], ev[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-            av[a] = sAp[r * 64 + ty + 16 * a];
-            ev[a] = sE[r * 64 + tx + 16 * a];
-        }
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-            for (int b = 0; b < 4; ++b) acc[a][b] = fma(av[a], ev[b], acc[a][b]);
-    }
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = i0 + ty + 16 * a, j = j0 + tx + 16 * b;
-            if (i < n && j < n) Spart[(size_t)panel * n * n + i * n + j] = acc[a][b];
-        }
-}
-
 // ------------------------------------------------------------------------------------------------------
 // k_post_reduce: part = [cost, S (n x n), G (n x n)];  one CTA per output row a, 128 columns x 8 groups.
 //   S = sum over panels of Spart (groups split the panels);
@@ -519,7 +25,10 @@ __global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__
                                                       // single-GEMM formulation (Lam != null): cost from N x N quantities, see below
                                                       const double* __restrict__ Lam, double* __restrict__ ls_part, unsigned* __restrict__ done,
                                                       const double* __restrict__ wpart, int nw, const double* __restrict__ tnorm2, double tau,
-                                                      int* __restrict__ flag) {
+                                                      int* __restrict__ flag,
+                                                      // lean path (aux != null, see panel::k_build_a): Spart holds Z = A~^T Y and F1/F2 hold
+                                                      // Y Lambda; the closed-form N x N terms are added here
+                                                      const double* __restrict__ aux) {
     __shared__ double redS[8][128], redG[8][128];
     __shared__ double redL[4];
     double ldot = 0.0;
@@ -581,9 +90,17 @@ __global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__
                 ss += redS[k][tx];
                 gg += redG[k][tx];
             }
-            part[1 + (size_t)a * n + b] = ss;
-            part[1 + (size_t)n * n + (size_t)a * n + b] = gcoef * gg;
-            if (Lam) ldot = fma(Lam[(size_t)a * n + b], ss, ldot);
+            if (aux) {
+                // S = G Lambda G - Z with G = diag(d);  G_ab = 4 U_ab o_b t_b - gather(Y Lambda);  ldot collects <Lambda, Z>
+                const double lab = Lam[(size_t)a * n + b];
+                part[1 + (size_t)a * n + b] = aux[n + a] * lab * aux[n + b] - ss;
+                part[1 + (size_t)n * n + (size_t)a * n + b] = 4.0 * U[(size_t)a * n + b] * aux[b] * aux[2 * n + b] - gcoef * gg;
+                ldot = fma(lab, ss, ldot);
+            } else {
+                part[1 + (size_t)a * n + b] = ss;
+                part[1 + (size_t)n * n + (size_t)a * n + b] = gcoef * gg;
+                if (Lam) ldot = fma(Lam[(size_t)a * n + b], ss, ldot);
+            }
         }
         __syncthreads();
     }
@@ -607,11 +124,127 @@ __global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__
             __threadfence();
             double ls = 0.0, w = 0.0;
             for (int i = 0; i < n; ++i) ls += __ldcg(ls_part + i);
-            for (int i = 0; i < nw; ++i) w += wpart[i];
+            if (aux) w = aux[3 * n];                     // |W~|^2 = tr(Lambda G Lambda G), closed form
+            else
+                for (int i = 0; i < nw; ++i) w += wpart[i];
             const double t2 = *tnorm2;
-            const double c = (t2 - w) + 2.0 * ls;
+            const double c = aux ? (t2 + w) - 2.0 * ls : (t2 - w) + 2.0 * ls;   // lean: ls = <Lambda, Z> = <T~, W~>
             part[0] = c;
             *flag = (c < tau * fmax(t2, w)) ? 1 : 0;     // also catches a (rounding-)negative value
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Lean path, CSA flavour: k_post_reduce split along the dependency graph of the evaluation.
+//   k_gather_g : G only -- all the derivative chain (chain::k_chain_d) waits for;
+//   k_reduce_s : S = G Lambda G - sum of the panels' Z, the lambda gradient straight into out (gradient.jl:30-41 order), the
+//                expanded cost and the cancellation flag -- runs on the side stream beside the derivative chain.
+// Same arithmetic and summation order as k_post_reduce with aux != null.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_gather_g(const double* __restrict__ F1, const double* __restrict__ F2, const double* __restrict__ sw,
+                                                   const double* __restrict__ U, int n, int Np, int packed, double gcoef, int row_begin,
+                                                   int row_end, const double* __restrict__ aux, double* __restrict__ part) {
+    __shared__ double redG[8][128];
+    const int a = blockIdx.x, tx = threadIdx.x & 127, grp = threadIdx.x >> 7;
+    for (int b0 = 0; b0 < n; b0 += 128) {
+        const int b = b0 + tx;
+        double g = 0.0;
+        if (b < n) {
+            if (packed) {
+#pragma unroll 4
+                for (int q = grp; q < n; q += 8) {
+                    const int lo = a < q ? a : q, hi = a < q ? q : a;
+                    const int r = hi * (hi + 1) / 2 + lo;
+                    const bool own = (r >= row_begin && r < row_end);
+                    const int rl = own ? r - row_begin : 0;
+                    double f = F1[(size_t)rl * Np + b];
+                    if (F2) f += F2[(size_t)rl * Np + b];
+                    const double w = own ? 2.0 * U[q * n + b] / sw[r] : 0.0;
+                    g = fma(w, f, g);
+                }
+            } else {
+#pragma unroll 4
+                for (int q = grp; q < n; q += 8) {
+                    const int r1 = a + n * q, r2 = q + n * a;
+                    const bool o1 = (r1 >= row_begin && r1 < row_end), o2 = (r2 >= row_begin && r2 < row_end);
+                    const int l1 = o1 ? r1 - row_begin : 0, l2 = o2 ? r2 - row_begin : 0;
+                    double f1 = F1[(size_t)l1 * Np + b], f2 = F1[(size_t)l2 * Np + b];
+                    if (F2) {
+                        f1 += F2[(size_t)l1 * Np + b];
+                        f2 += F2[(size_t)l2 * Np + b];
+                    }
+                    const double f = (o1 ? f1 : 0.0) + (o2 ? f2 : 0.0);
+                    g = fma(U[q * n + b], f, g);
+                }
+            }
+        }
+        redG[grp][tx] = g;
+        __syncthreads();
+        if (grp == 0 && b < n) {
+            double gg = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) gg += redG[k][tx];
+            part[1 + (size_t)n * n + (size_t)a * n + b] = 4.0 * U[(size_t)a * n + b] * aux[b] * aux[2 * n + b] - gcoef * gg;
+        }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_s(const double* __restrict__ Spart, int npanels, const double* __restrict__ Lam,
+                                                   const double* __restrict__ aux, int n, int lam_off, double* __restrict__ part,
+                                                   double* __restrict__ out, double* __restrict__ ls_part, unsigned* __restrict__ done,
+                                                   const double* __restrict__ tnorm2, double tau, int* __restrict__ flag) {
+    __shared__ double redS[8][128];
+    __shared__ double redL[4];
+    double ldot = 0.0;
+    const int a = blockIdx.x, tx = threadIdx.x & 127, grp = threadIdx.x >> 7;
+    for (int b0 = 0; b0 < n; b0 += 128) {
+        const int b = b0 + tx;
+        double s = 0.0;
+        if (b < n) {
+            const size_t o = (size_t)a * n + b;
+            double s0 = 0.0, s1 = 0.0;
+            int p = grp;
+            for (; p + 8 < npanels; p += 16) {
+                s0 += Spart[(size_t)p * n * n + o];
+                s1 += Spart[(size_t)(p + 8) * n * n + o];
+            }
+            if (p < npanels) s0 += Spart[(size_t)p * n * n + o];
+            s = s0 + s1;
+        }
+        redS[grp][tx] = s;
+        __syncthreads();
+        if (grp == 0 && b < n) {
+            double ss = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ss += redS[k][tx];
+            const double lab = Lam[(size_t)a * n + b];
+            const double sab = aux[n + a] * lab * aux[n + b] - ss;
+            part[1 + (size_t)a * n + b] = sab;
+            if (b <= a) out[1 + lam_off + a * (a + 1) / 2 + b] = 2.0 * sab * (a != b ? 2.0 : 1.0);
+            ldot = fma(lab, ss, ldot);
+        }
+        __syncthreads();
+    }
+    if (grp == 0) {
+        for (int o = 16; o > 0; o >>= 1) ldot += __shfl_xor_sync(0xffffffffu, ldot, o);
+        if ((tx & 31) == 0) redL[tx >> 5] = ldot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ls_part[a] = (redL[0] + redL[1]) + (redL[2] + redL[3]);
+        __threadfence();
+        const unsigned old = atomicAdd(done, 1u);
+        if (old == gridDim.x - 1) {
+            *done = 0;
+            __threadfence();
+            double ls = 0.0;
+            for (int i = 0; i < n; ++i) ls += __ldcg(ls_part + i);
+            const double w = aux[3 * n], t2 = *tnorm2;
+            const double c = (t2 + w) - 2.0 * ls;
+            part[0] = c;
+            *flag = (c < tau * fmax(t2, w)) ? 1 : 0;
         }
     }
 }
@@ -625,7 +258,8 @@ __global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__
 __global__ void k_sd_onebody(const double* __restrict__ x, const double* __restrict__ hT, const double* __restrict__ Rchain,
                              const int* __restrict__ s_ptr, int n, double* __restrict__ part, double* __restrict__ g1,
                              double* __restrict__ Dh /* n*n scratch */, double* __restrict__ DU /* n*n scratch */,
-                             double* __restrict__ hstore /* optional: h - for residual update */) {
+                             double* __restrict__ hstore /* optional: h - for residual update */,
+                             double* __restrict__ obc = nullptr /* optional: the one-body cost on its own */) {
     __shared__ double red[32];
     const double* U = Rchain + (size_t)(*s_ptr) * n * n;
     const double* l1 = x;
@@ -647,6 +281,7 @@ __global__ void k_sd_onebody(const double* __restrict__ x, const double* __restr
         double t = 0.0;
         for (int w = 0; w < (nt + 31) / 32; ++w) t += red[w];
         if (part) part[0] += t;
+        if (obc) *obc = t;
     }
     if (!part) return;
     // DU = (Dh + Dh^T) U ; G += DU .* l1
@@ -666,32 +301,6 @@ __global__ void k_sd_onebody(const double* __restrict__ x, const double* __restr
         for (int r = 0; r < n; ++r) s = fma(U[r * n + k], DU[r * n + k], s);
         g1[k] = 2.0 * s;
     }
-}
-
-// dX = G^T * 2^-s  (start of the derivative chain; Lt = Dexp(K)[G^T])
-__global__ void k_build_d(const double* __restrict__ part, const double* __restrict__ scale, int n, double* __restrict__ dX) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * n) return;
-    const int i = idx / n, j = idx % n;
-    dX[idx] = part[1 + n * n + j * n + i] * (*scale);
-}
-
-// out = [cost, (g1), g_lambda, g_theta]   (gradient.jl:148-151, 287-290)
-__global__ void k_assemble(const double* __restrict__ part, const double* __restrict__ g1, const double* __restrict__ dRchain,
-                           const int* __restrict__ s_ptr, int n, int sd, double* __restrict__ out) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int cL = n * (n + 1) / 2, uL = n * (n - 1) / 2, off = sd ? n : 0;
-    if (idx == 0) out[0] = part[0];
-    if (sd && idx < n) out[1 + idx] = g1[idx];
-    if (idx < n * n) {
-        const int i = idx / n, j = idx % n;
-        if (j <= i) out[1 + off + i * (i + 1) / 2 + j] = 2.0 * part[1 + idx] * (i != j ? 2.0 : 1.0);
-        if (i < j) {
-            const double* Lt = dRchain + (size_t)(*s_ptr) * n * n;
-            out[1 + off + cL + i * n - i * (i + 1) / 2 + (j - i - 1)] = 2.0 * (Lt[j * n + i] - Lt[i * n + j]);
-        }
-    }
-    (void)uL;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -826,11 +435,19 @@ __global__ void k_sumsq_add(const double* __restrict__ v, int len, const double*
 // ------------------------------------------------------------------------------------------------------
 // Exact-cost fallback of the single-GEMM formulation: take the sum of fused::k_fused's partials when `flag` is up.
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_cost_select(const int* __restrict__ flag, const double* __restrict__ cost_part, int ncost, double* __restrict__ part) {
-    if (threadIdx.x == 0 && *flag) {
+//   out == null (row-panel shards): the exact two-body cost replaces part[0] before the exchange.
+//   out != null (lean path, runs beside the derivative chain): out[0] = cost of the evaluation, exact or expanded, plus the
+//   one-body term *obc that k_sd_onebody already added to part[0].
+__global__ void k_cost_select(const int* __restrict__ flag, const double* __restrict__ cost_part, int ncost, double* __restrict__ part,
+                              double* __restrict__ out, const double* __restrict__ obc) {
+    if (threadIdx.x != 0) return;
+    if (*flag) {
         double c = 0.0;
         for (int i = 0; i < ncost; ++i) c += cost_part[i];
-        part[0] = c;
+        if (out) out[0] = c + (obc ? *obc : 0.0);
+        else part[0] = c;
+    } else if (out) {
+        out[0] = part[0];
     }
 }
 // per-CTA partial sums of squares of a (zero padded) array -> out[blockIdx.x]; fixed order within a CTA

@@ -240,34 +240,47 @@ def test_single_gemm_formulation_matches_two_gemm_kernel_and_falls_back(mb, lib,
     """The default evaluation (fused::k_ty: E = C~ - T~ A~, cost from N x N quantities) against the two-GEMM kernel
     (MAMBO_TWO_GEMM=1: D = B~ A~^T - T~ explicitly) on the same handle inputs, including the regime where the expanded
     cost cancels (x at / near a planted fragment) and the exact-cost pass must take over."""
+    import torch
     n = 13
     T, xs = o.planted_tbt(n, 1, 7)
     x_true = xs[0]
     rng = np.random.default_rng(2)
     probes = [o.random_x(n, 1), x_true, x_true + 1e-7 * rng.standard_normal(x_true.shape),
               x_true + 1e-3 * rng.standard_normal(x_true.shape)]
-    fast = mb.CSAEngine(T)
+    fast = mb.CSAEngine(T)                                  # lean path: N x N closed forms instead of the B~/C~ panel GEMMs
+    monkeypatch.setenv("MAMBO_NO_LEAN", "1")
+    mid = mb.CSAEngine(T)                                   # first single-GEMM formulation (Gram kernel + B~, C~)
+    monkeypatch.delenv("MAMBO_NO_LEAN")
     monkeypatch.setenv("MAMBO_TWO_GEMM", "1")
     slow = mb.CSAEngine(T)
     monkeypatch.delenv("MAMBO_TWO_GEMM")
     tt = float(np.sum(T * T))
     try:
         for x in probes:
-            cf, gf = fast.cost_grad(x)
             cs, gs = slow.cost_grad(x)
             c0, g0 = o.cost_grad_factored(x, T)
-            assert cf >= 0.0
             # cost: 1e-10 relative, down to what FP64 resolves: every element of D = W - T carries eps |T|, so
             # |D|^2 carries ~ eps |D| |T| (and eps^2 |T|^2 at the exact solution)
             ctol = 1e-10 * abs(c0) + 1e-14 * np.sqrt(abs(c0) * tt) + 1e-26 * tt
-            assert abs(cf - cs) <= ctol
-            assert abs(cf - c0) <= ctol
             # gradient: 1e-10 of its size, down to the FP64 floor of D itself (each element of D = W - T carries eps |T|)
             gtol = 1e-10 * float(np.max(np.abs(g0))) + 1e-13 * np.sqrt(tt)
-            assert float(np.max(np.abs(gf - gs))) <= gtol
-            assert float(np.max(np.abs(gf - g0))) <= gtol
+            for eng in (fast, mid):
+                cf, gf = eng.cost_grad(x)
+                assert cf >= 0.0
+                assert abs(cf - cs) <= ctol
+                assert abs(cf - c0) <= ctol
+                assert float(np.max(np.abs(gf - gs))) <= gtol
+                assert float(np.max(np.abs(gf - g0))) <= gtol
+                # the device-resident entry point takes the same tail (exact-cost pass beside the derivative chain)
+                d_x = torch.tensor(x, dtype=torch.float64, device="cuda")
+                d_o = torch.zeros(1 + len(x), dtype=torch.float64, device="cuda")
+                eng.eval_device(d_x.data_ptr(), d_o.data_ptr())
+                eng.synchronize()
+                out = d_o.cpu().numpy()
+                assert out[0] == cf and np.array_equal(out[1:], gf)
     finally:
         fast.close()
+        mid.close()
         slow.close()
 
 
