@@ -462,17 +462,20 @@ PrepKind eval_prep_kind(const mambo_csa* h) { return h->lean ? PREP_LEAN : (h->f
 // Row epilogue of one pass of the hot kernel: F = E~ Lambda and Spart = A~^T E~ per panel, where E~ is assembled from the
 // hot kernel's pieces: E (two-GEMM kernel), C~ - Y (first single-GEMM formulation) or Y itself (lean path: F = Y Lambda,
 // Spart = A~^T Y; the closed-form terms are added by k_post_reduce).
-int enqueue_post_f(mambo_csa* h, double* F, bool with_S = false) {
+//   do_F / do_S select the products; esum: column-split launches (NB >= 16) first sum the pieces once (k_esum) -- callers that
+//   run the two products on two streams do that before they fork.
+int enqueue_post_f(mambo_csa* h, double* F, bool do_S = false, bool do_F = true, bool esum = true) {
     const bool split = h->NB >= 16;           // column-split panel kernels (NB_PANEL_DISPATCH): sum the pieces once, up front
     const double* ct = (h->fast && !h->lean) ? h->Ct : nullptr;
-    if (split) {
+    if (split && esum) {
         const int ysplit = std::max(1, std::min(8, (2 * h->num_sms) / std::max(h->P, 1)));
         panel::k_esum<<<dim3(h->P, ysplit), 256, 0, h->stream>>>(h->Epiece, h->piece_first, h->Np, h->ld, h->EtP, ct);
         h->launches++;
     }
-    NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT, CST><<<dim3(h->P, CST), panel::NTHR, panel::post_smem<NBT, CST>(), h->stream>>>(
+    if (!do_F && !do_S) return MAMBO_OK;
+    NB_PANEL_DISPATCH(h->NB, (panel::k_post_mma<NBT, CST><<<dim3(h->P, CST), panel::NTHR, panel::post_smem_part<NBT, CST>(do_F, do_S), h->stream>>>(
                                  h->Epiece, h->piece_first, ct, split ? h->EtP : nullptr, h->LamP, h->At, h->N,
-                                 h->row_begin, F, h->Spart, with_S ? 1 : 0)));
+                                 h->row_begin, F, h->Spart, do_S ? 1 : 0, do_F ? 1 : 0)));
     h->launches += 1;
     CU(cudaGetLastError());
     return MAMBO_OK;
@@ -498,14 +501,6 @@ bool split_tail(const mambo_csa* h) { return h->lean && h->flavour == MAMBO_CSA;
 int enqueue_post_sr(mambo_csa* h, bool seq_tail) {
     const int n = h->N;
     const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
-    if (split_tail(h) && !seq_tail) {
-        // only G is needed by the derivative chain; S, the lambda gradient, the cost and the flag are produced beside it
-        small::k_gather_g<<<n, 1024, 0, h->stream>>>(h->F1, general ? h->F2 : nullptr, h->sw, h->U, n, h->Np, h->packed ? 1 : 0,
-                                                    general ? 1.0 : 2.0, h->row_begin, std::min(h->row_end, h->nR), h->aux, h->d_part);
-        h->launches++;
-        CU(cudaGetLastError());
-        return MAMBO_OK;
-    }
     small::k_post_reduce<<<n, 1024, 0, h->stream>>>(h->cost_part, h->fast ? 0 : h->G, h->Spart, h->P, h->F1, general ? h->F2 : nullptr,
                                                    h->sw, h->U, h->d_zero, n, h->Np, h->packed ? 1 : 0, general ? 1.0 : 2.0,
                                                    h->row_begin, std::min(h->row_end, h->nR), h->d_part,
@@ -528,26 +523,41 @@ int enqueue_finish(mambo_csa* h, const double* d_x, double* d_out, bool side_tai
         h->launches++;
     }
     side_tail = side_tail && h->fast;
+    const bool split = side_tail && split_tail(h);
     if (side_tail) {
+        const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
+        double* Flast = general ? h->F2 : h->F1;
+        if (split && h->NB >= 16) TRY(enqueue_post_f(h, Flast, false, false, true));   // k_esum only: before the fork
         CU(cudaEventRecord(h->ev_fork, h->stream));
         CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         cudaStream_t main_stream = h->stream;
         h->stream = h->side_stream;
-        if (split_tail(h)) {
+        int rc = MAMBO_OK;
+        if (split) {
+            // lean CSA evaluation: of the row epilogue only F = Y Lambda -> G feeds the derivative chain.  Z = A~^T Y, its
+            // reduction to S, the lambda gradient, the cost and the flagged exact-cost pass all run beside the chain.
+            rc = enqueue_post_f(h, Flast, true, false, false);
             small::k_reduce_s<<<n, 1024, 0, h->stream>>>(h->Spart, h->P, h->Lam, h->aux, n, h->lam_off, h->d_part, d_out, h->ls_part, h->d_done,
                                                         h->tnorm2, h->tau, h->d_flag);
             h->launches++;
         }
-        const int rc = enqueue_exact_pass(h, d_out);
+        if (!rc) rc = enqueue_exact_pass(h, d_out);
         h->stream = main_stream;
         TRY(rc);
         CU(cudaEventRecord(h->ev_join, h->side_stream));
+        if (split) {
+            TRY(enqueue_post_f(h, Flast, false, true, false));
+            small::k_gather_g<<<n, 1024, 0, h->stream>>>(h->F1, general ? h->F2 : nullptr, h->sw, h->U, n, h->Np, h->packed ? 1 : 0,
+                                                        general ? 1.0 : 2.0, h->row_begin, std::min(h->row_end, h->nR), h->aux, h->d_part);
+            h->launches++;
+            CU(cudaGetLastError());
+        }
     }
     chain::DParams p = h->cd;
     p.part = h->d_part; p.g1 = h->g1; p.n = n; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0;
     p.s_in = h->d_s; p.scale_in = h->d_scale; p.out = d_out; p.bar = h->d_bar; p.status = h->d_status; p.dbg = h->d_dbg;
     p.write_cost = side_tail ? 0 : 1;
-    p.write_lambda = (side_tail && split_tail(h)) ? 0 : 1;
+    p.write_lambda = split ? 0 : 1;
     void* args[] = {&p};
     TRY(launch_chain(h, true, args));
     h->launches++;
@@ -639,6 +649,9 @@ int enqueue_partial(mambo_csa* h, int s_host, bool need_grad, bool one_call) {
         if (general) {
             TRY(run_segment(h, h->g_mid, [&]() -> int { return enqueue_post_f(h, h->F1); }));
             TRY(launch_ty(h, make_yparams(h, h->T2)));
+        }
+        if (one_call && split_tail(h)) return MAMBO_OK;    // the last pass's row epilogue is part of the finish half (two streams)
+        if (general) {
             return run_segment(h, post, [&]() -> int {
                 TRY(enqueue_post_f(h, h->F2, true));
                 return enqueue_post_sr(h, !one_call);

@@ -59,6 +59,10 @@ struct Geo {
 };
 template <int NB, int CS> inline size_t prep_smem() { return (Geo<NB, CS>::panel_elems + Geo<NB, CS>::lam_elems) * 8 + 64; }
 template <int NB, int CS> inline size_t post_smem() { return (2 * Geo<NB, CS>::panel_elems + Geo<NB, CS>::lam_elems) * 8 + 64; }
+// k_post_mma restricted to one of its two products: E~ panel + Lambda slice (F) or E~ panel + A~ panel (S)
+template <int NB, int CS> inline size_t post_smem_part(bool do_F, bool do_S) {
+    return (Geo<NB, CS>::panel_elems + (do_S ? Geo<NB, CS>::panel_elems : 0) + (do_F ? Geo<NB, CS>::lam_elems : 0)) * 8 + 64;
+}
 
 // C[16 rows of this warp][its n-blocks] += A[rows][k] . B[cols][k]^T ; both operands k-contiguous with pitch LD
 template <int NB, int CS>
@@ -358,14 +362,17 @@ template <int NB, int CS>
 __global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__ Epiece, const int* __restrict__ piece_first,
                                                       const double* __restrict__ Ct, const double* __restrict__ Et,
                                                       const double* __restrict__ LamP, const double* __restrict__ At, int n,
-                                                      int row_begin, double* __restrict__ F, double* __restrict__ Spart, int do_S) {
+                                                      int row_begin, double* __restrict__ F, double* __restrict__ Spart, int do_S,
+                                                      int do_F) {
+    // do_F / do_S select the products (both by default); a launch that does only one of them needs only that product's
+    // operands in shared memory (post_smem_part), so two such launches can run side by side on different streams.
     using G = Geo<NB, CS>;
     constexpr int Np = G::Np, LD = G::LD, NBW = G::NBW, NBC = G::NBC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* sE = reinterpret_cast<double*>(smem_raw);
     double* sAp = sE + G::panel_elems;
-    double* sL = sAp + G::panel_elems;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(sL + G::lam_elems);
+    double* sL = do_S ? sAp + G::panel_elems : sAp;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(sL + (do_F ? G::lam_elems : 0));
     const int panel = blockIdx.x, cs = blockIdx.y;
     const int nb_lo = cs * NBC, nblk = min(NBC, NB - nb_lo);
     if (nblk <= 0) return;
@@ -374,9 +381,9 @@ __global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__
     if (threadIdx.x == 0) {
         mbar_init(mbar);
         const uint32_t lbytes = (uint32_t)((size_t)8 * nblk * LD * 8), pbytes = (uint32_t)(G::panel_elems * 8);
-        mbar_expect(mbar, lbytes + (do_S ? pbytes : 0u) + (Et ? pbytes : 0u));
+        mbar_expect(mbar, (do_F ? lbytes : 0u) + (do_S ? pbytes : 0u) + (Et ? pbytes : 0u));
         if (Et) bulk(sE, Et + (size_t)panel * ROWS * LD, pbytes, mbar);   // column-split launches: E~ was summed once by k_esum
-        bulk(sL, LamP + (size_t)8 * nb_lo * LD, lbytes, mbar);
+        if (do_F) bulk(sL, LamP + (size_t)8 * nb_lo * LD, lbytes, mbar);
         if (do_S) bulk(sAp, At + (size_t)(row_begin + panel * ROWS) * LD, pbytes, mbar);
     }
     if (!Et) {   // E~ panel -> shared memory while the TMA copies are in flight.  Four elements per thread and trip so that the
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(NTHR, 1) k_post_mma(const double* __restrict__
     __syncthreads();
     mbar_wait(mbar, 0);
     // ---- F = E~ Lambda --------------------------------------------------------------------------------------
-    {
+    if (do_F) {
         double acc[2][NBW][2];
         gemm_kk<NB, CS>(sE, sL, nblk, acc);
         const int wr = warp >> 1, wc = warp & 1;

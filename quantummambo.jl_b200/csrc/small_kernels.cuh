@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(1024) k_post_reduce(const double* __restrict__
                     const int rl = own ? r - row_begin : 0;
                     double f = F1[(size_t)rl * Np + b];
                     if (F2) f += F2[(size_t)rl * Np + b];
-                    const double w = own ? 2.0 * U[q * n + b] / sw[r] : 0.0;
+                    const double w = own ? (lo == hi ? 2.0 : 1.4142135623730951 /* 2 / sw_r, sw_r = sqrt(2) off the diagonal */) * U[q * n + b] : 0.0;
                     g = fma(w, f, g);
                 }
             } else {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(1024) k_gather_g(const double* __restrict__ F1
                     const int rl = own ? r - row_begin : 0;
                     double f = F1[(size_t)rl * Np + b];
                     if (F2) f += F2[(size_t)rl * Np + b];
-                    const double w = own ? 2.0 * U[q * n + b] / sw[r] : 0.0;
+                    const double w = own ? (lo == hi ? 2.0 : 1.4142135623730951 /* 2 / sw_r, sw_r = sqrt(2) off the diagonal */) * U[q * n + b] : 0.0;
                     g = fma(w, f, g);
                 }
             } else {
