@@ -98,4 +98,87 @@ void csa_lit_grad_theta(int n, const double* wu, const double* dU, int uL, const
     }
 }
 
+/* ---- CSA_SD (decompose.jl:221-231 -> fermionic.jl:58-72,85-92 -> unitaries.jl:266-272,314-320,366-384; gradient.jl:157-186,218-284) ---- */
+
+/* unitaries.jl:266-272: the GENERAL 4-index rotation the CSA_SD representer applies to the sparse cartan tensor (N^8 loop) */
+void csa_lit_tbt_rotation(int n, const double* U, const double* tbt, double* W) {
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b)
+            for (int c = 0; c < n; ++c)
+                for (int d = 0; d < n; ++d) {
+                    double s = 0.0;
+                    for (int l = 0; l < n; ++l)
+                        for (int k = 0; k < n; ++k)
+                            for (int m = 0; m < n; ++m)
+                                for (int p = 0; p < n; ++p)
+                                    s += U[a * n + l] * U[b * n + k] * U[c * n + m] * U[d * n + p] * tbt[IDX4(n, l, k, m, p)];
+                    W[IDX4(n, a, b, c, d)] = s;
+                }
+}
+
+/* unitaries.jl:314-320 */
+void csa_lit_obt_rotation(int n, const double* U, const double* obt, double* h) {
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) s += U[a * n + i] * U[b * n + j] * obt[i * n + j];
+            h[a * n + b] = s;
+        }
+}
+
+/* cost.jl:21-25: one-body part of L2_partial_cost */
+double csa_lit_cost_ob(int n, const double* hT, const double* h) {
+    double c = 0.0;
+    for (int i = 0; i < n * n; ++i) {
+        const double d = hT[i] - h[i];
+        c += d * d;
+    }
+    return c;
+}
+
+/* gradient.jl:157-186: cartan_ob_grad[k] = sum(2 diff_ob .* (U[:,k] U[:,k]')) */
+void csa_lit_grad_l_ob(int n, const double* U, const double* diff_ob, double* g) {
+    for (int k = 0; k < n; ++k) {
+        double cl = 0.0;
+        for (int r = 0; r < n; ++r)
+            for (int s = 0; s < n; ++s) cl += 2.0 * diff_ob[r * n + s] * U[r * n + k] * U[s * n + k];
+        g[k] = cl;
+    }
+}
+
+/* gradient.jl:218-231: hu[r,s,a,j] (n^4), a = r and a = s terms */
+void csa_lit_del_h_u(int n, const double* U, const double* lam1, double* hu) {
+    memset(hu, 0, sizeof(double) * (size_t)n * n * n * n);
+    for (int r = 0; r < n; ++r)
+        for (int s = 0; s < n; ++s)
+            for (int j = 0; j < n; ++j) {
+                hu[IDX4(n, r, s, r, j)] += U[s * n + j] * lam1[j];
+                hu[IDX4(n, r, s, s, j)] += U[r * n + j] * lam1[j];
+            }
+}
+
+/* gradient.jl:266-284: u_grad[k] = 2 (sum(diff_tb .* (wu . u_theta_k)) + sum(diff_ob .* (hu . u_theta_k))) */
+void csa_lit_grad_theta_sd(int n, const double* wu, const double* hu, const double* dU, int uL, const double* diff_tb,
+                           const double* diff_ob, double* g) {
+    const size_t n4 = (size_t)n * n * n * n, n2 = (size_t)n * n;
+    for (int k = 0; k < uL; ++k) {
+        const double* ut = dU + (size_t)k * n2;
+        double tot = 0.0;
+        for (size_t i = 0; i < n4; ++i) {
+            const double* w = wu + i * n2;
+            double wt = 0.0;
+            for (size_t ab = 0; ab < n2; ++ab) wt += w[ab] * ut[ab];
+            tot += diff_tb[i] * wt;
+        }
+        for (size_t pq = 0; pq < n2; ++pq) {
+            const double* hh = hu + pq * n2;
+            double ht = 0.0;
+            for (size_t ab = 0; ab < n2; ++ab) ht += hh[ab] * ut[ab];
+            tot += diff_ob[pq] * ht;
+        }
+        g[k] = 2.0 * tot;
+    }
+}
+
 void csa_lit_free(void* p) { free(p); }

@@ -153,13 +153,15 @@ __global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ w
     for (int i = threadIdx.x; i < lenpad; i += 1024) vnext[i] = i < len ? w[i] * inv : 0.0;
 }
 
-// start vector: deterministic, positive, symmetric under p <-> q (so that for a p<->q-symmetric tensor the whole Krylov
-// space, and with it the returned operator, is symmetric to rounding); normalised by k_normalise afterwards
-__global__ void k_start(double* __restrict__ w, int len, const int* __restrict__ pa, const int* __restrict__ pq, int n) {
+// start vector: deterministic and positive.  Packed mode (rows are the pairs p <= q) needs nothing else.  In the unpacked modes the
+// key distinguishes (p,q) from (q,p): a start vector that is symmetric under p <-> q would confine the whole Krylov space to the
+// symmetric subspace whenever the tensor commutes with that swap, and a dominant ANTI-symmetric eigenvector -- the anti-Hermitian
+// branch of tbt_svd_1st (guesses.jl:67-75) -- would never be found.  normalised by k_normalise afterwards.
+__global__ void k_start(double* __restrict__ w, int len, const int* __restrict__ pa, const int* __restrict__ pq, int n, int packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < len) {
         const int p = pa[i], q = pq[i];
-        const int key = min(p, q) * n + max(p, q);
+        const int key = packed ? min(p, q) * n + max(p, q) : p * n + q;
         unsigned long long z = 0x9E3779B97F4A7C15ull * (unsigned long long)(key + 1);
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;

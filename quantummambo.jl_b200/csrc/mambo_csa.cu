@@ -750,6 +750,12 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad, bool nowait = false
     return check_status(h);
 }
 
+// frees a temporary device allocation on every exit of the enclosing scope (error returns included)
+struct DevTemp {
+    void* p = nullptr;
+    ~DevTemp() { if (p) cudaFree(p); }
+};
+
 template <typename T>
 int dalloc(T** p, size_t count) {
     CU(cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)));
@@ -764,20 +770,28 @@ int build_residual(mambo_csa* h, const double* tbt, const double* obt, unsigned 
     // ---- upload the tensor (or use it in place when it is already on the device) and analyse its symmetry ----
     const size_t n4 = (size_t)n * n * n * n;
     const bool on_dev = flags & MAMBO_TBT_ON_DEVICE;
+    if (h->flavour == MAMBO_CSA_SD && !obt) return fail(MAMBO_EINVAL, "CSA_SD needs the one-body tensor");
+    if (h->nshards > 1 && (flags & MAMBO_SYM_MASK) == MAMBO_SYM_GENERAL)
+        return fail(MAMBO_EINVAL, "row-panel sharding needs a (pq)<->(rs) symmetric tensor (SURVEY 8e.2)");
     double* mem = nullptr;
+    DevTemp upload, stats_buf;              // the 8 N^4-byte upload and the statistics words never outlive this function
     if (on_dev) {
+        // the caller's producer may still be running on another stream (this handle's stream does not synchronise with the
+        // legacy default stream): wait for the device once before reading the tensor
+        CU(cudaDeviceSynchronize());
         mem = const_cast<double*>(tbt);
     } else {
         CU(cudaMalloc((void**)&mem, n4 * sizeof(double)));
+        upload.p = mem;
         CU(cudaMemcpyAsync(mem, tbt, n4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     }
     double* d_stats = nullptr;
     TRY(dalloc(&d_stats, 4));
+    stats_buf.p = d_stats;
     small::k_sym_stats<<<h->num_sms * 8, 256, 0, h->stream>>>(mem, n, d_stats);
     double stats[4];
     CU(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    CU(cudaFree(d_stats));
     const double tmax = stats[0] > 0 ? stats[0] : 1.0;
     h->asym_pair = stats[1] / tmax;
     h->asym_pq = std::max(stats[2], stats[3]) / tmax;
@@ -839,10 +853,12 @@ int build_residual(mambo_csa* h, const double* tbt, const double* obt, unsigned 
     }
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(h->stream));
-    if (!on_dev) CU(cudaFree(mem));
+    if (upload.p) {                         // release the upload before the remaining allocations (high-water mark)
+        cudaFree(upload.p);
+        upload.p = nullptr;
+    }
 
     if (h->flavour == MAMBO_CSA_SD) {
-        if (!obt) return fail(MAMBO_EINVAL, "CSA_SD needs the one-body tensor");
         TRY(dalloc(&h->hT, (size_t)n * n));
         CU(cudaMemcpy(h->hT, obt, sizeof(double) * n * n, on_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     }
@@ -1135,6 +1151,17 @@ int mambo_csa_scratch_host(mambo_csa* h, void** ptr) {   // 128 bytes of pinned 
     return MAMBO_OK;
 }
 void mambo_set_error(const char* msg) { g_err = msg ? msg : ""; }
+// Library-internal (optimizer.cu): the device status word travels with the scalars of every optimiser evaluation, so an
+// out-of-range orbital rotation or a peer time-out ends the run with an error code instead of a garbage minimum.
+int mambo_csa_status_fetch(mambo_csa* h) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    return MAMBO_OK;
+}
+int mambo_csa_status_check(mambo_csa* h) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    return check_status(h);
+}
 
 int mambo_csa_get_stream(mambo_csa* h, void** stream, int* device) {
     if (!h) return fail(MAMBO_EINVAL, "null handle");
@@ -1296,20 +1323,28 @@ int mambo_csa_cost_grad_batch(mambo_csa** lanes, int nlanes, int K, const double
         if (!lanes[i] || lanes[i]->L != L) return fail(MAMBO_EINVAL, "lanes must be handles of the same problem");
     for (int k0 = 0; k0 < K; k0 += nlanes) {
         const int nw = std::min(nlanes, K - k0);
-        for (int i = 0; i < nw; ++i) {
-            lanes[i]->memo_valid = false;
-            TRY(eval_host(lanes[i], xs + (size_t)(k0 + i) * L, true, true));
+        int rc_first = MAMBO_OK, enq = 0;
+        for (; enq < nw; ++enq) {
+            lanes[enq]->memo_valid = false;
+            rc_first = eval_host(lanes[enq], xs + (size_t)(k0 + enq) * L, true, true);
+            if (rc_first) break;                          // lanes 0..enq-1 are in flight: drain them below before returning
         }
-        int rc_first = MAMBO_OK;
-        for (int i = 0; i < nw; ++i) {
+        std::string first_msg = g_err;
+        for (int i = 0; i < enq; ++i) {
             const int rc = eval_host_wait(lanes[i]);      // every lane is drained even after a failure
-            if (rc && !rc_first) rc_first = rc;
+            if (rc && !rc_first) {
+                rc_first = rc;
+                first_msg = g_err;
+            }
             if (!rc) {
                 if (costs) costs[k0 + i] = lanes[i]->h_out[0];
                 if (grads) std::memcpy(grads + (size_t)(k0 + i) * L, lanes[i]->h_out + 1, sizeof(double) * L);
             }
         }
-        if (rc_first) return rc_first;
+        if (rc_first) {
+            g_err = first_msg;
+            return rc_first;
+        }
     }
     return MAMBO_OK;
 }
@@ -1687,7 +1722,7 @@ int mambo_csa_leading_eig(mambo_csa* h, double tol, int max_iter, double* eigval
     const int vblocks = (R + 255) / 256;
     const int mv_grid = (R + lanczos::SYMV_RPC - 1) / lanczos::SYMV_RPC;   // one CTA per group of rows, scheduled dynamically
     const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
-    lanczos::k_start<<<vblocks, 256, 0, st>>>(w, R, h->pa, h->pq, n);
+    lanczos::k_start<<<vblocks, 256, 0, st>>>(w, R, h->pa, h->pq, n, h->packed ? 1 : 0);
     lanczos::k_normalise<<<1, 1024, 0, st>>>(w, R, (int)ldv, V, beta, mmax);   // beta[mmax] is scratch
     h->launches += 2;
     std::vector<double> ha(mmax + 1), hb(mmax + 1), z;

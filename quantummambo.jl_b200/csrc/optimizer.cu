@@ -28,6 +28,8 @@
 extern "C" void mambo_set_error(const char* msg);   // defined in mambo_csa.cu (thread-local message)
 extern "C" int mambo_csa_scratch(mambo_csa* h, size_t bytes, void** ptr);   // handle-owned device scratch (mambo_csa.cu)
 extern "C" int mambo_csa_scratch_host(mambo_csa* h, void** ptr);            // handle-owned pinned scalars (128 bytes)
+extern "C" int mambo_csa_status_fetch(mambo_csa* h);    // enqueue the D2H of the device status word on the handle's stream
+extern "C" int mambo_csa_status_check(mambo_csa* h);    // after a synchronise: MAMBO_ERANGE / MAMBO_ESTATE if it was raised
 
 namespace {
 
@@ -297,7 +299,17 @@ int phi(Opt* o, double alpha, double* f, double* df) {
     k_dot_absmax<<<1, 1024, 0, o->stream>>>(o->out + 1, o->p, o->L, o->scal);
     OCU(cudaMemcpyAsync(o->h_scal, o->scal, 2 * sizeof(double), cudaMemcpyDeviceToHost, o->stream));
     OCU(cudaMemcpyAsync(o->h_scal + 8, o->out, sizeof(double), cudaMemcpyDeviceToHost, o->stream));
+    rc = mambo_csa_status_fetch(o->h);            // device status word (||K||_1 out of range, NaN in x, peer time-out) ...
+    if (rc) {
+        snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+        return rc;
+    }
     OCU(cudaStreamSynchronize(o->stream));
+    rc = mambo_csa_status_check(o->h);            // ... checked with the scalars of the same evaluation
+    if (rc) {
+        snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+        return rc;
+    }
     *df = o->h_scal[0];
     *f = o->h_scal[8];
     return MAMBO_OK;
@@ -371,11 +383,13 @@ int line_search(Opt* o, double f0, double df0, double alpha1, double* alpha_out,
         }
         return MAMBO_OK;
     };
+    bool last_valid = false;      // the last point evaluated (o->xt / o->out) is a_prev with f_prev, a sufficient-decrease point
     for (int i = 0; i < 25; ++i) {
         int rc = phi(o, a, &f, &df);
         if (rc) return rc;
         if (!(f == f)) {  // NaN: shrink
             a = 0.5 * (a_prev + a);
+            last_valid = false;
             continue;
         }
         if (f > f0 + c1 * a * df0 || (i > 0 && f >= f_prev)) return zoom(a_prev, f_prev, df_prev, a, f, df);
@@ -385,11 +399,15 @@ int line_search(Opt* o, double f0, double df0, double alpha1, double* alpha_out,
         }
         if (df >= 0) return zoom(a, f, df, a_prev, f_prev, df_prev);
         a_prev = a; f_prev = f; df_prev = df;
+        last_valid = true;
         a = std::min(2.0 * a, amax);
         if (a_prev >= amax) break;
     }
-    if (f < f0) {  // accept the last decreasing point
-        *alpha_out = a_prev > 0 ? a_prev : a; *f_out = f; *ok = (a_prev > 0 ? false : true);
+    // The bracket phase ran out of doublings (or reached amax) with the cost still falling along p: a long step that satisfies
+    // the sufficient-decrease condition is a usable step, not a failure (Optim's HagerZhang would carry on from it as well).
+    // o->xt / o->out hold exactly this point, so alpha and f come from the same evaluation.
+    if (last_valid && f_prev < f0) {
+        *alpha_out = a_prev; *f_out = f_prev; *ok = true;
     }
     return MAMBO_OK;
 }

@@ -38,6 +38,11 @@ class OptimResult:
     converged: bool = False
 
 
+def _npz_name(name: str) -> str:
+    """np.savez appends '.npz' to names without it; the resume check must look for the file that was written."""
+    return name if name.endswith(".npz") else name + ".npz"
+
+
 def _bfgs(engine: CSAEngine, x0, g_tol: float = 1e-8, maxiter: int = 1000, native: bool = False) -> OptimResult:
     if native:
         x, res = engine.optimize(x0, g_tol=g_tol, max_iter=maxiter)
@@ -121,6 +126,7 @@ def _greedy(H: F_OP, alpha_max: int, flavour: str, decomp_tol: float, verbose: b
     Farr: list[F_FRAG] = []
     X = np.zeros((tot_L, alpha_max))
     a_curr = 0
+    SAVENAME = _npz_name(SAVENAME)
     with CSAEngine(H.tbt, H.obt if sd else None, flavour=flavour, device=device) as eng:   # F_rem = copy(H) on the device
         if SAVELOAD and os.path.exists(SAVENAME):
             with np.load(SAVENAME) as z:
@@ -147,8 +153,12 @@ def _greedy(H: F_OP, alpha_max: int, flavour: str, decomp_tol: float, verbose: b
             eng.subtract_fragment(sol.minimizer)                  # decompose.jl:56
             curr_cost = sol.minimum
             X[:, a_curr - 1] = sol.minimizer
-            if SAVELOAD:
-                np.savez(SAVENAME, **{f"{group}/x": X[:, :a_curr]})   # decompose.jl:58-64
+            if SAVELOAD:                                          # decompose.jl:58-64: only this group's "x" is rewritten
+                keep = {}
+                if os.path.exists(SAVENAME):
+                    with np.load(SAVENAME) as z:
+                        keep = {k: z[k] for k in z.files if k != f"{group}/x"}
+                np.savez(SAVENAME, **keep, **{f"{group}/x": X[:, :a_curr]})
         if verbose:
             print(f"Finished {group} decomposition, total number of fragments is {a_curr}, remainder L2-norm is {curr_cost}")
         if curr_cost > decomp_tol and (verbose or not sd):

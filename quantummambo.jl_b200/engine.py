@@ -62,6 +62,26 @@ class CSAEngine:
         self.device = device
         self.L = self._lib.mambo_csa_num_params(self._h)
 
+    @classmethod
+    def from_device(cls, d_tbt_ptr: int, N: int, d_obt_ptr: int = 0, flavour="CSA", device: int = 0, sym: int = SYM_AUTO,
+                    shard: int = 0, nshards: int = 1) -> "CSAEngine":
+        """The same handle from a tensor that already lies on `device` (MAMBO_TBT_ON_DEVICE): d_tbt_ptr points to N^4 doubles in
+        the Julia memory order (element (p,q,r,s) at p + N q + N^2 r + N^3 s), d_obt_ptr to N^2 (CSA_SD).  The library packs
+        its own copy; the caller's buffers may be freed afterwards."""
+        self = object.__new__(cls)
+        self._h = C.c_void_p()
+        self._lib = _lib.load()
+        self.N = int(N)
+        self.flavour = _flavour_id(flavour)
+        if self.flavour == CSA_SD and not d_obt_ptr:
+            raise ValueError("CSA_SD needs obt")
+        _lib.check(self._lib.mambo_csa_create_sharded(
+            C.byref(self._h), self.N, self.flavour, C.c_void_p(d_tbt_ptr), C.c_void_p(d_obt_ptr) if d_obt_ptr else None,
+            device, sym | TBT_ON_DEVICE, shard, nshards))
+        self.device = device
+        self.L = self._lib.mambo_csa_num_params(self._h)
+        return self
+
     # -- lifetime -----------------------------------------------------------------------------------------
     def lane(self) -> "CSAEngine":
         """Another evaluation context on the same GPU sharing this engine's device-resident residual

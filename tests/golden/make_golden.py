@@ -13,6 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.join(HERE, "..", "..", "oracle"))
 import csa_oracle as o  # noqa: E402
+import csa_oracle_ld as ld  # noqa: E402
 
 CASES = [  # (name, N, flavour, tensor kind, seed)
     ("csa_n3_sym", 3, "CSA", "dense_sym", 0),
@@ -23,6 +24,9 @@ CASES = [  # (name, N, flavour, tensor kind, seed)
     ("sd_n4_general", 4, "CSA_SD", "general", 5),
     ("sd_n5_pair", 5, "CSA_SD", "pairsym", 6),
     ("sd_n7_sym", 7, "CSA_SD", "dense_sym", 7),
+    ("csa_n12_sym", 12, "CSA", "dense_sym", 8),
+    ("sd_n10_pair", 10, "CSA_SD", "pairsym", 9),
+    ("csa_n9_general", 9, "CSA", "general", 10),
 ]
 KINDS = {"dense_sym": o.dense_sym_tbt, "pairsym": o.pairsym_tbt, "general": o.general_tbt}
 
@@ -42,6 +46,10 @@ def main():
         out[f"{name}/x"] = x
         out[f"{name}/cost"] = np.array(cost)
         out[f"{name}/grad"] = grad
+        # extended-precision ground truth (long double factored form, own expm; oracle/csa_oracle_ld.py), rounded to FP64
+        c_ld, g_ld = ld.cost_grad_factored_ld(x, T, obt, fl)
+        out[f"{name}/cost_ld"] = np.array(float(c_ld))
+        out[f"{name}/grad_ld"] = g_ld.astype(np.float64)
         out[f"{name}/W"] = W
         if obt is not None:
             out[f"{name}/obt"] = obt

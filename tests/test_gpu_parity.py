@@ -69,6 +69,9 @@ def test_golden_vectors(mb, lib, golden):
             W, h = e.reconstruct(c["x"])
         assert abs(cost - float(c["cost"])) <= RTOL * abs(float(c["cost"])), name
         assert rel(grad, c["grad"]) <= RTOL, name
+        # extended-precision ground truth (long-double factored form with its own expm, oracle/csa_oracle_ld.py)
+        assert abs(cost - float(c["cost_ld"])) <= 1e-12 * abs(float(c["cost_ld"])), name
+        assert rel(grad, c["grad_ld"]) <= 1e-12, name
         assert rel(W, c["W"]) <= RTOL, name
         if sd:
             assert rel(h, c["h"]) <= RTOL, name
@@ -468,6 +471,32 @@ def test_svd_initial_guess_matches_oracle(mb, lib):
             mb.tbt_svd_1st(e)
 
 
+def test_leading_eigenpair_in_the_antisymmetric_subspace(mb, lib):
+    """A (pq)<->(rs)-symmetric tensor whose dominant eigenvector is ANTI-symmetric under p <-> q (the anti-Hermitian branch of
+    tbt_svd_1st, guesses.jl:67-75).  The tensor commutes with the p <-> q swap, so a Krylov space started from a swap-symmetric
+    vector would never leave the symmetric subspace: the start vector of the unpacked modes must not be symmetric."""
+    n = 6
+    rng = np.random.default_rng(12)
+    a = rng.standard_normal((n, n))
+    a = a - a.T
+    sy = rng.standard_normal((n, n))
+    sy = sy + sy.T
+    T = 3.0 * np.einsum("pq,rs->pqrs", a, a) + 0.1 * np.einsum("pq,rs->pqrs", sy, sy)
+    with mb.CSAEngine(T) as e:
+        assert e.info()["mode_name"] == "pairsym"
+        lam, vec, st = e.leading_eig()
+        coeffs_g, _ = mb.tbt_svd_1st(e)
+    assert abs(lam - 3.0 * float(np.sum(a * a))) <= 1e-10 * abs(lam)
+    assert np.max(np.abs(vec + vec.T)) <= 1e-10                                   # antisymmetric operator
+    assert min(rel(vec, a / np.linalg.norm(a)), rel(-vec, a / np.linalg.norm(a))) <= 1e-9
+    coeffs_o, _ = o.tbt_svd_1st(T, fix_sign=True)
+    assert rel(coeffs_g, coeffs_o) <= 1e-9
+    # pure anti-symmetric rank one: T w0 vanished for the old (symmetric) start vector and the call returned 0
+    with mb.CSAEngine(np.einsum("pq,rs->pqrs", a, a)) as e:
+        lam2, _, _ = e.leading_eig()
+    assert abs(lam2 - float(np.sum(a * a))) <= 1e-10 * abs(lam2)
+
+
 def test_leading_eigenpair_full_size(mb, lib):
     """N = 50 (R = 1275 packed rows): eigen-residual and eigenvalue against LAPACK on the 2500 x 2500 view."""
     n = 50
@@ -600,21 +629,59 @@ def test_native_lbfgs_mode_finds_planted_fragment(mb, lib):
 
 def test_greedy_decomposition_matches_oracle_driver(mb, lib):
     """decompose.jl:1-80 end to end at LiH size (N=6 stand-in: planted R=2 + small symmetric noise): same x0s, same
-    BFGS (scipy) on both sides -> same fragments' cost trail and final 1-norm."""
+    BFGS (scipy) on both sides -> same fragments, final 1-norm (lcu.jl:139-182) within north_star's 1e-8."""
     n = 6
     T, xs = o.planted_tbt(n, 2, 2, sigma=1e-3)
     rng = np.random.default_rng(3)
     x0s = [xs[k] + 0.05 * rng.standard_normal(xs[k].shape) for k in range(2)] + [o.random_x(n, 9)]
     H = mb.F_OP(([0.0], [0.0], T))
-    frags = mb.CSA_greedy_decomposition(H, 3, x0s=x0s, decomp_tol=1e-7)
-    oxs, ocosts, t_rem, _ = o.greedy_decomposition(T, 3, x0s=x0s, decomp_tol=1e-7)
-    assert len(frags) == len(oxs)
+    frags = mb.CSA_greedy_decomposition(H, 2, x0s=x0s, decomp_tol=1e-7, g_tol=1e-11, maxiter=4000)
+    oxs, ocosts, t_rem, _ = o.greedy_decomposition(T, 2, x0s=x0s, decomp_tol=1e-7, gtol=1e-11, maxiter=4000)
+    assert len(frags) == len(oxs) == 2
+    cL = o.cartan_2b_num_params(n)
     l1 = sum(mb.CSA_L1(f) for f in frags)
-    l1_o = sum(o.CSA_L1(x[:o.cartan_2b_num_params(n)], n) for x in oxs)
-    assert l1 == pytest.approx(l1_o, rel=1e-6)
+    l1_o = sum(o.CSA_L1(x[:cL], n) for x in oxs)
+    assert abs(l1 - l1_o) <= 1e-8 * abs(l1_o)
+    for f, x in zip(frags, oxs):                      # fragment by fragment too
+        assert abs(mb.CSA_L1(f) - o.CSA_L1(x[:cL], n)) <= 1e-8 * o.CSA_L1(x[:cL], n)
     # the fragments reproduce the tensor to the same residual as the oracle's
     W = sum(o.reconstruct_factored(f.x(), n)[1] for f in frags)
-    assert float(np.sum((T - W) ** 2)) == pytest.approx(float(np.sum(t_rem ** 2)), rel=1e-4, abs=1e-10)
+    assert float(np.sum((T - W) ** 2)) == pytest.approx(float(np.sum(t_rem ** 2)), rel=1e-6, abs=1e-12)
+
+
+def test_csa_sd_greedy_decomposition_final_norms_match_oracle(mb, lib):
+    """decompose.jl:122-205 end to end (N = 5, planted one- and two-body fragments): total CSA 1-norm of the fragments'
+    two-body coefficients (lcu.jl:139-182) and one_body_L1 of what is left (lcu.jl:262-267 with ob_correction,
+    fermionic.jl:457-479) agree with the oracle's driver to 1e-8."""
+    n = 5
+    cL = o.cartan_2b_num_params(n)
+    T, xs = o.planted_tbt(n, 2, 11, sigma=1e-3)
+    rng = np.random.default_rng(4)
+    obt = np.zeros((n, n))
+    x_sd = []
+    for k in range(2):
+        lam1 = rng.standard_normal(n)
+        U = o.one_body_unitary(xs[k][cL:], n)
+        obt += (U * lam1) @ U.T
+        x_sd.append(np.concatenate([lam1, xs[k]]))
+    obt += 1e-3 * np.diag(rng.standard_normal(n))
+    x0s = [x + 0.03 * rng.standard_normal(x.shape) for x in x_sd]
+    H = mb.F_OP(([0.0], obt, T))
+    frags = mb.CSA_SD_greedy_decomposition(H, 2, x0s=x0s, decomp_tol=1e-9, g_tol=1e-11, maxiter=4000)
+    oxs, ocosts, t_rem, o_rem = o.greedy_decomposition(T, 2, obt=obt, flavour="CSA_SD", x0s=x0s, decomp_tol=1e-9, gtol=1e-11,
+                                                       maxiter=4000)
+    assert len(frags) == len(oxs) == 2
+    l1 = sum(mb.CSA_L1(f) for f in frags)
+    l1_o = sum(o.CSA_L1(x[n:n + cL], n) for x in oxs)
+    assert abs(l1 - l1_o) <= 1e-8 * abs(l1_o)
+    # what is left after the fragments, through the engine's own greedy state
+    with mb.CSAEngine(T, obt, "CSA_SD") as e:
+        for f in frags:
+            e.subtract_fragment(f.x())
+        Tr, hr = e.get_residual()
+    ob_l1 = mb.one_body_L1(mb.F_OP(([0.0], hr, Tr)))
+    ob_l1_o = o.one_body_L1(o_rem, t_rem)
+    assert abs(ob_l1 - ob_l1_o) <= 1e-8 * max(abs(ob_l1_o), 1.0)
 
 
 def test_csa_sd_greedy_step_molecule_sizes(mb, lib):
@@ -685,3 +752,33 @@ def test_full_size_properties(mb, lib, n):
     for name, (c, g) in res.items():
         assert abs(c - c0) <= RTOL * abs(c0), name
         assert rel(g, g0) <= RTOL, name
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [152, 160])
+def test_largest_configuration_and_last_bucket_against_oracle(mb, lib, n):
+    """BASELINE configs[4] size (N = 152, 19 n-blocks) and the last kernel bucket (N = 160, 21 n-blocks, six-way column
+    split of the panel kernels): the dense-sym tensor is generated on the device (4.3 / 5.2 GB) and handed to the library
+    in place (MAMBO_TBT_ON_DEVICE); the oracle evaluates the same array once on the host."""
+    import torch
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(n)
+    G = torch.randn((n, n, n, n), generator=g, dtype=torch.float64, device=dev)
+    G = G + G.permute(1, 0, 2, 3)
+    G = G + G.permute(0, 1, 3, 2)
+    G = (G + G.permute(2, 3, 0, 1)).mul_(1.0 / (n * n)).contiguous()
+    # 8-fold symmetric, so the C-ordered torch array read in Julia (column-major) order is the same tensor
+    x = o.random_x(n, 1)
+    torch.cuda.synchronize()
+    with mb.CSAEngine.from_device(G.data_ptr(), n) as e:
+        info = e.info()
+        c, gr = e.cost_grad(x)
+        c1 = e.cost(x + 0.0)
+    assert info["mode_name"] == "fullsym-packed" and c1 == c
+    T = G.cpu().numpy()
+    del G
+    torch.cuda.empty_cache()
+    c0, g0 = o.cost_grad_factored(x, T)
+    rc, rg = abs(c - c0) / abs(c0), rel(gr, g0)
+    print(f"N={n}: rows {info['rows']}, cost rel.err {rc:.2e}, gradient max-norm rel.err {rg:.2e}")
+    assert rc <= RTOL and rg <= RTOL

@@ -15,7 +15,7 @@ def _obt(n, seed):
     return np.random.default_rng(100 + seed).standard_normal((n, n)) / n
 
 
-@pytest.mark.parametrize("n", [3, 4, 5])
+@pytest.mark.parametrize("n", [3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
 @pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
 @pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
 def test_literal_equals_factored(n, flavour, kind):
@@ -178,12 +178,91 @@ def test_svd_initial_guess_reproduces_leading_fragment():
     assert checked >= 1
 
 
-@pytest.mark.parametrize("n", [3, 5, 7])
-def test_c_literal_restatement_matches_numpy_oracle(n):
+@pytest.mark.parametrize("n", [3, 5, 7, 9])
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+@pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
+def test_c_literal_restatement_matches_numpy_oracle(n, flavour, kind):
+    """oracle/csa_literal.c: the reference's loop nests as plain C loops (N^6 cartan rotation, N^8 general rotation for
+    CSA_SD, dense N^6 del_w_u, uL x N^6 theta contraction) against the factored numpy form -- all tensor kinds, so the
+    one-sided lambda gradient (Q2) and the full product rule (Q3) are pinned on non-symmetric inputs too."""
     import csa_literal as cl
-    T = o.pairsym_tbt(n, n)
-    x = o.random_x(n, 1)
-    c, g = cl.cost_grad_literal_c(x, T)
-    c0, g0 = o.cost_grad_factored(x, T)
+    T = KINDS[kind](n, n)
+    obt = _obt(n, n) if flavour == "CSA_SD" else None
+    x = o.random_x(n, 1, flavour)
+    c, g = cl.cost_grad_literal_c(x, T, obt, flavour)
+    c0, g0 = o.cost_grad_factored(x, T, obt, flavour)
     assert abs(c - c0) <= 1e-12 * abs(c0)
     assert np.max(np.abs(g - g0)) <= 1e-11 * np.max(np.abs(g0))
+
+
+# ---- extended-precision ground truth (oracle/csa_oracle_ld.py): independent arithmetic, no scipy / LAPACK / BLAS --------
+
+def _ld_tol(c_ld, tt):
+    # cost: 1e-12 relative, down to what FP64 resolves (every element of D = W - T carries eps |T|)
+    return 1e-12 * abs(c_ld) + 1e-14 * np.sqrt(abs(c_ld) * tt) + 1e-26 * tt
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+@pytest.mark.parametrize("kind", ["dense_sym", "general"])
+def test_mpmath_literal_reference_formulas_equal_long_double_factored_form(n, flavour, kind):
+    """The reference's formulas loop for loop at 40 digits (mpmath expm, mpmath eig for del_u_theta with the 1e-8 switch,
+    gradient.jl:113-126) against the factored form in long double: two restatements that share neither arithmetic nor
+    libraries agree to 1e-15, so the factorisation (and the adjoint-Frechet theta gradient) is the reference's function."""
+    import csa_oracle_ld as ld
+    T = KINDS[kind](n, 10 + n)
+    obt = _obt(n, 3) if flavour == "CSA_SD" else None
+    x = o.random_x(n, 11, flavour)
+    cm, gm = ld.cost_grad_literal_mp(x, T, obt, flavour)
+    cl_, gl_ = ld.cost_grad_factored_ld(x, T, obt, flavour)
+    assert abs(float(cl_) - cm) <= 1e-15 * abs(cm)
+    assert np.max(np.abs(gl_.astype(float) - gm)) <= 1e-15 * np.max(np.abs(gm))
+
+
+@pytest.mark.parametrize("n", [3, 6, 9, 12, 16])
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+@pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
+def test_fp64_oracle_within_1e12_of_extended_precision(n, flavour, kind):
+    import csa_oracle_ld as ld
+    T = KINDS[kind](n, n + 1)
+    obt = _obt(n, n) if flavour == "CSA_SD" else None
+    x = o.random_x(n, 5, flavour)
+    c, g = o.cost_grad_factored(x, T, obt, flavour)
+    cl_, gl_ = ld.cost_grad_factored_ld(x, T, obt, flavour)
+    assert abs(c - float(cl_)) <= 1e-12 * abs(float(cl_))
+    assert np.max(np.abs(g - gl_.astype(float))) <= 1e-12 * np.max(np.abs(gl_.astype(float)))
+    if n <= 9:
+        cq, gq = o.cost_literal(x, T, obt, flavour), o.gradient_literal(x, T, obt, flavour)
+        assert abs(cq - float(cl_)) <= 1e-12 * abs(float(cl_))
+        assert np.max(np.abs(gq - gl_.astype(float))) <= 1e-12 * np.max(np.abs(gl_.astype(float)))
+
+
+@pytest.mark.parametrize("n", [5, 9, 13])
+def test_fp64_oracle_in_the_cancellation_regime_against_extended_precision(n):
+    """x at / near a planted fragment: the residual is tiny against the tensor, so cost and gradient are differences of
+    O(|T|) quantities.  The FP64 oracle must stay within FP64's floor of the long-double value (the same tolerance model
+    the CUDA engine is held to in tests/test_gpu_parity.py)."""
+    import csa_oracle_ld as ld
+    T, xs = o.planted_tbt(n, 1, n)
+    tt = float(np.sum(T * T))
+    rng = np.random.default_rng(0)
+    for eps in (0.0, 1e-7, 1e-3):
+        x = xs[0] + eps * rng.standard_normal(xs[0].shape)
+        c, g = o.cost_grad_factored(x, T)
+        cl_, gl_ = ld.cost_grad_factored_ld(x, T)
+        assert abs(c - float(cl_)) <= _ld_tol(float(cl_), tt)
+        assert np.max(np.abs(g - gl_.astype(float))) <= 1e-12 * np.max(np.abs(gl_.astype(float))) + 1e-13 * np.sqrt(tt)
+
+
+def test_golden_vectors_carry_the_extended_precision_values(golden):
+    """tests/golden/csa_golden.npz stores, next to the literal FP64 values, cost / gradient from the long-double factored
+    form (rounded to FP64): the CUDA engine is compared with both (tests/test_gpu_parity.py::test_golden_vectors)."""
+    import csa_oracle_ld as ld
+    for name, c in golden.items():
+        n, sd = int(c["meta"][0]), int(c["meta"][1])
+        fl = "CSA_SD" if sd else "CSA"
+        cl_, gl_ = ld.cost_grad_factored_ld(c["x"], c["tbt"], c.get("obt"), fl)
+        assert float(cl_) == float(c["cost_ld"]), name
+        assert np.array_equal(gl_.astype(float), c["grad_ld"]), name
+        assert abs(float(c["cost"]) - float(c["cost_ld"])) <= 1e-12 * abs(float(c["cost_ld"])), name
+        assert np.max(np.abs(c["grad"] - c["grad_ld"])) <= 1e-12 * np.max(np.abs(c["grad_ld"])), name
