@@ -103,9 +103,15 @@ int  mambo_csa_cost(mambo_csa* h, const double* x, double* cost);
 int  mambo_csa_grad(mambo_csa* h, const double* x, double* grad);
 int  mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* grad);
 /* The same closure at K points x[k*L .. (k+1)*L) in one call (K independent runs of a multistart): point k is evaluated on
- * lanes[k mod nlanes] (a handle and lanes created from it, see mambo_csa_create_lane); the evaluations of a wave overlap
- * on the device.  costs: K doubles, grads: K*L doubles (either may be NULL).                                          */
+ * lanes[k mod nlanes] (a handle and lanes created from it, see mambo_csa_create_lane).  Every lane is kept busy: as soon as
+ * point k has been collected, point k + nlanes is enqueued on the same lane while the other lanes are still computing.
+ * costs: K doubles, grads: K*L doubles (either may be NULL).                                                          */
 int  mambo_csa_cost_grad_batch(mambo_csa** lanes, int nlanes, int K, const double* x, double* costs, double* grads);
+
+/* How the host closures wait for the device: 0 (default) spins in cudaStreamSynchronize -- lowest latency, one busy core per
+ * caller; 1 sleeps on a cudaEventBlockingSync event -- for callers that outnumber the host cores (lanes x ranks on one box).
+ * Lanes inherit the mode of their parent at creation; MAMBO_BLOCKING_WAIT=1 in the environment makes 1 the default.       */
+int  mambo_csa_set_wait_mode(mambo_csa* h, int blocking);
 
 /* --- greedy driver state (device-resident residual) ------------------------------------------------------ */
 /* On a row-panel shard both return the shard-local part of the cost (the caller sums over shards; the replicated

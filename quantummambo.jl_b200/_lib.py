@@ -74,6 +74,7 @@ SIGNATURES = {
     "mambo_csa_grad": (C.c_int, [_P, _P, _P]),
     "mambo_csa_cost_grad": (C.c_int, [_P, _P, _D, _P]),
     "mambo_csa_cost_grad_batch": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, _P]),
+    "mambo_csa_set_wait_mode": (C.c_int, [_P, C.c_int]),
     "mambo_csa_subtract_fragment": (C.c_int, [_P, _P, _D]),
     "mambo_csa_residual_cost": (C.c_int, [_P, _D]),
     "mambo_csa_get_residual": (C.c_int, [_P, _P, _P]),

@@ -122,6 +122,10 @@ struct mambo_csa {
     double* obc = nullptr;                     // one-body cost of the last evaluation (CSA_SD), 0 for CSA
     cudaStream_t side_stream = nullptr;        // the flagged exact-cost pass runs beside the derivative chain
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // how the host closures wait for the device: spinning (lowest latency, one busy core per caller) or sleeping on an event
+    // created with cudaEventBlockingSync (callers that outnumber the host cores: many lanes / many ranks per box)
+    bool blocking_wait = false;
+    cudaEvent_t ev_done = nullptr;
     double* Ct = nullptr;                      // C~ = A~ (Lambda G) rows of the local panels [P*64][ld]
     double* GLP = nullptr;                     // G Lambda with the panel pitch [Np][ld] (k_gram)
     double* wpart = nullptr;                   // per (panel, column split) <B~, C~>
@@ -703,9 +707,18 @@ int check_status(mambo_csa* h) {
 }
 
 // full evaluation from a host x; results land in h->h_out (pinned) after synchronisation
+int host_wait(mambo_csa* h) {        // wait for everything enqueued on the handle's stream, spinning or sleeping (blocking_wait)
+    if (h->blocking_wait) {
+        CU(cudaEventRecord(h->ev_done, h->stream));
+        CU(cudaEventSynchronize(h->ev_done));
+    } else {
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return MAMBO_OK;
+}
 int eval_host_wait(mambo_csa* h) {   // second half of eval_host: results are in h->h_out afterwards
     CU(cudaSetDevice(h->device));
-    CU(cudaStreamSynchronize(h->stream));
+    TRY(host_wait(h));
     return check_status(h);
 }
 
@@ -730,7 +743,7 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad, bool nowait = false
         }));
         h->launches_last_eval = (int)(h->launches - l0);
         if (nowait) return MAMBO_OK;
-        CU(cudaStreamSynchronize(h->stream));
+        TRY(host_wait(h));
         return check_status(h);
     }
     CU(cudaMemcpyAsync(h->d_x, h->h_x, sizeof(double) * h->L, cudaMemcpyHostToDevice, h->stream));
@@ -746,7 +759,7 @@ int eval_host(mambo_csa* h, const double* x, bool need_grad, bool nowait = false
     CU(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     h->launches_last_eval = (int)(h->launches - l0);
     if (nowait) return MAMBO_OK;
-    CU(cudaStreamSynchronize(h->stream));
+    TRY(host_wait(h));
     return check_status(h);
 }
 
@@ -1006,6 +1019,8 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
     CU(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming | cudaEventBlockingSync));
+    h->blocking_wait = parent ? parent->blocking_wait : (std::getenv("MAMBO_BLOCKING_WAIT") != nullptr);
     TRY(dalloc(&h->d_s, 1));
     TRY(dalloc(&h->d_bar, 4));                  // [0] barrier counter, [1] exit counter, [2] scratch target of release operations
     if (std::getenv("MAMBO_CHAIN_DEBUG")) TRY(dalloc(&h->d_dbg, 6 * 16));
@@ -1256,6 +1271,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     if (h->peer_done) cudaFree(h->peer_done);
     for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
     for (cudaEvent_t e : h->seg_pool) cudaEventDestroy(e);
+    if (h->ev_done) cudaEventDestroy(h->ev_done);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -1313,39 +1329,57 @@ int mambo_csa_cost_grad(mambo_csa* h, const double* x, double* cost, double* gra
 int mambo_csa_cost(mambo_csa* h, const double* x, double* cost) { return mambo_csa_cost_grad(h, x, cost, nullptr); }
 int mambo_csa_grad(mambo_csa* h, const double* x, double* grad) { return mambo_csa_cost_grad(h, x, nullptr, grad); }
 
-// K independent evaluations (multistart: one point per run) in ONE call: point k goes to lane k mod nlanes; each wave
-// enqueues one evaluation per lane without waiting (H2D from the lane's pinned staging, kernels, D2H), then collects them
-// in lane order.  The lanes overlap on the device as they do under one caller thread each, without needing those threads.
+// K independent evaluations (multistart: one point per run) in ONE call: point k goes to lane k mod nlanes.  Every lane is kept
+// busy: the call enqueues one evaluation per lane without waiting (H2D from the lane's pinned staging, kernels, D2H), then walks
+// the points in order -- wait for point k's lane, copy its result out, and at once enqueue that lane's next point (k + nlanes)
+// while the other lanes are still computing.  The lanes overlap on the device as they do under one caller thread each, without
+// needing those threads.
 int mambo_csa_cost_grad_batch(mambo_csa** lanes, int nlanes, int K, const double* xs, double* costs, double* grads) {
     if (!lanes || nlanes < 1 || K < 0 || !xs) return fail(MAMBO_EINVAL, "bad arguments");
     const int L = lanes[0] ? lanes[0]->L : 0;
     for (int i = 0; i < nlanes; ++i)
         if (!lanes[i] || lanes[i]->L != L) return fail(MAMBO_EINVAL, "lanes must be handles of the same problem");
-    for (int k0 = 0; k0 < K; k0 += nlanes) {
-        const int nw = std::min(nlanes, K - k0);
-        int rc_first = MAMBO_OK, enq = 0;
-        for (; enq < nw; ++enq) {
-            lanes[enq]->memo_valid = false;
-            rc_first = eval_host(lanes[enq], xs + (size_t)(k0 + enq) * L, true, true);
-            if (rc_first) break;                          // lanes 0..enq-1 are in flight: drain them below before returning
+    int rc_first = MAMBO_OK;
+    std::string first_msg;
+    std::vector<char> inflight(nlanes, 0);
+    auto note = [&](int rc) {
+        if (rc && !rc_first) {
+            rc_first = rc;
+            first_msg = g_err;
         }
-        std::string first_msg = g_err;
-        for (int i = 0; i < enq; ++i) {
-            const int rc = eval_host_wait(lanes[i]);      // every lane is drained even after a failure
-            if (rc && !rc_first) {
-                rc_first = rc;
-                first_msg = g_err;
-            }
-            if (!rc) {
-                if (costs) costs[k0 + i] = lanes[i]->h_out[0];
-                if (grads) std::memcpy(grads + (size_t)(k0 + i) * L, lanes[i]->h_out + 1, sizeof(double) * L);
-            }
-        }
-        if (rc_first) {
-            g_err = first_msg;
-            return rc_first;
-        }
+    };
+    auto enqueue = [&](int k) {
+        mambo_csa* ln = lanes[k % nlanes];
+        ln->memo_valid = false;
+        const int rc = eval_host(ln, xs + (size_t)k * L, true, true);
+        if (!rc) inflight[k % nlanes] = 1;
+        note(rc);
+    };
+    for (int k = 0; k < std::min(K, nlanes) && !rc_first; ++k) enqueue(k);
+    for (int k = 0; k < K && !rc_first; ++k) {
+        mambo_csa* ln = lanes[k % nlanes];
+        const int rc = eval_host_wait(ln);
+        inflight[k % nlanes] = 0;
+        note(rc);
+        if (rc) break;
+        if (costs) costs[k] = ln->h_out[0];
+        if (grads) std::memcpy(grads + (size_t)k * L, ln->h_out + 1, sizeof(double) * L);
+        if (k + nlanes < K) enqueue(k + nlanes);
     }
+    if (rc_first) {
+        for (int i = 0; i < nlanes; ++i)                  // every lane still in flight is drained before the error is returned
+            if (inflight[i]) eval_host_wait(lanes[i]);
+        g_err = first_msg;
+        return rc_first;
+    }
+    return MAMBO_OK;
+}
+
+// 0: the host closures spin in cudaStreamSynchronize (default; lowest latency); 1: they sleep on a blocking-sync event, which
+// frees the core while the device works -- for callers that outnumber the host cores (lanes x ranks per box).
+int mambo_csa_set_wait_mode(mambo_csa* h, int blocking) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    h->blocking_wait = blocking != 0;
     return MAMBO_OK;
 }
 

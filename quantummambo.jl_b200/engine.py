@@ -196,6 +196,10 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_optimize(self._h, x0.ctypes.data, xm.ctypes.data, C.byref(opt), C.byref(res)))
         return xm, {k: getattr(res, k) for k, _ in res._fields_}
 
+    def set_wait_mode(self, blocking: bool):
+        """mambo_csa_set_wait_mode: spin (False, default) or sleep on a blocking-sync event (True) inside the host closures."""
+        _lib.check(self._lib.mambo_csa_set_wait_mode(self._h, 1 if blocking else 0))
+
     # -- device-resident entry points (torch tensors carry the device memory; no host sync) -------------------
     def set_stream(self, cuda_stream_ptr: int | None):
         _lib.check(self._lib.mambo_csa_set_stream(self._h, cuda_stream_ptr))

@@ -266,3 +266,15 @@ def test_golden_vectors_carry_the_extended_precision_values(golden):
         assert np.array_equal(gl_.astype(float), c["grad_ld"]), name
         assert abs(float(c["cost"]) - float(c["cost_ld"])) <= 1e-12 * abs(float(c["cost_ld"])), name
         assert np.max(np.abs(c["grad"] - c["grad_ld"])) <= 1e-12 * np.max(np.abs(c["grad_ld"])), name
+
+
+@pytest.mark.parametrize("n", [2, 5, 12, 23])
+def test_packed_single_gemm_restatement_equals_factored(n):
+    """oracle.cost_grad_packed restates the ALGORITHM of the CUDA engine (packed rows, lean single-GEMM formulation with
+    the N x N closed forms) on the CPU; bench.py times it as `cpu_baseline_packed`.  Same numbers as the factored form."""
+    T = o.dense_sym_tbt(n, 3)
+    x = o.random_x(n, 4)
+    c0, g0 = o.cost_grad_factored(x, T)
+    c, g = o.cost_grad_packed(x, o.pack_tbt(T), n)
+    assert abs(c - c0) <= 1e-12 * abs(c0)
+    assert np.max(np.abs(g - g0)) <= 1e-12 * np.max(np.abs(g0))
