@@ -121,6 +121,20 @@ int  mambo_csa_residual_cost(mambo_csa* h, double* cost);
 int  mambo_csa_get_residual(mambo_csa* h, double* tbt_out, double* obt_out);
 int  mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double* obt_out);
 
+/* --- final norms and the checkpoint block --------------------------------------------------------------- */
+/* H.mbts[2] + ob_correction(H) for the RESIDENT residual (lcu.jl:262-267 with fermionic.jl:457-479): out = obt +
+ * (spin_orb ? 1 : 2) sum_r tbt[:,:,r,r], N x N column-major.  obt is the handle's one-body residual (CSA_SD) or obt_in (CSA
+ * handles; may be NULL).  One pass over N of the residual's rows.  The N x N `eigen` of to_OBF stays with the caller:
+ * one_body_L1 = sum |eigenvalues| (x 1/2 for spin orbitals).                                                             */
+int  mambo_csa_one_body_matrix(mambo_csa* h, int spin_orb, const double* obt_in, double* out);
+/* CSA_L1(frag) (lcu.jl:139-182) from the fragment's parameter vector x (flavour: MAMBO_CSA / MAMBO_CSA_SD).            */
+int  mambo_csa_frag_l1(int N, int flavour, int spin_orb, const double* x, double* l1);
+/* The checkpoint dataset "<group>/x" (decompose.jl:58-64: Float64 tot_L x alpha, column-major) as a raw file: "MAMBOX01",
+ * 16-byte group name, int64 tot_L, int64 alpha, the doubles.  Written beside the target and renamed.  INTEGRATION.md has
+ * the Julia lines that h5write it (no libhdf5 in this image).  read: X == NULL reads the header only.                   */
+int  mambo_csa_write_x_block(const char* path, const char* group, long long tot_L, long long alpha, const double* X);
+int  mambo_csa_read_x_block(const char* path, char* group16, long long* tot_L, long long* alpha, double* X, long long cap);
+
 /* --- initial guess (guesses.jl:51-84) ------------------------------------------------------------------- */
 /* The eigenpair of largest |eigenvalue| of Symmetric(reshape(tbt_residual, (N^2, N^2))) -- what tbt_svd_1st keeps of
  * its O(N^6) `eigen` (guesses.jl:55-63) -- by Lanczos with full re-orthogonalisation on the device-resident residual

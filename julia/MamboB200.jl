@@ -30,8 +30,21 @@ mutable struct Engine
     L::Int
 end
 
-"Upload F.mbts[3] (and F.mbts[2] for CSA_SD) once; the residual then lives on the device."
-function Engine(F::F_OP, flavour::Cint; device::Integer = 0, flags::Integer = 0)
+# flags of mambo_csa_create (include/mambo_csa.h): how the symmetry of F.mbts[3] is exploited
+const MAMBO_SYM_AUTO    = Cuint(0)   # detect on the device (relative tolerance 1e-13), pick the cheapest valid mode
+const MAMBO_SYM_GENERAL = Cuint(1)   # assume nothing: matches the reference for ANY tensor (incl. its one-sided lambda gradient)
+const MAMBO_SYM_PAIR    = Cuint(2)   # tbt[p,q,r,s] == tbt[r,s,p,q]
+const MAMBO_SYM_FULL    = Cuint(3)   # 8-fold symmetry of real-orbital integrals (what get_tbt / BLISS produce)
+
+"""
+    Engine(F, flavour; device = 0, flags = MAMBO_SYM_AUTO)
+
+Upload F.mbts[3] (and F.mbts[2] for CSA_SD) once; the residual then lives on the device until `destroy!(e)` (or, failing
+that, the finalizer).  The default `flags` lets the library detect the symmetry of the tensor; pass `MAMBO_SYM_GENERAL` to
+force the symmetry-agnostic mode for inputs that are only approximately symmetric (asymmetry above 1e-13 relative).
+GPU memory is invisible to Julia's GC (it sees a 16-byte object), so long-lived loops should call `destroy!` themselves.
+"""
+function Engine(F::F_OP, flavour::Cint; device::Integer = 0, flags::Integer = MAMBO_SYM_AUTO)
     href = Ref{Ptr{Cvoid}}(C_NULL)
     tbt = F.mbts[3]::Array{Float64,4}                       # column-major, passed as it lies in memory
     obt = flavour == MAMBO_CSA_SD ? Matrix{Float64}(F.mbts[2]) : Float64[]
@@ -43,6 +56,15 @@ function Engine(F::F_OP, flavour::Cint; device::Integer = 0, flags::Integer = 0)
     e = Engine(href[], Int(ccall((:mambo_csa_num_params, LIB), Cint, (Ptr{Cvoid},), href[])))
     finalizer(x -> (x.h != C_NULL && ccall((:mambo_csa_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.h); x.h = C_NULL), e)
     return e
+end
+
+"Release the device memory of `e` now (idempotent; the finalizer becomes a no-op)."
+function destroy!(e::Engine)
+    if e.h != C_NULL
+        ccall((:mambo_csa_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.h)
+        e.h = C_NULL
+    end
+    return nothing
 end
 
 function cost(e::Engine, x::Vector{Float64})
@@ -164,13 +186,33 @@ function multistart(engines::Vector{Engine}, X0::Matrix{Float64}; max_iter = 100
 end
 
 # ---- drop-in greedy steps (same signatures as decompose.jl:82, :207) ---------------------------------------------
-function _optimize(e::Engine, x0, print)
+function _optimize(e::Engine, x0, print, do_grad)
     c(x) = cost(e, x)                                       # decompose.jl:96-99   / :221-224
     g!(storage::Vector{Float64}, x::Vector{Float64}) = grad!(e, storage, x)   # decompose.jl:101-105 / :226-231
-    if print == false
-        return optimize(c, g!, x0, BFGS())
-    else
-        return optimize(c, g!, x0, BFGS(), Optim.Options(show_every = print, show_trace = true, extended_trace = true))
+    if do_grad                                              # decompose.jl:107-119 / :233-245, branch for branch
+        if print == false
+            return optimize(c, g!, x0, BFGS())
+        else
+            return optimize(c, g!, x0, BFGS(), Optim.Options(show_every = print, show_trace = true, extended_trace = true))
+        end
+    else                                                    # finite-difference gradients of the (GPU) cost, as in the reference
+        if print == false
+            return optimize(c, x0, BFGS())
+        else
+            return optimize(c, x0, BFGS(), Optim.Options(show_every = print, show_trace = true, extended_trace = true))
+        end
+    end
+end
+
+# A step that had to create its own Engine (the path the UNMODIFIED CSA_greedy_decomposition takes: one call per fragment)
+# releases it before returning: GPU memory must not wait for Julia's GC, which does not see it.
+function _with_engine(f, F::F_OP, flavour::Cint, engine)
+    own = engine === nothing
+    e = own ? Engine(F, flavour) : engine
+    try
+        return f(e)
+    finally
+        own && destroy!(e)
     end
 end
 
@@ -178,30 +220,32 @@ function QuantumMAMBO.CSA_greedy_step(F::F_OP, do_svd = SVD_for_CSA, print = DEC
     cartan_L = cartan_2b_num_params(F.N)
     unitary_L = real_orbital_rotation_num_params(F.N)
     x0 = zeros(cartan_L + unitary_L)
-    e = engine === nothing ? Engine(F, MAMBO_CSA) : engine       # with `engine`, F_rem is the engine's residual
-    if do_svd
-        frag = tbt_svd_1st(e, F.N)                                 # largest SVD fragment of the *residual*
-        x0[1:cartan_L] = frag.C.λ
-        x0[cartan_L+1:end] = frag.U[1].θs
-    else
-        x0[cartan_L+1:end] = 2π * rand(unitary_L)
+    return _with_engine(F, MAMBO_CSA, engine) do e               # with `engine`, F_rem is the engine's residual
+        if do_svd
+            frag = tbt_svd_1st(e, F.N)                             # largest SVD fragment of the *residual*
+            x0[1:cartan_L] = frag.C.λ
+            x0[cartan_L+1:end] = frag.U[1].θs
+        else
+            x0[cartan_L+1:end] = 2π * rand(unitary_L)
+        end
+        _optimize(e, x0, print, do_grad)
     end
-    return _optimize(e, x0, print)
 end
 
 function QuantumMAMBO.CSA_SD_greedy_step(F::F_OP, do_svd = SVD_for_CSA_SD, print = DECOMPOSITION_PRINT, do_grad = true; engine = nothing)
     cartan_L = cartan_2b_num_params(F.N)
     unitary_L = real_orbital_rotation_num_params(F.N)
     x0 = zeros(cartan_L + unitary_L + F.N)
-    e = engine === nothing ? Engine(F, MAMBO_CSA_SD) : engine
-    if do_svd
-        frag = tbt_svd_1st(e, F.N)
-        x0[F.N+1:F.N+cartan_L] = frag.C.λ
-        x0[F.N+cartan_L+1:end] = frag.U[1].θs
-    else
-        x0[F.N+cartan_L+1:end] = 2π * rand(unitary_L)
+    return _with_engine(F, MAMBO_CSA_SD, engine) do e
+        if do_svd
+            frag = tbt_svd_1st(e, F.N)
+            x0[F.N+1:F.N+cartan_L] = frag.C.λ
+            x0[F.N+cartan_L+1:end] = frag.U[1].θs
+        else
+            x0[F.N+cartan_L+1:end] = 2π * rand(unitary_L)
+        end
+        _optimize(e, x0, print, do_grad)
     end
-    return _optimize(e, x0, print)
 end
 
 """
@@ -215,17 +259,21 @@ function CSA_greedy_decomposition_b200(H::F_OP, α_max; decomp_tol = ϵ, verbose
     e = Engine(H, flavour)
     cartan_L = cartan_2b_num_params(H.N)
     Farr = F_FRAG[]
-    curr_cost = residual_cost(e)                                           # decompose.jl:40
-    α = 0
-    while curr_cost > decomp_tol && α < α_max
-        α += 1
-        sol = flavour == MAMBO_CSA ? QuantumMAMBO.CSA_greedy_step(H; engine = e) : QuantumMAMBO.CSA_SD_greedy_step(H; engine = e)
-        frag = flavour == MAMBO_CSA ? CSA_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L) :
-                                      CSA_SD_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L)
-        push!(Farr, frag)
-        subtract_fragment!(e, sol.minimizer)                                # decompose.jl:56
-        curr_cost = sol.minimum
-        verbose && println("Current L2 cost after $α fragments is $(sol.minimum)")
+    try
+        curr_cost = residual_cost(e)                                           # decompose.jl:40
+        α = 0
+        while curr_cost > decomp_tol && α < α_max
+            α += 1
+            sol = flavour == MAMBO_CSA ? QuantumMAMBO.CSA_greedy_step(H; engine = e) : QuantumMAMBO.CSA_SD_greedy_step(H; engine = e)
+            frag = flavour == MAMBO_CSA ? CSA_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L) :
+                                          CSA_SD_x_to_F_FRAG(sol.minimizer, H.N, H.spin_orb, cartan_L)
+            push!(Farr, frag)
+            subtract_fragment!(e, sol.minimizer)                                # decompose.jl:56
+            curr_cost = sol.minimum
+            verbose && println("Current L2 cost after $α fragments is $(sol.minimum)")
+        end
+    finally
+        destroy!(e)
     end
     return Farr
 end

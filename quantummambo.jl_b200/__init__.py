@@ -4,7 +4,8 @@ The directory name carries a dot (it mirrors the reference repository's name), s
 `mambo_b200.py` at the repository root, which registers it as the module `quantummambo_jl_b200`.
 """
 from ._lib import build, load, MamboError  # noqa: F401
-from .engine import (CSAEngine, multistart, cost_grad_batch, CSA, CSA_SD, SYM_AUTO, SYM_GENERAL, SYM_PAIR, SYM_FULL)  # noqa: F401
+from .engine import (CSAEngine, multistart, cost_grad_batch, frag_l1, write_x_block, read_x_block, CSA, CSA_SD, SYM_AUTO,  # noqa: F401
+                     SYM_GENERAL, SYM_PAIR, SYM_FULL)
 from .structures import (F_OP, F_FRAG, cartan_2b, cartan_SD, real_orbital_rotation, CSA_x_to_F_FRAG,  # noqa: F401
                          CSA_SD_x_to_F_FRAG, CSA_L1, ob_correction, one_body_L1, cartan_2b_num_params, cartan_SD_num_params,
                          real_orbital_rotation_num_params)

@@ -75,6 +75,10 @@ SIGNATURES = {
     "mambo_csa_cost_grad": (C.c_int, [_P, _P, _D, _P]),
     "mambo_csa_cost_grad_batch": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, _P]),
     "mambo_csa_set_wait_mode": (C.c_int, [_P, C.c_int]),
+    "mambo_csa_one_body_matrix": (C.c_int, [_P, C.c_int, _P, _P]),
+    "mambo_csa_frag_l1": (C.c_int, [C.c_int, C.c_int, C.c_int, _P, _D]),
+    "mambo_csa_write_x_block": (C.c_int, [C.c_char_p, C.c_char_p, C.c_longlong, C.c_longlong, _P]),
+    "mambo_csa_read_x_block": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), _P, C.c_longlong]),
     "mambo_csa_subtract_fragment": (C.c_int, [_P, _P, _D]),
     "mambo_csa_residual_cost": (C.c_int, [_P, _D]),
     "mambo_csa_get_residual": (C.c_int, [_P, _P, _P]),

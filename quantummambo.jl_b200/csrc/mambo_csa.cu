@@ -1879,6 +1879,92 @@ int mambo_csa_get_residual(mambo_csa* h, double* tbt_out, double* obt_out) {
     return MAMBO_OK;
 }
 
+// ---- final-norm pieces (lcu.jl:139-208, 262-267; fermionic.jl:457-479) ----------------------------------------------------
+// The one-body matrix whose eigenvalues give one_body_L1 (lcu.jl:262-267): H.mbts[2] + ob_correction(H) of the RESIDENT residual,
+// ob_correction = (spin_orb ? 1 : 2) sum_r tbt[:,:,r,r].  CSA handles hold no one-body tensor: obt_in (N x N column-major, may be
+// NULL) is added instead; CSA_SD handles add their own resident one-body residual.  out: N x N column-major.  The N x N `eigen`
+// of to_OBF (fermionic.jl:527-538) stays with the caller, like the other N x N eigenproblems of the path.
+int mambo_csa_one_body_matrix(mambo_csa* h, int spin_orb, const double* obt_in, double* out) {
+    if (!h || !out) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "one_body_matrix needs an unsharded handle");
+    CU(cudaSetDevice(h->device));
+    const int n = h->N, nn = n * n;
+    const double* Tt = h->T1;                 // T1[pair(r,s)][pair(p,q)] = tbt[p,q,r,s] in every mode (see k_unpack)
+    const double* add = nullptr;
+    if (h->flavour == MAMBO_CSA_SD) add = h->hT;
+    else if (obt_in) {
+        CU(cudaMemcpyAsync(h->Dh, obt_in, sizeof(double) * nn, cudaMemcpyHostToDevice, h->stream));
+        add = h->Dh;
+    }
+    CU(cudaMemsetAsync(h->DU, 0, sizeof(double) * nn, h->stream));
+    small::k_ob_correction<<<(h->nR + 255) / 256, 256, 0, h->stream>>>(Tt, n, h->packed ? 1 : 0, h->sw, h->pa, h->pq, h->nR, h->ldT,
+                                                                       spin_orb ? 1.0 : 2.0, add, h->DU);
+    h->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, h->DU, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->memo_valid = false;       // Dh / DU are scratch of the evaluation as well
+    return MAMBO_OK;
+}
+
+// CSA_L1 of one fragment (lcu.jl:139-182): a weighted abs-sum over the fragment's two-body Cartan coefficients -- O(N^2) host
+// arithmetic on x, no tensor work.  flavour picks where lambda starts in x (CSA: 0, CSA_SD: N).
+int mambo_csa_frag_l1(int N, int flavour, int spin_orb, const double* x, double* l1) {
+    if (N < 1 || !x || !l1) return fail(MAMBO_EINVAL, "bad arguments");
+    const double* lam = x + (flavour == MAMBO_CSA_SD ? N : 0);
+    double s = 0.0;
+    int idx = 0;
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j <= i; ++j, ++idx) {
+            if (spin_orb) {
+                if (i != j) s += 0.5 * std::fabs(lam[idx]);
+            } else {
+                s += (i != j ? 2.0 : 0.5) * std::fabs(lam[idx]);
+            }
+        }
+    *l1 = s;
+    return MAMBO_OK;
+}
+
+// ---- checkpoint block (decompose.jl:58-64): the dataset "<group>/x" = tot_L x alpha Float64, column-major, as a raw file ----
+// Layout: 8 bytes magic "MAMBOX01", 16 bytes group name (zero padded), int64 tot_L, int64 alpha, then tot_L*alpha doubles.
+// There is no libhdf5 in this image; INTEGRATION.md shows the ten Julia lines that turn the file into the HDF5 dataset.
+int mambo_csa_write_x_block(const char* path, const char* group, long long tot_L, long long alpha, const double* X) {
+    if (!path || !group || tot_L < 1 || alpha < 0 || (!X && alpha > 0)) return fail(MAMBO_EINVAL, "bad arguments");
+    const std::string tmp = std::string(path) + ".tmp";
+    FILE* f = std::fopen(tmp.c_str(), "wb");
+    if (!f) return fail(MAMBO_EINVAL, std::string("cannot open ") + tmp);
+    char name[16] = {0};
+    std::strncpy(name, group, 15);
+    bool ok = std::fwrite("MAMBOX01", 1, 8, f) == 8 && std::fwrite(name, 1, 16, f) == 16 && std::fwrite(&tot_L, 8, 1, f) == 1 &&
+              std::fwrite(&alpha, 8, 1, f) == 1;
+    const size_t cnt = (size_t)tot_L * (size_t)alpha;
+    ok = ok && (cnt == 0 || std::fwrite(X, sizeof(double), cnt, f) == cnt);
+    ok = (std::fclose(f) == 0) && ok;
+    if (!ok || std::rename(tmp.c_str(), path) != 0) {    // written beside the target and renamed: a crash never leaves half a checkpoint
+        std::remove(tmp.c_str());
+        return fail(MAMBO_EINVAL, std::string("cannot write ") + path);
+    }
+    return MAMBO_OK;
+}
+// X == NULL: only the header is read (tot_L, alpha, group); otherwise X must hold tot_L*alpha doubles (cap = its capacity).
+int mambo_csa_read_x_block(const char* path, char* group16, long long* tot_L, long long* alpha, double* X, long long cap) {
+    if (!path || !tot_L || !alpha) return fail(MAMBO_EINVAL, "bad arguments");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(MAMBO_EINVAL, std::string("cannot open ") + path);
+    char magic[8], name[16];
+    bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "MAMBOX01", 8) == 0 && std::fread(name, 1, 16, f) == 16 &&
+              std::fread(tot_L, 8, 1, f) == 1 && std::fread(alpha, 8, 1, f) == 1 && *tot_L >= 1 && *alpha >= 0;
+    if (ok && group16) std::memcpy(group16, name, 16);
+    if (ok && X) {
+        const long long cnt = *tot_L * *alpha;
+        ok = cnt <= cap && (cnt == 0 || std::fread(X, sizeof(double), (size_t)cnt, f) == (size_t)cnt);
+    }
+    std::fclose(f);
+    if (!ok) return fail(MAMBO_EINVAL, std::string("not a valid x block: ") + path);
+    return MAMBO_OK;
+}
+
 int mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double* obt_out) {
     if (!h || !x) return fail(MAMBO_EINVAL, "null argument");
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "reconstruct needs an unsharded handle");

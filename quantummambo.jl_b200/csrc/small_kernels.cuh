@@ -378,6 +378,28 @@ __global__ void k_unpack(const double* __restrict__ Tt, int n, int packed, const
     }
 }
 
+// ob_correction (fermionic.jl:457-479) of the resident residual: out[p + n q] = coef * sum_r tbt[p,q,r,r] (+ hT[p + n q] when given).
+// T~ holds tbt[p,q,r,s] at [pair(r,s)][pair(p,q)], so the n rows pair(r,r) are read contiguously: one thread per column pair.
+__global__ void __launch_bounds__(256) k_ob_correction(const double* __restrict__ Tt, int n, int packed, const double* __restrict__ sw,
+                                                       const int* __restrict__ pa, const int* __restrict__ pq, int nR, long long ldT,
+                                                       double coef, const double* __restrict__ hT, double* __restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nR) return;
+    double a0 = 0.0, a1 = 0.0;
+    int r = 0;
+    for (; r + 1 < n; r += 2) {
+        const long long i0 = packed ? (long long)r * (r + 1) / 2 + r : (long long)r * n + r;
+        const long long i1 = packed ? (long long)(r + 1) * (r + 2) / 2 + r + 1 : (long long)(r + 1) * n + r + 1;
+        a0 += Tt[i0 * ldT + j];
+        a1 += Tt[i1 * ldT + j];
+    }
+    if (r < n) a0 += Tt[(packed ? (long long)r * (r + 1) / 2 + r : (long long)r * n + r) * ldT + j];
+    const double v = coef * (a0 + a1) / sw[j];              // the diagonal pairs (r,r) carry weight 1
+    const int p = pa[j], q = pq[j];
+    out[p + (long long)n * q] = v + (hT ? hT[p + (long long)n * q] : 0.0);
+    if (packed && p != q) out[q + (long long)n * p] = v + (hT ? hT[q + (long long)n * p] : 0.0);
+}
+
 // W[p + nq + n^2 r + n^3 s] = sum_m B~[pair(r,s)][m] A~[pair(p,q)][m] / (sw sw)   (to_OP(frag), not hot)
 __global__ void k_reconstruct(const double* __restrict__ At, const double* __restrict__ Bt, int n, int ld, int packed,
                               const double* __restrict__ sw, double* __restrict__ out) {

@@ -17,7 +17,7 @@ from typing import Optional
 
 import numpy as np
 
-from .engine import CSAEngine, CSA as _CSA, CSA_SD as _CSA_SD
+from .engine import CSAEngine, write_x_block, CSA as _CSA, CSA_SD as _CSA_SD
 from .guesses import tbt_svd_1st
 from .structures import (F_OP, F_FRAG, CSA_x_to_F_FRAG, CSA_SD_x_to_F_FRAG, cartan_2b_num_params,
                          real_orbital_rotation_num_params)
@@ -159,6 +159,8 @@ def _greedy(H: F_OP, alpha_max: int, flavour: str, decomp_tol: float, verbose: b
                     with np.load(SAVENAME) as z:
                         keep = {k: z[k] for k in z.files if k != f"{group}/x"}
                 np.savez(SAVENAME, **keep, **{f"{group}/x": X[:, :a_curr]})
+                # the same dataset as the library's raw block, for the Julia side to h5write
+                write_x_block(SAVENAME[:-4] + f".{group}.xblk", group, X[:, :a_curr])
         if verbose:
             print(f"Finished {group} decomposition, total number of fragments is {a_curr}, remainder L2-norm is {curr_cost}")
         if curr_cost > decomp_tol and (verbose or not sd):

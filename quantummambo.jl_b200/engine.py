@@ -7,6 +7,7 @@ decompose.jl:56,182.  All numerics run in the CUDA library; numpy only carries b
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -160,6 +161,22 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_get_residual(self._h, t.ctypes.data, None if o is None else o.ctypes.data))
         return t, o
 
+    def one_body_matrix(self, spin_orb: bool = False, obt=None) -> np.ndarray:
+        """obt + ob_correction of the RESIDENT residual (mambo_csa_one_body_matrix; lcu.jl:262-267, fermionic.jl:457-479): the
+        matrix whose eigenvalues give one_body_L1.  CSA_SD engines use their own one-body residual, CSA engines add `obt`."""
+        n = self.N
+        out = np.empty((n, n), order="F")
+        oin = None if obt is None else np.asfortranarray(np.asarray(obt, dtype=np.float64))
+        _lib.check(self._lib.mambo_csa_one_body_matrix(self._h, 1 if spin_orb else 0, None if oin is None else oin.ctypes.data,
+                                                       out.ctypes.data))
+        return out
+
+    def one_body_L1(self, spin_orb: bool = False, obt=None) -> float:
+        """lcu.jl:262-267 for the resident residual: sum |eigenvalues| of one_body_matrix (the N x N eigen stays on the host)."""
+        M = self.one_body_matrix(spin_orb, obt)
+        D = np.linalg.eigvalsh(M) if np.allclose(M, M.T) else np.real(np.linalg.eigvals(M))
+        return float(np.sum(np.abs(D))) * (0.5 if spin_orb else 1.0)
+
     def reconstruct(self, x):
         x = _f64(x, self.L)
         n = self.N
@@ -288,3 +305,30 @@ def multistart(engines, x0s, g_tol: float = 1e-8, max_iter: int = 1000, lbfgs_me
     best = C.c_int(-1)
     _lib.check(lib.mambo_multistart_run(hs, len(engines), K, x0s.ctypes.data, xm.ctypes.data, C.byref(opt), res, C.byref(best)))
     return xm, [{k: getattr(r, k) for k, _ in r._fields_} for r in res], best.value
+
+
+def frag_l1(x, N: int, flavour="CSA", spin_orb: bool = False) -> float:
+    """CSA_L1 of the fragment with parameter vector x (mambo_csa_frag_l1; lcu.jl:139-182)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = C.c_double()
+    _lib.check(_lib.load().mambo_csa_frag_l1(int(N), _flavour_id(flavour), 1 if spin_orb else 0, x.ctypes.data, C.byref(out)))
+    return out.value
+
+
+def write_x_block(path: str, group: str, X) -> None:
+    """The checkpoint dataset "<group>/x" (decompose.jl:58-64; tot_L x alpha, column-major) as the library's raw block file."""
+    X = np.asfortranarray(np.asarray(X, dtype=np.float64))
+    if X.ndim != 2:
+        raise ValueError("X must be tot_L x alpha")
+    _lib.check(_lib.load().mambo_csa_write_x_block(os.fsencode(path), group.encode(), X.shape[0], X.shape[1], X.ctypes.data))
+
+
+def read_x_block(path: str):
+    """(group, X [tot_L, alpha]) from a file written by write_x_block / mambo_csa_write_x_block."""
+    lib = _lib.load()
+    name = C.create_string_buffer(16)
+    tot_L, alpha = C.c_longlong(), C.c_longlong()
+    _lib.check(lib.mambo_csa_read_x_block(os.fsencode(path), name, C.byref(tot_L), C.byref(alpha), None, 0))
+    X = np.empty((tot_L.value, alpha.value), order="F")
+    _lib.check(lib.mambo_csa_read_x_block(os.fsencode(path), name, C.byref(tot_L), C.byref(alpha), X.ctypes.data, X.size))
+    return name.value.decode(), X

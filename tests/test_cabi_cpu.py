@@ -102,3 +102,30 @@ def test_synthetic_inputs_are_deterministic_and_symmetric(mb):
     import csa_oracle as o
     assert np.array_equal(a, o.dense_sym_tbt(4, 3))
     assert np.array_equal(syn.random_x(4, 1, "CSA_SD"), o.random_x(4, 1, "CSA_SD"))
+
+
+def test_frag_l1_and_x_block_round_trip(tmp_path):
+    """The host-only entries of the C-ABI (no GPU involved): CSA_L1 of a fragment (lcu.jl:139-182) against the oracle, and the
+    raw checkpoint block (decompose.jl:58-64 layout: tot_L x alpha, column-major) written / read back bit for bit."""
+    import numpy as np
+    import csa_oracle as o
+    import mambo_b200 as mb
+    n = 5
+    cL = o.cartan_2b_num_params(n)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(cL + n * (n - 1) // 2)
+    assert mb.frag_l1(x, n) == o.CSA_L1(x[:cL], n)
+    assert mb.frag_l1(x, n, spin_orb=True) == o.CSA_L1(x[:cL], n, spin_orb=True)
+    xsd = np.concatenate([rng.standard_normal(n), x])
+    assert mb.frag_l1(xsd, n, "CSA_SD") == o.CSA_L1(x[:cL], n)
+    X = rng.standard_normal((len(x), 3))
+    path = str(tmp_path / "frags.xblk")
+    mb.write_x_block(path, "CSA", X)
+    group, Y = mb.read_x_block(path)
+    assert group == "CSA" and np.array_equal(X, Y) and Y.flags["F_CONTIGUOUS"]
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"MAMBOX01" and len(raw) == 8 + 16 + 16 + X.size * 8
+    assert np.array_equal(np.frombuffer(raw[40:], dtype="<f8").reshape(X.shape, order="F"), X)   # Julia: reshape(reinterpret(Float64, ...), tot_L, alpha)
+    mb.write_x_block(path, "CSA_SD", X[:, :0])                                                      # empty block is valid
+    group, Y = mb.read_x_block(path)
+    assert group == "CSA_SD" and Y.shape == (len(x), 0)

@@ -782,3 +782,29 @@ def test_largest_configuration_and_last_bucket_against_oracle(mb, lib, n):
     rc, rg = abs(c - c0) / abs(c0), rel(gr, g0)
     print(f"N={n}: rows {info['rows']}, cost rel.err {rc:.2e}, gradient max-norm rel.err {rg:.2e}")
     assert rc <= RTOL and rg <= RTOL
+
+
+@pytest.mark.parametrize("kind", ["dense_sym", "pairsym", "general"])
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+def test_one_body_matrix_of_the_resident_residual(mb, lib, kind, flavour):
+    """mambo_csa_one_body_matrix (lcu.jl:262-267, fermionic.jl:457-479): obt + 2 sum_r tbt[:,:,r,r] of the device-resident
+    residual, before and after a fragment has been subtracted; one_body_L1 from it against the oracle."""
+    n = 9
+    T = KINDS[kind](n, 21)
+    obt = _obt(n, 2)
+    obt = (obt + obt.T) / 2
+    x = o.random_x(n, 3, flavour)
+    with mb.CSAEngine(T, obt if flavour == "CSA_SD" else None, flavour) as e:
+        M = e.one_body_matrix(False, None if flavour == "CSA_SD" else obt)
+        assert rel(M, obt + o.ob_correction(T)) <= 1e-13
+        assert rel(e.one_body_matrix(True, None if flavour == "CSA_SD" else obt), obt + o.ob_correction(T, True)) <= 1e-13
+        if kind != "general":      # one_body_L1 diagonalises a symmetric matrix
+            assert abs(e.one_body_L1(False, None if flavour == "CSA_SD" else obt) - o.one_body_L1(obt, T)) <= 1e-12 * o.one_body_L1(obt, T)
+        e.subtract_fragment(x)
+        h, W = o.reconstruct_factored(x, n, flavour)
+        o_rem = obt - h if flavour == "CSA_SD" else obt
+        M2 = e.one_body_matrix(False, None if flavour == "CSA_SD" else obt)
+        assert rel(M2, o_rem + o.ob_correction(T - W)) <= 1e-12
+        c, g = e.cost_grad(x)                      # the call leaves the evaluation state intact
+    c0, g0 = o.cost_grad_factored(x, T - W, o_rem if flavour == "CSA_SD" else None, flavour)
+    assert abs(c - c0) <= RTOL * abs(c0) and rel(g, g0) <= RTOL
