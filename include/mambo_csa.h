@@ -216,6 +216,43 @@ int  mambo_csa_optimize_reserve(mambo_csa* h, int lbfgs_memory);
 int  mambo_multistart_run(mambo_csa** handles, int nhandles, int K, const double* x0, double* x_min,
                           const mambo_opt_options_t* opt, mambo_opt_result_t* res, int* best);
 
+/* --- double factorisation of the RESIDENT residual ------------------------------------------------------
+ * Replaces DF_decomposition (decompose.jl:297-398, do_Givens = false) and DF_based_greedy (decompose.jl:400-436).
+ * The reference diagonalises the whole N^2 x N^2 view with LAPACK (:326-330), keeps the eigenpairs with |eigenvalue| >= tol
+ * ordered by decreasing magnitude (:332-350, SVD_tol = 1e-8) and diagonalises every reshaped eigenvector (:352-354).  Here:
+ * Lanczos tridiagonalisation with full re-orthogonalisation on the device-resident matrix (restarted on breakdown, so
+ * degenerate eigenvalues and low-rank tensors are handled), bisection + twisted factorisation for the tridiagonal, a
+ * tensor-core GEMM back to the row space, and a batched Jacobi eigensolver for the N x N fragment matrices.  The result
+ * stays on the device, owned by the handle, until the next call or destroy.                                              */
+typedef struct mambo_df_stats_t {
+    int    krylov_dim;        /* Lanczos steps (= dimension of the tridiagonal)                                       */
+    int    restarts;          /* breakdowns of the recurrence (each opens a new unreduced block)                      */
+    int    num_frags;         /* eigenpairs kept: |eigenvalue| >= tol                                                 */
+    int    anti_frags;        /* fragments whose matrix is anti-symmetric (the Hermitian(1im * L) branch, :356-361);
+                                 their coefficient is already negated, omega / U are left zero: the complex N x N eigen
+                                 stays with the caller                                                                */
+    int    jacobi_sweeps_max; /* most sweeps any fragment needed (negative: some fragment did not converge)           */
+    double ortho_dev_before;  /* max |Z^T Z - I| of the tridiagonal eigenvectors before / after the Newton-Schulz     */
+    double ortho_dev_after;   /*   re-orthonormalisation                                                              */
+    double max_rel_residual;  /* max ||T y - theta y|| / max|theta| over the kept eigenpairs (only with verify != 0)  */
+    double seconds_lanczos, seconds_tridiag, seconds_backtransform, seconds_fragments;
+} mambo_df_stats_t;
+/* tol <= 0: the reference's SVD_tol = 1e-8.  max_frags <= 0: no limit, otherwise only the max_frags leading eigenpairs are
+ * turned into fragments.  verify != 0 additionally measures the eigen-residuals with one matvec per fragment.           */
+int  mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, int* num_frags, mambo_df_stats_t* stats);
+/* Fragments [first, first + count) of the last decomposition, in the reference's order (decreasing |eigenvalue|); any
+ * output may be NULL.  coeff[count]: F_FRAG.coeff; omega[count][N]: cartan_1b lambda (ascending, like LAPACK);
+ * U[count][N x N]: f_matrix_rotation.mat, column-major; L[count][N x N]: the fragment's matrix, column-major
+ * (to_OP(frag).mbts[3] = coeff * L (x) L, fermionic.jl:94-116); kind[count]: 0 symmetric, 1 anti-symmetric.             */
+int  mambo_csa_df_get(mambo_csa* h, int first, int count, double* coeff, double* omega, double* U, double* L, int* kind);
+/* DF_based_greedy (decompose.jl:400-436) from the last decomposition: lambda (N(N+1)/2, lower-triangular row-major, the
+ * cartan_mat_to_2b order), U1 (N x N column-major: the frame of the leading fragment), Lmat (N x N, may be NULL).        */
+int  mambo_csa_df_based_greedy(mambo_csa* h, double* lambda, double* U1, double* Lmat);
+/* C[M x N] = op(A) B on the device with the library's FP64 tensor-core GEMM (row-major, leading dimensions in doubles and
+ * even, 16-byte aligned pointers; trans_a != 0: A is stored K x M).  Exported for tests and bandwidth/flop measurements. */
+int  mambo_dgemm_device(int device, void* stream, int trans_a, int M, int N, int K, const double* d_A, long long lda,
+                        const double* d_B, long long ldb, double* d_C, long long ldc);
+
 #ifdef __cplusplus
 }
 #endif

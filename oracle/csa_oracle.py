@@ -502,6 +502,71 @@ def tbt_svd_1st(tbt, tiny: float = 1e-12, fix_sign: bool = False):
 
 
 # ----------------------------------------------------------------------------------------------
+# double factorisation (decompose.jl:297-436): SURVEY 8(f)3
+# ----------------------------------------------------------------------------------------------
+
+def DF_decomposition(tbt, tol: float = 1e-8, tiny: float = 1e-12):
+    """decompose.jl:297-398 with do_Givens = DF_GIVENS = false (config.jl:14; SVD_tol = 1e-8, SVD_tiny = 1e-12, config.jl:21-22).
+
+    Returns a list of fragments (coeff, omega (n), U (n x n), L (n x n)), ordered by decreasing |eigenvalue| of the
+    N^2 x N^2 view: to_OP(frag) = coeff * sum_lm omega_l omega_m U[:,l] U[:,l]' (x) U[:,m] U[:,m]' = coeff * L (x) L with
+    L = U diag(omega) U' (fermionic.jl:94-116).  The anti-Hermitian branch (:346-352: eigen of Hermitian(1im * L), coefficient
+    negated) returns complex U, as the reference does."""
+    n = tbt.shape[0]
+    N2 = n * n
+    full = np.reshape(tbt, (N2, N2), order="F")                       # :317
+    res = np.triu(full) + np.triu(full, 1).T                          # Symmetric(tbt_full): the upper triangle (:318)
+    if np.sum(np.abs(full - res)) > tiny:                             # :319-322 (a general `eigen` in the reference)
+        raise ValueError("non-symmetric two-body tensor: the reference falls back to a non-symmetric eigen here (not restated)")
+    lam, U = np.linalg.eigh(res)                                      # :326-330
+    ind = np.argsort(np.abs(lam), kind="stable")[::-1]                # :332
+    lam, U = lam[ind], U[:, ind]
+    num_ops = N2                                                      # :336-345
+    for i in range(N2):
+        if abs(lam[i]) < tol:
+            num_ops = i
+            break
+    frags = []
+    for i in range(num_ops):                                          # :352-381
+        full_l = np.reshape(U[:, i], (n, n), order="F")
+        cur_l = np.triu(full_l) + np.triu(full_l, 1).T                # Symmetric(full_l)
+        coeff = lam[i]
+        if np.sum(np.abs(cur_l - full_l) ** 2) > tiny:
+            if np.sum(np.abs(full_l + full_l.T)) > tiny:
+                raise ValueError(f"DF fragment {i + 1} is neither Hermitian or anti-Hermitian!")
+            cur = 1j * full_l
+            cur_l = np.triu(cur) + np.triu(cur, 1).conj().T           # Hermitian(1im * full_l)
+            coeff = -coeff
+        w, Ul = np.linalg.eigh(cur_l)
+        frags.append((coeff, w, Ul, cur_l))
+    return frags
+
+
+def DF_to_tbt(frags, n: int):
+    """sum of to_OP(frag).mbts[3] over DF fragments (fermionic.jl:94-116, the debug branch decompose.jl:383-387)."""
+    tbt = np.zeros((n, n, n, n), dtype=complex if any(np.iscomplexobj(f[3]) for f in frags) else float)
+    for coeff, w, Ul, _ in frags:
+        Lm = (Ul * w) @ Ul.conj().T if np.iscomplexobj(Ul) else (Ul * w) @ Ul.T
+        tbt += coeff * np.einsum("ab,cd->abcd", Lm, Lm)
+    return tbt
+
+
+def DF_based_greedy(tbt, tol: float = 1e-8):
+    """decompose.jl:400-436: CSA fragment in the orbital frame of the largest DF fragment; its Cartan coefficients collect
+    every DF fragment in that frame.  Returns (lambda (cL, lower-triangular row-major), U1 (n x n), Lmat (n x n))."""
+    frags = DF_decomposition(tbt, tol)
+    n = tbt.shape[0]
+    c1, w1, U1, _ = frags[0]
+    Lmat = c1 * np.outer(w1, w1)                                      # :406-413
+    for cm, wm, Um, _ in frags[1:]:                                   # :418-430
+        Vm = Um @ U1.conj().T                                         # Vm = Um * U1dag
+        v = (np.abs(Vm) ** 2) @ wm                                    # sum_p lambda_p |Vm[i,p]|^2
+        Lmat = Lmat + cm * np.outer(v, v)
+    lam = np.array([(Lmat[i, j] + Lmat[j, i]) / 2 for i in range(n) for j in range(i + 1)])   # cartan_mat_to_2b, fermionic.jl:34-48
+    return lam, U1, Lmat
+
+
+# ----------------------------------------------------------------------------------------------
 # greedy drivers (decompose.jl:1-246) with scipy BFGS standing in for Optim.jl BFGS
 # ----------------------------------------------------------------------------------------------
 

@@ -18,22 +18,49 @@ INCLUDE = PKG_DIR.parent / "include"
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
+    "-Xcompiler", "-fPIC",
 ]
-SOURCES = ["mambo_csa.cu", "optimizer.cu"]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
+SOURCES = ["mambo_csa.cu", "optimizer.cu", "df.cu"]
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile the CUDA engine for sm_100a into csrc/libmambo_b200.so (no GPU needed: nvcc cross-compiles)."""
+    """Compile the CUDA engine for sm_100a into csrc/libmambo_b200.so (no GPU needed: nvcc cross-compiles).
+    Every translation unit is compiled to its own object (in parallel, only when it or a header changed), then linked."""
+    from concurrent.futures import ThreadPoolExecutor
+    import re
     srcs = [CSRC / s for s in SOURCES]
-    deps = srcs + list(CSRC.glob("*.cuh")) + [INCLUDE / "mambo_csa.h"]
-    if not force and LIB_PATH.exists() and all(LIB_PATH.stat().st_mtime >= d.stat().st_mtime for d in deps):
-        return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", str(LIB_PATH), *map(str, srcs)]
-    if verbose:
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True, cwd=str(CSRC))
+
+    def deps_of(path: Path, seen=None):
+        """the file and, transitively, every header it includes with quotes"""
+        seen = set() if seen is None else seen
+        path = path.resolve()
+        if path in seen or not path.exists():
+            return seen
+        seen.add(path)
+        for inc in re.findall(r'^\s*#include\s+"([^"]+)"', path.read_text(), flags=re.M):
+            deps_of(path.parent / inc, seen)
+        return seen
+
+    def compile_one(src: Path):
+        obj = src.with_suffix(".o")
+        if not force and obj.exists() and obj.stat().st_mtime >= max(d.stat().st_mtime for d in deps_of(src)):
+            return obj, False
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", str(obj), str(src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True, cwd=str(CSRC))
+        return obj, True
+
+    with ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        done = list(pool.map(compile_one, srcs))
+    objs = [o for o, _ in done]
+    if force or not LIB_PATH.exists() or any(ch for _, ch in done) or any(LIB_PATH.stat().st_mtime < o.stat().st_mtime for o in objs):
+        cmd = [nvcc, *LINK_FLAGS, "-o", str(LIB_PATH), *map(str, objs)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.run(cmd, check=True, cwd=str(CSRC))
     return LIB_PATH
 
 
@@ -56,6 +83,13 @@ class OptOptions(C.Structure):
 class OptResult(C.Structure):
     _fields_ = [("minimum", C.c_double), ("iterations", C.c_int), ("evaluations", C.c_int),
                 ("converged", C.c_int), ("device", C.c_int)]
+
+
+class DfStats(C.Structure):
+    _fields_ = [("krylov_dim", C.c_int), ("restarts", C.c_int), ("num_frags", C.c_int), ("anti_frags", C.c_int),
+                ("jacobi_sweeps_max", C.c_int), ("ortho_dev_before", C.c_double), ("ortho_dev_after", C.c_double),
+                ("max_rel_residual", C.c_double), ("seconds_lanczos", C.c_double), ("seconds_tridiag", C.c_double),
+                ("seconds_backtransform", C.c_double), ("seconds_fragments", C.c_double)]
 
 
 _P = C.c_void_p
@@ -102,6 +136,10 @@ SIGNATURES = {
     "mambo_csa_set_profiling": (C.c_int, [_P, C.c_int]),
     "mambo_csa_get_segments": (C.c_int, [_P, _D, C.POINTER(C.c_int)]),
     "mambo_csa_get_profile": (C.c_int, [_P, _D, C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
+    "mambo_csa_df_decompose": (C.c_int, [_P, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(DfStats)]),
+    "mambo_csa_df_get": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "mambo_csa_df_based_greedy": (C.c_int, [_P, _P, _P, _P]),
+    "mambo_dgemm_device": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong]),
     "mambo_csa_optimize": (C.c_int, [_P, _P, _P, C.POINTER(OptOptions), C.POINTER(OptResult)]),
     "mambo_csa_optimize_reserve": (C.c_int, [_P, C.c_int]),
     "mambo_multistart_run": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.POINTER(OptOptions),

@@ -1,0 +1,19 @@
+// internal.h -- library-internal seams between the translation units of libmambo_b200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/mambo_csa.h"
+
+// read-only view of the resident residual of an unsharded handle (df.cu)
+struct mambo_resident_view {
+    int N, mode, packed, rows, device;
+    long long ldT;
+    const double *T1, *T2;          // T~ (and its transpose in GENERAL mode), row-major, pitch ldT
+    const int *pa, *pq;             // row -> (p, q)
+    const double* sw;               // sqrt(weight) of the packed rows
+    cudaStream_t stream;
+};
+extern "C" int mambo_csa_resident_view(mambo_csa* h, mambo_resident_view* v);
+// one opaque, handle-owned state object per handle (the double factorisation); freed by mambo_csa_destroy through `destroy`
+extern "C" void** mambo_csa_df_slot(mambo_csa* h, void (*destroy)(void*));
+extern "C" void mambo_set_error(const char* msg);
+extern "C" void mambo_csa_count_launches(mambo_csa* h, long long n);

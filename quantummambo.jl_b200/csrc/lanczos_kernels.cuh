@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(256) k_symv(const double* __restrict__ T, cons
 }
 
 // c[k] = V[k] . w  (k < nv); V vectors have pitch ldv.  One CTA per vector, fixed-order reduction.
-__global__ void __launch_bounds__(256) k_dots(const double* __restrict__ V, long long ldv, int len, const double* __restrict__ w,
+static __global__ void __launch_bounds__(256) k_dots(const double* __restrict__ V, long long ldv, int len, const double* __restrict__ w,
                                               double* __restrict__ c) {
     __shared__ double red[8];
     const double* vk = V + (long long)blockIdx.x * ldv;
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) k_dots(const double* __restrict__ V, long
 }
 
 // w -= sum_k c[k] V[k]; block 0 also accumulates the coefficient of the newest vector: alpha[j] (+)= c[j]
-__global__ void __launch_bounds__(256) k_project(const double* __restrict__ V, long long ldv, int len, int nv, const double* __restrict__ c,
+static __global__ void __launch_bounds__(256) k_project(const double* __restrict__ V, long long ldv, int len, int nv, const double* __restrict__ c,
                                                  double* __restrict__ w, double* __restrict__ alpha, int j, int accumulate) {
     extern __shared__ double sc[];
     for (int k = threadIdx.x; k < nv; k += 256) sc[k] = c[k];
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) k_project(const double* __restrict__ V, l
 }
 
 // beta[j] = ||w||; vnext = w / beta (zero when w vanished: invariant subspace reached, the host stops on beta)
-__global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ w, int len, int lenpad, double* __restrict__ vnext,
+static __global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ w, int len, int lenpad, double* __restrict__ vnext,
                                                     double* __restrict__ beta, int j) {
     __shared__ double red[32];
     __shared__ double s_inv;
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(1024) k_normalise(const double* __restrict__ w
 // key distinguishes (p,q) from (q,p): a start vector that is symmetric under p <-> q would confine the whole Krylov space to the
 // symmetric subspace whenever the tensor commutes with that swap, and a dominant ANTI-symmetric eigenvector -- the anti-Hermitian
 // branch of tbt_svd_1st (guesses.jl:67-75) -- would never be found.  normalised by k_normalise afterwards.
-__global__ void k_start(double* __restrict__ w, int len, const int* __restrict__ pa, const int* __restrict__ pq, int n, int packed) {
+static __global__ void k_start(double* __restrict__ w, int len, const int* __restrict__ pa, const int* __restrict__ pq, int n, int packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < len) {
         const int p = pa[i], q = pq[i];
@@ -172,7 +172,7 @@ __global__ void k_start(double* __restrict__ w, int len, const int* __restrict__
 
 // Ritz vector y = sum_k s[k] V[k] (rows of the matrix) scattered to the N x N column-major operator of the reference:
 // packed mode undoes the sqrt(2) row scaling and mirrors (p,q) -> (q,p).
-__global__ void __launch_bounds__(256) k_combine(const double* __restrict__ V, long long ldv, int len, int nv, const double* __restrict__ s,
+static __global__ void __launch_bounds__(256) k_combine(const double* __restrict__ V, long long ldv, int len, int nv, const double* __restrict__ s,
                                                  const int* __restrict__ pa, const int* __restrict__ pq, const double* __restrict__ sw,
                                                  int n, int packed, double* __restrict__ out) {
     extern __shared__ double sc[];

@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/mambo_csa.h"
+#include "internal.h"
 #include "fused_kernel.cuh"
 #include "small_kernels.cuh"
 #include "chain_kernels.cuh"
@@ -169,6 +170,9 @@ struct mambo_csa {
     void* opt_ws = nullptr;
     size_t opt_ws_bytes = 0;
     void* opt_hs = nullptr;                    // pinned host scalars of the optimiser (128 bytes)
+    // double factorisation of the resident residual (df.cu): opaque state + its destructor
+    void* df_state = nullptr;
+    void (*df_destroy)(void*) = nullptr;
     // CUDA-graph segments of the small-kernel sequences
     bool use_graphs = true;
     bool capturing = false;               // a graph segment is being captured: nested segments run inline
@@ -1178,6 +1182,21 @@ int mambo_csa_status_check(mambo_csa* h) {
     return check_status(h);
 }
 
+// Library-internal (df.cu): the resident residual of an unsharded handle, read-only.
+int mambo_csa_resident_view(mambo_csa* h, mambo_resident_view* v) {
+    if (!h || !v) return fail(MAMBO_EINVAL, "null argument");
+    if (h->nshards != 1) return fail(MAMBO_ESTATE, "the double factorisation needs an unsharded handle");
+    v->N = h->N; v->mode = h->mode; v->packed = h->packed ? 1 : 0; v->rows = h->nR; v->device = h->device;
+    v->ldT = h->ldT; v->T1 = h->T1; v->T2 = h->T2; v->pa = h->pa; v->pq = h->pq; v->sw = h->sw; v->stream = h->stream;
+    return MAMBO_OK;
+}
+void** mambo_csa_df_slot(mambo_csa* h, void (*destroy)(void*)) {
+    if (!h) return nullptr;
+    if (destroy) h->df_destroy = destroy;
+    return &h->df_state;
+}
+void mambo_csa_count_launches(mambo_csa* h, long long n) { if (h) h->launches += n; }
+
 int mambo_csa_get_stream(mambo_csa* h, void** stream, int* device) {
     if (!h) return fail(MAMBO_EINVAL, "null handle");
     if (stream) *stream = (void*)h->stream;
@@ -1246,6 +1265,7 @@ void mambo_csa_destroy(mambo_csa* h) {
     cudaSetDevice(h->device);
     if (h->own_stream) cudaStreamSynchronize(h->own_stream);
     if (h->side_stream) cudaStreamSynchronize(h->side_stream);
+    if (h->df_state && h->df_destroy) h->df_destroy(h->df_state);
     for (auto* v : {&h->g_pre, &h->g_fin, &h->g_host, &h->g_pre_b, &h->g_fin_seq})
         for (GraphSeg& g : *v)
             if (g.exec) cudaGraphExecDestroy(g.exec);

@@ -194,6 +194,46 @@ class CSAEngine:
         _lib.check(self._lib.mambo_csa_leading_eig(self._h, tol, max_iter, C.byref(lam), vec.ctypes.data, C.byref(it), C.byref(res)))
         return lam.value, vec, {"iterations": it.value, "residual": res.value}
 
+    # -- double factorisation (decompose.jl:297-436) ------------------------------------------------------------
+    def df_decompose(self, tol: float = 0.0, max_frags: int = 0, verify: bool = False) -> dict:
+        """DF_decomposition of the resident residual on the device (mambo_csa_df_decompose).  Returns the statistics; the
+        fragments stay on the device until fetched with `df_get`."""
+        nf = C.c_int()
+        st = _lib.DfStats()
+        _lib.check(self._lib.mambo_csa_df_decompose(self._h, tol, max_frags, 1 if verify else 0, C.byref(nf), C.byref(st)))
+        out = {k: getattr(st, k) for k, _ in st._fields_}
+        out["num_frags"] = nf.value
+        return out
+
+    def df_get(self, first: int = 0, count: int | None = None, want_L: bool = True, want_U: bool = True):
+        """(coeff [k], omega [k, N], U [k, N, N], L [k, N, N], kind [k]) of fragments [first, first + count): U[e] and L[e] are
+        ordinary numpy matrices (U[e][:, l] = eigenvector l)."""
+        n = self.N
+        if count is None:
+            raise ValueError("count is required")
+        coeff = np.empty(count)
+        omega = np.empty((count, n))
+        kind = np.empty(count, dtype=np.int32)
+        U = np.empty((count, n, n)) if want_U else None
+        L = np.empty((count, n, n)) if want_L else None
+        _lib.check(self._lib.mambo_csa_df_get(self._h, first, count, coeff.ctypes.data, omega.ctypes.data,
+                                              U.ctypes.data if want_U else None, L.ctypes.data if want_L else None, kind.ctypes.data))
+        # the library writes column-major N x N blocks: as C-ordered numpy blocks they are the transposes
+        if want_U:
+            U = U.transpose(0, 2, 1)
+        if want_L:
+            L = L.transpose(0, 2, 1)
+        return coeff, omega, U, L, kind
+
+    def df_based_greedy(self):
+        """DF_based_greedy (decompose.jl:400-436) from the last `df_decompose`: (lambda (cL), U1 (N x N), Lmat (N x N))."""
+        n = self.N
+        lam = np.empty(n * (n + 1) // 2)
+        U1 = np.empty((n, n), order="F")
+        Lm = np.empty((n, n), order="F")
+        _lib.check(self._lib.mambo_csa_df_based_greedy(self._h, lam.ctypes.data, U1.ctypes.data, Lm.ctypes.data))
+        return lam, U1, Lm
+
     def symv_device(self, d_v_ptr: int, d_y_ptr: int):
         """y = T~ v on the device (rows_padded doubles each): one HBM pass over the resident residual."""
         _lib.check(self._lib.mambo_csa_symv_device(self._h, d_v_ptr, d_y_ptr))
