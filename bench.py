@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-rowpanel", action="store_true")
     ap.add_argument("--cpu-evals", type=int, default=0, help="evaluations timed for the CPU baseline (0 = auto)")
     ap.add_argument("--no-greedy", action="store_true", help="skip the greedy-CSA time-to-tolerance leg")
+    ap.add_argument("--no-df", action="store_true", help="skip the double-factorisation leg")
     ap.add_argument("--lanes", type=int, default=0,
                     help="evaluation lanes per GPU (mambo_csa_create_lane); 0 = auto (see main), 1..8")
     return ap.parse_args()
@@ -343,6 +344,58 @@ def greedy_time_to_tolerance(mb, syn, device: int, n: int = 50, R: int = 4, tol_
     return out
 
 
+
+def df_leg(mb, syn, eng, device: int, hbm_peak, n_cpu: int = 50, cpu: bool = True):
+    """DF_decomposition (decompose.jl:297-398) + DF_based_greedy (:400-436) of the resident residual on the
+    device (Lanczos tridiagonalisation to completion, bisection + twisted factorisation, DMMA back-transformation, batched
+    Jacobi for the fragment matrices).  `eng` holds the bench's own N = 100 tensor; the oracle's LAPACK path (the reference
+    algorithm: `eigh` of the N^2 x N^2 view) runs beside it at N = n_cpu, where it finishes in seconds."""
+    out = {}
+
+    def one(e, tag):
+        info = e.info()
+        R = info["rows"]
+        e.df_decompose(max_frags=1)                                   # warm-up: workspaces, attributes
+        t0 = time.perf_counter()
+        st = e.df_decompose(verify=False)
+        dt = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        lam, U1, Lm = e.df_based_greedy()
+        t_g = time.perf_counter() - t1
+        m = st["krylov_dim"]
+        # HBM traffic of the tridiagonalisation: one pass over T~ per step plus, twice per step, a dot pass and a projection
+        # pass over the j + 1 Krylov vectors found so far
+        lanczos_bytes = 8.0 * R * R * m + 4.0 * 8.0 * R * (m * (m + 1) / 2.0)
+        gbs = lanczos_bytes / max(st["seconds_lanczos"], 1e-12) / 1e9
+        out[tag] = {"N": info["N"], "rows": R, "fragments": st["num_frags"], "krylov_dim": m, "restarts": st["restarts"],
+                    "seconds_total": dt, "seconds_lanczos": st["seconds_lanczos"], "seconds_tridiagonal": st["seconds_tridiag"],
+                    "seconds_backtransform": st["seconds_backtransform"], "seconds_fragment_eigen": st["seconds_fragments"],
+                    "seconds_df_based_greedy": t_g, "ortho_dev": st["ortho_dev_after"], "jacobi_sweeps_max": st["jacobi_sweeps_max"],
+                    "roofline": {"bound": "hbm", "kernel": "Lanczos step: lanczos::k_symv + k_dots + df::k_project_split (x2)",
+                                 "achieved": gbs, "peak": hbm_peak or 6534.5, "unit": "GB/s", "frac": gbs / (hbm_peak or 6534.5),
+                                 "algorithmic_bytes": lanczos_bytes, "traffic": None,
+                                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if hbm_peak else "fallback 6534.5 GB/s (file absent)"}}
+        return st
+
+    one(eng, "device")
+    if cpu:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import csa_oracle as oracle  # noqa: E402  (baseline only)
+        cores = use_all_host_threads()
+        Tc = syn.dense_sym_tbt(n_cpu, 0)
+        with mb.CSAEngine(Tc, device=device) as e2:
+            one(e2, "device_small")
+            coeff, _, _, _, _ = e2.df_get(0, out["device_small"]["fragments"], want_L=False, want_U=False)
+        t0 = time.perf_counter()
+        fr = oracle.DF_decomposition(Tc)
+        t_cpu = time.perf_counter() - t0
+        c_ref = np.array([f[0] for f in fr])
+        out["cpu_small"] = {"what": f"oracle.DF_decomposition (numpy/LAPACK eigh of the N^2 x N^2 view + one eigh per fragment), N={n_cpu}",
+                            "cores": cores, "kind": "port", "seconds": t_cpu, "fragments": len(fr),
+                            "coeff_parity_rel": float(np.max(np.abs(coeff - c_ref)) / np.max(np.abs(c_ref))) if len(fr) == len(coeff) else None,
+                            "gpu_speedup": t_cpu / out["device_small"]["seconds_total"]}
+    return out
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -545,6 +598,18 @@ def main():
         except Exception as exc:  # noqa: BLE001  (a side leg must never cost the main line)
             guess = {"error": repr(exc)}
             eng.set_stream(None)
+
+    dfres = None
+    if rank == 0 and world == 1 and not args.no_df:
+        try:
+            hbm = None
+            try:
+                hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+            except Exception:
+                pass
+            dfres = df_leg(mb, syn, eng, local_rank, hbm, cpu=not args.no_cpu_baseline)
+        except Exception as exc:  # noqa: BLE001  (a side leg must never cost the main line)
+            dfres = {"error": repr(exc)}
 
     # caller threads per rank: one per lane, but never more than this rank's share of the host cores (the synchronous closure
     # spins in cudaStreamSynchronize by default: 64 spinning threads on a 32-core host added nothing in round 1).  When the
@@ -773,6 +838,8 @@ def main():
             line["greedy"] = greedy
         if guess is not None:
             line["initial_guess"] = guess
+        if dfres is not None:
+            line["double_factorisation"] = dfres
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

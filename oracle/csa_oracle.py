@@ -505,13 +505,24 @@ def tbt_svd_1st(tbt, tiny: float = 1e-12, fix_sign: bool = False):
 # double factorisation (decompose.jl:297-436): SURVEY 8(f)3
 # ----------------------------------------------------------------------------------------------
 
-def DF_decomposition(tbt, tol: float = 1e-8, tiny: float = 1e-12):
+def _first_max_positive(v):
+    """sign convention shared with the CUDA library: the largest-magnitude entry (the first one) is positive"""
+    flat = v.reshape(-1, order="F")
+    k = int(np.argmax(np.abs(flat)))
+    return -v if flat[k] < 0 else v
+
+
+def DF_decomposition(tbt, tol: float = 1e-8, tiny: float = 1e-12, fix_sign: bool = False):
     """decompose.jl:297-398 with do_Givens = DF_GIVENS = false (config.jl:14; SVD_tol = 1e-8, SVD_tiny = 1e-12, config.jl:21-22).
 
     Returns a list of fragments (coeff, omega (n), U (n x n), L (n x n)), ordered by decreasing |eigenvalue| of the
     N^2 x N^2 view: to_OP(frag) = coeff * sum_lm omega_l omega_m U[:,l] U[:,l]' (x) U[:,m] U[:,m]' = coeff * L (x) L with
     L = U diag(omega) U' (fermionic.jl:94-116).  The anti-Hermitian branch (:346-352: eigen of Hermitian(1im * L), coefficient
-    negated) returns complex U, as the reference does."""
+    negated) returns complex U, as the reference does.
+
+    fix_sign: LAPACK leaves the sign of every eigenvector to chance, and DF_based_greedy depends on it (Vm = Um * U1dag contracts
+    the EIGENVECTOR indices of both frames, decompose.jl:421).  fix_sign pins the convention the CUDA library documents (largest-
+    magnitude entry of every N^2-eigenvector and of every column of U positive) so that the two can be compared entry by entry."""
     n = tbt.shape[0]
     N2 = n * n
     full = np.reshape(tbt, (N2, N2), order="F")                       # :317
@@ -529,6 +540,8 @@ def DF_decomposition(tbt, tol: float = 1e-8, tiny: float = 1e-12):
     frags = []
     for i in range(num_ops):                                          # :352-381
         full_l = np.reshape(U[:, i], (n, n), order="F")
+        if fix_sign:
+            full_l = _first_max_positive(full_l)
         cur_l = np.triu(full_l) + np.triu(full_l, 1).T                # Symmetric(full_l)
         coeff = lam[i]
         if np.sum(np.abs(cur_l - full_l) ** 2) > tiny:
@@ -538,6 +551,8 @@ def DF_decomposition(tbt, tol: float = 1e-8, tiny: float = 1e-12):
             cur_l = np.triu(cur) + np.triu(cur, 1).conj().T           # Hermitian(1im * full_l)
             coeff = -coeff
         w, Ul = np.linalg.eigh(cur_l)
+        if fix_sign and not np.iscomplexobj(Ul):
+            Ul = np.stack([_first_max_positive(Ul[:, k]) for k in range(n)], axis=1)
         frags.append((coeff, w, Ul, cur_l))
     return frags
 
@@ -551,10 +566,10 @@ def DF_to_tbt(frags, n: int):
     return tbt
 
 
-def DF_based_greedy(tbt, tol: float = 1e-8):
+def DF_based_greedy(tbt, tol: float = 1e-8, fix_sign: bool = False):
     """decompose.jl:400-436: CSA fragment in the orbital frame of the largest DF fragment; its Cartan coefficients collect
     every DF fragment in that frame.  Returns (lambda (cL, lower-triangular row-major), U1 (n x n), Lmat (n x n))."""
-    frags = DF_decomposition(tbt, tol)
+    frags = DF_decomposition(tbt, tol, fix_sign=fix_sign)
     n = tbt.shape[0]
     c1, w1, U1, _ = frags[0]
     Lmat = c1 * np.outer(w1, w1)                                      # :406-413

@@ -38,6 +38,7 @@ double now_s() {
 
 struct DfState {
     int device = 0, N = 0, nfrag = 0;
+    bool valid = false;               // a decomposition has completed on this handle (it may hold zero fragments)
     double *d_coeff = nullptr, *d_omega = nullptr, *d_U = nullptr, *d_L = nullptr;
     std::vector<double> coeff;
     std::vector<int> kind;
@@ -46,6 +47,7 @@ struct DfState {
         for (double** p : {&d_coeff, &d_omega, &d_U, &d_L})
             if (*p) { cudaFree(*p); *p = nullptr; }
         nfrag = 0;
+        valid = false;
         coeff.clear();
         kind.clear();
     }
@@ -281,6 +283,7 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
     const int ne = (int)order.size();
     sts.num_frags = ne;
     if (ne == 0) {
+        S->valid = true;
         if (num_frags) *num_frags = 0;
         sts.seconds_tridiag = now_s() - t1;
         if (stats) *stats = sts;
@@ -380,6 +383,8 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
     DCU(cudaMalloc((void**)&S->d_coeff, sizeof(double) * ne));
     if (!v.packed) DCU(cudaMemsetAsync(S->d_L, 0, sizeof(double) * nn * ne, st));
     df::k_frag_matrix<<<dim3(vblocks, ne), 256, 0, st>>>(Y, ldv, R, v.pa, v.pq, v.sw, n, v.packed, S->d_L);
+    df::k_frag_fix_sign<<<ne, 256, 0, st>>>(S->d_L, n);
+    launches += 1;
     double *d_sym = nullptr, *d_asym = nullptr;
     int* d_status = nullptr;
     DCU(scr.get((void**)&d_sym, sizeof(double) * ne));
@@ -398,7 +403,7 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
         DCU(cudaFuncSetAttribute(df::k_jacobi_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_full));
         df::k_jacobi_batch<true><<<ne, jthreads, sm_full, st>>>(S->d_L, n, S->d_omega, S->d_U, nullptr, d_status, 60);
     } else {
-        double* Ut = B1;                                   // ne x n x n scratch: B1 holds at least ne x ldv >= ne x n^2 / 2 ... use a buffer of its own
+        double* Ut = nullptr;                              // ne x n x n: the transposed eigenvector accumulators live in global memory / L2
         DCU(scr.get((void**)&Ut, sizeof(double) * nn * ne));
         DCU(cudaFuncSetAttribute(df::k_jacobi_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_half));
         df::k_jacobi_batch<false><<<ne, jthreads, sm_half, st>>>(S->d_L, n, S->d_omega, S->d_U, Ut, d_status, 60);
@@ -431,6 +436,7 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
     DCU(cudaMemcpyAsync(S->d_coeff, S->coeff.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, st));
     DCU(cudaStreamSynchronize(st));
     S->nfrag = ne;
+    S->valid = !unconverged;
     sts.seconds_fragments = now_s() - t3;
     mambo_csa_count_launches(h, launches);
     if (num_frags) *num_frags = ne;
@@ -443,7 +449,7 @@ int mambo_csa_df_get(mambo_csa* h, int first, int count, double* coeff, double* 
     if (!h) return dfail(MAMBO_EINVAL, "null handle");
     void** slot = mambo_csa_df_slot(h, nullptr);
     DfState* S = slot ? static_cast<DfState*>(*slot) : nullptr;
-    if (!S || S->nfrag == 0) return dfail(MAMBO_ESTATE, "no double factorisation on this handle (call mambo_csa_df_decompose first)");
+    if (!S || !S->valid) return dfail(MAMBO_ESTATE, "no double factorisation on this handle (call mambo_csa_df_decompose first)");
     if (first < 0 || count < 0 || first + count > S->nfrag) return dfail(MAMBO_EINVAL, "fragment range out of bounds");
     if (count == 0) return MAMBO_OK;
     DCU(cudaSetDevice(S->device));
@@ -465,7 +471,8 @@ int mambo_csa_df_based_greedy(mambo_csa* h, double* lambda, double* U1, double* 
     if (!h || !lambda || !U1) return dfail(MAMBO_EINVAL, "null argument");
     void** slot = mambo_csa_df_slot(h, nullptr);
     DfState* S = slot ? static_cast<DfState*>(*slot) : nullptr;
-    if (!S || S->nfrag == 0) return dfail(MAMBO_ESTATE, "no double factorisation on this handle (call mambo_csa_df_decompose first)");
+    if (!S || !S->valid) return dfail(MAMBO_ESTATE, "no double factorisation on this handle (call mambo_csa_df_decompose first)");
+    if (S->nfrag == 0) return dfail(MAMBO_ESTATE, "the double factorisation holds no fragment (every |eigenvalue| is below the tolerance)");
     for (int k : S->kind)
         if (k) return dfail(MAMBO_ESTATE, "DF_based_greedy with anti-symmetric (complex) fragments is not available on the device");
     mambo_resident_view v;

@@ -353,6 +353,38 @@ static __global__ void __launch_bounds__(256) k_frag_matrix(const double* __rest
     }
 }
 
+// Sign convention: an eigenvector is defined up to its sign, and DF_based_greedy (decompose.jl:418-430) depends on it through the
+// order of omega.  Here every fragment matrix gets its largest-magnitude entry (the first one in column-major order) positive.
+// One CTA per fragment.
+static __global__ void __launch_bounds__(256) k_frag_fix_sign(double* __restrict__ Lm, int n) {
+    __shared__ double bv[8];
+    __shared__ int bi[8];
+    __shared__ int s_flip;
+    double* L = Lm + (long long)blockIdx.x * n * n;
+    double best = -1.0;
+    int bidx = 0x7fffffff;
+    for (int idx = threadIdx.x; idx < n * n; idx += 256) {
+        const double a = fabs(L[idx]);
+        if (a > best) { best = a; bidx = idx; }          // ascending idx per thread: the first maximum is kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+        if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = bidx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (bv[w] > best || (bv[w] == best && bi[w] < bidx)) { best = bv[w]; bidx = bi[w]; }
+        s_flip = best > 0.0 && L[bidx] < 0.0;
+    }
+    __syncthreads();
+    if (s_flip)
+        for (int idx = threadIdx.x; idx < n * n; idx += 256) L[idx] = -L[idx];
+}
+
 // Symmetry class of every fragment matrix (decompose.jl:354-361): sym[e] = sum (Symmetric(L) - L)^2 (upper triangle kept),
 // asym[e] = sum |L + L'|.  One CTA per fragment.
 static __global__ void __launch_bounds__(256) k_frag_symmetry(const double* __restrict__ Lm, int n, double* __restrict__ sym, double* __restrict__ asym) {
@@ -506,10 +538,26 @@ __global__ void __launch_bounds__(1024) k_jacobi_batch(const double* __restrict_
         pr[i] = rank;                 // pairs scratch is free now (np >= n entries x 2)
         om[rank] = wi;
     }
+    // sign convention: the largest-magnitude component (the first one) of every eigenvector is positive
+    for (int i = tid >> 5; i < n; i += nt >> 5) {
+        double best = -1.0;
+        int bidx = 0x7fffffff;
+        for (int r = tid & 31; r < n; r += 32) {
+            const double a = fabs(Ut[(size_t)i * n + r]);
+            if (a > best) { best = a; bidx = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+            if (ob > best || (ob == best && oi < bidx)) { best = ob; bidx = oi; }
+        }
+        if ((tid & 31) == 0) cs[i] = Ut[(size_t)i * n + bidx] < 0.0 ? -1.0 : 1.0;     // rotation scratch is free now
+    }
     __syncthreads();
     for (int idx = tid; idx < n * n; idx += nt) {
         const int i = idx / n, r = idx % n;
-        Uo[r + (long long)n * pr[i]] = Ut[(size_t)i * n + r];
+        Uo[r + (long long)n * pr[i]] = cs[i] * Ut[(size_t)i * n + r];
     }
     if (tid == 0) status[e] = converged ? sweep : -sweep;
 }

@@ -1162,10 +1162,10 @@ int mambo_csa_scratch(mambo_csa* h, size_t bytes, void** ptr) {
     *ptr = h->opt_ws;
     return MAMBO_OK;
 }
-int mambo_csa_scratch_host(mambo_csa* h, void** ptr) {   // 128 bytes of pinned host memory owned by the handle
+int mambo_csa_scratch_host(mambo_csa* h, void** ptr) {   // 1 KB of pinned host memory owned by the handle
     if (!h || !ptr) return fail(MAMBO_EINVAL, "null argument");
     CU(cudaSetDevice(h->device));
-    if (!h->opt_hs) CU(cudaMallocHost(&h->opt_hs, 128));
+    if (!h->opt_hs) CU(cudaMallocHost(&h->opt_hs, 1024));
     *ptr = h->opt_hs;
     return MAMBO_OK;
 }

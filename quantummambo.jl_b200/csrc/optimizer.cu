@@ -3,7 +3,8 @@
 // Stands in for `optimize(cost, grad!, x0, BFGS())` of /root/reference/src/UTILS/decompose.jl:107-119, 233-243
 // (Optim.jl: dense inverse-Hessian BFGS, g_tol = 1e-8 on the inf-norm of the gradient, 1000 iterations) when the
 // whole greedy step should stay on the GPU: x, the gradient and the dense L x L inverse Hessian live in HBM,
-// one fused pass per iteration applies the pending rank-2 update and forms H*g (2 * 8 L^2 bytes of traffic),
+// one fused pass per iteration over the lower-triangular tiles of the (symmetric) matrix applies the pending rank-2 update and
+// forms H*g (8 L^2 bytes of traffic: every stored element is read and written once, and used for both u_i and u_j),
 // only scalars cross PCIe.  The line search is a strong-Wolfe bracketing/zoom search (Nocedal & Wright
 // alg. 3.5/3.6; c1 = 1e-4, c2 = 0.9) -- Optim's HagerZhang is a different member of the same family, so
 // trajectories are compared at convergence (final cost / 1-norm), not step by step.
@@ -79,37 +80,113 @@ __global__ void __launch_bounds__(1024) k_dot_absmax(const double* __restrict__ 
         res[1] = M;
     }
 }
-__global__ void k_set_identity(double* __restrict__ H, long long n, double diag) {
-    const long long total = n * n;
+// The dense inverse Hessian is symmetric: only the 128 x 128 tiles on and below the diagonal are ever read or written (the
+// allocation stays square, pitch ldh = L rounded up to 4 doubles so that rows start on 32-byte sectors).
+constexpr int STB = 128;
+__global__ void k_set_identity(double* __restrict__ H, long long ldh, long long n, double diag) {
+    const long long total = n * ldh;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
-        H[idx] = (idx / n == idx % n) ? diag : 0.0;
+        H[idx] = (idx / ldh == idx % ldh) ? diag : 0.0;
 }
 __global__ void k_scale(double* __restrict__ out, const double* __restrict__ a, double f, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = f * a[i];
 }
-// One pass over the dense inverse Hessian: (optionally) apply the pending (self-scaled) BFGS update
+
+struct DevState;
+__device__ __forceinline__ bool dev_halted(const DevState* st);
+__device__ __forceinline__ void dev_pending(const DevState* st, const double* s0, const double* s1, const double* hy0, const double* hy1,
+                                            const double** s, const double** Hy, double* rho, double* c, int* apply);
+
+// One pass over the lower-triangular tiles of the inverse Hessian: (optionally) apply the pending (self-scaled) BFGS update
 //     H <- tau H - rho (s Hy^T + Hy s^T) + c s s^T          (rho already carries the factor tau)
-// and form u = H g with the updated matrix.  One warp per row, fixed-order shuffle reduction.
-__global__ void __launch_bounds__(256) k_update_gemv(double* __restrict__ H, int n, const double* __restrict__ s,
-                                                     const double* __restrict__ Hy, double tau, double rho, double c, int apply,
-                                                     const double* __restrict__ g, double* __restrict__ u) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 8 + warp;
-    if (row >= n) return;
-    double* hr = H + (size_t)row * n;
-    const double si = apply ? s[row] : 0.0, hyi = apply ? Hy[row] : 0.0;
-    double acc = 0.0;
-    for (int j = lane; j < n; j += 32) {
-        double h = hr[j];
-        if (apply) {
-            h = tau * h - rho * (si * Hy[j] + hyi * s[j]) + c * si * s[j];
-            hr[j] = h;
-        }
-        acc = fma(h, g[j], acc);
+// and accumulate u = H g with the updated matrix: tile (I, J), J <= I, contributes its row sums to block I of u and -- below the
+// diagonal -- its column sums (the mirrored tile) to block J.  Both go to P[block][slot][128], slot = the OTHER tile index, so every
+// (block, slot) pair is written exactly once and the fixed-order sum over slots (sym_gemv_sum) is bit-reproducible.
+// 8 L^2 bytes of HBM traffic per iteration instead of 16 L^2.  st != NULL: the parameters come from the device state.
+__global__ void __launch_bounds__(256) k_sym_update_gemv(double* __restrict__ H, long long ldh, int n, const DevState* __restrict__ st,
+                                                         const double* __restrict__ s0, const double* __restrict__ s1,
+                                                         const double* __restrict__ hy0, const double* __restrict__ hy1, double tau, double rho,
+                                                         double c, int apply, const double* __restrict__ g, double* __restrict__ P, int ntb) {
+    const int I = blockIdx.y, J = blockIdx.x;
+    if (J > I) return;
+    const double *s = s0, *Hy = hy0;
+    if (st) {
+        if (dev_halted(st)) return;
+        dev_pending(st, s0, s1, hy0, hy1, &s, &Hy, &rho, &c, &apply);
+        tau = 1.0;
     }
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) u[row] = acc;
+    __shared__ double sI[STB], hI[STB], gI[STB], sJ[STB], hJ[STB], gJ[STB], rowsum[STB];
+    __shared__ double colsum[8][STB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < STB) {
+        const int i = I * STB + tid, j = J * STB + tid;
+        sI[tid] = (apply && i < n) ? s[i] : 0.0;
+        hI[tid] = (apply && i < n) ? Hy[i] : 0.0;
+        gI[tid] = i < n ? g[i] : 0.0;
+        sJ[tid] = (apply && j < n) ? s[j] : 0.0;
+        hJ[tid] = (apply && j < n) ? Hy[j] : 0.0;
+        gJ[tid] = j < n ? g[j] : 0.0;
+    }
+    __syncthreads();
+    const bool diag = (I == J);
+    const int c0 = 2 * lane, c1 = 64 + 2 * lane;                       // two double2 per row and lane
+    const bool v0 = J * STB + c0 < n, v1 = J * STB + c1 < n;           // (an odd n leaves one pad column inside the last double2: g = 0 there)
+    double ca0 = 0.0, ca1 = 0.0, ca2 = 0.0, ca3 = 0.0;
+    for (int r = warp; r < STB; r += 8) {
+        const int i = I * STB + r;
+        if (i >= n) {
+            if (lane == 0) rowsum[r] = 0.0;
+            continue;
+        }
+        double* hr = H + (long long)i * ldh + (long long)J * STB;
+        double2 a = v0 ? *reinterpret_cast<double2*>(hr + c0) : make_double2(0.0, 0.0);
+        double2 b = v1 ? *reinterpret_cast<double2*>(hr + c1) : make_double2(0.0, 0.0);
+        if (apply) {
+            const double si = sI[r], hi = hI[r];
+            a.x = tau * a.x - rho * (si * hJ[c0] + hi * sJ[c0]) + c * (si * sJ[c0]);
+            a.y = tau * a.y - rho * (si * hJ[c0 + 1] + hi * sJ[c0 + 1]) + c * (si * sJ[c0 + 1]);
+            b.x = tau * b.x - rho * (si * hJ[c1] + hi * sJ[c1]) + c * (si * sJ[c1]);
+            b.y = tau * b.y - rho * (si * hJ[c1 + 1] + hi * sJ[c1 + 1]) + c * (si * sJ[c1 + 1]);
+            if (v0) *reinterpret_cast<double2*>(hr + c0) = a;
+            if (v1) *reinterpret_cast<double2*>(hr + c1) = b;
+        }
+        double acc = fma(a.x, gJ[c0], fma(a.y, gJ[c0 + 1], fma(b.x, gJ[c1], b.y * gJ[c1 + 1])));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) rowsum[r] = acc;
+        if (!diag) {
+            const double gi = gI[r];
+            ca0 = fma(a.x, gi, ca0);
+            ca1 = fma(a.y, gi, ca1);
+            ca2 = fma(b.x, gi, ca2);
+            ca3 = fma(b.y, gi, ca3);
+        }
+    }
+    if (!diag) {
+        colsum[warp][c0] = ca0; colsum[warp][c0 + 1] = ca1; colsum[warp][c1] = ca2; colsum[warp][c1 + 1] = ca3;
+    }
+    __syncthreads();
+    if (tid < STB) {
+        P[((long long)I * ntb + J) * STB + tid] = rowsum[tid];
+        if (!diag) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += colsum[w][tid];
+            P[((long long)J * ntb + I) * STB + tid] = t;
+        }
+    }
+}
+// u[i] = sum over slots of P[block(i)][slot][i mod 128], fixed order
+__device__ __forceinline__ double sym_gemv_sum(const double* __restrict__ P, int ntb, int i) {
+    const double* q = P + (long long)(i / STB) * ntb * STB + (i % STB);
+    double t = 0.0;
+    for (int sl = 0; sl < ntb; ++sl) t += q[(long long)sl * STB];
+    return t;
+}
+__global__ void k_sym_reduce(const double* __restrict__ P, int ntb, int n, double* __restrict__ u) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) u[i] = sym_gemv_sum(P, ntb, i);
 }
 __global__ void k_scale_neg(double* __restrict__ out, const double* __restrict__ a, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -238,6 +315,202 @@ __global__ void k_store_pair(double* __restrict__ Sslot, double* __restrict__ Ys
     if (i == 0) *rho_slot = rho;
 }
 
+
+// ---- device-driven iterations (the common case: the first trial step satisfies the strong-Wolfe conditions) -------------
+// The host loop above costs three host round trips per iteration (line-search scalars, s.y / y.y, the direction's dots): at
+// N = 50 they are longer than the evaluation itself.  In the fast path every scalar of the iteration lives in DevState on
+// the device and four kernels around the evaluation take all decisions there; the host only enqueues iterations (two in
+// flight) and reads a copy of the state that trails each one.  Whenever the device cannot decide alone -- the trial step
+// fails a Wolfe condition (zoom / extension needed), the direction is not a descent direction, a NaN appears -- it raises
+// `halt`, every later kernel of the fast path returns at once (the evaluations queued behind it are wasted, nothing else
+// is touched), and the host runs that one iteration through the line search above before it resumes the fast path.
+struct DevState {
+    double f, df0, alpha_prev, df0_prev, gnorm, rho, cc, a1, gtol, sy, yy, f_new, gmax_new;
+    int pending, parity, halt, it;     // halt: 0 running, 1 converged, 2 line search needs the host, 3 not a descent direction
+};
+__device__ __forceinline__ bool dev_halted(const DevState* st) { return st->halt != 0; }
+// the pending pair is the one stored by the PREVIOUS iteration: the buffer the current parity does not point at
+__device__ __forceinline__ void dev_pending(const DevState* st, const double* s0, const double* s1, const double* hy0, const double* hy1,
+                                            const double** s, const double** Hy, double* rho, double* c, int* apply) {
+    *s = st->parity ? s0 : s1;
+    *Hy = st->parity ? hy0 : hy1;
+    *rho = st->rho;
+    *c = st->cc;
+    *apply = st->pending;
+}
+
+// fixed-order sum (or max) of per-CTA partials part[cta][4] by one warp; every CTA that calls it gets the same bits
+__device__ __forceinline__ void sum_partials(const double* __restrict__ part, int nb, double* sh /* 4 doubles of shared memory */, bool last_is_max) {
+    if (threadIdx.x < 32) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        for (int b = threadIdx.x; b < nb; b += 32) {
+            a0 += part[4 * b];
+            a1 += part[4 * b + 1];
+            a2 += part[4 * b + 2];
+            a3 = last_is_max ? fmax(a3, part[4 * b + 3]) : a3 + part[4 * b + 3];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+            const double t = __shfl_xor_sync(0xffffffffu, a3, o);
+            a3 = last_is_max ? fmax(a3, t) : a3 + t;
+        }
+        if (threadIdx.x == 0) { sh[0] = a0; sh[1] = a1; sh[2] = a2; sh[3] = a3; }
+    }
+    __syncthreads();
+}
+// per-CTA reduction of four running values into part[blockIdx.x][4]
+__device__ __forceinline__ void store_partials(double v0, double v1, double v2, double v3, bool last_is_max, double* __restrict__ part) {
+    __shared__ double sd[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        const double t = __shfl_xor_sync(0xffffffffu, v3, o);
+        v3 = last_is_max ? fmax(v3, t) : v3 + t;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        sd[0][threadIdx.x >> 5] = v0; sd[1][threadIdx.x >> 5] = v1; sd[2][threadIdx.x >> 5] = v2; sd[3][threadIdx.x >> 5] = v3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t = (last_is_max && threadIdx.x == 3) ? fmax(t, sd[3][w]) : t + sd[threadIdx.x][w];
+        part[4 * blockIdx.x + threadIdx.x] = t;
+    }
+}
+
+// All kernels below: 256 threads, blocks(L) CTAs unless stated otherwise.
+__global__ void __launch_bounds__(256) k_fast_trial(DevState* __restrict__ st, const double* __restrict__ x, const double* __restrict__ p,
+                                                    double* __restrict__ xt, int n) {
+    if (st->halt) return;
+    const double df0 = st->df0;
+    if (!(df0 < 0.0)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->halt = 3;
+        return;
+    }
+    const double ap = st->alpha_prev;
+    double a1 = ap * (st->df0_prev / df0);                        // Nocedal & Wright (3.60), same clamps as the host rule
+    a1 = fmin(1.0, fmax(0.5 * ap, fmin(a1, 2.0 * ap)));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) xt[i] = fma(a1, p[i], x[i]);
+    if (i == 0) st->a1 = a1;
+}
+
+// after the evaluation at xt (out = [cost, grad]): partial sums of g_new.p, s.y, y.y and max|g_new|  (s = xt - x, y = g_new - g)
+__global__ void __launch_bounds__(256) k_fast_wolfe_part(const DevState* __restrict__ st, const double* __restrict__ x, const double* __restrict__ xt,
+                                                         const double* __restrict__ g, const double* __restrict__ p, const double* __restrict__ out,
+                                                         double* __restrict__ part, int n) {
+    if (st->halt) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double df = 0.0, sy = 0.0, yy = 0.0, gm = 0.0;
+    if (i < n) {
+        const double gi = out[1 + i], si = xt[i] - x[i], yi = gi - g[i];
+        df = gi * p[i];
+        sy = si * yi;
+        yy = yi * yi;
+        gm = fabs(gi);
+    }
+    store_partials(df, sy, yy, gm, true, part);
+}
+// strong-Wolfe test of the trial step (every CTA takes the same decision from the same partials); on success s and y are
+// written into the current pair buffers.  CTA 0 records the outcome in the state (none of those fields is read by this kernel).
+__global__ void __launch_bounds__(256) k_fast_wolfe_apply(DevState* __restrict__ st, const double* __restrict__ x, const double* __restrict__ xt,
+                                                          const double* __restrict__ g, const double* __restrict__ out, const double* __restrict__ part,
+                                                          int nb, double* __restrict__ s0, double* __restrict__ s1, double* __restrict__ y, int n) {
+    __shared__ double sh[4];
+    if (st->halt) return;
+    sum_partials(part, nb, sh, true);
+    const double c1 = 1e-4, c2 = 0.9;
+    const double f = out[0], f0 = st->f, df0 = st->df0, a = st->a1;
+    const bool ok = (f <= f0 + c1 * a * df0) && (fabs(sh[0]) <= -c2 * df0) && (f <= f0);      // NaN fails every comparison
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (ok) {
+            st->sy = sh[1]; st->yy = sh[2]; st->f_new = f; st->gmax_new = sh[3];
+            st->df0_prev = df0; st->alpha_prev = a;
+        } else {
+            st->halt = 2;
+        }
+    }
+    if (!ok) return;
+    double* s = st->parity ? s1 : s0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        s[i] = xt[i] - x[i];
+        y[i] = out[1 + i] - g[i];
+    }
+}
+
+// u = sum of the tile partials of k_sym_update_gemv, Hy = u + p, partial sums of y.Hy, Hy.g_new, s.g_new, u.g_new
+__global__ void __launch_bounds__(256) k_fast_dots(const DevState* __restrict__ st, const double* __restrict__ P, int ntb, const double* __restrict__ p,
+                                                   const double* __restrict__ out, const double* __restrict__ s0, const double* __restrict__ s1,
+                                                   double* __restrict__ hy0, double* __restrict__ hy1, const double* __restrict__ y,
+                                                   double* __restrict__ u, double* __restrict__ part, int n) {
+    if (st->halt) return;
+    const double* s = st->parity ? s1 : s0;
+    double* Hy = st->parity ? hy1 : hy0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double yHy = 0.0, hyg = 0.0, sg = 0.0, ug = 0.0;
+    if (i < n) {
+        const double ui = sym_gemv_sum(P, ntb, i);
+        const double hy = ui + p[i];              // H y = H g_new - H g = u + p   (p = -H g)
+        u[i] = ui;
+        Hy[i] = hy;
+        const double gi = out[1 + i];
+        yHy = y[i] * hy;
+        hyg = hy * gi;
+        sg = s[i] * gi;
+        ug = ui * gi;
+    }
+    store_partials(yHy, hyg, sg, ug, false, part);
+}
+// the direction of the updated matrix (the matrix itself is updated by the next pass over H), x <- xt, g <- g_new
+__global__ void __launch_bounds__(256) k_fast_direction(const DevState* __restrict__ st, const double* __restrict__ part, int nb, double* __restrict__ x,
+                                                        const double* __restrict__ xt, double* __restrict__ g, double* __restrict__ p,
+                                                        const double* __restrict__ out, const double* __restrict__ u, const double* __restrict__ s0,
+                                                        const double* __restrict__ s1, const double* __restrict__ hy0, const double* __restrict__ hy1, int n) {
+    __shared__ double sh[4];
+    if (st->halt) return;
+    sum_partials(part, nb, sh, false);
+    const double yHy = sh[0], hyg = sh[1], sg = sh[2];
+    const double sy = st->sy;
+    const bool upd = sy > 1e-300;
+    const double r1 = upd ? 1.0 / sy : 0.0;
+    const double rho = r1, cc = r1 * (1.0 + r1 * yHy);
+    const double* s = st->parity ? s1 : s0;
+    const double* Hy = st->parity ? hy1 : hy0;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        p[i] = upd ? -(u[i] - rho * (s[i] * hyg + Hy[i] * sg) + cc * s[i] * sg) : -u[i];
+        x[i] = xt[i];
+        g[i] = out[1 + i];
+    }
+}
+// the scalars of the finished iteration (one warp): the only kernel that advances parity / pending / f / it
+__global__ void __launch_bounds__(32) k_fast_state(DevState* __restrict__ st, const double* __restrict__ part, int nb) {
+    __shared__ double sh[4];
+    if (st->halt) return;
+    sum_partials(part, nb, sh, false);
+    if (threadIdx.x == 0) {
+        const double yHy = sh[0], hyg = sh[1], sg = sh[2], ug = sh[3];
+        const double sy = st->sy;
+        const bool upd = sy > 1e-300;
+        const double r1 = upd ? 1.0 / sy : 0.0;
+        const double rho = r1, cc = r1 * (1.0 + r1 * yHy);
+        st->df0 = upd ? -(ug - rho * (sg * hyg + hyg * sg) + cc * sg * sg) : -ug;
+        st->rho = rho; st->cc = cc;
+        st->pending = upd ? 1 : 0;
+        if (upd) st->parity ^= 1;
+        st->f = st->f_new;
+        st->gnorm = st->gmax_new;
+        st->it += 1;
+        if (st->gnorm <= st->gtol) st->halt = 1;
+    }
+}
+
 struct Opt {
     mambo_csa* h = nullptr;
     int L = 0, device = 0;
@@ -245,7 +518,11 @@ struct Opt {
     double *x = nullptr, *g = nullptr, *p = nullptr, *xt = nullptr, *out = nullptr, *s = nullptr, *y = nullptr, *Hy = nullptr,
            *s2 = nullptr, *Hy2 = nullptr, *u = nullptr, *H = nullptr, *scal = nullptr;
     double *LS = nullptr, *LY = nullptr, *Lrho = nullptr;   // L-BFGS ring (lbfgs_memory > 0)
-    double* h_scal = nullptr;  // pinned
+    double* h_scal = nullptr;  // pinned (128 bytes of scalars, then the status ring of the device-driven iterations)
+    DevState* dstate = nullptr;
+    double *P = nullptr, *part = nullptr;   // tile partials of the symmetric H pass; per-CTA partial sums of the fast path
+    long long ldh = 0;
+    int ntb = 0;
     int evals = 0;
     bool sharded = false;
     char err[256] = {0};
@@ -261,8 +538,9 @@ int opt_free(Opt* o) {   // device buffers and pinned scalars live in the handle
 // doubles of device scratch one optimisation run needs (layout: optimize_impl)
 size_t opt_scratch_doubles(int L, int mem) {
     const size_t Lp = ((size_t)L + 1 + 15) & ~(size_t)15;
-    const size_t big = mem > 0 ? (2 * (size_t)mem * L + 64) : (size_t)L * L;
-    return 11 * Lp + 16 + big;
+    const size_t ldh = ((size_t)L + 3) & ~(size_t)3, ntb = ((size_t)L + STB - 1) / STB;
+    const size_t big = mem > 0 ? (2 * (size_t)mem * L + 64) : ldh * L + ntb * ntb * STB;
+    return 11 * Lp + 16 + 32 + 4 * (((size_t)L + 255) / 256) + 16 + big;      // + DevState and the per-CTA partials of the device-driven iterations
 }
 
 // several dot products and max|m| in one kernel + one host round trip; out[k] = a_k.b_k, *amax = max|m|
@@ -459,12 +737,19 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         }
         o->scal = q;
         q += 16;
+        o->dstate = reinterpret_cast<DevState*>(q);
+        q += 32;
+        o->part = q;
+        q += 4 * (((size_t)L + 255) / 256) + 16;
+        o->ldh = (long long)(((size_t)L + 3) & ~(size_t)3);
+        o->ntb = (L + STB - 1) / STB;
         if (lbfgs) {
             o->LS = q;
             o->LY = q + (size_t)mem * L;
             o->Lrho = q + 2 * (size_t)mem * L;
         } else {
             o->H = q;
+            o->P = q + (size_t)o->ldh * L;
         }
         void* hs = nullptr;
         rc = mambo_csa_scratch_host(h, &hs);
@@ -482,7 +767,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         return false;
     };
     if (CK(cudaMemcpyAsync(o->x, x0, sizeof(double) * L, cudaMemcpyHostToDevice, o->stream), "H2D x0")) return finish(MAMBO_ECUDA);
-    if (!lbfgs) k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
+    if (!lbfgs) k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, o->ldh, L, 1.0);
 
     // f, g at x0
     double f = 0, dfdummy = 0;
@@ -513,13 +798,104 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     double df0_prev = -1.0;        // directional derivative at the start of the previous line search
     int l_used = 0, l_head = -1;   // L-BFGS ring state
     double l_gamma = 1.0;
+    // ---- device-driven iterations (see DevState): eligible in the reference's mode (dense BFGS, no self-scaling) on unsharded handles
+    constexpr int RING = 4, DEPTH = 2;
+    static_assert(sizeof(DevState) <= 128, "status ring slots are 128 bytes");
+    const bool fast_ok = !lbfgs && !o->sharded && !selfscale && std::getenv("MAMBO_OPT_HOSTLOOP") == nullptr;
+    cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
+    auto ring_slot = [&](int k) { return reinterpret_cast<DevState*>(reinterpret_cast<char*>(o->h_scal) + 128 + 128 * (k % RING)); };
+    struct EvGuard {
+        cudaEvent_t* e;
+        ~EvGuard() {
+            for (int k = 0; k < RING; ++k)
+                if (e[k]) cudaEventDestroy(e[k]);
+        }
+    } ev_guard{ring_ev};
+    int fast_iterations = 0;
+    // runs device-driven iterations until the device halts or the iteration budget is used; returns the halt code in *halt_out
+    auto fast_run = [&](int* halt_out) -> int {
+        for (int k = 0; k < RING; ++k)
+            if (!ring_ev[k] && CK(cudaEventCreateWithFlags(&ring_ev[k], cudaEventDisableTiming), "event")) return MAMBO_ECUDA;
+        DevState hs;
+        std::memset(&hs, 0, sizeof(hs));
+        hs.f = f; hs.df0 = df0; hs.alpha_prev = alpha_prev; hs.df0_prev = df0_prev; hs.gnorm = gnorm; hs.rho = rho; hs.cc = cc;
+        hs.gtol = opt.g_tol; hs.pending = pending ? 1 : 0; hs.parity = (s_cur == o->s) ? 0 : 1; hs.halt = 0; hs.it = it;
+        DevState* up = ring_slot(RING - 1);                 // pinned staging for the upload (not in use: nothing is in flight)
+        *up = hs;
+        if (CK(cudaMemcpyAsync(o->dstate, up, sizeof(DevState), cudaMemcpyHostToDevice, o->stream), "H2D state")) return MAMBO_ECUDA;
+        if (CK(cudaStreamSynchronize(o->stream), "sync")) return MAMBO_ECUDA;       // `up` is reused as a ring slot below
+        int budget = opt.max_iter - it, enq = 0, seen = 0, halt = 0;
+        DevState last = hs;
+        while (true) {
+            if (enq < budget && enq - seen < DEPTH) {
+                k_fast_trial<<<blocks(L), 256, 0, o->stream>>>(o->dstate, o->x, o->p, o->xt, L);
+                int rc2 = mambo_csa_eval_device(o->h, o->xt, o->out);
+                if (rc2) {
+                    snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+                    return rc2;
+                }
+                o->evals++;
+                const int nb = blocks(L);
+                k_fast_wolfe_part<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->p, o->out, o->part, L);
+                k_fast_wolfe_apply<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->out, o->part, nb, o->s, o->s2, o->y, L);
+                k_sym_update_gemv<<<dim3(o->ntb, o->ntb), 256, 0, o->stream>>>(o->H, o->ldh, L, o->dstate, o->s, o->s2, o->Hy, o->Hy2, 1.0, 0.0, 0.0, 0,
+                                                                                 o->out + 1, o->P, o->ntb);
+                k_fast_dots<<<nb, 256, 0, o->stream>>>(o->dstate, o->P, o->ntb, o->p, o->out, o->s, o->s2, o->Hy, o->Hy2, o->y, o->u, o->part, L);
+                k_fast_direction<<<nb, 256, 0, o->stream>>>(o->dstate, o->part, nb, o->x, o->xt, o->g, o->p, o->out, o->u, o->s, o->s2, o->Hy, o->Hy2, L);
+                k_fast_state<<<1, 32, 0, o->stream>>>(o->dstate, o->part, nb);
+                if (CK(cudaMemcpyAsync(ring_slot(enq), o->dstate, sizeof(DevState), cudaMemcpyDeviceToHost, o->stream), "D2H state") ||
+                    CK(cudaEventRecord(ring_ev[enq % RING], o->stream), "event record"))
+                    return MAMBO_ECUDA;
+                ++enq;
+                continue;
+            }
+            if (seen == enq) break;
+            if (CK(cudaEventSynchronize(ring_ev[seen % RING]), "event sync")) return MAMBO_ECUDA;
+            last = *ring_slot(seen);
+            ++seen;
+            if (last.halt && !halt) {
+                halt = last.halt;
+                budget = enq;                               // nothing more is enqueued; the iterations in flight are no-ops
+            }
+            if (opt.verbose && !last.halt && (last.it % opt.verbose == 0))
+                fprintf(stderr, "[mambo bfgs] it %d f=%.10e |g|inf=%.3e alpha=%.3e evals=%d (device-driven)\n", last.it, last.f, last.gnorm,
+                        last.alpha_prev, o->evals);
+        }
+        int rc2 = mambo_csa_status_fetch(o->h);             // ||K||_1 out of range / NaN in x during any of the evaluations
+        if (!rc2 && CK(cudaStreamSynchronize(o->stream), "sync")) return MAMBO_ECUDA;
+        if (!rc2) rc2 = mambo_csa_status_check(o->h);
+        if (rc2) {
+            snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+            return rc2;
+        }
+        fast_iterations += last.it - it;
+        f = last.f; df0 = last.df0; alpha_prev = last.alpha_prev; df0_prev = last.df0_prev; gnorm = last.gnorm; rho = last.rho; cc = last.cc;
+        tau = 1.0;
+        pending = last.pending != 0;
+        if (last.parity == 0) { s_cur = o->s; Hy_cur = o->Hy; s_prev = o->s2; Hy_prev = o->Hy2; }
+        else { s_cur = o->s2; Hy_cur = o->Hy2; s_prev = o->s; Hy_prev = o->Hy; }
+        it = last.it;
+        *halt_out = halt;
+        return MAMBO_OK;
+    };
     for (; it < opt.max_iter; ++it) {
         if (gnorm <= opt.g_tol) {
             converged = 1;
             break;
         }
+        if (fast_ok && !fresh && it > 0 && df0 < 0) {
+            int halt = 0;
+            rc = fast_run(&halt);
+            if (rc) return finish(rc);
+            if (halt == 1 || gnorm <= opt.g_tol) {
+                converged = 1;
+                break;
+            }
+            if (it >= opt.max_iter) break;
+            // halt 2 / 3: this iteration needs the host's line search (or a restart); it runs below, then the fast path resumes
+        }
         if (!(df0 < 0)) {  // not a descent direction: restart from steepest descent
-            if (!lbfgs) k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, 1.0);
+            if (!lbfgs) k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, o->ldh, L, 1.0);
             pending = false;
             fresh = true;
             l_used = 0;
@@ -576,13 +952,15 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
             if (fresh && sy > 1e-300) {
                 // Nocedal & Wright (6.20): H0 <- (s.y / y.y) I before the first update, so the first curvature pair sets the scale
                 const double gamma = sy / yy;
-                k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, L, gamma);
+                k_set_identity<<<1184, 256, 0, o->stream>>>(o->H, o->ldh, L, gamma);
                 k_scale<<<blocks(L), 256, 0, o->stream>>>(o->u, o->out + 1, gamma, L);     // u  = H g_new
                 k_scale<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->y, gamma, L);          // Hy = H y
                 fresh = false;
             } else {
-                // one pass over H: fold in the pending update of the previous iteration and form u = H g_new
-                k_update_gemv<<<(L + 7) / 8, 256, 0, o->stream>>>(o->H, L, s_prev, Hy_prev, tau, rho, cc, pending ? 1 : 0, o->out + 1, o->u);
+                // one pass over (the lower triangle of) H: fold in the pending update of the previous iteration and form u = H g_new
+                k_sym_update_gemv<<<dim3(o->ntb, o->ntb), 256, 0, o->stream>>>(o->H, o->ldh, L, nullptr, s_prev, nullptr, Hy_prev, nullptr, tau, rho, cc,
+                                                                                 pending ? 1 : 0, o->out + 1, o->P, o->ntb);
+                k_sym_reduce<<<blocks(L), 256, 0, o->stream>>>(o->P, o->ntb, L, o->u);
                 // Hy = H y = H g_new - H g = u + p   (p = -H g)
                 k_axpy<<<blocks(L), 256, 0, o->stream>>>(Hy_cur, o->u, o->p, 1.0, L);
             }

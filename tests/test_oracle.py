@@ -278,3 +278,45 @@ def test_packed_single_gemm_restatement_equals_factored(n):
     c, g = o.cost_grad_packed(x, o.pack_tbt(T), n)
     assert abs(c - c0) <= 1e-12 * abs(c0)
     assert np.max(np.abs(g - g0)) <= 1e-12 * np.max(np.abs(g0))
+
+
+# ---- double factorisation (decompose.jl:297-436) ---------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [3, 5, 8])
+def test_df_oracle_reconstructs_the_tensor_and_orders_fragments(n):
+    T = o.dense_sym_tbt(n, n)
+    fr = o.DF_decomposition(T)
+    assert len(fr) == n * (n + 1) // 2                       # rank of an 8-fold-symmetric tensor's matrix view
+    c = np.array([f[0] for f in fr])
+    assert np.all(np.diff(np.abs(c)) <= 0)                   # decreasing |eigenvalue| (decompose.jl:332)
+    assert np.max(np.abs(o.DF_to_tbt(fr, n) - T)) <= 1e-13 * np.max(np.abs(T)) * n * n
+    for coeff, w, U, L in fr:
+        assert np.max(np.abs((U * w) @ U.T - L)) <= 1e-13 and abs(np.linalg.norm(L) - 1) <= 1e-13
+
+
+def test_df_oracle_truncates_at_tol_and_takes_the_antihermitian_branch():
+    n = 4
+    T = o.dense_sym_tbt(n, 0)
+    fr = o.DF_decomposition(T, tol=abs(o.DF_decomposition(T)[3][0]) * 0.999)
+    assert len(fr) == 4
+    # pair-symmetric tensor with an anti-symmetric eigenvector: coefficient negated, complex frame (decompose.jl:355-361)
+    rng = np.random.default_rng(1)
+    A = rng.standard_normal((n, n)); A = A - A.T; A /= np.linalg.norm(A)
+    Tanti = 0.3 * np.einsum("ab,cd->abcd", A, A)
+    fr = o.DF_decomposition(Tanti)
+    assert len(fr) == 1 and abs(fr[0][0] + 0.3) <= 1e-14 and np.iscomplexobj(fr[0][2])
+    assert np.max(np.abs(o.DF_to_tbt(fr, n) - Tanti)) <= 1e-14
+
+
+def test_df_based_greedy_oracle_known_answer():
+    """a single planted DF fragment c * L (x) L: the greedy CSA fragment in its own frame is lambda_ij = c w_i w_j"""
+    n = 5
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((n, n)); A = A + A.T; A /= np.linalg.norm(A)
+    T = 1.7 * np.einsum("ab,cd->abcd", A, A)
+    lam, U1, Lm = o.DF_based_greedy(T)
+    w = np.linalg.eigvalsh(A)
+    ref = 1.7 * np.outer(w, w)
+    assert np.max(np.abs(Lm - ref)) <= 1e-13 or np.max(np.abs(Lm - ref[::-1, ::-1])) <= 1e-13
+    # and the CSA fragment it defines reproduces the tensor: W = sum_ij Lm_ij U1[:,i]U1[:,i]' (x) U1[:,j]U1[:,j]'
+    W = np.einsum("ij,ai,bi,cj,dj->abcd", Lm, U1, U1, U1, U1)
+    assert np.max(np.abs(W - T)) <= 1e-13
