@@ -325,8 +325,9 @@ __global__ void k_store_pair(double* __restrict__ Sslot, double* __restrict__ Ys
 // `halt`, every later kernel of the fast path returns at once (the evaluations queued behind it are wasted, nothing else
 // is touched), and the host runs that one iteration through the line search above before it resumes the fast path.
 struct DevState {
-    double f, df0, alpha_prev, df0_prev, gnorm, rho, cc, a1, gtol, sy, yy, f_new, gmax_new;
+    double f, df0, alpha_prev, df0_prev, gnorm, rho, cc, a1, gtol, sy, yy, f_new, gmax_new, l_gamma;
     int pending, parity, halt, it;     // halt: 0 running, 1 converged, 2 line search needs the host, 3 not a descent direction
+    int l_used, l_head;                // L-BFGS ring (limited-memory mode)
 };
 __device__ __forceinline__ bool dev_halted(const DevState* st) { return st->halt != 0; }
 // the pending pair is the one stored by the PREVIOUS iteration: the buffer the current parity does not point at
@@ -511,6 +512,150 @@ __global__ void __launch_bounds__(32) k_fast_state(DevState* __restrict__ st, co
     }
 }
 
+// ---- limited-memory mode of the device-driven iterations ------------------------------------------------------------------
+// the ring slot the pair of this iteration goes to, the number of pairs in use and H_0's scale, from the state BEFORE the update
+__device__ __forceinline__ void lbfgs_next(const DevState* st, int mem, int* head, int* used, double* gamma) {
+    const bool upd = st->sy > 1e-300;
+    *head = upd ? (st->l_head + 1) % mem : (st->l_head < 0 ? 0 : st->l_head);
+    *used = upd ? min(st->l_used + 1, mem) : st->l_used;
+    *gamma = upd ? st->sy / st->yy : st->l_gamma;
+}
+// x <- xt, g <- g_new, and the accepted pair (s, y, 1 / s.y) into its ring slot
+__global__ void __launch_bounds__(256) k_fast_lbfgs_store(const DevState* __restrict__ st, const double* __restrict__ s, const double* __restrict__ y,
+                                                          double* __restrict__ LS, double* __restrict__ LY, double* __restrict__ Lrho, int mem,
+                                                          double* __restrict__ x, const double* __restrict__ xt, double* __restrict__ g,
+                                                          const double* __restrict__ out, int n) {
+    if (st->halt) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    x[i] = xt[i];
+    g[i] = out[1 + i];
+    if (st->sy > 1e-300) {
+        int head, used;
+        double gamma;
+        lbfgs_next(st, mem, &head, &used, &gamma);
+        LS[(size_t)head * n + i] = s[i];
+        LY[(size_t)head * n + i] = y[i];
+        if (i == 0) Lrho[head] = 1.0 / st->sy;
+    }
+}
+// The two-loop recursion is 2 m dependent reductions over L: a single-CTA kernel that costs as much as a third of the evaluation
+// at N = 152.  The device-driven iterations use the compact representation instead (Byrd, Nocedal & Schnabel 1994, eq. 3.1):
+//     H = gamma I + [S  gamma Y] [ R^-T (D + gamma Y^T Y) R^-1   -R^-T ] [ S^T       ]
+//                                [ -R^-1                          0    ] [ gamma Y^T ]
+// with R the upper triangle of S^T Y (pairs ordered oldest to newest) and D its diagonal: ONE multi-CTA pass forms the Gram
+// blocks S^T Y, Y^T Y and S^T g, Y^T g, g.g (per-CTA partials, fixed-order sum), one warp solves the two m x m triangular
+// systems, and one more multi-CTA pass assembles p = -H g.  The directional derivative g.p comes out of the same scalars.
+constexpr int LB_FAST_MAX = 24;      // largest memory the shared-memory Gram kernel takes (2 x 24 x 257 doubles)
+constexpr int LB_W = 256, LB_WP = 257;
+__host__ __device__ inline int lb_ldp(int mem) { return 2 * mem * mem + 2 * mem + 1; }
+__device__ __forceinline__ int lb_slot(int head, int used, int mem, int k) { return (head - (used - 1) + k + 2 * mem) % mem; }   // k = 0: oldest
+
+__global__ void __launch_bounds__(256) k_fast_lbfgs_gram(const DevState* __restrict__ st, const double* __restrict__ S, const double* __restrict__ Y,
+                                                         const double* __restrict__ g, int mem, int n, double* __restrict__ part) {
+    extern __shared__ double lsm[];
+    if (st->halt) return;
+    int head, used;
+    double gamma;
+    lbfgs_next(st, mem, &head, &used, &gamma);
+    double* Ss = lsm;                              // [used][LB_WP]
+    double* Ys = lsm + (size_t)mem * LB_WP;
+    double* gs = lsm + (size_t)2 * mem * LB_WP;    // [LB_W]
+    const int i = blockIdx.x * LB_W + threadIdx.x;
+    for (int k = 0; k < used; ++k) {
+        const int slot = lb_slot(head, used, mem, k);
+        Ss[k * LB_WP + threadIdx.x] = i < n ? S[(size_t)slot * n + i] : 0.0;
+        Ys[k * LB_WP + threadIdx.x] = i < n ? Y[(size_t)slot * n + i] : 0.0;
+    }
+    gs[threadIdx.x] = i < n ? g[i] : 0.0;
+    __syncthreads();
+    double* out = part + (size_t)blockIdx.x * lb_ldp(mem);
+    const int nsy = used * used, total = 2 * nsy + 2 * used + 1;
+    for (int e = threadIdx.x; e < total; e += 256) {
+        const double *a, *b;
+        if (e < nsy) { a = Ss + (e / used) * LB_WP; b = Ys + (e % used) * LB_WP; }                       // S^T Y [k][l]
+        else if (e < 2 * nsy) { a = Ys + ((e - nsy) / used) * LB_WP; b = Ys + ((e - nsy) % used) * LB_WP; }   // Y^T Y [k][l]
+        else if (e < 2 * nsy + used) { a = Ss + (e - 2 * nsy) * LB_WP; b = gs; }                         // S^T g
+        else if (e < 2 * nsy + 2 * used) { a = Ys + (e - 2 * nsy - used) * LB_WP; b = gs; }              // Y^T g
+        else { a = gs; b = gs; }                                                                         // g.g
+        double acc = 0.0;
+        for (int c = 0; c < LB_W; ++c) acc = fma(a[c], b[c], acc);
+        out[e] = acc;
+    }
+}
+// one CTA: fixed-order sum of the partials, the two triangular solves, the coefficients of p over the ring slots, state update
+__global__ void __launch_bounds__(256) k_fast_lbfgs_solve(DevState* __restrict__ st, const double* __restrict__ part, int nb, int mem,
+                                                          double* __restrict__ coef) {
+    extern __shared__ double lsm[];
+    if (st->halt) return;
+    int head, used;
+    double gamma;
+    lbfgs_next(st, mem, &head, &used, &gamma);
+    const int nsy = used * used, total = 2 * nsy + 2 * used + 1, ldp = lb_ldp(mem);
+    double* G = lsm;                                 // the summed Gram data, layout of k_fast_lbfgs_gram
+    double* a = lsm + ldp;                           // [mem]
+    double* t = a + mem;                             // [mem]
+    for (int e = threadIdx.x; e < total; e += 256) {
+        double acc = 0.0;
+        for (int b = 0; b < nb; ++b) acc += part[(size_t)b * ldp + e];
+        G[e] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double *SY = G, *YY = G + nsy, *u = G + 2 * nsy, *v = u + used;
+        const double gg = G[2 * nsy + 2 * used];
+        for (int k = used - 1; k >= 0; --k) {        // a = R^-1 u,  R = upper triangle of S^T Y
+            double r = u[k];
+            for (int l = k + 1; l < used; ++l) r -= SY[k * used + l] * a[l];
+            a[k] = r / SY[k * used + k];
+        }
+        for (int k = 0; k < used; ++k) {             // t = (D + gamma Y^T Y) a - gamma v
+            double r = SY[k * used + k] * a[k] - gamma * v[k];
+            for (int l = 0; l < used; ++l) r = fma(gamma * YY[k * used + l], a[l], r);
+            t[k] = r;
+        }
+        for (int k = 0; k < used; ++k) {             // top = R^-T t  (forward substitution), kept in t
+            double r = t[k];
+            for (int l = 0; l < k; ++l) r -= SY[l * used + k] * t[l];
+            t[k] = r / SY[k * used + k];
+        }
+        double hgg = gamma * gg;                     // g.H g
+        for (int k = 0; k < used; ++k) hgg += t[k] * u[k] - gamma * a[k] * v[k];
+        for (int sl = 0; sl < 2 * mem; ++sl) coef[sl] = 0.0;
+        for (int k = 0; k < used; ++k) {
+            const int slot = lb_slot(head, used, mem, k);
+            coef[slot] = t[k];                       // coefficient of S[slot] in H g
+            coef[mem + slot] = -gamma * a[k];        // coefficient of Y[slot]
+        }
+        coef[2 * mem] = gamma;
+        const bool upd = st->sy > 1e-300;
+        st->df0 = -hgg;
+        st->l_head = upd ? head : st->l_head;
+        st->l_used = used;
+        st->l_gamma = gamma;
+        st->f = st->f_new;
+        st->gnorm = st->gmax_new;
+        st->it += 1;
+        if (st->gnorm <= st->gtol) st->halt = 1;
+    }
+}
+// p = -(gamma g + sum_slots cS S + cY Y); runs after the state has advanced (l_used / l_head are the new ring state)
+__global__ void __launch_bounds__(256) k_fast_lbfgs_apply(const DevState* __restrict__ st, const double* __restrict__ coef, const double* __restrict__ S,
+                                                          const double* __restrict__ Y, const double* __restrict__ g, int mem, int n,
+                                                          double* __restrict__ p) {
+    if (st->halt > 1) return;                        // (halt == 1: converged in this very iteration; p is not needed any more but harmless)
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int used = st->l_used, head = st->l_head < 0 ? 0 : st->l_head;
+    double acc = coef[2 * mem] * g[i];
+    for (int k = 0; k < used; ++k) {
+        const int slot = lb_slot(head, used, mem, k);
+        acc = fma(coef[slot], S[(size_t)slot * n + i], acc);
+        acc = fma(coef[mem + slot], Y[(size_t)slot * n + i], acc);
+    }
+    p[i] = -acc;
+}
+
 struct Opt {
     mambo_csa* h = nullptr;
     int L = 0, device = 0;
@@ -521,6 +666,7 @@ struct Opt {
     double* h_scal = nullptr;  // pinned (128 bytes of scalars, then the status ring of the device-driven iterations)
     DevState* dstate = nullptr;
     double *P = nullptr, *part = nullptr;   // tile partials of the symmetric H pass; per-CTA partial sums of the fast path
+    double *lpart = nullptr, *lcoef = nullptr;   // limited-memory mode: per-CTA Gram partials, coefficients of p over the ring slots
     long long ldh = 0;
     int ntb = 0;
     int evals = 0;
@@ -539,7 +685,8 @@ int opt_free(Opt* o) {   // device buffers and pinned scalars live in the handle
 size_t opt_scratch_doubles(int L, int mem) {
     const size_t Lp = ((size_t)L + 1 + 15) & ~(size_t)15;
     const size_t ldh = ((size_t)L + 3) & ~(size_t)3, ntb = ((size_t)L + STB - 1) / STB;
-    const size_t big = mem > 0 ? (2 * (size_t)mem * L + 64) : ldh * L + ntb * ntb * STB;
+    const size_t nb = ((size_t)L + 255) / 256;
+    const size_t big = mem > 0 ? (2 * (size_t)mem * L + 64 + nb * lb_ldp(mem) + 2 * mem + 16) : ldh * L + ntb * ntb * STB;
     return 11 * Lp + 16 + 32 + 4 * (((size_t)L + 255) / 256) + 16 + big;      // + DevState and the per-CTA partials of the device-driven iterations
 }
 
@@ -738,7 +885,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         o->scal = q;
         q += 16;
         o->dstate = reinterpret_cast<DevState*>(q);
-        q += 32;
+        q += 32;                     // (256 bytes)
         o->part = q;
         q += 4 * (((size_t)L + 255) / 256) + 16;
         o->ldh = (long long)(((size_t)L + 3) & ~(size_t)3);
@@ -747,6 +894,8 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
             o->LS = q;
             o->LY = q + (size_t)mem * L;
             o->Lrho = q + 2 * (size_t)mem * L;
+            o->lpart = o->Lrho + 64;
+            o->lcoef = o->lpart + (((size_t)L + 255) / 256) * lb_ldp(mem);
         } else {
             o->H = q;
             o->P = q + (size_t)o->ldh * L;
@@ -800,10 +949,14 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     double l_gamma = 1.0;
     // ---- device-driven iterations (see DevState): eligible in the reference's mode (dense BFGS, no self-scaling) on unsharded handles
     constexpr int RING = 4, DEPTH = 2;
-    static_assert(sizeof(DevState) <= 128, "status ring slots are 128 bytes");
-    const bool fast_ok = !lbfgs && !o->sharded && !selfscale && std::getenv("MAMBO_OPT_HOSTLOOP") == nullptr;
+    static_assert(sizeof(DevState) <= 192, "status ring slots are 192 bytes");
+    const bool fast_ok = !selfscale && std::getenv("MAMBO_OPT_HOSTLOOP") == nullptr && (!lbfgs || mem <= LB_FAST_MAX);
+    const size_t lb_smem = sizeof(double) * ((size_t)2 * mem * LB_WP + LB_W);
+    if (lbfgs && fast_ok && lb_smem > 48 * 1024 &&
+        CK(cudaFuncSetAttribute(k_fast_lbfgs_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb_smem), "smem attribute"))
+        return finish(MAMBO_ECUDA);
     cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
-    auto ring_slot = [&](int k) { return reinterpret_cast<DevState*>(reinterpret_cast<char*>(o->h_scal) + 128 + 128 * (k % RING)); };
+    auto ring_slot = [&](int k) { return reinterpret_cast<DevState*>(reinterpret_cast<char*>(o->h_scal) + 128 + 192 * (k % RING)); };
     struct EvGuard {
         cudaEvent_t* e;
         ~EvGuard() {
@@ -820,6 +973,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         std::memset(&hs, 0, sizeof(hs));
         hs.f = f; hs.df0 = df0; hs.alpha_prev = alpha_prev; hs.df0_prev = df0_prev; hs.gnorm = gnorm; hs.rho = rho; hs.cc = cc;
         hs.gtol = opt.g_tol; hs.pending = pending ? 1 : 0; hs.parity = (s_cur == o->s) ? 0 : 1; hs.halt = 0; hs.it = it;
+        hs.l_used = l_used; hs.l_head = l_head; hs.l_gamma = l_gamma;
         DevState* up = ring_slot(RING - 1);                 // pinned staging for the upload (not in use: nothing is in flight)
         *up = hs;
         if (CK(cudaMemcpyAsync(o->dstate, up, sizeof(DevState), cudaMemcpyHostToDevice, o->stream), "H2D state")) return MAMBO_ECUDA;
@@ -829,7 +983,9 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         while (true) {
             if (enq < budget && enq - seen < DEPTH) {
                 k_fast_trial<<<blocks(L), 256, 0, o->stream>>>(o->dstate, o->x, o->p, o->xt, L);
-                int rc2 = mambo_csa_eval_device(o->h, o->xt, o->out);
+                // (row-panel shards: the exchange inside the evaluation returns identical bits on every rank, every rank takes the
+                // same decisions from them and enqueues the same number of evaluations, so the peer epochs stay aligned)
+                int rc2 = o->sharded ? mambo_csa_eval_sharded_device(o->h, o->xt, o->out) : mambo_csa_eval_device(o->h, o->xt, o->out);
                 if (rc2) {
                     snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
                     return rc2;
@@ -838,11 +994,18 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
                 const int nb = blocks(L);
                 k_fast_wolfe_part<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->p, o->out, o->part, L);
                 k_fast_wolfe_apply<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->out, o->part, nb, o->s, o->s2, o->y, L);
-                k_sym_update_gemv<<<dim3(o->ntb, o->ntb), 256, 0, o->stream>>>(o->H, o->ldh, L, o->dstate, o->s, o->s2, o->Hy, o->Hy2, 1.0, 0.0, 0.0, 0,
-                                                                                 o->out + 1, o->P, o->ntb);
-                k_fast_dots<<<nb, 256, 0, o->stream>>>(o->dstate, o->P, o->ntb, o->p, o->out, o->s, o->s2, o->Hy, o->Hy2, o->y, o->u, o->part, L);
-                k_fast_direction<<<nb, 256, 0, o->stream>>>(o->dstate, o->part, nb, o->x, o->xt, o->g, o->p, o->out, o->u, o->s, o->s2, o->Hy, o->Hy2, L);
-                k_fast_state<<<1, 32, 0, o->stream>>>(o->dstate, o->part, nb);
+                if (lbfgs) {
+                    k_fast_lbfgs_store<<<nb, 256, 0, o->stream>>>(o->dstate, o->s, o->y, o->LS, o->LY, o->Lrho, mem, o->x, o->xt, o->g, o->out, L);
+                    k_fast_lbfgs_gram<<<nb, 256, lb_smem, o->stream>>>(o->dstate, o->LS, o->LY, o->g, mem, L, o->lpart);
+                    k_fast_lbfgs_solve<<<1, 256, sizeof(double) * (lb_ldp(mem) + 2 * mem), o->stream>>>(o->dstate, o->lpart, nb, mem, o->lcoef);
+                    k_fast_lbfgs_apply<<<nb, 256, 0, o->stream>>>(o->dstate, o->lcoef, o->LS, o->LY, o->g, mem, L, o->p);
+                } else {
+                    k_sym_update_gemv<<<dim3(o->ntb, o->ntb), 256, 0, o->stream>>>(o->H, o->ldh, L, o->dstate, o->s, o->s2, o->Hy, o->Hy2, 1.0, 0.0, 0.0, 0,
+                                                                                     o->out + 1, o->P, o->ntb);
+                    k_fast_dots<<<nb, 256, 0, o->stream>>>(o->dstate, o->P, o->ntb, o->p, o->out, o->s, o->s2, o->Hy, o->Hy2, o->y, o->u, o->part, L);
+                    k_fast_direction<<<nb, 256, 0, o->stream>>>(o->dstate, o->part, nb, o->x, o->xt, o->g, o->p, o->out, o->u, o->s, o->s2, o->Hy, o->Hy2, L);
+                    k_fast_state<<<1, 32, 0, o->stream>>>(o->dstate, o->part, nb);
+                }
                 if (CK(cudaMemcpyAsync(ring_slot(enq), o->dstate, sizeof(DevState), cudaMemcpyDeviceToHost, o->stream), "D2H state") ||
                     CK(cudaEventRecord(ring_ev[enq % RING], o->stream), "event record"))
                     return MAMBO_ECUDA;
@@ -874,6 +1037,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         pending = last.pending != 0;
         if (last.parity == 0) { s_cur = o->s; Hy_cur = o->Hy; s_prev = o->s2; Hy_prev = o->Hy2; }
         else { s_cur = o->s2; Hy_cur = o->Hy2; s_prev = o->s; Hy_prev = o->Hy; }
+        l_used = last.l_used; l_head = last.l_head; l_gamma = last.l_gamma;
         it = last.it;
         *halt_out = halt;
         return MAMBO_OK;
@@ -883,7 +1047,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
             converged = 1;
             break;
         }
-        if (fast_ok && !fresh && it > 0 && df0 < 0) {
+        if (fast_ok && (lbfgs || !fresh) && it > 0 && df0 < 0) {
             int halt = 0;
             rc = fast_run(&halt);
             if (rc) return finish(rc);
