@@ -12,4 +12,4 @@ from .structures import (F_OP, F_FRAG, cartan_2b, cartan_SD, real_orbital_rotati
 from .decompose import (CSA_greedy_decomposition, CSA_greedy_step, CSA_SD_greedy_decomposition,  # noqa: F401
                         CSA_SD_greedy_step, to_OP, OptimResult)
 from . import synthetic  # noqa: F401
-from .guesses import tbt_svd_1st, SVD_to_CSA, SOn_unitary_to_params  # noqa: F401
+from .guesses import tbt_svd_1st, SVD_to_CSA, SOn_unitary_to_params, DF_based_greedy  # noqa: F401

@@ -429,7 +429,17 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
             sts.anti_frags++;
             continue;
         }
-        if (hstat[e] < 0) unconverged = true;
+        if (hstat[e] < 0) {
+            if (!unconverged && std::getenv("MAMBO_DF_DEBUG")) {
+                std::vector<double> Lh(nn);
+                cudaMemcpy(Lh.data(), S->d_L + (size_t)e * nn, sizeof(double) * nn, cudaMemcpyDeviceToHost);
+                double mx = 0.0, mn = 1e300, fro = 0.0;
+                for (double x : Lh) { mx = std::max(mx, std::fabs(x)); if (x != 0.0) mn = std::min(mn, std::fabs(x)); fro += x * x; }
+                fprintf(stderr, "[mambo df] fragment %d (theta %.3e) Jacobi status %d: max|L| %.3e min nonzero %.3e ||L||^2 %.6e\n", e, sel_theta[e],
+                        hstat[e], mx, mn, fro);
+            }
+            unconverged = true;
+        }
         sweeps_max = std::max(sweeps_max, std::abs(hstat[e]));
     }
     sts.jacobi_sweeps_max = unconverged ? -sweeps_max : sweeps_max;

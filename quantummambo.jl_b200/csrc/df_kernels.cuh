@@ -523,7 +523,9 @@ __global__ void __launch_bounds__(1024) k_jacobi_batch(const double* __restrict_
             }
             __syncthreads();
         }
-        if (*rotated == 0) { converged = true; ++sweep; break; }
+        const int rot = *rotated;          // every thread reads the flag before thread 0 may clear it for the next sweep
+        __syncthreads();
+        if (rot == 0) { converged = true; ++sweep; break; }
     }
     // ascending order by counting ranks
     double* om = omega + e * n;

@@ -51,3 +51,22 @@ def tbt_svd_1st(engine: CSAEngine, tiny: float = SVD_tiny, tol: float = 0.0, max
     else:
         omega, Ul = np.linalg.eigh(cur_l)
     return SVD_to_CSA(lead, omega, Ul)
+
+
+def DF_based_greedy(engine: CSAEngine, tol: float = 0.0, as_x: bool = True):
+    """decompose.jl:400-436 on the engine's device-resident residual: the CSA fragment in the orbital frame of the largest
+    double-factorisation fragment, its Cartan coefficients collecting every DF fragment in that frame (mambo_csa_df_decompose
+    + mambo_csa_df_based_greedy; the reference runs DF_decomposition's full `eigen` first, decompose.jl:402).
+
+    as_x: return (lambda (cL), theta (uL)), i.e. the fragment as a start vector x0 = [lambda; theta] of CSA_greedy_step -- the
+    frame goes through SOn_unitary_to_params like SVD_to_CSA's (guesses.jl:20); a column of U1 is negated first when
+    det U1 = -1 (an eigenvector's sign is free and the fragment does not depend on it, but log needs a proper rotation).
+    Otherwise return (lambda, U1) with the frame as a matrix, like the reference's f_matrix_rotation."""
+    engine.df_decompose(tol=tol)
+    lam, U1, _ = engine.df_based_greedy()
+    if not as_x:
+        return lam, U1
+    U1 = np.array(U1)
+    if np.linalg.det(U1) < 0:
+        U1[:, 0] = -U1[:, 0]
+    return lam, SOn_unitary_to_params(U1)

@@ -13,7 +13,7 @@ rngn = np.random.default_rng(5)
 g = rngn.standard_normal((n, n, n, n)); g = g + g.transpose(1, 0, 2, 3); g = g + g.transpose(0, 1, 3, 2); g = g + g.transpose(2, 3, 0, 1)
 T = T + 1e-9 * g / 8.0
 cL, uL = n * (n + 1) // 2, n * (n - 1) // 2
-for start in ("svd", "random"):
+for start in ("df", "svd", "random"):
     for lb in (0, 10):
         rng = np.random.default_rng(1)
         with mb.CSAEngine(T) as e:
@@ -22,7 +22,10 @@ for start in ("svd", "random"):
             for a in range(amax):
                 if c <= 1e-6 * c0:
                     break
-                if start == "svd":
+                if start == "df":
+                    lam, th = mb.DF_based_greedy(e)
+                    x0 = np.concatenate([lam, th])
+                elif start == "svd":
                     lam, th = mb.tbt_svd_1st(e)
                     x0 = np.concatenate([lam, th])
                 else:
