@@ -278,4 +278,50 @@ function CSA_greedy_decomposition_b200(H::F_OP, α_max; decomp_tol = ϵ, verbose
     return Farr
 end
 
+# ---- double factorisation on the resident residual (decompose.jl:297-436) -------------------------------------------------
+struct DfStats               # mambo_df_stats_t
+    krylov_dim::Cint; restarts::Cint; num_frags::Cint; anti_frags::Cint; jacobi_sweeps_max::Cint
+    ortho_dev_before::Cdouble; ortho_dev_after::Cdouble; max_rel_residual::Cdouble
+    seconds_lanczos::Cdouble; seconds_tridiag::Cdouble; seconds_backtransform::Cdouble; seconds_fragments::Cdouble
+end
+
+"""
+    DF_decomposition(e::Engine, n; tol = SVD_tol) -> Vector{F_FRAG}
+
+decompose.jl:297-398 (do_Givens = false) of the tensor resident in `e`: the N^2 x N^2 `eigen` (:326-330), the ordering and
+truncation (:332-350) and the per-fragment `eigen(cur_l)` (:354) all run on the GPU; this wrapper only builds the F_FRAGs
+(:372-378).  Anti-Hermitian fragments (:356-361) come back with their coefficient negated and the matrix L; their complex
+`eigen(Hermitian(1im * L))` is done here.
+"""
+function QuantumMAMBO.DF_decomposition(e::Engine, n::Integer; tol = SVD_tol, spin_orb = false)
+    nf = Ref{Cint}(0)
+    st = Ref{DfStats}()
+    check(ccall((:mambo_csa_df_decompose, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cint, Cint, Ref{Cint}, Ref{DfStats}), e.h, tol, 0, 0, nf, st))
+    k = Int(nf[])
+    coeff = Vector{Float64}(undef, k); omega = Matrix{Float64}(undef, n, k); kind = Vector{Cint}(undef, k)
+    U = Array{Float64,3}(undef, n, n, k); L = Array{Float64,3}(undef, n, n, k)
+    k > 0 && check(ccall((:mambo_csa_df_get, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Cint}),
+                         e.h, 0, k, coeff, omega, U, L, kind))
+    FRAGS = F_FRAG[]
+    for i in 1:k
+        if kind[i] == 0
+            Rl = f_matrix_rotation(n, U[:, :, i]); ωl = omega[:, i]
+        else
+            ωl, Ul = eigen(Hermitian(1im * L[:, :, i]))                           # decompose.jl:359
+            Rl = c_matrix_rotation(n, Ul)
+        end
+        push!(FRAGS, F_FRAG(1, tuple(Rl), DF(), cartan_1b(spin_orb, ωl, n), n, spin_orb, coeff[i], true))
+    end
+    return FRAGS
+end
+
+"""
+    DF_based_greedy(e::Engine, n) -> F_FRAG      (decompose.jl:400-436, after DF_decomposition(e, n))
+"""
+function QuantumMAMBO.DF_based_greedy(e::Engine, n::Integer; spin_orb = false)
+    lam = Vector{Float64}(undef, cartan_2b_num_params(n)); U1 = Matrix{Float64}(undef, n, n)
+    check(ccall((:mambo_csa_df_based_greedy, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), e.h, lam, U1, C_NULL))
+    return F_FRAG(1, tuple(f_matrix_rotation(n, U1)), CSA(), cartan_2b(spin_orb, lam, n), n, spin_orb)
+end
+
 end # module

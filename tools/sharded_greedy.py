@@ -38,12 +38,16 @@ with mb.CSAEngine(np.zeros((n, n, n, n)), device=local) as e:
     for _ in range(R):
         W, _ = e.reconstruct(np.concatenate([rng.standard_normal(cL), 2 * np.pi * rng.random(uL)]))
         T += W
-g = rng.standard_normal((n, n, n, n))
-g = g + g.transpose(1, 0, 2, 3)
-g = g + g.transpose(0, 1, 3, 2)
-g = g + g.transpose(2, 3, 0, 1)
-T += 1e-9 * g / 8.0
+# the noise is drawn and symmetrised on the GPU (4.3 GB at N = 152: numpy would take longer than the whole decomposition)
+gen = torch.Generator(device="cuda")
+gen.manual_seed(1234)
+g = torch.randn((n, n, n, n), dtype=torch.float64, device="cuda", generator=gen)
+g = g + g.permute(1, 0, 2, 3)
+g = g + g.permute(0, 1, 3, 2)
+g = g + g.permute(2, 3, 0, 1)
+T += (1e-9 / 8.0) * g.permute(3, 2, 1, 0).contiguous().cpu().numpy().T      # (any fixed layout: the noise is symmetric noise)
 del g
+torch.cuda.empty_cache()
 T = np.asfortranarray(T)
 # initial guess of the first step: tbt_svd_1st (guesses.jl:51-84) needs the whole matrix view -> an unsharded handle on this
 # rank's GPU (deterministic, so every rank gets the same x0); later steps start from random theta like CSA_greedy_step
