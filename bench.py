@@ -297,6 +297,26 @@ def greedy_time_to_tolerance(mb, syn, device: int, n: int = 50, R: int = 4, tol_
                 "ms_per_evaluation_incl_optimizer": dt / max(evals, 1) * 1e3, "first_step": first}, x0_first
 
     out, x0_first = run(0)
+    try:   # HBM roofline of the dense BFGS's pass over the inverse Hessian, at this leg's L and at the bench tensor's (N = 100)
+        import ctypes as C
+        lib = mb.load()
+        peak = None
+        try:
+            peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            pass
+        out["bfgs_pass_roofline"] = {}
+        for L_ in (n * n, 100 * 100):
+            ms_, by_ = C.c_double(), C.c_double()
+            if lib.mambo_debug_bfgs_pass(device, L_, 20, C.byref(ms_), C.byref(by_)) == 0:
+                gbs = by_.value / (ms_.value * 1e-3) / 1e9
+                out["bfgs_pass_roofline"][f"L={L_}"] = {
+                    "bound": "hbm", "kernel": "k_sym_update_gemv + k_sym_reduce (rank-2 update of the symmetric inverse Hessian fused with H g)",
+                    "achieved": gbs, "peak": peak or 6534.5, "unit": "GB/s", "frac": gbs / (peak or 6534.5), "ms_per_pass": ms_.value,
+                    "algorithmic_bytes": by_.value, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peak else "fallback 6534.5 GB/s (file absent)"}
+    except Exception as exc:  # noqa: BLE001
+        out["bfgs_pass_roofline"] = {"error": repr(exc)}
     out["workload"] = (f"planted N={n} R={R} + 1e-9 noise, greedy CSA to {tol_rel:g} x the initial squared-norm cost, <= {alpha_max} "
                        f"fragments x <= {max_iter} BFGS iterations (native dense BFGS like Optim.jl's), SVD start")
     out["lbfgs_memory_10"], _ = run(10)
@@ -618,10 +638,14 @@ def main():
     host_nl = max(1, min(nl, cores_total // max(world, 1)))
     while BATCH % host_nl:
         host_nl -= 1
-    blocking = world * (host_nl + 1) > cores_total
-    if blocking:
+    # wait mode per leg: spinning callers (lowest latency) as long as every spinning thread of the box has a core of its own,
+    # blocking-sync events otherwise
+    def set_wait(threads_per_rank: int) -> bool:
+        blk = world * threads_per_rank > max(1, cores_total - 2)
         for e in group:
-            e.set_wait_mode(True)
+            e.set_wait_mode(blk)
+        return blk
+
     def batch_leg():
         """The step's BATCH points through ONE C-ABI call per step (mambo_csa_cost_grad_batch over the lanes): host x in,
         H2D, kernels, D2H of every cost+grad inside the timed region, a single caller thread."""
@@ -643,8 +667,11 @@ def main():
             dt_ = float(t.item())
         return dt_
 
+    blocking1 = set_wait(1)
     t_e2e1 = host_leg(1)
+    blocking = set_wait(host_nl)
     t_e2e = host_leg(host_nl) if host_nl > 1 else t_e2e1
+    set_wait(1)
     t_batch = batch_leg()
     sampler.stop()
     e2e_threads = evals_total / t_e2e
@@ -822,7 +849,9 @@ def main():
                                         "what": "mambo_csa_cost_grad, one synchronous call per point, one caller thread per lane"},
                     "batch_call": {"value": e2e_batch, "what": "one mambo_csa_cost_grad_batch call per step from a single caller "
                                    "thread: the step's points over the lanes, each lane re-armed as soon as its point is collected"},
-                    "single_caller": e2e_value1, "wait_mode": "blocking-sync event" if blocking else "spin"},
+                    "single_caller": e2e_value1,
+                    "wait_mode": {"closure_threads": "blocking-sync event" if blocking else "spin",
+                                  "batch_call / single_caller": "blocking-sync event" if blocking1 else "spin"}},
             "single_lane": {"value": value1, "ms_per_step": ms1 / args.steps,
                             "note": "one evaluation in flight at a time (the sequential BFGS case)"},
             "gpu_launches": int(launches), "launches_per_eval": launches / (BATCH * args.steps),

@@ -216,6 +216,10 @@ int  mambo_csa_optimize_reserve(mambo_csa* h, int lbfgs_memory);
 int  mambo_multistart_run(mambo_csa** handles, int nhandles, int K, const double* x0, double* x_min,
                           const mambo_opt_options_t* opt, mambo_opt_result_t* res, int* best);
 
+/* Measurement aid: average device time (CUDA events) of one pass of the dense BFGS's inverse-Hessian kernel at L parameters
+ * (pending rank-2 update + H g over the lower-triangular 128 x 128 tiles) and its algorithmic HBM bytes, 16 B x L (L + 1) / 2. */
+int  mambo_debug_bfgs_pass(int device, int L, int reps, double* ms_per_pass, double* bytes_per_pass);
+
 /* --- double factorisation of the RESIDENT residual ------------------------------------------------------
  * Replaces DF_decomposition (decompose.jl:297-398, do_Givens = false) and DF_based_greedy (decompose.jl:400-436).
  * The reference diagonalises the whole N^2 x N^2 view with LAPACK (:326-330), keeps the eigenpairs with |eigenvalue| >= tol

@@ -142,6 +142,7 @@ SIGNATURES = {
     "mambo_dgemm_device": (C.c_int, [C.c_int, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_longlong, _P, C.c_longlong, _P, C.c_longlong]),
     "mambo_csa_optimize": (C.c_int, [_P, _P, _P, C.POINTER(OptOptions), C.POINTER(OptResult)]),
     "mambo_csa_optimize_reserve": (C.c_int, [_P, C.c_int]),
+    "mambo_debug_bfgs_pass": (C.c_int, [C.c_int, C.c_int, C.c_int, _D, _D]),
     "mambo_multistart_run": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, _P, _P, C.POINTER(OptOptions),
                                        C.POINTER(OptResult), C.POINTER(C.c_int)]),
 }

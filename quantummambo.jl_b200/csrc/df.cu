@@ -160,6 +160,8 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
     DCU(scr.get((void**)&d_alpha, sizeof(double) * (R + 2)));
     DCU(scr.get((void**)&d_beta, sizeof(double) * (R + 2)));
     DCU(scr.get((void**)&d_rnorm, sizeof(double) * 2));
+    double* npart = nullptr;
+    DCU(scr.get((void**)&npart, sizeof(double) * ((size_t)(R + 255) / 256 + 1)));
     DCU(cudaMemsetAsync(d_alpha, 0, sizeof(double) * (R + 2), st));
     DCU(cudaMemsetAsync(d_beta, 0, sizeof(double) * (R + 2), st));
     const int vblocks = (R + 255) / 256;
@@ -173,8 +175,9 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
             df::k_project_split<<<dim3(vblocks, KS), 256, 0, st>>>(V, ldv, R, nv, cvec, part, (int)ldv);
             launches += 2;
         }
-        df::k_apply_norm<<<1, 1024, 0, st>>>(vec, R, (int)ldv, part, nv > 0 ? KS : 0, dst, cvec, d_alpha, d_beta, j, mode, d_rnorm);
-        launches += 1;
+        df::k_apply_part<<<vblocks, 256, 0, st>>>(vec, R, (int)ldv, part, nv > 0 ? KS : 0, npart);
+        df::k_scale_norm<<<(int)((ldv + 255) / 256), 256, 0, st>>>(vec, R, (int)ldv, npart, vblocks, dst, cvec, d_alpha, d_beta, j, mode, d_rnorm);
+        launches += 2;
     };
     lanczos::k_start<<<vblocks, 256, 0, st>>>(w, R, v.pa, v.pq, n, v.packed);
     reorth(w, 0, V, 0, 2);

@@ -6,7 +6,7 @@
 // into the orbital frame of the first one.  Here everything runs on the matrix the engine already holds in HBM:
 //
 //   tridiagonalisation : Lanczos with full re-orthogonalisation run to completion (df.cu) on lanczos::k_symv (HBM-bound);
-//                        k_project_split / k_apply_norm below are the two-stage, bit-reproducible projection of that driver
+//                        k_project_split / k_apply_part / k_scale_norm below are the bit-reproducible projection of that driver
 //   k_bisect           : all eigenvalues of the (block-diagonal) tridiagonal, one thread per eigenvalue (Sturm counts)
 //   k_twisted          : eigenvectors of the tridiagonal by twisted factorisation, one thread per eigenvector
 //   k_dgemm<TA>        : FP64 tensor-core GEMM (DMMA.8x8x4) C = op(A) B for the Gram matrix Z^T Z, the Newton-Schulz
@@ -28,7 +28,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 // ---- re-orthogonalisation of the Lanczos driver ---------------------------------------------------------------------------
 // part[ks][i] = sum_{k in chunk ks} c[k] V[k][i]   (grid: (ceil(len/256), KS); chunk = ceil(nv / KS) vectors)
 // A single thread per element with all nv vectors in sequence (lanczos::k_project) keeps only len/256 CTAs busy; the
-// split over KS chunks fills the device and the fixed-order combine in k_apply_norm keeps the result bit-reproducible.
+// split over KS chunks fills the device and the fixed-order combine in k_apply_part keeps the result bit-reproducible.
 static __global__ void __launch_bounds__(256) k_project_split(const double* __restrict__ V, long long ldv, int len, int nv, const double* __restrict__ c,
                                                        double* __restrict__ part, int lenpad) {
     __shared__ double sc[512];
@@ -58,46 +58,59 @@ static __global__ void __launch_bounds__(256) k_project_split(const double* __re
     if (i < len) part[(long long)blockIdx.y * lenpad + i] = (a0 + a1) + (a2 + a3);
 }
 
-// w <- w - sum_ks part[ks]  (fixed order), nrm = ||w||, vnext = w / nrm  (single CTA, 1024 threads).
-//   mode 0 (first pass of step j):  alpha[j] = c[j];  beta[j] = nrm
-//   mode 1 (second pass, on the unit vector): alpha[j] += beta[j] * c[j];  beta[j] *= nrm
-//   mode 2 (restart vector): neither alpha nor beta is touched; rnorm[0] = nrm
-// w may alias vnext (the second pass works in place on V[j+1]).
-static __global__ void __launch_bounds__(1024) k_apply_norm(double* w, int len, int lenpad, const double* __restrict__ part, int KS,
-                                                     double* vnext, const double* __restrict__ c, double* __restrict__ alpha,
-                                                     double* __restrict__ beta, int j, int mode, double* __restrict__ rnorm) {
-    __shared__ double red[32];
-    __shared__ double s_inv;
-    double a = 0.0;
-    for (int i = threadIdx.x; i < len; i += 1024) {
+// w <- w - sum_ks part[ks]  (fixed order) and the per-CTA partial sums of |w|^2  (grid: ceil(len / 256) CTAs of 256 threads)
+static __global__ void __launch_bounds__(256) k_apply_part(double* w, int len, int lenpad, const double* __restrict__ part, int KS,
+                                                           double* __restrict__ npart) {
+    __shared__ double red[8];
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    double v = 0.0;
+    if (i < len) {
         double s = 0.0;
         for (int ks = 0; ks < KS; ++ks) s += part[(long long)ks * lenpad + i];
-        const double v = w[i] - s;
+        v = w[i] - s;
         w[i] = v;
-        a = fma(v, v, a);
     }
+    double a = v * v;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
     __syncthreads();
     if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) t += red[q];
+        npart[blockIdx.x] = t;
+    }
+}
+// nrm = sqrt(sum of the partials, fixed order), vnext = w / nrm (zero in the padding); grid: ceil(lenpad / 256) CTAs.
+//   mode 0 (first pass of step j):  alpha[j] = c[j];  beta[j] = nrm
+//   mode 1 (second pass, on the unit vector): alpha[j] += beta[j] * c[j];  beta[j] *= nrm
+//   mode 2 (restart vector): neither alpha nor beta is touched; rnorm[0] = nrm
+// w may alias vnext (the second pass works in place on V[j+1]).  Only CTA 0 touches alpha / beta / rnorm.
+static __global__ void __launch_bounds__(256) k_scale_norm(const double* w, int len, int lenpad, const double* __restrict__ npart, int nparts,
+                                                           double* vnext, const double* __restrict__ c, double* __restrict__ alpha,
+                                                           double* __restrict__ beta, int j, int mode, double* __restrict__ rnorm) {
+    __shared__ double s_inv;
+    if (threadIdx.x == 0) {
         double s = 0.0;
-        for (int q = 0; q < 32; ++q) s += red[q];
+        for (int q = 0; q < nparts; ++q) s += npart[q];
         const double nrm = sqrt(s);
-        if (mode == 0) {
-            alpha[j] = c[j];
-            beta[j] = nrm;
-        } else if (mode == 1) {
-            alpha[j] += beta[j] * c[j];
-            beta[j] *= nrm;
-        } else {
-            rnorm[0] = nrm;
+        if (blockIdx.x == 0) {
+            if (mode == 0) {
+                alpha[j] = c[j];
+                beta[j] = nrm;
+            } else if (mode == 1) {
+                alpha[j] += beta[j] * c[j];
+                beta[j] *= nrm;
+            } else {
+                rnorm[0] = nrm;
+            }
         }
         s_inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
     }
     __syncthreads();
-    const double inv = s_inv;
-    for (int i = threadIdx.x; i < lenpad; i += 1024) vnext[i] = i < len ? w[i] * inv : 0.0;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < lenpad) vnext[i] = i < len ? w[i] * s_inv : 0.0;
 }
 
 // pseudo-random restart vector (deterministic in `seed`), entries in (-1, 1)

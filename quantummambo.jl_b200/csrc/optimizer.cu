@@ -1247,4 +1247,50 @@ int mambo_multistart_run(mambo_csa** handles, int nhandles, int K, const double*
     return MAMBO_OK;
 }
 
+// Measurement aid: `reps` passes of the inverse-Hessian kernel of the dense BFGS (pending rank-2 update + H g over the lower-
+// triangular tiles, then the fixed-order reduction) on an L x L identity, timed with CUDA events on a stream of its own.
+// ms_per_pass: average device time; bytes_per_pass: the algorithmic HBM traffic 16 B x L (L + 1) / 2 (every stored element read
+// and written once).
+int mambo_debug_bfgs_pass(int device, int L, int reps, double* ms_per_pass, double* bytes_per_pass) {
+    if (L < 1 || reps < 1 || !ms_per_pass) return MAMBO_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return MAMBO_ECUDA;
+    const long long ldh = ((long long)L + 3) & ~3LL;
+    const int ntb = (L + STB - 1) / STB;
+    double *H = nullptr, *v = nullptr, *P = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int rc = MAMBO_ECUDA;
+    do {
+        if (cudaMalloc((void**)&H, sizeof(double) * ldh * L) != cudaSuccess) { rc = MAMBO_ENOMEM; break; }
+        if (cudaMalloc((void**)&v, sizeof(double) * 4 * (size_t)L) != cudaSuccess) { rc = MAMBO_ENOMEM; break; }
+        if (cudaMalloc((void**)&P, sizeof(double) * (size_t)ntb * ntb * STB) != cudaSuccess) { rc = MAMBO_ENOMEM; break; }
+        if (cudaStreamCreate(&st) != cudaSuccess || cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) break;
+        k_set_identity<<<1184, 256, 0, st>>>(H, ldh, L, 1.0);
+        cudaMemsetAsync(v, 0, sizeof(double) * 4 * (size_t)L, st);          // s, Hy, g, u := 0
+        double *s = v, *Hy = v + L, *g = v + 2 * (size_t)L, *u = v + 3 * (size_t)L;
+        for (int r = 0; r < 2; ++r) {
+            k_sym_update_gemv<<<dim3(ntb, ntb), 256, 0, st>>>(H, ldh, L, nullptr, s, nullptr, Hy, nullptr, 1.0, 1e-3, 1e-3, 1, g, P, ntb);
+            k_sym_reduce<<<blocks(L), 256, 0, st>>>(P, ntb, L, u);
+        }
+        cudaEventRecord(e0, st);
+        for (int r = 0; r < reps; ++r) {
+            k_sym_update_gemv<<<dim3(ntb, ntb), 256, 0, st>>>(H, ldh, L, nullptr, s, nullptr, Hy, nullptr, 1.0, 1e-3, 1e-3, 1, g, P, ntb);
+            k_sym_reduce<<<blocks(L), 256, 0, st>>>(P, ntb, L, u);
+        }
+        cudaEventRecord(e1, st);
+        if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        *ms_per_pass = ms / reps;
+        if (bytes_per_pass) *bytes_per_pass = 16.0 * (double)L * ((double)L + 1.0) / 2.0;
+        rc = MAMBO_OK;
+    } while (false);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (st) cudaStreamDestroy(st);
+    cudaFree(H); cudaFree(v); cudaFree(P);
+    if (rc) mambo_set_error("mambo_debug_bfgs_pass failed");
+    return rc;
+}
+
 }  // extern "C"

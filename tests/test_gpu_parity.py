@@ -627,6 +627,38 @@ def test_native_lbfgs_mode_finds_planted_fragment(mb, lib):
         assert abs(c_l - rl["minimum"]) <= 1e-12 * tt
 
 
+def test_device_driven_iterations_agree_with_the_host_loop(mb, lib, monkeypatch):
+    """mambo_csa_optimize keeps the scalars of an iteration on the device while the first trial step satisfies the strong-Wolfe
+    conditions and hands single iterations back to the host's line search otherwise; MAMBO_OPT_HOSTLOOP=1 forces the host
+    loop for every iteration.  Same decisions, same arithmetic up to the order of a few sums: on a non-trivial landscape
+    (dense random tensor, random start -- many line searches need the host) both must follow the same trajectory for a
+    short run, and on a planted tensor both must converge to the planted fragment; dense and limited-memory mode."""
+    n = 8
+    T = o.dense_sym_tbt(n, 5)
+    x0 = o.random_x(n, 2)
+    for mem in (0, 6, 40):                       # 40 > LB_FAST_MAX: the limited-memory mode falls back to the host loop by itself
+        with mb.CSAEngine(T) as e:
+            monkeypatch.delenv("MAMBO_OPT_HOSTLOOP", raising=False)
+            xf, rf = e.optimize(x0, g_tol=1e-9, max_iter=25, lbfgs_memory=mem)
+            monkeypatch.setenv("MAMBO_OPT_HOSTLOOP", "1")
+            xh, rh = e.optimize(x0, g_tol=1e-9, max_iter=25, lbfgs_memory=mem)
+            monkeypatch.delenv("MAMBO_OPT_HOSTLOOP", raising=False)
+        assert rf["iterations"] == rh["iterations"] == 25
+        assert abs(rf["minimum"] - rh["minimum"]) <= 1e-7 * abs(rh["minimum"])
+        assert rel(xf, xh) <= 1e-6
+        assert rf["evaluations"] >= rh["evaluations"]      # speculative evaluations behind a halted iteration are counted
+        c_chk = o.cost_grad_factored(xf, T, need_grad=False)
+        c_chk = c_chk[0] if isinstance(c_chk, tuple) else c_chk
+        assert abs(c_chk - rf["minimum"]) <= 1e-10 * abs(c_chk)
+    Tp, xs = o.planted_tbt(n, 1, 9)
+    xp0 = xs[0] + 0.02 * np.random.default_rng(3).standard_normal(xs[0].shape)
+    tt = float(np.sum(Tp * Tp))
+    for mem in (0, 8):
+        with mb.CSAEngine(Tp) as e:
+            xm, res = e.optimize(xp0, g_tol=1e-9, max_iter=800, lbfgs_memory=mem)
+        assert res["minimum"] < 1e-9 * tt, (mem, res)        # (the limited-memory run is at 3e-12 tt after 800 iterations, still falling)
+
+
 def test_greedy_decomposition_matches_oracle_driver(mb, lib):
     """decompose.jl:1-80 end to end at LiH size (N=6 stand-in: planted R=2 + small symmetric noise): same x0s, same
     BFGS (scipy) on both sides -> same fragments, final 1-norm (lcu.jl:139-182) within north_star's 1e-8."""
