@@ -44,7 +44,8 @@ int fail(int code, const std::string& msg) {
         if (rc__) return rc__;  \
     } while (0)
 
-const int kNBBuckets[] = {1, 2, 4, 7, 10, 13, 16, 19, 21};
+// every multiple of 8 columns up to 168 has its own instantiation: the DMMA work is never padded by more than one n-block
+const int kNBBuckets[] = {1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21};
 
 // Opt-in dynamic shared memory of a kernel is a per-function (per-process) attribute: handles of different N share the
 // non-templated kernels, so the limit is only ever RAISED -- a later, smaller problem must not lower it under an
@@ -238,12 +239,24 @@ int launch_fused(mambo_csa* h, const Params& p) {
     switch (h->NB) {
         case 1: return launch_fused_nb<1, DO_E, STORE>(h, p);
         case 2: return launch_fused_nb<2, DO_E, STORE>(h, p);
+        case 3: return launch_fused_nb<3, DO_E, STORE>(h, p);
         case 4: return launch_fused_nb<4, DO_E, STORE>(h, p);
+        case 5: return launch_fused_nb<5, DO_E, STORE>(h, p);
+        case 6: return launch_fused_nb<6, DO_E, STORE>(h, p);
         case 7: return launch_fused_nb<7, DO_E, STORE>(h, p);
+        case 8: return launch_fused_nb<8, DO_E, STORE>(h, p);
+        case 9: return launch_fused_nb<9, DO_E, STORE>(h, p);
         case 10: return launch_fused_nb<10, DO_E, STORE>(h, p);
+        case 11: return launch_fused_nb<11, DO_E, STORE>(h, p);
+        case 12: return launch_fused_nb<12, DO_E, STORE>(h, p);
         case 13: return launch_fused_nb<13, DO_E, STORE>(h, p);
+        case 14: return launch_fused_nb<14, DO_E, STORE>(h, p);
+        case 15: return launch_fused_nb<15, DO_E, STORE>(h, p);
         case 16: return launch_fused_nb<16, DO_E, STORE>(h, p);
+        case 17: return launch_fused_nb<17, DO_E, STORE>(h, p);
+        case 18: return launch_fused_nb<18, DO_E, STORE>(h, p);
         case 19: return launch_fused_nb<19, DO_E, STORE>(h, p);
+        case 20: return launch_fused_nb<20, DO_E, STORE>(h, p);
         case 21: return launch_fused_nb<21, DO_E, STORE>(h, p);
     }
     return fail(MAMBO_EINVAL, "unsupported NB bucket");
@@ -290,12 +303,24 @@ int launch_ty(mambo_csa* h, const YParams& p) {
     switch (h->NB) {
         case 1: return launch_ty_nb<1>(h, p);
         case 2: return launch_ty_nb<2>(h, p);
+        case 3: return launch_ty_nb<3>(h, p);
         case 4: return launch_ty_nb<4>(h, p);
+        case 5: return launch_ty_nb<5>(h, p);
+        case 6: return launch_ty_nb<6>(h, p);
         case 7: return launch_ty_nb<7>(h, p);
+        case 8: return launch_ty_nb<8>(h, p);
+        case 9: return launch_ty_nb<9>(h, p);
         case 10: return launch_ty_nb<10>(h, p);
+        case 11: return launch_ty_nb<11>(h, p);
+        case 12: return launch_ty_nb<12>(h, p);
         case 13: return launch_ty_nb<13>(h, p);
+        case 14: return launch_ty_nb<14>(h, p);
+        case 15: return launch_ty_nb<15>(h, p);
         case 16: return launch_ty_nb<16>(h, p);
+        case 17: return launch_ty_nb<17>(h, p);
+        case 18: return launch_ty_nb<18>(h, p);
         case 19: return launch_ty_nb<19>(h, p);
+        case 20: return launch_ty_nb<20>(h, p);
         case 21: return launch_ty_nb<21>(h, p);
     }
     return fail(MAMBO_EINVAL, "unsupported NB bucket");
@@ -422,22 +447,34 @@ int enqueue_unitary(mambo_csa* h, const double* d_x, int s_host) {
     return MAMBO_OK;
 }
 
-// NB bucket -> (NBT, CST, CSP): panel-kernel instantiation, column split of k_post_mma (CST = 4 above N = 104, 6 above N = 152,
+// NB bucket -> (NBT, CST, CSP): panel-kernel instantiation, column split of k_post_mma (CST = 4 above N = 112, 6 above N = 160,
 // so that the panels plus the Lambda slice fit in shared memory) and of k_prep_mma (CSP; a split of 2 for 72 < N <= 104 -- two
 // 100 KB CTAs per SM, twice as many CTAs as panels -- was measured 2 us slower than 1: the kernel is not GEMM-bound)
 #define NB_PANEL_DISPATCH(nb, CALL)                 \
     switch (nb) {                                   \
         case 1: { constexpr int NBT = 1, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
         case 2: { constexpr int NBT = 2, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 3: { constexpr int NBT = 3, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
         case 4: { constexpr int NBT = 4, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 5: { constexpr int NBT = 5, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 6: { constexpr int NBT = 6, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
         case 7: { constexpr int NBT = 7, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
-        case 10: { constexpr int NBT = 10, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; } \
-        case 13: { constexpr int NBT = 13, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; } \
-        case 16: { constexpr int NBT = 16, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
-        case 19: { constexpr int NBT = 19, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; } \
+        case 8: { constexpr int NBT = 8, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 9: { constexpr int NBT = 9, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 10: { constexpr int NBT = 10, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 11: { constexpr int NBT = 11, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 12: { constexpr int NBT = 12, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 13: { constexpr int NBT = 13, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 14: { constexpr int NBT = 14, CST = 1, CSP = 1; (void)CSP; (void)CST; CALL; break; }   \
+        case 15: { constexpr int NBT = 15, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; }   \
+        case 16: { constexpr int NBT = 16, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; }   \
+        case 17: { constexpr int NBT = 17, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; }   \
+        case 18: { constexpr int NBT = 18, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; }   \
+        case 19: { constexpr int NBT = 19, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; }   \
+        case 20: { constexpr int NBT = 20, CST = 4, CSP = 4; (void)CSP; (void)CST; CALL; break; }   \
         default: { constexpr int NBT = 21, CST = 6, CSP = 6; (void)CSP; (void)CST; CALL; break; } \
     }
-int panel_cs(int nb) { return nb >= 21 ? 6 : (nb >= 16 ? 4 : 1); }   // == CST / CSP of NB_PANEL_DISPATCH
+int panel_cs(int nb) { return nb >= 21 ? 6 : (nb >= 15 ? 4 : 1); }   // == CST / CSP of NB_PANEL_DISPATCH
 
 // Operand build after the orbital rotation.
 //   PREP_LEAN : A~ (all rows) and the N x N closed forms only (panel::k_build_a) -- the lean single-GEMM evaluation
@@ -470,10 +507,10 @@ PrepKind eval_prep_kind(const mambo_csa* h) { return h->lean ? PREP_LEAN : (h->f
 // Row epilogue of one pass of the hot kernel: F = E~ Lambda and Spart = A~^T E~ per panel, where E~ is assembled from the
 // hot kernel's pieces: E (two-GEMM kernel), C~ - Y (first single-GEMM formulation) or Y itself (lean path: F = Y Lambda,
 // Spart = A~^T Y; the closed-form terms are added by k_post_reduce).
-//   do_F / do_S select the products; esum: column-split launches (NB >= 16) first sum the pieces once (k_esum) -- callers that
+//   do_F / do_S select the products; esum: column-split launches (NB >= 15) first sum the pieces once (k_esum) -- callers that
 //   run the two products on two streams do that before they fork.
 int enqueue_post_f(mambo_csa* h, double* F, bool do_S = false, bool do_F = true, bool esum = true) {
-    const bool split = h->NB >= 16;           // column-split panel kernels (NB_PANEL_DISPATCH): sum the pieces once, up front
+    const bool split = panel_cs(h->NB) > 1;   // column-split panel kernels (NB_PANEL_DISPATCH): sum the pieces once, up front
     const double* ct = (h->fast && !h->lean) ? h->Ct : nullptr;
     if (split && esum) {
         const int ysplit = std::max(1, std::min(8, (2 * h->num_sms) / std::max(h->P, 1)));
@@ -535,7 +572,7 @@ int enqueue_finish(mambo_csa* h, const double* d_x, double* d_out, bool side_tai
     if (side_tail) {
         const bool general = (h->mode == (int)MAMBO_SYM_GENERAL);
         double* Flast = general ? h->F2 : h->F1;
-        if (split && h->NB >= 16) TRY(enqueue_post_f(h, Flast, false, false, true));   // k_esum only: before the fork
+        if (split && panel_cs(h->NB) > 1) TRY(enqueue_post_f(h, Flast, false, false, true));   // k_esum only: before the fork
         CU(cudaEventRecord(h->ev_fork, h->stream));
         CU(cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
         cudaStream_t main_stream = h->stream;

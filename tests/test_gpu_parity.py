@@ -731,11 +731,12 @@ def test_csa_sd_greedy_step_molecule_sizes(mb, lib):
 
 
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [70, 110, 130])
+@pytest.mark.parametrize("n", [20, 36, 44, 60, 70, 84, 92, 110, 116, 124, 130, 140])
 def test_large_kernel_buckets_match_oracle(mb, lib, n):
-    """The kernel instantiations between the benchmark sizes: n = 70 (10 n-blocks), 110 (16 n-blocks: column-split panel
-    kernels, k_esum, shallower operand ring) and 130 (19 n-blocks: no T~ look-ahead registers) -- the code path of the
-    N = 152 configuration at a size whose host tensor stays small."""
+    """The kernel instantiations between the benchmark sizes (every multiple of 8 columns has its own: n-blocks 3, 5, 6, 8, 9, 11,
+    12, 14, 15, 16, 17, 18 here; 1, 2, 4, 7, 10, 13, 19, 20, 21 elsewhere in this file): n = 116 and up take the column-split
+    panel kernels with k_esum and the shallower operand ring, n = 140 has no T~ look-ahead registers -- the code paths of
+    the N = 152 configuration at sizes whose host tensor stays small."""
     T = o.dense_sym_tbt(n, 5)
     x = o.random_x(n, 6)
     c0, g0 = o.cost_grad_factored(x, T)
@@ -787,11 +788,12 @@ def test_full_size_properties(mb, lib, n):
 
 
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [152, 160])
+@pytest.mark.parametrize("n", [152, 160, 168])
 def test_largest_configuration_and_last_bucket_against_oracle(mb, lib, n):
-    """BASELINE configs[4] size (N = 152, 19 n-blocks) and the last kernel bucket (N = 160, 21 n-blocks, six-way column
-    split of the panel kernels): the dense-sym tensor is generated on the device (4.3 / 5.2 GB) and handed to the library
-    in place (MAMBO_TBT_ON_DEVICE); the oracle evaluates the same array once on the host."""
+    """BASELINE configs[4] size (N = 152, 19 n-blocks) and the last kernel buckets (N = 160: 20 n-blocks; N = 168: 21 n-blocks,
+    six-way column split of the panel kernels, the largest N the library takes): the dense-sym tensor is generated on the
+    device (4.3 / 5.2 / 6.4 GB) and handed to the library in place (MAMBO_TBT_ON_DEVICE); the oracle evaluates the same array
+    once on the host."""
     import torch
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(n)
