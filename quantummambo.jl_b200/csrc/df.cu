@@ -73,16 +73,24 @@ struct Scratch {
     }
 };
 
-bool g_gemm_ready = false;
+// Opt-in dynamic shared memory is only ever RAISED (per device): handles of different N on one GPU share these kernels.
+template <class K>
+cudaError_t raise_smem(K kernel, size_t bytes) {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaFuncGetAttributes(&a, (const void*)kernel);
+    if (e != cudaSuccess) return e;
+    if ((size_t)a.maxDynamicSharedSizeBytes >= bytes) return cudaSuccess;
+    return cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+// opt-in dynamic shared memory of the GEMM instantiations: a per-device attribute, so it is (re)set for the current device on
+// every entry (a few microseconds) rather than remembered in a process-wide flag
 cudaError_t gemm_setup() {
-    if (g_gemm_ready) return cudaSuccess;
     cudaError_t e;
     const int bytes = (int)df::GEMM_SMEM;
     if ((e = cudaFuncSetAttribute(df::k_dgemm<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(df::k_dgemm<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(df::k_dgemm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    g_gemm_ready = true;     // per device in principle; the attribute is per function and context, set again is harmless
-    return cudaSuccess;
+    return cudaFuncSetAttribute(df::k_dgemm<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 template <bool TA, int EPI>
 void gemm(cudaStream_t st, int M, int N, int K, const double* A, long long lda, const double* B, long long ldb, double* C, long long ldc) {
@@ -403,12 +411,12 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
     if (!usm && sm_half > 232448) return dfail(MAMBO_EINVAL, "N too large for the shared-memory Jacobi eigensolver");
     const int jthreads = n >= 64 ? 1024 : (n >= 24 ? 256 : 64);
     if (usm) {
-        DCU(cudaFuncSetAttribute(df::k_jacobi_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_full));
+        DCU(raise_smem(df::k_jacobi_batch<true>, sm_full));
         df::k_jacobi_batch<true><<<ne, jthreads, sm_full, st>>>(S->d_L, n, S->d_omega, S->d_U, nullptr, d_status, 60);
     } else {
         double* Ut = nullptr;                              // ne x n x n: the transposed eigenvector accumulators live in global memory / L2
         DCU(scr.get((void**)&Ut, sizeof(double) * nn * ne));
-        DCU(cudaFuncSetAttribute(df::k_jacobi_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_half));
+        DCU(raise_smem(df::k_jacobi_batch<false>, sm_half));
         df::k_jacobi_batch<false><<<ne, jthreads, sm_half, st>>>(S->d_L, n, S->d_omega, S->d_U, Ut, d_status, 60);
     }
     launches += 1;
@@ -499,7 +507,7 @@ int mambo_csa_df_based_greedy(mambo_csa* h, double* lambda, double* U1, double* 
     DCU(scr.get((void**)&vv, sizeof(double) * (size_t)n * nf));
     DCU(scr.get((void**)&d_Lmat, sizeof(double) * (size_t)n * n));
     const size_t smem = sizeof(double) * (size_t)n * n;
-    DCU(cudaFuncSetAttribute(df::k_df_frame, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)1024)));
+    DCU(raise_smem(df::k_df_frame, smem));
     df::k_df_frame<<<nf, 256, smem, st>>>(S->d_U, S->d_omega, n, nf, vv);
     df::k_df_lmat<<<(n * n + 255) / 256, 256, 0, st>>>(vv, S->d_coeff, n, nf, d_Lmat);
     DCU(cudaGetLastError());

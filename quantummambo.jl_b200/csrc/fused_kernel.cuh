@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
     if (TPREF && tbeg < tend) loadT(tn, panel, ct);
 
     // ---- operand ring: sub-tile g = 2*step + column group lives in slot g % S; the producer role rotates over the warps
-    // (sub-tile g is requested by lane 0 of warp g % NCONS) so that no single warp carries the ~650 cycles per request
-    // and paces the CTA (see k_ty below).  The B~ panel (once per row panel) stays with warp 0.
+    // of the column group that consumes the sub-tile (see k_ty below); no single warp carries the ~650 cycles per request
+    // and paces the CTA.  The B~ panel (once per row panel) stays with warp 0.
     const int g_total = 2 * (int)(tend - tbeg);
     int lookahead = p.lookahead > 0 ? min(p.lookahead, S - 2) : ((S >= 6) ? 2 : (S - 2));   // sub-tiles requested ahead of use
     lookahead &= ~1;
@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
         mbar_expect_tx(&full[slot], sub_bytes);
         bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ctg * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
     };
+    auto requester = [&](int g) { return 4 * (g & 1) + ((g >> 1) & 3); };   // a warp of column group g & 1 (wc = warp >> 2)
     if (lane == 0)
-        for (int g = warp; g < lookahead && g < g_total; g += NCONS) request(g);
+        for (int g = 0; g < lookahead && g < g_total; ++g)
+            if (requester(g) == warp) request(g);
     __syncwarp();
 
     const double* sBrow = sB + (16 * wr + prow) * ld + 2 * t0;
@@ -191,8 +193,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
                     mbar_expect_tx(bfull, panel_bytes);
                     bulk_g2s(sB, p.Brow + (size_t)panel * ROWS * ld, panel_bytes, bfull);
                 }
-                if (g1 < g_total && g1 % NCONS == warp) request(g1);
-                if (g1 + 1 < g_total && (g1 + 1) % NCONS == warp) request(g1 + 1);
+                if (g1 < g_total && requester(g1) == warp) request(g1);
+                if (g1 + 1 < g_total && requester(g1 + 1) == warp) request(g1 + 1);
             }
             __syncwarp();
         }
@@ -244,6 +246,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
         }
         const bool lastp = (ct == Q - 1) || (t == tend - 1);
         if (lastp) {  // the B~ panel is no longer needed by this warp: let the producer refill it
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads before the async-proxy refill
             __syncwarp();
             if (lane == 0) mbar_arrive(bempty);
         }
@@ -327,6 +330,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) k_fused(Params p) {
                 }
             }
         }
+        // The slot is refilled by the TMA engine (async proxy) as soon as the empty barrier completes; this warp's operand loads
+        // (generic proxy) have been ISSUED at this point, not necessarily performed -- nvcc schedules the arrive right behind
+        // the last LDS and the DMMAs that consume it afterwards.  The proxy fence orders them before the arrive.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);
 
@@ -456,8 +463,15 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
     int gi = 0, pv = 0;
     if (TPREF && tbeg < tend) loadT(tn, panel, ct);
 
-    // ---- operand ring: sub-tile g = 2*step + column group lives in slot g % S.  The producer role ROTATES over the
-    // warps: sub-tile g is requested by lane 0 of warp g % (number of warps), `lookahead` sub-tiles ahead of its use.  One
+    // ---- operand ring: sub-tile g = 2*step + column group lives in slot g % S.  The producer role ROTATES over the warps
+    // of the column group that consumes the sub-tile: sub-tile g is requested by lane 0 of warp NWR (g & 1) + (g / 2) % NWR,
+    // `lookahead` sub-tiles ahead of its use (a requester of the consumer group has itself consumed the slot's previous
+    // occupant, so the parity it waits for on empty[slot] cannot be confused with an older phase).
+    // Cross-proxy hazard (found in round 2): the consumers read a slot with LDS (generic proxy) and the TMA engine (async proxy)
+    // refills it as soon as empty[slot] completes.  Without a proxy fence in front of the consumers' arrive the refill can
+    // overtake operand loads that are issued but not yet performed: rare single-row operand errors (1e-5 relative in Y, 0.2 - 60 %
+    // of launches) at every ring shape that refills a slot in the step right after its consumption (S - lookahead = 2:
+    // N = 129..144 and, in k_fused, N = 121..144), never where a slot rests for a step (the benchmark sizes).  One
     // request (empty-slot wait + expect_tx + UBLKCP) costs ~650 cycles of the issuing warp; with a fixed producer warp
     // those 2 x 650 cycles per step made that warp 17 % slower than the others, and because every other warp can only
     // run as far ahead as the ring holds, the whole CTA ran at its pace (clock64 stamps, tools/ty_stamps.py).
@@ -467,15 +481,17 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
     lookahead &= ~1;                                   // even: both sub-tiles of a step are requested in the same step
     const int ct0 = ct;
     const uint32_t sub_bytes = (uint32_t)(SUB * ld * 8);
-    auto request = [&](int g) {                        // called by lane 0 of warp g % NWARPS
+    auto request = [&](int g) {                        // called by lane 0 of warp requester(g)
         const int slot = g % S, use = g / S, c = g & 1;
         const int ctg = (ct0 + (g >> 1)) % Q;
         if (use > 0) mbar_wait(&empty[slot], (use - 1) & 1);
         mbar_expect_tx(&full[slot], sub_bytes);
         bulk_g2s(sA + (size_t)slot * SUB * ld, p.Acol + ((size_t)ctg * COLS + c * SUB) * ld, sub_bytes, &full[slot]);
     };
+    auto requester = [&](int g) { return NWR * (g & 1) + ((g >> 1) % NWR); };   // a warp of column group g & 1 (wc = warp / NWR)
     if (lane == 0)
-        for (int g = warp; g < lookahead && g < g_total; g += NWARPS) request(g);
+        for (int g = 0; g < lookahead && g < g_total; ++g)
+            if (requester(g) == warp) request(g);
     __syncwarp();
 
     const bool dbg = p.dbg && blockIdx.x == 0 && lane == 0;
@@ -486,8 +502,8 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
         {
             const int g1 = 2 * gi + lookahead;
             if (lane == 0) {
-                if (g1 < g_total && g1 % NWARPS == warp) request(g1);
-                if (g1 + 1 < g_total && (g1 + 1) % NWARPS == warp) request(g1 + 1);
+                if (g1 < g_total && requester(g1) == warp) request(g1);
+                if (g1 + 1 < g_total && requester(g1 + 1) == warp) request(g1 + 1);
             }
             __syncwarp();
         }
@@ -567,6 +583,10 @@ __global__ void __launch_bounds__(64 * (8 / MB), 1) k_ty(YParams p) {
                 for (int mb = 0; mb < MB; ++mb) dmma(e[mb][NB - 1][0], e[mb][NB - 1][1], acc[mb][kb][1], t1v);
             }
         }
+        // The slot is refilled by the TMA engine (async proxy) as soon as the empty barrier completes; this warp's operand loads
+        // (generic proxy) have been ISSUED at this point, not necessarily performed -- nvcc schedules the arrive right behind
+        // the last LDS and the DMMAs that consume it afterwards.  The proxy fence orders them before the arrive.
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[slot]);
         if (dbg && gi < 64) p.dbg[(warp * 64 + gi) * 4 + 3] = clock64();

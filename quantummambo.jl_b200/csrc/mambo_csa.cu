@@ -1104,6 +1104,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         TRY(dalloc(&h->ls_part, (size_t)n));
         TRY(dalloc(&h->d_done, 1));
         int Sy = 8;
+        if (const char* e = std::getenv("MAMBO_TY_RING")) Sy = std::max(2, std::min(8, std::atoi(e)));
         while (Sy > 2 && smem_bytes_y(h->ld, Sy) > prop.sharedMemPerBlockOptin) --Sy;
         if (smem_bytes_y(h->ld, Sy) > prop.sharedMemPerBlockOptin) return fail(MAMBO_EINVAL, "operand ring does not fit in shared memory");
         h->Sy = Sy;
@@ -2052,6 +2053,33 @@ int mambo_csa_reconstruct(mambo_csa* h, const double* x, double* tbt_out, double
         CU(cudaStreamSynchronize(h->stream));
     }
     return MAMBO_OK;
+}
+
+// Development aid (not part of the public header): copy one of the handle's internal device buffers to the host after a
+// synchronise, so that repeated evaluations can be compared buffer by buffer.  which: 0 U, 1 A~, 2 Y pieces, 3 E~ panels (column-
+// split launches), 4 F, 5 Spart, 6 part, 7 out, 8 aux.  Returns the number of doubles of the buffer (copies min(count, that)).
+long long mambo_debug_fetch(mambo_csa* h, int which, double* out, long long count) {
+    if (!h) return -1;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->side_stream) cudaStreamSynchronize(h->side_stream);
+    const long long n = h->N;
+    const double* src = nullptr;
+    long long len = 0;
+    switch (which) {
+        case 0: src = h->U; len = n * n; break;
+        case 1: src = h->At; len = (long long)h->nRpad * h->ld; break;
+        case 2: src = h->Epiece; len = (long long)h->visits * 2 * ROWS * h->Np; break;
+        case 3: src = h->EtP; len = h->EtP ? (long long)h->P * ROWS * h->ld : 0; break;
+        case 4: src = h->F1; len = (long long)h->P * ROWS * h->Np; break;
+        case 5: src = h->Spart; len = (long long)h->P * n * n; break;
+        case 6: src = h->d_part; len = 1 + 2 * n * n; break;
+        case 7: src = h->d_out; len = 1 + h->L; break;
+        case 8: src = h->aux; len = h->aux ? 3 * n + 1 : 0; break;
+        default: return -1;
+    }
+    if (out && src && len > 0) cudaMemcpy(out, src, sizeof(double) * (size_t)std::min(count, len), cudaMemcpyDeviceToHost);
+    return len;
 }
 
 }  // extern "C"

@@ -952,9 +952,13 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
     static_assert(sizeof(DevState) <= 192, "status ring slots are 192 bytes");
     const bool fast_ok = !selfscale && std::getenv("MAMBO_OPT_HOSTLOOP") == nullptr && (!lbfgs || mem <= LB_FAST_MAX);
     const size_t lb_smem = sizeof(double) * ((size_t)2 * mem * LB_WP + LB_W);
-    if (lbfgs && fast_ok && lb_smem > 48 * 1024 &&
-        CK(cudaFuncSetAttribute(k_fast_lbfgs_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb_smem), "smem attribute"))
-        return finish(MAMBO_ECUDA);
+    if (lbfgs && fast_ok && lb_smem > 48 * 1024) {      // raised only: concurrent runs on lanes of this GPU may use other memories
+        cudaFuncAttributes fa;
+        if (CK(cudaFuncGetAttributes(&fa, (const void*)k_fast_lbfgs_gram), "kernel attributes")) return finish(MAMBO_ECUDA);
+        if ((size_t)fa.maxDynamicSharedSizeBytes < lb_smem &&
+            CK(cudaFuncSetAttribute(k_fast_lbfgs_gram, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lb_smem), "smem attribute"))
+            return finish(MAMBO_ECUDA);
+    }
     cudaEvent_t ring_ev[RING] = {nullptr, nullptr, nullptr, nullptr};
     auto ring_slot = [&](int k) { return reinterpret_cast<DevState*>(reinterpret_cast<char*>(o->h_scal) + 128 + 192 * (k % RING)); };
     struct EvGuard {
