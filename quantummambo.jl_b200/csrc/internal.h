@@ -15,5 +15,8 @@ struct mambo_resident_view {
 extern "C" int mambo_csa_resident_view(mambo_csa* h, mambo_resident_view* v);
 // one opaque, handle-owned state object per handle (the double factorisation); freed by mambo_csa_destroy through `destroy`
 extern "C" void** mambo_csa_df_slot(mambo_csa* h, void (*destroy)(void*));
+// the handle's own device-resident x (num_params) and [cost, grad] (1 + num_params) buffers: an evaluation called with exactly these
+// pointers skips its two device-to-device copies (optimizer.cu works in them)
+extern "C" int mambo_csa_io_buffers(mambo_csa* h, double** d_x, double** d_out);
 extern "C" void mambo_set_error(const char* msg);
 extern "C" void mambo_csa_count_launches(mambo_csa* h, long long n);

@@ -1234,6 +1234,12 @@ void** mambo_csa_df_slot(mambo_csa* h, void (*destroy)(void*)) {
     return &h->df_state;
 }
 void mambo_csa_count_launches(mambo_csa* h, long long n) { if (h) h->launches += n; }
+int mambo_csa_io_buffers(mambo_csa* h, double** d_x, double** d_out) {
+    if (!h || !d_x || !d_out) return fail(MAMBO_EINVAL, "null argument");
+    *d_x = h->d_x;
+    *d_out = h->d_out;
+    return MAMBO_OK;
+}
 
 int mambo_csa_get_stream(mambo_csa* h, void** stream, int* device) {
     if (!h) return fail(MAMBO_EINVAL, "null handle");

@@ -26,7 +26,7 @@
 
 #include "../../include/mambo_csa.h"
 
-extern "C" void mambo_set_error(const char* msg);   // defined in mambo_csa.cu (thread-local message)
+#include "internal.h"
 extern "C" int mambo_csa_scratch(mambo_csa* h, size_t bytes, void** ptr);   // handle-owned device scratch (mambo_csa.cu)
 extern "C" int mambo_csa_scratch_host(mambo_csa* h, void** ptr);            // handle-owned pinned scalars (128 bytes)
 extern "C" int mambo_csa_status_fetch(mambo_csa* h);    // enqueue the D2H of the device status word on the handle's stream
@@ -881,6 +881,12 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         for (double** v : vecs) {
             *v = q;
             q += Lp;
+        }
+        // the trial point and the evaluation's output live in the handle's own buffers: no device-to-device copy per evaluation
+        rc = mambo_csa_io_buffers(h, &o->xt, &o->out);
+        if (rc) {
+            snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+            return finish(rc);
         }
         o->scal = q;
         q += 16;
