@@ -12,8 +12,9 @@ module MamboB200
 
 using QuantumMAMBO
 import QuantumMAMBO: F_OP, F_FRAG, CSA_x_to_F_FRAG, CSA_SD_x_to_F_FRAG, cartan_2b_num_params,
-                     real_orbital_rotation_num_params, tbt_svd_1st, SVD_to_CSA, SVD_for_CSA, SVD_for_CSA_SD, SVD_tiny,
-                     DECOMPOSITION_PRINT, ϵ
+                     real_orbital_rotation_num_params, tbt_svd_1st, SVD_to_CSA, SVD_for_CSA, SVD_for_CSA_SD, SVD_tiny, SVD_tol,
+                     DECOMPOSITION_PRINT, ϵ, CSA, DF, cartan_1b, cartan_2b, f_matrix_rotation, c_matrix_rotation,
+                     DF_decomposition, DF_based_greedy
 using Optim
 using LinearAlgebra
 
