@@ -128,6 +128,10 @@ constexpr int SYNC_GRID = 0, SYNC_CLUSTER = 1;
 
 template <int SYNC>
 __device__ __forceinline__ void step_barrier(unsigned* ctr, unsigned& target, long long* stamps = nullptr) {
+    // Every thread orders its generic-proxy accesses to the operand strips (the LDS of this step's products) before the
+    // async-proxy refills that follow the barrier.  The barrier itself makes a real overlap implausible, but the fused
+    // kernels' operand ring showed in round 2 that a TMA refill may overtake loads that are merely issued; a few cycles per step.
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (SYNC == SYNC_CLUSTER) {
         asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
         asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
