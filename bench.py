@@ -766,9 +766,69 @@ def main():
                         "parity_rel": parity(d_out[0]) if rank == 0 else None,
                         "parity_what": "max(cost rel.err, gradient max-norm rel.err) of the sharded evaluation at x[0] against "
                                        "oracle.cost_grad_factored on rank 0 (tolerance 1e-10)"}
+            # ---- several sharded evaluations in flight per GPU: lanes of the shard handle, each with its own peer buffers, the
+            # peers' flags awaited by the stream (mambo_csa_set_peer_wait) so that no spinning kernel holds an SM ------------------
+            try:
+                nls = max(1, min(nl, BATCH))
+                lanes_s = [engs] + [engs.lane() for _ in range(nls - 1)]
+                okl = torch.ones(1, dtype=torch.int32, device=dev)
+                try:
+                    for ln in lanes_s[1:]:
+                        hl = [None] * world
+                        dist.all_gather_object(hl, ln.peer_export())
+                        for r, hd in enumerate(hl):
+                            if r != rank:
+                                ln.peer_attach(r, hd)
+                    for ln in lanes_s:
+                        ln.set_peer_wait(True)
+                except Exception:  # noqa: BLE001
+                    okl.zero_()
+                dist.all_reduce(okl, op=dist.ReduceOp.MIN)
+                if int(okl.item()) == 1:
+                    lstreams = [torch.cuda.Stream(dev) for _ in range(nls)]
+                    for ln, st_ in zip(lanes_s, lstreams):
+                        ln.set_stream(st_.cuda_stream)
+
+                    def step_lanes():
+                        for i in range(BATCH):
+                            lanes_s[i % nls].eval_sharded_device(d_x0[i].data_ptr(), d_out[i].data_ptr())
+
+                    for _ in range(3):
+                        step_lanes()
+                    torch.cuda.synchronize(); dist.barrier()
+                    e0.record(stream)
+                    for st_ in lstreams:
+                        st_.wait_stream(stream)
+                    for _ in range(args.steps):
+                        step_lanes()
+                    for st_ in lstreams:
+                        stream.wait_stream(st_)
+                    e1.record(stream)
+                    torch.cuda.synchronize(); dist.barrier()
+                    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    lanes_ms = float(t.item())
+                    for ln in lanes_s:
+                        ln.synchronize()
+                    rowpanel["lanes"] = {"value": BATCH * args.steps / (lanes_ms * 1e-3), "unit": "evals/s", "lanes_per_gpu": nls,
+                                         "ms_per_eval": lanes_ms / (BATCH * args.steps),
+                                         "parity_rel": parity(d_out[0]) if rank == 0 else None,
+                                         "what": "the same sharded evaluations with lanes_per_gpu of them in flight on every GPU (lanes of the "
+                                                 "shard handle, stream-ordered wait for the peers' flags): throughput of the row-panel "
+                                                 "partition, where `value` above is its latency-bound single-evaluation rate"}
+                    for ln in lanes_s:
+                        ln.set_stream(None)
+                for ln in lanes_s[1:]:
+                    ln.close()
+                engs.set_stream(stream.cuda_stream)
+            except Exception as exc:  # noqa: BLE001  (a side leg must never cost the main line)
+                rowpanel["lanes"] = {"error": repr(exc)}
         else:
             rowpanel["peer_exchange"] = "unavailable on this box (CUDA IPC mapping failed on some rank)"
         engs.close()
+        lp = (rowpanel.get("lanes") or {}).get("parity_rel")
+        if rank == 0 and lp is not None and not (lp <= 1e-10):
+            raise SystemExit(f"row-panel sharded evaluation over lanes disagrees with the oracle: rel {lp:.3e} > 1e-10")
         if rank == 0 and rowpanel.get("parity_rel") is not None and not (rowpanel["parity_rel"] <= 1e-10):
             raise SystemExit(f"row-panel sharded evaluation disagrees with the oracle: rel {rowpanel['parity_rel']:.3e} > 1e-10")
 

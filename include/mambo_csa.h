@@ -172,6 +172,12 @@ int  mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double*
 int  mambo_csa_peer_export(mambo_csa* h, unsigned char* handle64);
 int  mambo_csa_peer_attach(mambo_csa* h, int rank, const unsigned char* handle64);
 int  mambo_csa_peer_attach_local(mambo_csa* h, int rank, mambo_csa* peer);
+/* How eval_sharded_finish waits for the peers' flags: 0 (default) the sum kernel polls them and gives up after ~4 s (a dead peer
+ * becomes MAMBO_ESTATE); 1 the STREAM waits (cuStreamWaitValue64, fetched from the driver at run time) and no SM is held while
+ * waiting -- required when several sharded evaluations are in flight per GPU (lanes created from a shard handle, each with its
+ * own peer_export / peer_attach): a spinning kernel holds its SM and the hot kernel needs every SM, so spinning sums of different
+ * lanes could wait for each other across two GPUs.                                                                            */
+int  mambo_csa_set_peer_wait(mambo_csa* h, int stream_ordered);
 int  mambo_csa_eval_sharded_push_device(mambo_csa* h, const double* d_x);
 int  mambo_csa_eval_sharded_finish_device(mambo_csa* h, double* d_out);
 int  mambo_csa_eval_sharded_device(mambo_csa* h, const double* d_x, double* d_out);

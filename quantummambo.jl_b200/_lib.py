@@ -128,6 +128,7 @@ SIGNATURES = {
     "mambo_csa_peer_export": (C.c_int, [_P, _P]),
     "mambo_csa_peer_attach": (C.c_int, [_P, C.c_int, _P]),
     "mambo_csa_peer_attach_local": (C.c_int, [_P, C.c_int, _P]),
+    "mambo_csa_set_peer_wait": (C.c_int, [_P, C.c_int]),
     "mambo_csa_eval_sharded_push_device": (C.c_int, [_P, _P]),
     "mambo_csa_eval_sharded_finish_device": (C.c_int, [_P, _P]),
     "mambo_csa_eval_sharded_device": (C.c_int, [_P, _P, _P]),

@@ -140,6 +140,10 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
     mambo_resident_view v;
     int rc = mambo_csa_resident_view(h, &v);
     if (rc) return rc;
+    // decompose.jl:317-322: a matrix view that is not symmetric goes through a general (complex) `eigen` in the reference; that
+    // branch is not reproduced here (every input of the path is symmetric: ferm_utils.py:471-507, bliss.jl:17-26, residuals)
+    if (v.mode == (int)MAMBO_SYM_GENERAL && v.asym_pair > 1e-12)
+        return dfail(MAMBO_EINVAL, "double factorisation needs a (pq)<->(rs)-symmetric two-body tensor");
     DCU(cudaSetDevice(v.device));
     DCU(gemm_setup());
     if (!(tol > 0.0)) tol = 1e-8;                       // SVD_tol, config.jl:22

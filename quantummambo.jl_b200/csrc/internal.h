@@ -6,6 +6,7 @@
 // read-only view of the resident residual of an unsharded handle (df.cu)
 struct mambo_resident_view {
     int N, mode, packed, rows, device;
+    double asym_pair;               // measured relative asymmetry under (pq) <-> (rs) of the tensor given to create
     long long ldT;
     const double *T1, *T2;          // T~ (and its transpose in GENERAL mode), row-major, pitch ldT
     const int *pa, *pq;             // row -> (p, q)

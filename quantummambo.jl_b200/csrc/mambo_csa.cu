@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include <cuda.h>            // types of the driver entry point fetched at run time (no link dependency on libcuda)
 #include <cuda_runtime.h>
 
 #include "../../include/mambo_csa.h"
@@ -163,6 +164,7 @@ struct mambo_csa {
     int peer_attached = 0;
     int plen_pad = 0;
     unsigned long long peer_epoch = 0;
+    bool peer_stream_wait = false;             // mambo_csa_set_peer_wait: the stream, not a spinning kernel, waits for the peers' flags
     // Lanczos workspace of mambo_csa_leading_eig (allocated on first use, kept: cudaMalloc/cudaFree of tens of MB cost more
     // than the iteration itself)
     double* eig_ws = nullptr;
@@ -1225,7 +1227,7 @@ int mambo_csa_resident_view(mambo_csa* h, mambo_resident_view* v) {
     if (!h || !v) return fail(MAMBO_EINVAL, "null argument");
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "the double factorisation needs an unsharded handle");
     v->N = h->N; v->mode = h->mode; v->packed = h->packed ? 1 : 0; v->rows = h->nR; v->device = h->device;
-    v->ldT = h->ldT; v->T1 = h->T1; v->T2 = h->T2; v->pa = h->pa; v->pq = h->pq; v->sw = h->sw; v->stream = h->stream;
+    v->asym_pair = h->asym_pair; v->ldT = h->ldT; v->T1 = h->T1; v->T2 = h->T2; v->pa = h->pa; v->pq = h->pq; v->sw = h->sw; v->stream = h->stream;
     return MAMBO_OK;
 }
 void** mambo_csa_df_slot(mambo_csa* h, void (*destroy)(void*)) {
@@ -1646,18 +1648,58 @@ int mambo_csa_eval_sharded_push_device(mambo_csa* h, const double* d_x) {
     return MAMBO_OK;
 }
 
+// The peers' epoch flags are awaited by the STREAM (cuStreamWaitValue64, a front-end memory operation) before the sum kernel is
+// released: a kernel that spins on a flag holds its SM, and fused::k_ty needs every SM empty, so with several sharded
+// evaluations in flight per GPU (lanes on shard handles) spinning sums of different lanes could wait for each other's hot kernels
+// across two GPUs.  The entry point comes from the driver at run time (cudaGetDriverEntryPoint): no link dependency on libcuda.
+// k_peer_sum keeps its acquire-polling loop (satisfied at once) as the fall-back when the entry point is unavailable.
+typedef CUresult (*stream_wait64_fn)(CUstream, CUdeviceptr, cuuint64_t, unsigned int);
+static stream_wait64_fn stream_wait64() {
+    static stream_wait64_fn fn = []() -> stream_wait64_fn {
+        if (std::getenv("MAMBO_NO_STREAM_WAIT")) return nullptr;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue64", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<stream_wait64_fn>(p);
+    }();
+    return fn;
+}
+
 int mambo_csa_eval_sharded_finish_device(mambo_csa* h, double* d_out) {
     if (!h || !d_out) return fail(MAMBO_EINVAL, "null argument");
     if (h->peer_attached != h->nshards) return fail(MAMBO_ESTATE, "peer exchange not set up");
     CU(cudaSetDevice(h->device));
     const long long l0 = h->launches;
     const int plen = 1 + 2 * h->N * h->N;
+    stream_wait64_fn wait = h->peer_stream_wait ? stream_wait64() : nullptr;
+    if (wait) {
+        const int parity = (int)(h->peer_epoch & 1ull);
+        for (int r = 0; r < h->nshards; ++r) {
+            const unsigned long long* f = h->peer_flags + (size_t)parity * small::MAXPEERS + r;
+            if (wait((CUstream)h->stream, (CUdeviceptr)(uintptr_t)f, (cuuint64_t)h->peer_epoch, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+                return fail(MAMBO_ECUDA, "cuStreamWaitValue64 failed");
+        }
+    }
     small::k_peer_sum<<<std::min(64, (plen + 255) / 256), 256, 0, h->stream>>>(h->peer_recv, h->peer_flags, plen, h->plen_pad, h->nshards,
                                                                              h->peer_epoch, h->d_part, h->d_status);
     h->launches++;
     TRY(enqueue_finish_seg(h, -1, false));
     if (d_out != h->d_out) CU(cudaMemcpyAsync(d_out, h->d_out, sizeof(double) * (1 + h->L), cudaMemcpyDeviceToDevice, h->stream));
     h->launches_last_eval += (int)(h->launches - l0);
+    return MAMBO_OK;
+}
+
+// How the finish half waits for the peers: 0 (default) the sum kernel polls the flags and gives up after ~4 s (a dead peer
+// becomes MAMBO_ESTATE); 1 the stream waits (cuStreamWaitValue64) and the kernel starts only when every flag is there -- no SM
+// is held while waiting, which several sharded evaluations in flight per GPU (lanes of a shard handle) need; a peer that
+// never publishes then blocks the stream for good.  Returns MAMBO_ESTATE if the driver offers no stream memory operations.
+int mambo_csa_set_peer_wait(mambo_csa* h, int stream_ordered) {
+    if (!h) return fail(MAMBO_EINVAL, "null handle");
+    if (stream_ordered && !stream_wait64()) return fail(MAMBO_ESTATE, "cuStreamWaitValue64 is not available from this driver");
+    h->peer_stream_wait = stream_ordered != 0;
     return MAMBO_OK;
 }
 

@@ -1194,8 +1194,28 @@ extern "C" {
 // Allocate everything mambo_csa_optimize will need on this handle (device scratch for the given mode, pinned scalars) so
 // that the run itself allocates nothing.  cudaMalloc / cudaMallocHost synchronise the whole device: with several handles
 // on one GPU (lanes, shards in one process) an allocation in one thread would otherwise wait for kernels of another.
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, and that load waits for kernels that are
+// running in the context -- a shard spinning for a peer whose thread is stuck in such a load (several shards driven from one
+// process on one GPU) would time out.  Touching every optimiser kernel here loads them before any run starts.
+static void preload_optimizer_kernels() {
+    cudaFuncAttributes a;
+    const void* ks[] = {(const void*)k_axpy, (const void*)k_sub, (const void*)k_dot_absmax, (const void*)k_set_identity, (const void*)k_scale,
+                        (const void*)k_sym_update_gemv, (const void*)k_sym_reduce, (const void*)k_scale_neg, (const void*)k_direction,
+                        (const void*)k_multi_dot, (const void*)k_lbfgs_direction, (const void*)k_store_pair, (const void*)k_fast_trial,
+                        (const void*)k_fast_wolfe_part, (const void*)k_fast_wolfe_apply, (const void*)k_fast_dots,
+                        (const void*)k_fast_direction, (const void*)k_fast_state, (const void*)k_fast_lbfgs_store,
+                        (const void*)k_fast_lbfgs_gram, (const void*)k_fast_lbfgs_solve, (const void*)k_fast_lbfgs_apply};
+    for (const void* k : ks) cudaFuncGetAttributes(&a, k);
+    cudaGetLastError();
+}
+
 int mambo_csa_optimize_reserve(mambo_csa* h, int lbfgs_memory) {
     if (!h) return MAMBO_EINVAL;
+    {
+        void* st = nullptr;
+        int dev = 0;
+        if (mambo_csa_get_stream(h, &st, &dev) == MAMBO_OK && cudaSetDevice(dev) == cudaSuccess) preload_optimizer_kernels();
+    }
     const int L = mambo_csa_num_params(h);
     if (L <= 0) return MAMBO_EINVAL;
     const int mem = std::min(std::max(lbfgs_memory, 0), 64);

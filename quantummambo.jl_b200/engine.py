@@ -286,6 +286,10 @@ class CSAEngine:
     def peer_attach_local(self, rank: int, peer: "CSAEngine"):
         _lib.check(self._lib.mambo_csa_peer_attach_local(self._h, rank, peer._h))
 
+    def set_peer_wait(self, stream_ordered: bool):
+        """mambo_csa_set_peer_wait: let the stream (not a spinning kernel) wait for the peers' flags -- needed for lanes on shards."""
+        _lib.check(self._lib.mambo_csa_set_peer_wait(self._h, 1 if stream_ordered else 0))
+
     def eval_sharded_push_device(self, d_x_ptr: int):
         _lib.check(self._lib.mambo_csa_eval_sharded_push_device(self._h, d_x_ptr))
 

@@ -114,6 +114,15 @@ def test_df_zero_tensor_and_errors(mb):
             e.df_based_greedy()
 
 
+def test_df_refuses_a_nonsymmetric_matrix_view(mb):
+    """decompose.jl:319-322: the reference leaves the symmetric eigenproblem for such input; the library says so"""
+    with mb.CSAEngine(o.general_tbt(4, 1)) as e:
+        with pytest.raises(mb.MamboError):
+            e.df_decompose()
+    with mb.CSAEngine(o.dense_sym_tbt(4, 1), sym=mb.SYM_GENERAL) as e:      # forced mode, symmetric tensor: fine
+        assert e.df_decompose()["num_frags"] == 10
+
+
 def test_df_follows_the_greedy_residual(mb):
     """the decomposition is of the RESIDENT residual: after subtract_fragment it sees T - W(x)"""
     n = 6

@@ -239,6 +239,55 @@ def test_peer_exchange_of_shards_on_one_gpu(mb, lib):
                 e.close()
 
 
+def test_lanes_on_shards_with_stream_ordered_peer_wait(mb, lib):
+    """Several sharded evaluations in flight per GPU: lanes created from shard handles (each with its own peer buffers), the
+    peers' flags awaited by the stream (mambo_csa_set_peer_wait) instead of a spinning kernel.  All shards and lanes live on
+    one GPU of one process here and every call is only enqueued -- with stream-ordered waits nothing blocks an SM, so the
+    order of the launches does not matter (the spinning variant would need every push before any finish)."""
+    import torch
+    n, world, nl = 14, 2, 3
+    dev = torch.device("cuda", 0)
+    T = o.dense_sym_tbt(n, 2)
+    shards = [mb.CSAEngine(T, shard=r, nshards=world) for r in range(world)]
+    lanes = [[e] + [e.lane() for _ in range(nl - 1)] for e in shards]          # lanes[r][k]
+    streams = [[torch.cuda.Stream(dev) for _ in range(nl)] for _ in range(world)]
+    try:
+        for k in range(nl):
+            for r in range(world):
+                lanes[r][k].peer_export()
+            for r in range(world):
+                for q in range(world):
+                    if q != r:
+                        lanes[r][k].peer_attach_local(q, lanes[q][k])
+        for r in range(world):
+            for k in range(nl):
+                lanes[r][k].set_peer_wait(True)
+                lanes[r][k].set_stream(streams[r][k].cuda_stream)
+        xs = [o.random_x(n, 30 + i) for i in range(2 * nl)]                   # two points per lane: two epochs each
+        d_x = torch.from_numpy(np.stack(xs)).to(dev)
+        d_out = torch.zeros(world, len(xs), len(xs[0]) + 1, dtype=torch.float64, device=dev)
+        for i in range(len(xs)):
+            for r in range(world):                                            # shard 0 enqueues push AND finish before shard 1 pushes
+                lanes[r][i % nl].eval_sharded_device(d_x[i].data_ptr(), d_out[r, i].data_ptr())
+        torch.cuda.synchronize()
+        for r in range(world):
+            for k in range(nl):
+                lanes[r][k].synchronize()
+        res = d_out.cpu().numpy()
+        for i, x in enumerate(xs):
+            c0, g0 = o.cost_grad_factored(x, T)
+            for r in range(world):
+                assert abs(res[r, i, 0] - c0) <= RTOL * abs(c0) and rel(res[r, i, 1:], g0) <= RTOL
+            assert np.array_equal(res[0, i], res[1, i])                       # identical bits on every shard
+    finally:
+        for r in range(world):
+            for ln in lanes[r]:
+                ln.set_stream(None)
+            for ln in lanes[r][1:]:
+                ln.close()
+            shards[r].close()
+
+
 def test_single_gemm_formulation_matches_two_gemm_kernel_and_falls_back(mb, lib, monkeypatch):
     """The default evaluation (fused::k_ty: E = C~ - T~ A~, cost from N x N quantities) against the two-GEMM kernel
     (MAMBO_TWO_GEMM=1: D = B~ A~^T - T~ explicitly) on the same handle inputs, including the regime where the expanded
