@@ -786,7 +786,8 @@ def test_csa_sd_greedy_decomposition_final_norms_match_oracle(mb, lib):
 
 
 def test_csa_sd_greedy_step_molecule_sizes(mb, lib):
-    """H2O / N2 sizes (N = 7, 10; configs[1]): integrals cannot be generated here (no pyscf), planted stand-ins."""
+    """H2O / N2 sizes (N = 7, 10; configs[1]) on planted tensors, where the exact minimum is known (cost 0); the molecules
+    themselves are in tests/test_molecules_gpu.py."""
     for n in (7, 10):
         T, xs = o.planted_tbt(n, 1, n)
         lam1 = np.random.default_rng(n).standard_normal(n)
