@@ -151,6 +151,9 @@ int  mambo_csa_symv_device(mambo_csa* h, const double* d_v, double* d_y);
 /* Host half of the Lanczos driver (no GPU): largest-|eigenvalue| Ritz pair of the m x m symmetric tridiagonal with
  * diagonal alpha[0..m) and off-diagonal beta[0..m-1) (bisection + inverse iteration); z receives the unit vector.   */
 int  mambo_debug_tridiag_leading(const double* alpha, const double* beta, int m, double* theta, double* z);
+/* Host half of the double factorisation (no GPU): unit eigenvectors of a cluster of k numerically coincident eigenvalues
+ * theta[0..k) (ascending) of the unreduced m x m tridiagonal; Z receives k rows of m doubles (orthonormal).            */
+int  mambo_debug_tridiag_cluster(const double* alpha, const double* beta, int m, const double* theta, int k, double* Z);
 
 /* --- device-resident entry points (no host synchronisation; used by the multi-GPU host and bench) -------- */
 /* Run all engine work on `stream` (a cudaStream_t); NULL restores the handle's own stream (so the legacy
@@ -242,6 +245,8 @@ typedef struct mambo_df_stats_t {
                                  their coefficient is already negated, omega / U are left zero: the complex N x N eigen
                                  stays with the caller                                                                */
     int    jacobi_sweeps_max; /* most sweeps any fragment needed (negative: some fragment did not converge)           */
+    int    cluster_vectors;   /* tridiagonal eigenvectors recomputed on the host because their eigenvalues coincide to
+                                 rounding inside one block (inverse iteration + Gram-Schmidt, like LAPACK's dstein)      */
     double ortho_dev_before;  /* max |Z^T Z - I| of the tridiagonal eigenvectors before / after the Newton-Schulz     */
     double ortho_dev_after;   /*   re-orthonormalisation                                                              */
     double max_rel_residual;  /* max ||T y - theta y|| / max|theta| over the kept eigenpairs (only with verify != 0)  */

@@ -281,7 +281,7 @@ end
 
 # ---- double factorisation on the resident residual (decompose.jl:297-436) -------------------------------------------------
 struct DfStats               # mambo_df_stats_t
-    krylov_dim::Cint; restarts::Cint; num_frags::Cint; anti_frags::Cint; jacobi_sweeps_max::Cint
+    krylov_dim::Cint; restarts::Cint; num_frags::Cint; anti_frags::Cint; jacobi_sweeps_max::Cint; cluster_vectors::Cint
     ortho_dev_before::Cdouble; ortho_dev_after::Cdouble; max_rel_residual::Cdouble
     seconds_lanczos::Cdouble; seconds_tridiag::Cdouble; seconds_backtransform::Cdouble; seconds_fragments::Cdouble
 end

@@ -87,7 +87,7 @@ class OptResult(C.Structure):
 
 class DfStats(C.Structure):
     _fields_ = [("krylov_dim", C.c_int), ("restarts", C.c_int), ("num_frags", C.c_int), ("anti_frags", C.c_int),
-                ("jacobi_sweeps_max", C.c_int), ("ortho_dev_before", C.c_double), ("ortho_dev_after", C.c_double),
+                ("jacobi_sweeps_max", C.c_int), ("cluster_vectors", C.c_int), ("ortho_dev_before", C.c_double), ("ortho_dev_after", C.c_double),
                 ("max_rel_residual", C.c_double), ("seconds_lanczos", C.c_double), ("seconds_tridiag", C.c_double),
                 ("seconds_backtransform", C.c_double), ("seconds_fragments", C.c_double)]
 
@@ -120,6 +120,7 @@ SIGNATURES = {
     "mambo_csa_leading_eig": (C.c_int, [_P, C.c_double, C.c_int, _D, _P, C.POINTER(C.c_int), _D]),
     "mambo_csa_symv_device": (C.c_int, [_P, _P, _P]),
     "mambo_debug_tridiag_leading": (C.c_int, [_P, _P, C.c_int, _D, _P]),
+    "mambo_debug_tridiag_cluster": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, _P]),
     "mambo_csa_set_stream": (C.c_int, [_P, _P]),
     "mambo_csa_get_stream": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int)]),
     "mambo_csa_eval_device": (C.c_int, [_P, _P, _P]),

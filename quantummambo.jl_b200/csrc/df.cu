@@ -117,9 +117,138 @@ __global__ void __launch_bounds__(256) k_eig_residual(const double* __restrict__
     }
 }
 
+// ---- eigenvectors of numerically degenerate clusters of the tridiagonal (host) -------------------------------------------------
+// k_twisted takes one step of inverse iteration from the twist index: two eigenvalues of one unreduced block that agree to
+// rounding (a degenerate eigenvalue of the tensor found twice in one block once the recurrence runs on rounding noise --
+// molecular integrals: the pi shells, rank deficiency) get the SAME vector.  Such clusters are rare and short, so they are
+// redone here the way LAPACK's dstein does it: inverse iteration on (T - sigma) with partial pivoting, shifts of a cluster
+// spread by a few ulps of |T|, pseudo-random start, modified Gram-Schmidt against the cluster's earlier vectors in every
+// iteration.  The vectors span the cluster's invariant subspace to working precision; which basis of it is immaterial (the
+// Newton-Schulz step mixes inside close clusters anyway, and neither residuals nor the sum of the fragments change).
+struct TriLU {          // (T - sigma I) = P L U of a symmetric tridiagonal, row interchanges as in dgttrf
+    std::vector<double> d, du, du2, l;
+    std::vector<char> swp;
+};
+void tri_factor(const double* a, const double* b, int n, double sigma, double tiny, TriLU& f) {
+    f.d.assign(n, 0.0); f.du.assign(n, 0.0); f.du2.assign(n, 0.0); f.l.assign(n, 0.0); f.swp.assign(n, 0);
+    for (int i = 0; i < n; ++i) f.d[i] = a[i] - sigma;
+    for (int i = 0; i + 1 < n; ++i) f.du[i] = b[i];
+    for (int i = 0; i + 1 < n; ++i) {
+        const double sub = b[i];
+        if (std::fabs(f.d[i]) >= std::fabs(sub)) {
+            if (std::fabs(f.d[i]) < tiny) f.d[i] = f.d[i] < 0.0 ? -tiny : tiny;
+            const double m = sub / f.d[i];
+            f.l[i] = m;
+            f.d[i + 1] -= m * f.du[i];
+        } else {                                        // interchange rows i and i + 1
+            const double m = f.d[i] / sub;
+            f.swp[i] = 1;
+            f.l[i] = m;
+            f.d[i] = sub;
+            const double t = f.du[i];
+            f.du[i] = f.d[i + 1];
+            f.d[i + 1] = t - m * f.d[i + 1];
+            if (i + 2 < n) {
+                f.du2[i] = f.du[i + 1];
+                f.du[i + 1] = -m * f.du[i + 1];
+            }
+        }
+    }
+    if (std::fabs(f.d[n - 1]) < tiny) f.d[n - 1] = f.d[n - 1] < 0.0 ? -tiny : tiny;
+}
+void tri_solve(const TriLU& f, int n, std::vector<double>& x) {   // x <- (T - sigma)^-1 x
+    for (int i = 0; i + 1 < n; ++i) {
+        if (f.swp[i]) std::swap(x[i], x[i + 1]);
+        x[i + 1] -= f.l[i] * x[i];
+    }
+    x[n - 1] /= f.d[n - 1];
+    if (n > 1) x[n - 2] = (x[n - 2] - f.du[n - 2] * x[n - 1]) / f.d[n - 2];
+    for (int i = n - 3; i >= 0; --i) x[i] = (x[i] - f.du[i] * x[i + 1] - f.du2[i] * x[i + 2]) / f.d[i];
+}
+// a[0..n), b[0..n-1): one unreduced block; theta[0..k) ascending: a cluster of its eigenvalues; Z: k vectors of length n.
+void tridiag_cluster_vectors(const double* a, const double* b, int n, const double* theta, int k, double tnorm, std::vector<double>& Z) {
+    const double eps = 2.220446049250313e-16;
+    const double tiny = eps * std::max(tnorm, 1e-300);
+    Z.assign((size_t)k * n, 0.0);
+    std::vector<double> x(n);
+    TriLU f;
+    double sig_prev = 0.0;
+    unsigned long long rng = 0x9E3779B97F4A7C15ull;
+    for (int t = 0; t < k; ++t) {
+        double sigma = theta[t];
+        if (t > 0 && sigma - sig_prev < 10.0 * tiny) sigma = sig_prev + 10.0 * tiny;   // dstein's spread of coincident shifts
+        sig_prev = sigma;
+        tri_factor(a, b, n, sigma, tiny, f);
+        for (int i = 0; i < n; ++i) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            x[i] = ((double)(rng >> 11) / 9007199254740992.0) - 0.5;
+        }
+        for (int it = 0; it < 6; ++it) {
+            double s = 0.0;
+            for (int i = 0; i < n; ++i) s = std::max(s, std::fabs(x[i]));
+            s = (s > 0.0 ? 1.0 / s : 1.0);
+            for (int i = 0; i < n; ++i) x[i] *= s;
+            tri_solve(f, n, x);
+            for (int pass = 0; pass < 2; ++pass)
+                for (int u = 0; u < t; ++u) {
+                    const double* zu = Z.data() + (size_t)u * n;
+                    double dot = 0.0;
+                    for (int i = 0; i < n; ++i) dot = std::fma(zu[i], x[i], dot);
+                    for (int i = 0; i < n; ++i) x[i] -= dot * zu[i];
+                }
+            double nrm = 0.0;
+            for (int i = 0; i < n; ++i) nrm = std::fma(x[i], x[i], nrm);
+            nrm = std::sqrt(nrm);
+            if (!(nrm > 0.0)) {                          // annihilated by the projection: another start
+                for (int i = 0; i < n; ++i) {
+                    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                    x[i] = ((double)(rng >> 11) / 9007199254740992.0) - 0.5;
+                }
+                continue;
+            }
+            for (int i = 0; i < n; ++i) x[i] /= nrm;
+        }
+        int imax = 0;
+        for (int i = 1; i < n; ++i)
+            if (std::fabs(x[i]) > std::fabs(x[imax])) imax = i;
+        const double sgn = x[imax] < 0.0 ? -1.0 : 1.0;
+        for (int i = 0; i < n; ++i) Z[(size_t)t * n + i] = sgn * x[i];
+    }
+}
+// Groups of kept eigenvalues of one block whose neighbours are closer than ctol: indices into sel (positions 0..ne).
+void find_tight_clusters(const std::vector<double>& sel_theta, const std::vector<int>& sel_blk, int nblk, double ctol,
+                         std::vector<std::vector<int>>& clusters) {
+    clusters.clear();
+    std::vector<std::vector<int>> per(nblk);
+    for (int i = 0; i < (int)sel_theta.size(); ++i) per[sel_blk[i]].push_back(i);
+    for (auto& v : per) {
+        std::sort(v.begin(), v.end(), [&](int x, int y) { return sel_theta[x] != sel_theta[y] ? sel_theta[x] < sel_theta[y] : x < y; });
+        size_t i = 0;
+        while (i < v.size()) {
+            size_t j = i;
+            while (j + 1 < v.size() && sel_theta[v[j + 1]] - sel_theta[v[j]] <= ctol) ++j;
+            if (j > i) clusters.emplace_back(v.begin() + i, v.begin() + j + 1);
+            i = j + 1;
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+// Host half of the double factorisation on its own (no GPU): unit eigenvectors of a cluster of k (nearly) coincident eigenvalues
+// theta[0..k) (ascending) of the unreduced m x m tridiagonal (alpha, beta[0..m-1)); Z receives k rows of m doubles.  Exposed so
+// that the CPU test-suite can pin it against LAPACK.
+int mambo_debug_tridiag_cluster(const double* alpha, const double* beta, int m, const double* theta, int k, double* Z) {
+    if (!alpha || !beta || !theta || !Z || m < 1 || k < 1 || k > m) return dfail(MAMBO_EINVAL, "bad arguments");
+    double tn = 0.0;
+    for (int i = 0; i < m; ++i) tn = std::max(tn, std::fabs(alpha[i]) + (i > 0 ? std::fabs(beta[i - 1]) : 0.0) + (i + 1 < m ? std::fabs(beta[i]) : 0.0));
+    std::vector<double> z;
+    tridiag_cluster_vectors(alpha, beta, m, theta, k, tn, z);
+    std::memcpy(Z, z.data(), sizeof(double) * (size_t)k * m);
+    return MAMBO_OK;
+}
 
 int mambo_dgemm_device(int device, void* stream, int trans_a, int M, int N, int K, const double* d_A, long long lda, const double* d_B,
                        long long ldb, double* d_C, long long ldc) {
@@ -330,6 +459,26 @@ int mambo_csa_df_decompose(mambo_csa* h, double tol, int max_frags, int verify, 
     df::k_twisted<<<(ne + 63) / 64, 64, 0, st>>>(d_alpha, d_beta, m, d_blk, nblk, d_sel, d_selblk, ne, pivmin, B1, B2, ldz, Z, ldz);
     launches += 1;
     DCU(cudaGetLastError());
+    {   // numerically degenerate clusters inside one block: redo their vectors on the host (tridiag_cluster_vectors)
+        double tnorm = 0.0;
+        for (int i = 0; i < m; ++i) tnorm = std::max(tnorm, std::fabs(ha[i]) + (i > 0 ? std::fabs(hb[i - 1]) : 0.0) + std::fabs(hb[i]));
+        std::vector<std::vector<int>> clusters;
+        find_tight_clusters(sel_theta, sel_blk, nblk, 1e-11 * tnorm, clusters);
+        std::vector<double> zc, col;
+        for (const auto& cl : clusters) {
+            const int b = sel_blk[cl[0]], r0 = blk[3 * b], nr = blk[3 * b + 1], k = (int)cl.size();
+            std::vector<double> th(k);
+            for (int t = 0; t < k; ++t) th[t] = sel_theta[cl[t]];
+            tridiag_cluster_vectors(ha.data() + r0, hb.data() + r0, nr, th.data(), k, tnorm, zc);
+            for (int t = 0; t < k; ++t) {
+                col.assign(m, 0.0);
+                std::copy(zc.begin() + (size_t)t * nr, zc.begin() + (size_t)(t + 1) * nr, col.begin() + r0);
+                DCU(cudaMemcpy2DAsync(Z + cl[t], sizeof(double) * ldz, col.data(), sizeof(double), sizeof(double), m, cudaMemcpyHostToDevice, st));
+                DCU(cudaStreamSynchronize(st));          // col is reused
+            }
+            sts.cluster_vectors += k;
+        }
+    }
     // Newton-Schulz re-orthonormalisation Z <- Z (3 I - Z^T Z) / 2: eigenvectors of close eigenvalues come out of the twisted
     // factorisation orthogonal only to eps / gap; a mix inside such a cluster changes neither the residuals nor the sum of
     // the fragments.  C = 1.5 I - 0.5 Z^T Z comes straight out of the Gram GEMM; max |Z^T Z - I| = 2 max |C - I|.

@@ -125,3 +125,35 @@ def test_interaction_picture_step_on_bliss_shifted_molecules(mb, lib, fx, name):
     assert np.max(np.abs(Tr - (T - Wo))) <= 1e-12 * np.max(np.abs(T))
     ob = mb.one_body_L1(mb.F_OP(([0.0], hr, Tr)))
     assert abs(ob - o.one_body_L1(h - ho, T - Wo)) <= 1e-8 * ob
+
+
+@pytest.mark.parametrize("name", MOLS)
+@pytest.mark.parametrize("shift", ["", "_bliss"])
+def test_double_factorisation_of_molecular_tensors(mb, lib, fx, name, shift):
+    """DF_decomposition (decompose.jl:297-398) on molecular integrals: rank-deficient Coulomb matrices with exactly degenerate
+    eigenvalues (the pi shells of LiH / N2) -- Lanczos restarts, and eigenvalues that coincide to rounding inside one block
+    (their tridiagonal eigenvectors are redone on the host, `cluster_vectors`).  Coefficients against LAPACK to 1e-10, eigen-
+    residuals, the sum of the fragments, and DF_L1 (lcu.jl:210-221) fragment by fragment wherever the eigenvalue is isolated
+    (inside a degenerate eigenspace the basis, and with it sum |omega|, is LAPACK's or Lanczos' free choice)."""
+    n = MOLS[name]
+    T = fx[f"{name}{shift}_tbt"]
+    fr = o.DF_decomposition(T)
+    co = np.array([f[0] for f in fr])
+    with mb.CSAEngine(T) as e:
+        st = e.df_decompose(verify=True)
+        nf = st["num_frags"]
+        c, w, U, L, kind = e.df_get(0, nf)
+    scale = np.max(np.abs(co))
+    strict = np.abs(np.abs(co) - 1e-8) > 1e-11                    # eigenvalues sitting on the truncation threshold may fall either way
+    assert abs(nf - len(fr)) <= int(np.sum(~strict))
+    k = min(nf, len(fr))
+    assert np.max(np.abs(np.abs(c[:k]) - np.abs(co[:k]))) <= 1e-10 * scale
+    assert st["max_rel_residual"] < 1e-12 and not kind.any()
+    rec = np.einsum("e,epq,ers->pqrs", c, L, L)
+    assert np.max(np.abs(rec - T)) <= 5e-8
+    for i in range(k):
+        gap = min(abs(abs(co[i]) - abs(co[j])) for j in range(len(co)) if j != i)
+        if gap > 1e-6 * scale and abs(c[i] - co[i]) <= 1e-10 * scale:
+            l1, l1_o = 0.5 * abs(c[i]) * np.sum(np.abs(w[i])) ** 2, 0.5 * abs(co[i]) * np.sum(np.abs(fr[i][1])) ** 2
+            assert abs(l1 - l1_o) <= 1e-8 * max(l1_o, 1e-6 * scale)
+            assert np.max(np.abs((U[i] * w[i]) @ U[i].T - L[i])) <= 1e-12
