@@ -21,3 +21,8 @@ extern "C" void** mambo_csa_df_slot(mambo_csa* h, void (*destroy)(void*));
 extern "C" int mambo_csa_io_buffers(mambo_csa* h, double** d_x, double** d_out);
 extern "C" void mambo_set_error(const char* msg);
 extern "C" void mambo_csa_count_launches(mambo_csa* h, long long n);
+// 1 when the handle evaluates through the single-kernel path (tiny::k_eval): one evaluation is one plain kernel launch, so the
+// optimiser may capture a whole device-driven iteration into a CUDA graph
+extern "C" int mambo_csa_is_tiny(mambo_csa* h);
+// mambo_csa_eval_device without the argument checks and cudaSetDevice (safe inside a stream capture on the handle's stream)
+extern "C" int mambo_csa_enqueue_eval(mambo_csa* h, const double* d_x, double* d_out);

@@ -21,6 +21,7 @@
 #include "chain_kernels.cuh"
 #include "panel_kernels.cuh"
 #include "lanczos_kernels.cuh"
+#include "tiny_kernels.cuh"
 
 namespace {
 
@@ -121,6 +122,9 @@ struct mambo_csa {
     // lean single-GEMM path (unsharded handles): no B~/C~ panel GEMMs and no Gram kernel -- the N x N closed forms of
     // panel::k_build_a replace them; B~ is only built for the two-GEMM kernel (residual update, cost-only, exact-cost pass)
     bool lean = false;
+    // molecule-sized problems (N <= MAMBO_TINY_MAX, default 10; packed rows; unsharded): the whole evaluation is ONE single-CTA
+    // kernel (tiny::k_eval) instead of the 11-launch pipeline, whose every launch is latency-bound at that size
+    bool tiny = false;
     double* aux = nullptr;                     // [o | d | t | wn] of k_build_a (3 N + 1)
     double* obc = nullptr;                     // one-body cost of the last evaluation (CSA_SD), 0 for CSA
     cudaStream_t side_stream = nullptr;        // the flagged exact-cost pass runs beside the derivative chain
@@ -660,7 +664,26 @@ GraphSeg& seg_for(std::vector<GraphSeg>& v, int s_host) {  // index 0: device-de
 // stage A: everything up to the per-shard partial vector [cost, S, G] (x must already be in h->d_x).
 //   one_call: the finish half follows in the same call (eval_device / host closures), so the flagged exact-cost pass may be
 //   left to it (it then runs beside the derivative chain); otherwise part[0] is final when this segment ends.
+int enqueue_tiny(mambo_csa* h, bool need_grad) {
+    tiny::Params p;
+    p.x = h->d_x; p.T = h->T1; p.ldT = h->ldT; p.hT = h->flavour == MAMBO_CSA_SD ? h->hT : nullptr;
+    p.pa = h->pa; p.pq = h->pq; p.sw = h->sw;
+    p.n = h->N; p.M = h->nR; p.sd = h->flavour == MAMBO_CSA_SD ? 1 : 0; p.lam_off = h->lam_off; p.cL = h->cL;
+    p.need_grad = need_grad ? 1 : 0;
+    p.out = h->d_out; p.cost_out = h->d_part; p.obc = h->obc; p.status = h->d_status;
+    tiny::k_eval<<<1, tiny::NT, tiny::smem_bytes(h->N, h->nR), h->stream>>>(p);
+    h->launches++;
+    CU(cudaGetLastError());
+    return MAMBO_OK;
+}
+
 int enqueue_partial(mambo_csa* h, int s_host, bool need_grad, bool one_call) {
+    if (h->tiny && (one_call || !need_grad)) {            // molecule sizes: cost (+ gradient) in one single-CTA kernel
+        if (need_grad) TRY(seg_mark(h));
+        TRY(enqueue_tiny(h, need_grad));
+        if (need_grad) { TRY(seg_mark(h)); }
+        return MAMBO_OK;
+    }
     if (need_grad) TRY(seg_mark(h));
     if (!need_grad) {
         // cost only: reconstruction + residual norm with the two-GEMM kernel's first half (needs B~)
@@ -729,6 +752,10 @@ int enqueue_partial(mambo_csa* h, int s_host, bool need_grad, bool one_call) {
 }
 
 int enqueue_finish_seg(mambo_csa* h, int s_host, bool one_call) {
+    if (h->tiny && one_call) {                              // tiny::k_eval has written d_out already
+        TRY(seg_mark(h));
+        return seg_mark(h);
+    }
     TRY(seg_mark(h));
     TRY(run_segment(h, seg_for(one_call ? h->g_fin : h->g_fin_seq, s_host),
                     [&]() -> int { return enqueue_finish(h, h->d_x, h->d_out, one_call); }));
@@ -1087,6 +1114,13 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
         NB_PANEL_DISPATCH(h->NB, need_prep = (panel::prep_smem<NBT, CSP>()));
         if (std::max(need_post, need_prep) > prop.sharedMemPerBlockOptin || chain::smem_bytes(n, h->chain_ct) > prop.sharedMemPerBlockOptin)
             return fail(MAMBO_EINVAL, "N too large for the shared-memory budget of the panel / chain kernels");
+    }
+    {
+        int tiny_max = 10;
+        if (const char* e = std::getenv("MAMBO_TINY_MAX")) tiny_max = std::max(0, std::min(tiny::NMAX, std::atoi(e)));
+        if (std::getenv("MAMBO_NO_TINY")) tiny_max = 0;
+        h->tiny = h->packed && h->nshards == 1 && n <= tiny_max && tiny::smem_bytes(n, h->nR) <= prop.sharedMemPerBlockOptin;
+        if (h->tiny) CU(raise_smem(tiny::k_eval, (int)tiny::smem_bytes(n, h->nR)));
     }
     h->fast = std::getenv("MAMBO_TWO_GEMM") == nullptr;
     // lean path: unsharded handles only (a shard needs its own rows' |W~|^2, which has no N x N closed form); MAMBO_NO_LEAN=1
@@ -1543,10 +1577,16 @@ int mambo_csa_eval_finish_device(mambo_csa* h, const double* d_partial, double* 
     return MAMBO_OK;
 }
 
+int mambo_csa_is_tiny(mambo_csa* h) { return h && h->tiny ? 1 : 0; }
+
 int mambo_csa_eval_device(mambo_csa* h, const double* d_x, double* d_out) {
     if (!h || !d_x || !d_out) return fail(MAMBO_EINVAL, "null argument");
     if (h->nshards != 1) return fail(MAMBO_ESTATE, "sharded handle: use eval_partial_device / eval_finish_device around an allreduce");
     CU(cudaSetDevice(h->device));
+    return mambo_csa_enqueue_eval(h, d_x, d_out);
+}
+
+int mambo_csa_enqueue_eval(mambo_csa* h, const double* d_x, double* d_out) {
     const long long l0 = h->launches;
     if (d_x != h->d_x) CU(cudaMemcpyAsync(h->d_x, d_x, sizeof(double) * h->L, cudaMemcpyDeviceToDevice, h->stream));
     TRY(enqueue_partial(h, -1, true, true));

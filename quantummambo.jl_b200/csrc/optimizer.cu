@@ -975,6 +975,42 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         }
     } ev_guard{ring_ev};
     int fast_iterations = 0;
+    // Molecule-sized handles (single-kernel evaluation): the eight launches of one device-driven iteration cost more host time
+    // than the device needs to run them, so the iteration is captured once into a CUDA graph and replayed (every pointer in it
+    // is owned by the handle or by this optimiser's workspace).
+    const bool graph_iter = !o->sharded && mambo_csa_is_tiny(o->h) && std::getenv("MAMBO_OPT_NO_GRAPH") == nullptr;
+    struct GraphGuard {
+        cudaGraphExec_t exec = nullptr;
+        ~GraphGuard() { if (exec) cudaGraphExecDestroy(exec); }
+    } iter_graph;
+    // one device-driven iteration: trial point, evaluation, Wolfe test, update + direction, state
+    auto enqueue_iteration = [&](bool capturing) -> int {
+        const int nb = blocks(L);
+        k_fast_trial<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->p, o->xt, L);
+        // (row-panel shards: the exchange inside the evaluation returns identical bits on every rank, every rank takes the
+        // same decisions from them and enqueues the same number of evaluations, so the peer epochs stay aligned)
+        int rc2 = o->sharded ? mambo_csa_eval_sharded_device(o->h, o->xt, o->out)
+                             : (capturing ? mambo_csa_enqueue_eval(o->h, o->xt, o->out) : mambo_csa_eval_device(o->h, o->xt, o->out));
+        if (rc2) {
+            snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+            return rc2;
+        }
+        k_fast_wolfe_part<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->p, o->out, o->part, L);
+        k_fast_wolfe_apply<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->out, o->part, nb, o->s, o->s2, o->y, L);
+        if (lbfgs) {
+            k_fast_lbfgs_store<<<nb, 256, 0, o->stream>>>(o->dstate, o->s, o->y, o->LS, o->LY, o->Lrho, mem, o->x, o->xt, o->g, o->out, L);
+            k_fast_lbfgs_gram<<<nb, 256, lb_smem, o->stream>>>(o->dstate, o->LS, o->LY, o->g, mem, L, o->lpart);
+            k_fast_lbfgs_solve<<<1, 256, sizeof(double) * (lb_ldp(mem) + 2 * mem), o->stream>>>(o->dstate, o->lpart, nb, mem, o->lcoef);
+            k_fast_lbfgs_apply<<<nb, 256, 0, o->stream>>>(o->dstate, o->lcoef, o->LS, o->LY, o->g, mem, L, o->p);
+        } else {
+            k_sym_update_gemv<<<dim3(o->ntb, o->ntb), 256, 0, o->stream>>>(o->H, o->ldh, L, o->dstate, o->s, o->s2, o->Hy, o->Hy2, 1.0, 0.0, 0.0, 0,
+                                                                             o->out + 1, o->P, o->ntb);
+            k_fast_dots<<<nb, 256, 0, o->stream>>>(o->dstate, o->P, o->ntb, o->p, o->out, o->s, o->s2, o->Hy, o->Hy2, o->y, o->u, o->part, L);
+            k_fast_direction<<<nb, 256, 0, o->stream>>>(o->dstate, o->part, nb, o->x, o->xt, o->g, o->p, o->out, o->u, o->s, o->s2, o->Hy, o->Hy2, L);
+            k_fast_state<<<1, 32, 0, o->stream>>>(o->dstate, o->part, nb);
+        }
+        return MAMBO_OK;
+    };
     // runs device-driven iterations until the device halts or the iteration budget is used; returns the halt code in *halt_out
     auto fast_run = [&](int* halt_out) -> int {
         for (int k = 0; k < RING; ++k)
@@ -992,30 +1028,28 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         DevState last = hs;
         while (true) {
             if (enq < budget && enq - seen < DEPTH) {
-                k_fast_trial<<<blocks(L), 256, 0, o->stream>>>(o->dstate, o->x, o->p, o->xt, L);
-                // (row-panel shards: the exchange inside the evaluation returns identical bits on every rank, every rank takes the
-                // same decisions from them and enqueues the same number of evaluations, so the peer epochs stay aligned)
-                int rc2 = o->sharded ? mambo_csa_eval_sharded_device(o->h, o->xt, o->out) : mambo_csa_eval_device(o->h, o->xt, o->out);
-                if (rc2) {
-                    snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
-                    return rc2;
+                if (graph_iter) {
+                    if (!iter_graph.exec) {
+                        if (CK(cudaStreamBeginCapture(o->stream, cudaStreamCaptureModeThreadLocal), "begin capture")) return MAMBO_ECUDA;
+                        const int rcc = enqueue_iteration(true);
+                        cudaGraph_t g = nullptr;
+                        const cudaError_t ce = cudaStreamEndCapture(o->stream, &g);
+                        if (rcc) {
+                            if (g) cudaGraphDestroy(g);
+                            return rcc;
+                        }
+                        if (CK(ce, "end capture")) return MAMBO_ECUDA;
+                        const cudaError_t ci = cudaGraphInstantiate(&iter_graph.exec, g, 0);
+                        cudaGraphDestroy(g);
+                        if (CK(ci, "graph instantiate")) return MAMBO_ECUDA;
+                    }
+                    if (CK(cudaGraphLaunch(iter_graph.exec, o->stream), "graph launch")) return MAMBO_ECUDA;
+                    mambo_csa_count_launches(o->h, 1);
+                } else {
+                    const int rci = enqueue_iteration(false);
+                    if (rci) return rci;
                 }
                 o->evals++;
-                const int nb = blocks(L);
-                k_fast_wolfe_part<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->p, o->out, o->part, L);
-                k_fast_wolfe_apply<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->out, o->part, nb, o->s, o->s2, o->y, L);
-                if (lbfgs) {
-                    k_fast_lbfgs_store<<<nb, 256, 0, o->stream>>>(o->dstate, o->s, o->y, o->LS, o->LY, o->Lrho, mem, o->x, o->xt, o->g, o->out, L);
-                    k_fast_lbfgs_gram<<<nb, 256, lb_smem, o->stream>>>(o->dstate, o->LS, o->LY, o->g, mem, L, o->lpart);
-                    k_fast_lbfgs_solve<<<1, 256, sizeof(double) * (lb_ldp(mem) + 2 * mem), o->stream>>>(o->dstate, o->lpart, nb, mem, o->lcoef);
-                    k_fast_lbfgs_apply<<<nb, 256, 0, o->stream>>>(o->dstate, o->lcoef, o->LS, o->LY, o->g, mem, L, o->p);
-                } else {
-                    k_sym_update_gemv<<<dim3(o->ntb, o->ntb), 256, 0, o->stream>>>(o->H, o->ldh, L, o->dstate, o->s, o->s2, o->Hy, o->Hy2, 1.0, 0.0, 0.0, 0,
-                                                                                     o->out + 1, o->P, o->ntb);
-                    k_fast_dots<<<nb, 256, 0, o->stream>>>(o->dstate, o->P, o->ntb, o->p, o->out, o->s, o->s2, o->Hy, o->Hy2, o->y, o->u, o->part, L);
-                    k_fast_direction<<<nb, 256, 0, o->stream>>>(o->dstate, o->part, nb, o->x, o->xt, o->g, o->p, o->out, o->u, o->s, o->s2, o->Hy, o->Hy2, L);
-                    k_fast_state<<<1, 32, 0, o->stream>>>(o->dstate, o->part, nb);
-                }
                 if (CK(cudaMemcpyAsync(ring_slot(enq), o->dstate, sizeof(DevState), cudaMemcpyDeviceToHost, o->stream), "D2H state") ||
                     CK(cudaEventRecord(ring_ev[enq % RING], o->stream), "event record"))
                     return MAMBO_ECUDA;

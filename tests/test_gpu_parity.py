@@ -944,3 +944,52 @@ def test_one_body_matrix_of_the_resident_residual(mb, lib, kind, flavour):
         c, g = e.cost_grad(x)                      # the call leaves the evaluation state intact
     c0, g0 = o.cost_grad_factored(x, T - W, o_rem if flavour == "CSA_SD" else None, flavour)
     assert abs(c - c0) <= RTOL * abs(c0) and rel(g, g0) <= RTOL
+
+
+# ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 3, 6, 7, 10])
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+def test_molecule_sizes_single_kernel_and_main_pipeline_agree(mb, lib, monkeypatch, n, flavour):
+    """N <= 10 with an 8-fold symmetric tensor runs as ONE single-CTA kernel (tiny::k_eval); MAMBO_NO_TINY=1 keeps the
+    11-launch pipeline.  Both against the oracle, and against each other, at random points and at a planted minimum."""
+    T = o.dense_sym_tbt(n, 3)
+    obt = _obt(n, 3) if flavour == "CSA_SD" else None
+    if obt is not None:
+        obt = 0.5 * (obt + obt.T)
+    xs = [o.random_x(n, s, flavour) for s in (0, 5)]
+    one = mb.CSAEngine(T, obt, flavour)
+    monkeypatch.setenv("MAMBO_NO_TINY", "1")
+    pipe = mb.CSAEngine(T, obt, flavour)
+    monkeypatch.delenv("MAMBO_NO_TINY")
+    try:
+        for x in xs:
+            c1, g1 = one.cost_grad(x)
+            assert one.info()["launches_per_eval"] == 1
+            c2, g2 = pipe.cost_grad(x)
+            assert pipe.info()["launches_per_eval"] > 1
+            c0, g0 = o.cost_grad_factored(x, T, obt, flavour)
+            for c, g in ((c1, g1), (c2, g2)):
+                assert abs(c - c0) <= RTOL * abs(c0)
+                assert rel(g, g0) <= RTOL
+            assert abs(one.cost(x) - c0) <= RTOL * abs(c0)
+        assert abs(one.residual_cost() - pipe.residual_cost()) <= 1e-13 * pipe.residual_cost()
+    finally:
+        one.close()
+        pipe.close()
+
+
+@pytest.mark.parametrize("n", [11, 13, 16])
+def test_single_kernel_evaluation_up_to_its_largest_size(mb, lib, monkeypatch, n):
+    """MAMBO_TINY_MAX raises the threshold up to the kernel's limit (N = 16, 136 packed rows, 182 KB of shared memory)."""
+    monkeypatch.setenv("MAMBO_TINY_MAX", "16")
+    T = o.dense_sym_tbt(n, 1)
+    obt = _obt(n, 1)
+    obt = 0.5 * (obt + obt.T)
+    for flavour, ob in (("CSA", None), ("CSA_SD", obt)):
+        x = o.random_x(n, 2, flavour)
+        with mb.CSAEngine(T, ob, flavour) as e:
+            c, g = e.cost_grad(x)
+            assert e.info()["launches_per_eval"] == 1
+        c0, g0 = o.cost_grad_factored(x, T, ob, flavour)
+        assert abs(c - c0) <= RTOL * abs(c0)
+        assert rel(g, g0) <= RTOL
