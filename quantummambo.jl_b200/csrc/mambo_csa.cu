@@ -122,7 +122,7 @@ struct mambo_csa {
     // lean single-GEMM path (unsharded handles): no B~/C~ panel GEMMs and no Gram kernel -- the N x N closed forms of
     // panel::k_build_a replace them; B~ is only built for the two-GEMM kernel (residual update, cost-only, exact-cost pass)
     bool lean = false;
-    // molecule-sized problems (N <= MAMBO_TINY_MAX, default 10; packed rows; unsharded): the whole evaluation is ONE single-CTA
+    // molecule-sized problems (N <= MAMBO_TINY_MAX, default 12; packed rows; unsharded): the whole evaluation is ONE single-CTA
     // kernel (tiny::k_eval) instead of the 11-launch pipeline, whose every launch is latency-bound at that size
     bool tiny = false;
     double* aux = nullptr;                     // [o | d | t | wn] of k_build_a (3 N + 1)
@@ -1116,7 +1116,7 @@ int build_handle(mambo_csa* h, const double* tbt, const double* obt, unsigned fl
             return fail(MAMBO_EINVAL, "N too large for the shared-memory budget of the panel / chain kernels");
     }
     {
-        int tiny_max = 10;
+        int tiny_max = 12;                                   // measured (tools/tiny_threshold.py): 40 vs 65 us at N = 12, break-even at N = 15
         if (const char* e = std::getenv("MAMBO_TINY_MAX")) tiny_max = std::max(0, std::min(tiny::NMAX, std::atoi(e)));
         if (std::getenv("MAMBO_NO_TINY")) tiny_max = 0;
         h->tiny = h->packed && h->nshards == 1 && n <= tiny_max && tiny::smem_bytes(n, h->nR) <= prop.sharedMemPerBlockOptin;

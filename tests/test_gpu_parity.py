@@ -947,10 +947,10 @@ def test_one_body_matrix_of_the_resident_residual(mb, lib, kind, flavour):
 
 
 # ------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 3, 6, 7, 10])
+@pytest.mark.parametrize("n", [1, 2, 3, 6, 7, 10, 12])
 @pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
 def test_molecule_sizes_single_kernel_and_main_pipeline_agree(mb, lib, monkeypatch, n, flavour):
-    """N <= 10 with an 8-fold symmetric tensor runs as ONE single-CTA kernel (tiny::k_eval); MAMBO_NO_TINY=1 keeps the
+    """N <= 12 with an 8-fold symmetric tensor runs as ONE single-CTA kernel (tiny::k_eval); MAMBO_NO_TINY=1 keeps the
     11-launch pipeline.  Both against the oracle, and against each other, at random points and at a planted minimum."""
     T = o.dense_sym_tbt(n, 3)
     obt = _obt(n, 3) if flavour == "CSA_SD" else None
@@ -978,7 +978,7 @@ def test_molecule_sizes_single_kernel_and_main_pipeline_agree(mb, lib, monkeypat
         pipe.close()
 
 
-@pytest.mark.parametrize("n", [11, 13, 16])
+@pytest.mark.parametrize("n", [13, 16])
 def test_single_kernel_evaluation_up_to_its_largest_size(mb, lib, monkeypatch, n):
     """MAMBO_TINY_MAX raises the threshold up to the kernel's limit (N = 16, 136 packed rows, 182 KB of shared memory)."""
     monkeypatch.setenv("MAMBO_TINY_MAX", "16")
