@@ -512,6 +512,132 @@ __global__ void __launch_bounds__(32) k_fast_state(DevState* __restrict__ st, co
     }
 }
 
+// ---- single-CTA problems (L <= 256: molecule sizes): the same iteration in fewer launches ------------------------------------
+// With one CTA every "per-CTA partial -> fixed-order sum" pair collapses into one block reduction, so k_fast_wolfe_part +
+// k_fast_wolfe_apply become one kernel and k_fast_dots + k_fast_direction + k_fast_state + the NEXT iteration's k_fast_trial
+// another: an iteration is evaluation, A, k_sym_update_gemv, B instead of eight launches.  The arithmetic and its order are
+// those of the kernels above (block_sum4 adds in store_partials' order, and sum_partials over one CTA adds zeros), so the
+// trajectory is bit-identical to the unfused path (MAMBO_OPT_NO_FUSE=1; tested).
+__device__ __forceinline__ void block_sum4(double v0, double v1, double v2, double v3, bool last_is_max, double* sh /* 4 */) {
+    __shared__ double sd4[4][8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+        const double t = __shfl_xor_sync(0xffffffffu, v3, o);
+        v3 = last_is_max ? fmax(v3, t) : v3 + t;
+    }
+    __syncthreads();                                   // sd4 / sh may still be read from an earlier call
+    if ((threadIdx.x & 31) == 0) {
+        sd4[0][threadIdx.x >> 5] = v0; sd4[1][threadIdx.x >> 5] = v1; sd4[2][threadIdx.x >> 5] = v2; sd4[3][threadIdx.x >> 5] = v3;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t = (last_is_max && threadIdx.x == 3) ? fmax(t, sd4[3][w]) : t + sd4[threadIdx.x][w];
+        // sum_partials over a single CTA: 0 + t (0 max t) in lane 0, zeros elsewhere
+        sh[threadIdx.x] = (last_is_max && threadIdx.x == 3) ? fmax(0.0, t) : 0.0 + t;
+    }
+    __syncthreads();
+}
+// A: Wolfe sums + strong-Wolfe test + (on success) s, y            (1 CTA of 256 threads, n <= 256)
+__global__ void __launch_bounds__(256) k_fast_small_a(DevState* st, const double* x, const double* xt, const double* g, const double* p,
+                                                      const double* out, double* s0, double* s1, double* y, int n) {
+    __shared__ double sh[4];
+    if (st->halt) return;
+    const int i = threadIdx.x;
+    double df = 0.0, sy = 0.0, yy = 0.0, gm = 0.0;
+    if (i < n) {
+        const double gi = out[1 + i], si = xt[i] - x[i], yi = gi - g[i];
+        df = gi * p[i];
+        sy = si * yi;
+        yy = yi * yi;
+        gm = fabs(gi);
+    }
+    block_sum4(df, sy, yy, gm, true, sh);
+    const double c1 = 1e-4, c2 = 0.9;
+    const double f = out[0], f0 = st->f, df0 = st->df0, a = st->a1;
+    const int parity = st->parity;
+    const bool ok = (f <= f0 + c1 * a * df0) && (fabs(sh[0]) <= -c2 * df0) && (f <= f0);      // NaN fails every comparison
+    __syncthreads();                                   // every thread has read the state before thread 0 changes it
+    if (threadIdx.x == 0) {
+        if (ok) {
+            st->sy = sh[1]; st->yy = sh[2]; st->f_new = f; st->gmax_new = sh[3];
+            st->df0_prev = df0; st->alpha_prev = a;
+        } else {
+            st->halt = 2;
+        }
+    }
+    if (!ok) return;
+    double* s = parity ? s1 : s0;
+    if (i < n) {
+        s[i] = xt[i] - x[i];
+        y[i] = out[1 + i] - g[i];
+    }
+}
+// B: u, Hy and their dots; direction, x <- xt, g <- g_new; the scalars of the finished iteration; the next trial point
+__global__ void __launch_bounds__(256) k_fast_small_b(DevState* st, const double* P, int ntb, double* x, double* xt, double* g, double* p,
+                                                      const double* out, double* u, const double* s0, const double* s1, double* hy0, double* hy1,
+                                                      const double* y, int n) {
+    __shared__ double sh[4];
+    __shared__ double nxt[4];                          // halt, df0, alpha_prev, df0_prev of the NEW state
+    if (st->halt) return;
+    const int parity = st->parity;
+    const double* s = parity ? s1 : s0;
+    double* Hy = parity ? hy1 : hy0;
+    const int i = threadIdx.x;
+    double yHy = 0.0, hyg = 0.0, sg = 0.0, ug = 0.0, ui = 0.0, hy = 0.0, si = 0.0;
+    if (i < n) {
+        ui = sym_gemv_sum(P, ntb, i);
+        hy = ui + p[i];                                // H y = H g_new - H g = u + p   (p = -H g)
+        u[i] = ui;
+        Hy[i] = hy;
+        const double gi = out[1 + i];
+        si = s[i];
+        yHy = y[i] * hy;
+        hyg = hy * gi;
+        sg = si * gi;
+        ug = ui * gi;
+    }
+    block_sum4(yHy, hyg, sg, ug, false, sh);
+    const double syv = st->sy;
+    const bool upd = syv > 1e-300;
+    const double r1 = upd ? 1.0 / syv : 0.0;
+    const double rho = r1, cc = r1 * (1.0 + r1 * sh[0]);
+    if (i < n) {
+        p[i] = upd ? -(ui - rho * (si * sh[1] + hy * sh[2]) + cc * si * sh[2]) : -ui;
+        x[i] = xt[i];
+        g[i] = out[1 + i];
+    }
+    __syncthreads();                                   // every thread has read the state; p and x are complete
+    if (threadIdx.x == 0) {
+        const double hygv = sh[1], sgv = sh[2], ugv = sh[3];
+        const double df0n = upd ? -(ugv - rho * (sgv * hygv + hygv * sgv) + cc * sgv * sgv) : -ugv;
+        st->df0 = df0n;
+        st->rho = rho; st->cc = cc;
+        st->pending = upd ? 1 : 0;
+        if (upd) st->parity = parity ^ 1;
+        st->f = st->f_new;
+        const double gn = st->gmax_new;
+        st->gnorm = gn;
+        st->it += 1;
+        int halt = 0;
+        if (gn <= st->gtol) halt = 1;
+        else if (!(df0n < 0.0)) halt = 3;              // what the next iteration's k_fast_trial would find
+        if (halt) st->halt = halt;
+        nxt[0] = (double)halt; nxt[1] = df0n; nxt[2] = st->alpha_prev; nxt[3] = st->df0_prev;
+    }
+    __syncthreads();
+    if (nxt[0] != 0.0) return;
+    // k_fast_trial of the next iteration
+    const double ap = nxt[2];
+    double a1 = ap * (nxt[3] / nxt[1]);                // Nocedal & Wright (3.60), same clamps as the host rule
+    a1 = fmin(1.0, fmax(0.5 * ap, fmin(a1, 2.0 * ap)));
+    if (i < n) xt[i] = fma(a1, p[i], x[i]);
+    if (i == 0) st->a1 = a1;
+}
+
 // ---- limited-memory mode of the device-driven iterations ------------------------------------------------------------------
 // the ring slot the pair of this iteration goes to, the number of pairs in use and H_0's scale, from the state BEFORE the update
 __device__ __forceinline__ void lbfgs_next(const DevState* st, int mem, int* head, int* used, double* gamma) {
@@ -984,8 +1110,24 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         ~GraphGuard() { if (exec) cudaGraphExecDestroy(exec); }
     } iter_graph;
     // one device-driven iteration: trial point, evaluation, Wolfe test, update + direction, state
+    // single-CTA problems: fused kernels (k_fast_small_a / _b); the trial point of an iteration is then computed by the previous
+    // iteration's B kernel, so a run of iterations starts with one standalone k_fast_trial
+    const bool fuse_small = !lbfgs && !o->sharded && blocks(L) == 1 && std::getenv("MAMBO_OPT_NO_FUSE") == nullptr;
     auto enqueue_iteration = [&](bool capturing) -> int {
         const int nb = blocks(L);
+        if (fuse_small) {
+            int rc2 = capturing ? mambo_csa_enqueue_eval(o->h, o->xt, o->out) : mambo_csa_eval_device(o->h, o->xt, o->out);
+            if (rc2) {
+                snprintf(o->err, sizeof(o->err), "%s", mambo_last_error());
+                return rc2;
+            }
+            k_fast_small_a<<<1, 256, 0, o->stream>>>(o->dstate, o->x, o->xt, o->g, o->p, o->out, o->s, o->s2, o->y, L);
+            k_sym_update_gemv<<<dim3(o->ntb, o->ntb), 256, 0, o->stream>>>(o->H, o->ldh, L, o->dstate, o->s, o->s2, o->Hy, o->Hy2, 1.0, 0.0, 0.0, 0,
+                                                                             o->out + 1, o->P, o->ntb);
+            k_fast_small_b<<<1, 256, 0, o->stream>>>(o->dstate, o->P, o->ntb, o->x, o->xt, o->g, o->p, o->out, o->u, o->s, o->s2, o->Hy, o->Hy2,
+                                                     o->y, L);
+            return MAMBO_OK;
+        }
         k_fast_trial<<<nb, 256, 0, o->stream>>>(o->dstate, o->x, o->p, o->xt, L);
         // (row-panel shards: the exchange inside the evaluation returns identical bits on every rank, every rank takes the
         // same decisions from them and enqueues the same number of evaluations, so the peer epochs stay aligned)
@@ -1026,6 +1168,7 @@ int optimize_impl(mambo_csa* h, const double* x0, double* x_min, const mambo_opt
         if (CK(cudaStreamSynchronize(o->stream), "sync")) return MAMBO_ECUDA;       // `up` is reused as a ring slot below
         int budget = opt.max_iter - it, enq = 0, seen = 0, halt = 0;
         DevState last = hs;
+        if (fuse_small) k_fast_trial<<<blocks(L), 256, 0, o->stream>>>(o->dstate, o->x, o->p, o->xt, L);
         while (true) {
             if (enq < budget && enq - seen < DEPTH) {
                 if (graph_iter) {

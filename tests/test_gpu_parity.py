@@ -993,3 +993,33 @@ def test_single_kernel_evaluation_up_to_its_largest_size(mb, lib, monkeypatch, n
         c0, g0 = o.cost_grad_factored(x, T, ob, flavour)
         assert abs(c - c0) <= RTOL * abs(c0)
         assert rel(g, g0) <= RTOL
+
+
+@pytest.mark.parametrize("n,flavour", [(6, "CSA"), (7, "CSA_SD"), (10, "CSA"), (12, "CSA_SD")])
+def test_fused_and_graphed_optimiser_iterations_follow_the_same_trajectory(mb, lib, monkeypatch, n, flavour):
+    """Single-CTA problems (num_params <= 256) run a device-driven iteration as evaluation + two fused kernels around the pass
+    over the inverse Hessian, replayed from a CUDA graph on single-kernel handles.  Same arithmetic in the same order as the
+    eight-launch path (MAMBO_OPT_NO_FUSE=1, MAMBO_OPT_NO_GRAPH=1): bit-identical minimiser, minimum and iteration count."""
+    T = o.dense_sym_tbt(n, 4)
+    obt = None
+    if flavour == "CSA_SD":
+        obt = _obt(n, 4)
+        obt = 0.5 * (obt + obt.T)
+    x0 = o.random_x(n, 7, flavour)
+    runs = []
+    with mb.CSAEngine(T, obt, flavour) as e:
+        assert e.info()["num_params"] <= 256
+        for env in ({}, {"MAMBO_OPT_NO_GRAPH": "1"}, {"MAMBO_OPT_NO_FUSE": "1", "MAMBO_OPT_NO_GRAPH": "1"}):
+            for k in ("MAMBO_OPT_NO_FUSE", "MAMBO_OPT_NO_GRAPH"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            runs.append(e.optimize(x0, g_tol=1e-10, max_iter=120))
+    for k in ("MAMBO_OPT_NO_FUSE", "MAMBO_OPT_NO_GRAPH"):
+        monkeypatch.delenv(k, raising=False)
+    (xa, ra), (xb, rb), (xc, rc) = runs
+    assert ra["iterations"] == rb["iterations"] == rc["iterations"] and ra["iterations"] > 20
+    assert ra["minimum"] == rb["minimum"] == rc["minimum"]
+    assert np.array_equal(xa, xb) and np.array_equal(xa, xc)
+    c0, g0 = o.cost_grad_factored(xa, T, obt, flavour)
+    assert abs(c0 - ra["minimum"]) <= 1e-10 * abs(c0)
