@@ -7,7 +7,7 @@ from ._lib import build, load, MamboError  # noqa: F401
 from .engine import (CSAEngine, multistart, cost_grad_batch, frag_l1, write_x_block, read_x_block, CSA, CSA_SD, SYM_AUTO,  # noqa: F401
                      SYM_GENERAL, SYM_PAIR, SYM_FULL)
 from .structures import (F_OP, F_FRAG, cartan_2b, cartan_SD, real_orbital_rotation, CSA_x_to_F_FRAG,  # noqa: F401
-                         CSA_SD_x_to_F_FRAG, CSA_L1, ob_correction, one_body_L1, cartan_2b_num_params, cartan_SD_num_params,
+                         CSA_SD_x_to_F_FRAG, CSA_L1, DF_L1, ob_correction, one_body_L1, cartan_2b_num_params, cartan_SD_num_params,
                          real_orbital_rotation_num_params)
 from .decompose import (CSA_greedy_decomposition, CSA_greedy_step, CSA_SD_greedy_decomposition,  # noqa: F401
                         CSA_SD_greedy_step, to_OP, OptimResult)

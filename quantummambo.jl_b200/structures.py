@@ -129,6 +129,14 @@ def CSA_L1(F: F_FRAG) -> float:
     return l1
 
 
+def DF_L1(coeff, omega, spin_orb: bool = False) -> float:
+    """lcu.jl:210-221: 1-norm of a double-factorisation fragment, |coeff| (sum |lambda|)^2 / 2 (orbitals only, like the reference);
+    `coeff`, `omega` as returned per fragment by CSAEngine.df_get."""
+    if spin_orb:
+        raise ValueError("1-norm DF calculation not implemented for spin-orb=true")
+    return 0.5 * abs(float(coeff)) * float(np.sum(np.abs(omega))) ** 2
+
+
 def ob_correction(tbt, spin_orb: bool = False) -> np.ndarray:
     """fermionic.jl:457-479: one-body correction carried by the two-body tensor, (2x) sum_r tbt[:, :, r, r]."""
     tbt = np.asarray(tbt, dtype=np.float64)

@@ -38,7 +38,7 @@ def run(name, fx, cpu=True):
             st = e.df_decompose()
             c, w, _, _, _ = e.df_get(0, st["num_frags"], want_L=False, want_U=False)
         t_df = time.perf_counter() - t0
-        l_df = float(np.sum(0.5 * np.abs(c) * np.sum(np.abs(w), axis=1) ** 2))
+        l_df = float(sum(mb.DF_L1(c[k], w[k]) for k in range(len(c))))
         fr = o.DF_decomposition(T)
         l_df_o = float(sum(0.5 * abs(cc) * np.sum(np.abs(ww)) ** 2 for cc, ww, _, _ in fr))
         print(f"   lambda_DF  = lambda_1 + {l_df:.10f} ({st['num_frags']} fragments, {t_df * 1e3:.1f} ms incl. upload)   oracle {l_df_o:.10f} "
