@@ -320,3 +320,29 @@ def test_df_based_greedy_oracle_known_answer():
     # and the CSA fragment it defines reproduces the tensor: W = sum_ij Lm_ij U1[:,i]U1[:,i]' (x) U1[:,j]U1[:,j]'
     W = np.einsum("ij,ai,bi,cj,dj->abcd", Lm, U1, U1, U1, U1)
     assert np.max(np.abs(W - T)) <= 1e-13
+
+
+def test_ne2_known_answer():
+    """SURVEY 8c pin (3): the Ne^2 symmetry operator (symmetries.jl:8-13: tbt[i,i,j,j] = 1) is a CSA fragment at theta = 0.
+    Through cartan_2b_to_tbt (fermionic.jl:20-32) its coefficients are lambda = 1 everywhere: cost 0, gradient 0.  The vector
+    of Ne2_lambda_builder (symmetries.jl:28-45: 2 off the diagonal) is NOT that fragment under cartan_2b_to_tbt -- the
+    reconstruction carries 2 at [i,i,j,j], i != j -- so its cost against Ne^2 is N (N - 1); both facts are pinned here."""
+    for n in (3, 6, 9):
+        ne2 = np.zeros((n, n, n, n))
+        for i in range(n):
+            for j in range(n):
+                ne2[i, i, j, j] = 1.0
+        cL, uL = o.cartan_2b_num_params(n), o.real_orbital_rotation_num_params(n)
+        x = np.concatenate([np.ones(cL), np.zeros(uL)])
+        c, g = o.cost_grad_factored(x, ne2)
+        assert c < 1e-24 and np.max(np.abs(g)) < 1e-12
+        assert o.cost_literal(x, ne2) < 1e-24
+        lam_b = np.array([1.0 if i == j else 2.0 for i in range(n) for j in range(i + 1)])       # Ne2_lambda_builder
+        xb = np.concatenate([lam_b, np.zeros(uL)])
+        cb, _ = o.cost_grad_factored(xb, ne2)
+        assert abs(cb - n * (n - 1)) < 1e-10
+        assert abs(o.cost_literal(xb, ne2) - n * (n - 1)) < 1e-10
+        # Ne^2 is invariant under every orbital rotation: the cost does not depend on theta, the theta gradient vanishes
+        xr = np.concatenate([np.ones(cL), 2 * np.pi * np.random.default_rng(n).random(uL)])
+        cr, gr = o.cost_grad_factored(xr, ne2)
+        assert cr < 1e-20 and np.max(np.abs(gr[cL:])) < 1e-9
