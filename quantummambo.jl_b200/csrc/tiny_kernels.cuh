@@ -71,10 +71,9 @@ __global__ void __launch_bounds__(NT, 1) k_eval(Params p) {
     extern __shared__ __align__(16) double sm[];
     const int n = p.n, M = p.M, n2 = n * n, Mn = M * n, tid = threadIdx.x;
     double* K = sm;                    // n2 each
-    double* X = K + n2;
-    double* Lam = X + n2;
-    double* U = Lam + n2;
-    double* Gt = U + n2;               // G^T / 2^s
+    double* Lam = K + 2 * n2;          // (one n2 slot after K is spare)
+    double* Lbuf = Lam + n2;           // the derivative L (ping-pong with Dh during its squarings)
+    double* Gt = Lbuf + n2;            // G^T / 2^s
     double* Dh = Gt + n2;              // one-body difference (CSA_SD); scratch of the squarings otherwise
     double* Pw = Dh + n2;              // X^1 .. X^8
     double* dPw = Pw + 8 * n2;         // their derivatives
@@ -144,13 +143,25 @@ __global__ void __launch_bounds__(NT, 1) k_eval(Params p) {
         for (int r = 0; r < n; ++r) v = fma(A[a * n + r], B[r * n + b], v);
         return v;
     };
-    for (int e = tid; e < n2; e += NT) {
-        const double x = K[e] * sc;
-        X[e] = x;
-        Pw[e] = x;
-    }
+    // passes with only n2 independent elements (X^2, the squarings): LG lanes share one dot product (n2 * LG <= NT), fixed order
+    const int LG = (4 * n2 <= NT) ? 4 : ((2 * n2 <= NT) ? 2 : 1);
+    auto mm_split = [&](double* dst, const double* A, const double* B, const double* A2, const double* B2) {   // dst = A B (+ A2 B2)
+        const int e = tid / LG, sub = tid % LG;
+        double v = 0.0;
+        if (e < n2) {
+            const int a = e / n, b = e % n;
+            for (int r = sub; r < n; r += LG) {
+                v = fma(A[a * n + r], B[r * n + b], v);
+                if (A2) v = fma(A2[a * n + r], B2[r * n + b], v);
+            }
+        }
+        if (LG >= 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+        if (LG >= 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
+        if (e < n2 && sub == 0) dst[e] = v;
+    };
+    for (int e = tid; e < n2; e += NT) Pw[e] = K[e] * sc;
     __syncthreads();
-    for (int e = tid; e < n2; e += NT) Pw[n2 + e] = dot(Pw, Pw, e / n, e % n);                              // X^2
+    mm_split(Pw + n2, Pw, Pw, nullptr, nullptr);                                                             // X^2
     __syncthreads();
     for (int t = tid; t < 2 * n2; t += NT) {                                                                   // X^3, X^4
         const int q = t / n2, e = t % n2;
@@ -178,20 +189,10 @@ __global__ void __launch_bounds__(NT, 1) k_eval(Params p) {
     __syncthreads();
     for (int j = 1; j <= s; ++j) {
         const double* src = Esq + (size_t)(j - 1) * n2;
-        double* dst = Esq + (size_t)j * n2;
-        for (int e = tid; e < n2; e += NT) {
-            const int a = e / n, b = e % n;
-            double v = 0.0;
-            for (int r = 0; r < n; ++r) v = fma(src[a * n + r], src[r * n + b], v);
-            dst[e] = v;
-        }
+        mm_split(Esq + (size_t)j * n2, src, src, nullptr, nullptr);
         __syncthreads();
     }
-    {
-        const double* src = Esq + (size_t)s * n2;
-        for (int e = tid; e < n2; e += NT) U[e] = src[e];
-    }
-    __syncthreads();
+    const double* U = Esq + (size_t)s * n2;            // exp(K)
 
     // ---- operands A~, B~ ------------------------------------------------------------------------------------------------------
     for (int e = tid; e < Mn; e += NT) {
@@ -321,10 +322,10 @@ __global__ void __launch_bounds__(NT, 1) k_eval(Params p) {
         }
         return v;
     };
-    double* Ls = U;                                              // U is no longer needed: L is accumulated there
+    double* Ls = Lbuf;
     for (int e = tid; e < n2; e += NT) dPw[e] = Gt[e];
     __syncthreads();
-    for (int e = tid; e < n2; e += NT) dPw[n2 + e] = dot2(dPw, Pw, Pw, dPw, e / n, e % n);
+    mm_split(dPw + n2, dPw, Pw, Pw, dPw);
     __syncthreads();
     for (int t = tid; t < 2 * n2; t += NT) {
         const int q = t / n2, e = t % n2;
@@ -350,12 +351,12 @@ __global__ void __launch_bounds__(NT, 1) k_eval(Params p) {
         Ls[e] = v;
     }
     __syncthreads();
+    double* Lalt = Dh;                                           // the one-body difference is no longer needed
     for (int j = 0; j < s; ++j) {
         const double* Ej = Esq + (size_t)j * n2;
-        for (int e = tid; e < n2; e += NT) Dh[e] = dot2(Ej, Ls, Ls, Ej, e / n, e % n);
+        mm_split(Lalt, Ej, Ls, Ls, Ej);
         __syncthreads();
-        for (int e = tid; e < n2; e += NT) Ls[e] = Dh[e];
-        __syncthreads();
+        double* t = Ls; Ls = Lalt; Lalt = t;
     }
     double* gth = gout + p.lam_off + p.cL;
     for (int e = tid; e < n2; e += NT) {
