@@ -26,7 +26,6 @@ from __future__ import annotations
 import math
 import sys
 from functools import lru_cache
-from itertools import product
 from pathlib import Path
 
 import numpy as np

@@ -3,7 +3,7 @@ the pipeline for N = 8..16 (dense-sym tensors)."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import numpy as np, torch
+import torch
 import mambo_b200 as mb
 import csa_oracle as o
 REPS = 1000
