@@ -346,3 +346,47 @@ def test_ne2_known_answer():
         xr = np.concatenate([np.ones(cL), 2 * np.pi * np.random.default_rng(n).random(uL)])
         cr, gr = o.cost_grad_factored(xr, ne2)
         assert cr < 1e-20 and np.max(np.abs(gr[cL:])) < 1e-9
+
+
+@pytest.mark.parametrize("n", [4, 6])
+@pytest.mark.parametrize("flavour", ["CSA", "CSA_SD"])
+@pytest.mark.parametrize("kind", ["dense_sym", "general"])
+def test_gradient_against_reverse_mode_autodiff(n, flavour, kind):
+    """An independent derivative: the cost written as plain tensor algebra in torch (float64, matrix_exp) and differentiated by
+    reverse-mode autodiff, against the oracle's analytic gradient (gradient.jl:1-290).  On pair-symmetric targets every component
+    must agree; on general tensors the theta (and lambda_1) parts are exact (Q3) while the reference's one-sided lambda expression
+    (Q2) is not the derivative -- both facts are asserted."""
+    import torch
+    T = KINDS[kind](n, 2)
+    obt = _obt(n, 2) if flavour == "CSA_SD" else None
+    x = o.random_x(n, 4, flavour)
+    c0, g0 = o.cost_grad_factored(x, T, obt, flavour)
+    cL, uL = o.cartan_2b_num_params(n), o.real_orbital_rotation_num_params(n)
+    off = n if flavour == "CSA_SD" else 0
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    lam, th = xt[off:off + cL], xt[off + cL:]
+    iu = torch.triu_indices(n, n, 1)
+    K = torch.zeros((n, n), dtype=torch.float64)
+    K = K.index_put((iu[0], iu[1]), th)                     # upper triangle row-major (unitaries.jl:406-415)
+    K = K - K.T
+    U = torch.matrix_exp(K)
+    il = torch.tril_indices(n, n, 0)
+    L = torch.zeros((n, n), dtype=torch.float64).index_put((il[0], il[1]), lam)   # lower triangle row-major (fermionic.jl:20-32)
+    L = L + L.T - torch.diag(torch.diagonal(L))
+    W = torch.einsum("lm,pl,ql,rm,sm->pqrs", L, U, U, U, U)
+    cost = torch.sum((W - torch.tensor(T)) ** 2)
+    if flavour == "CSA_SD":
+        h = (U * xt[:n]) @ U.T
+        cost = cost + torch.sum((h - torch.tensor(obt)) ** 2)
+    cost.backward()
+    ga = xt.grad.numpy()
+    assert abs(float(cost.detach()) - c0) <= 1e-12 * abs(c0)
+    scale = np.max(np.abs(ga))
+    assert np.max(np.abs(ga[off + cL:] - g0[off + cL:])) <= 1e-10 * scale          # theta: exact for any tensor
+    if flavour == "CSA_SD":
+        assert np.max(np.abs(ga[:n] - g0[:n])) <= 1e-10 * scale                    # lambda_1
+    dl = np.max(np.abs(ga[off:off + cL] - g0[off:off + cL]))
+    if kind == "dense_sym":
+        assert dl <= 1e-10 * scale
+    else:
+        assert dl > 1e-3 * scale                                                   # the reference's one-sided expression (Q2)
